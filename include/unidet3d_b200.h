@@ -1,0 +1,195 @@
+/*
+ * unidet3d_b200 -- C-ABI of the B200-native UniDet3D forward hot path.
+ *
+ * The reference (filaPro/unidet3d) has no native code and no FFI: its hot path calls
+ * Python APIs of un-vendored CUDA wheels (spconv, MinkowskiEngine, torch_scatter, mmcv,
+ * torch).  Each entry point below therefore cites the reference *Python call site* whose
+ * native work it replaces (paths relative to the reference checkout).  INTEGRATION.md
+ * shows the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative UD3D_E* code on failure;
+ *     ud3d_last_error() returns a thread-local message for the last failure;
+ *   - all pointers are DEVICE pointers unless the name ends in _host; buffers are
+ *     caller-owned, the library never allocates or frees caller-visible memory;
+ *   - scratch memory comes from a caller-supplied workspace (pointer + size, with a
+ *     *_workspace_bytes() query);
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises the host;
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails.
+ */
+#ifndef UNIDET3D_B200_H_
+#define UNIDET3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UD3D_OK 0
+#define UD3D_EINVAL (-1)    /* bad argument (shape / alignment / NULL) */
+#define UD3D_ECUDA (-2)     /* CUDA runtime error (message has the CUDA string) */
+#define UD3D_EWORKSPACE (-3)/* workspace too small */
+#define UD3D_EUNSUPPORTED (-4)
+
+#define UD3D_TILE_M 128     /* output rows per CTA tile of the gather-GEMM (tile_mask granularity) */
+
+int ud3d_version(void);
+const char* ud3d_last_error(void);
+/* number of this library's kernels launched by the calling thread since the last reset */
+int64_t ud3d_launch_count(int reset);
+
+/* ------------------------------------------------------------------ voxelisation
+ * reference: unidet3d/unidet3d.py:136-176 (UniDet3D.collate -> ME.utils.batch_sparse_collate,
+ * ME.TensorField(...).sparse(), field.inverse_mapping).
+ *
+ * ud3d_point_coords: per scene b (points [scene_offsets[b], scene_offsets[b+1])):
+ *   coords[p] = (b, floor((xyz - min_b) / voxel_size))  int32, IEEE fp32 division
+ *   feats[p]  = (rgb, xyz - mean_b)                      fp32 [n,6]
+ *   max_coord[3] = max over the batch of coords[:,1:4]   (spatial_shape = clip(max+1, 128))
+ * points fp32 [n,6] (x,y,z,r,g,b); scene_offsets int32 [B+1]; stats fp32 [B,6] out (min, mean).
+ * ws: >= ud3d_point_coords_workspace_bytes(B). */
+size_t ud3d_point_coords_workspace_bytes(int B);
+int ud3d_point_coords(const float* points, int n, const int32_t* scene_offsets, int B, float voxel_size,
+                      int32_t* coords, float* feats, float* stats, int32_t* max_coord,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ occupancy grid ("hash-grid")
+ * A collision-free spatial hash of the active voxel set: one bit per cell of the dense
+ * (B, X, Y, Z) box (z fastest, Z padded to 32) + an exclusive popcount prefix per 32-bit
+ * word.  rank(b,x,y,z) = prefix[word] + popc(word & below(z)) is the row of the voxel in
+ * canonical ascending (b,x,y,z) order -- no probing, no sort, deterministic.
+ * It replaces MinkowskiEngine's coordinate hash map (unidet3d.py:171-174) and spconv's
+ * indice-pair hash (every SubMConv3d/SparseConv3d with an indice_key: spconv_unet.py:43-56,
+ * 148-154; unidet3d.py:96-103).
+ * dims_host = {B, X, Y, Z} (host array). */
+size_t ud3d_grid_workspace_bytes(const int32_t dims_host[4]);
+/* set bits for coords [n,4] (rows with coords[i][0] < 0 are skipped), build prefix;
+ * *n_unique (device int32) = number of distinct cells. */
+int ud3d_grid_build(const int32_t* coords, int n, const int32_t dims_host[4], void* ws, size_t ws_bytes,
+                    int32_t* n_unique, void* stream);
+/* rank_out[i] = canonical row of coords[i] or -1 (absent / outside the grid / coords[i][0] < 0) */
+int ud3d_grid_rank(const int32_t* coords, int n, const int32_t dims_host[4], const void* ws,
+                   int32_t* rank_out, void* stream);
+/* coords_out [n_unique,4]: the distinct cells in canonical order */
+int ud3d_grid_coords(const int32_t dims_host[4], const void* ws, int32_t* coords_out, int n_unique,
+                     void* stream);
+
+/* per-voxel unweighted mean of point features (ME TensorField UNWEIGHTED_AVERAGE, unidet3d.py:171-173)
+ * feats_pts [n,C], rank [n] (from ud3d_grid_rank), out [n_vox,C]; ws >= n_vox*4 bytes. */
+int ud3d_voxel_mean(const float* feats_pts, const int32_t* rank, int n, int C, int n_vox, float* out,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ rulebooks (integer, bit-exact)
+ * SubMConv3d(k=3,pad=1) neighbour table (spconv_unet.py:43-56 `subm{l}`, unidet3d.py:96-103):
+ *   table[k][i] = row of voxel coords[i] + (kx-1,ky-1,kz-1), k = kx*9+ky*3+kz, or -1.
+ * The grid must have been built from `coords`.  row_of_rank: NULL when coords are already in
+ * canonical order (row == rank), else an int32 [n] scratch the call fills (rank -> input row).
+ * tile_mask [ceil(n/UD3D_TILE_M)] (optional, may be NULL): bit k set iff some row of the tile has
+ * an input for offset k. */
+int ud3d_rulebook_subm3(const int32_t* coords, int n, const int32_t dims_host[4], const void* ws,
+                        int32_t* row_of_rank, int32_t* table, uint32_t* tile_mask, void* stream);
+
+/* SparseConv3d(k=2,s=2) (spconv_unet.py:148-154 `spconv{l}`), phase 1:
+ *   parents[i] = (b, x/2, y/2, z/2), or b=-1 when x/2 >= out_shape (odd extent, last index dropped),
+ *   out_shape = (in_shape-2)/2+1.  Then the caller builds a grid on `parents`
+ *   (ud3d_grid_build) and reads back n_coarse. */
+int ud3d_down2_parents(const int32_t* coords, int n, const int32_t in_shape_host[3], int32_t* parents,
+                       void* stream);
+/* phase 2: child[s][p] = fine row feeding coarse row p through slot s = (x&1)*4+(y&1)*2+(z&1);
+ * up[s][i] = coarse row of fine row i (slot s), both -1-filled elsewhere.  The pair list is shared by
+ * SparseInverseConv3d (spconv_unet.py:178-183).  coarse_ws = grid built on `parents`.
+ * child_mask/up_mask: optional tile masks like ud3d_rulebook_subm3. */
+int ud3d_rulebook_down2(const int32_t* coords, const int32_t* parents, int n_fine, int n_coarse,
+                        const int32_t coarse_dims_host[4], const void* coarse_ws,
+                        int32_t* child, int32_t* up, uint32_t* child_mask, uint32_t* up_mask, void* stream);
+
+/* ------------------------------------------------------------------ gather-GEMM (sparse conv + linear)
+ * reference: every spconv.SubMConv3d / SparseConv3d / SparseInverseConv3d forward
+ * (spconv_unet.py:37-72,148-191; unidet3d.py:96-103) with the preceding BatchNorm(eval)+ReLU
+ * (spconv_unet.py:42,49,147,177) folded into the operand load and the residual add / concat
+ * (spconv_unet.py:88-89,229-230) folded into the epilogue; also every torch.nn.Linear of the
+ * encoder (encoder.py:19-22,55-61,138-163).
+ *
+ *   out[o, :] = act( sum_k  pre(in[table[k][o], :]) @ W_k  + bias ) + residual[o, :]
+ *   pre(x) = relu?( x * in_scale + in_shift )   (per input channel; skipped for missing rows)
+ *
+ * W is given in the reference parameter layout [C_out, K, C_in] (spconv [C_out,k0,k1,k2,C_in]
+ * flattened; nn.Linear [C_out, C_in] with K = 1) and packed once by ud3d_gemm_pack_weight into
+ * the kernel's shared-memory image (bf16 hi/lo split, 128B-swizzled K-major tiles).
+ * Numerics: each fp32 operand is split into bf16 hi+lo, three tcgen05 MMAs (hi*hi + lo*hi + hi*lo)
+ * accumulate in fp32 in TMEM: ~2e-5 relative to an fp32 reference over the whole backbone. */
+typedef struct {
+  const float* in; int32_t ld_in; int32_t c_in;
+  const int32_t* table;        /* [K, n_out]; NULL => identity gather (requires K == 1) */
+  const uint32_t* tile_mask;   /* optional [ceil(n_out/128)] */
+  int32_t K; int32_t n_out;
+  const void* w_packed;        /* from ud3d_gemm_pack_weight */
+  float* out; int32_t ld_out; int32_t c_out;
+  const float* in_scale; const float* in_shift; int32_t in_relu;  /* in_scale NULL => no affine */
+  const float* bias;           /* [c_out] or NULL */
+  int32_t act;                 /* 0 none, 1 relu, 2 gelu(erf) */
+  const float* residual; int32_t ld_res;
+} ud3d_gemm_args;
+size_t ud3d_gemm_packed_weight_bytes(int K, int c_in, int c_out);
+int ud3d_gemm_pack_weight(const float* w, int K, int c_in, int c_out, void* packed, void* stream);
+int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream);
+/* same contract, plain fp32 CUDA-core kernel on the unpacked weight w [C_out,K,C_in]
+ * (diagnostic cross-check of the tensor-core path; not used by the product path) */
+int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream);
+
+/* ------------------------------------------------------------------ superpoint pooling
+ * reference: torch_scatter.scatter_mean at unidet3d.py:130 (features, with the output
+ * BatchNorm+ReLU of unidet3d.py:104-111,129 and the x.features[inverse_mapping] gather fused)
+ * and unidet3d.py:446-447 (superpoint centres).
+ *   out[s,:] = mean_{p: seg[p]==s} pre(src[gather ? gather[p] : p, :]),  empty s -> 0.
+ * seg int64 [n] (reference loader dtype), out [n_seg,C]; ws >= n_seg*4 bytes. */
+int ud3d_segmented_mean(const float* src, int ld_src, int C, const int32_t* gather, const int64_t* seg,
+                        int n, int n_seg, const float* scale, const float* shift, int relu,
+                        float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ encoder pieces
+ * LayerNorm(eps) of (x + residual) per row (encoder.py:38-39,77-78,189); C % 32 == 0, C <= 1024 */
+int ud3d_layernorm(const float* x, const float* residual, const float* gamma, const float* beta,
+                   float* out, int rows, int C, float eps, void* stream);
+/* multi-head self-attention core of nn.MultiheadAttention (encoder.py:37) on packed projections:
+ * qkv [T_total, 3*d] (q|k|v, heads contiguous, head_dim = 32), cu_seqlens int32 [B+1] scene
+ * boundaries (no cross-scene attention, no mask/padding), out [T_total, d] = softmax(QK^T/sqrt(32))V */
+int ud3d_attention_fwd(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
+                       float* out, void* stream);
+/* PredBBox exp + _bbox_pred_to_bbox (encoder.py:109-111,241-283): raw [T,ld_raw>=8], centres [T,3]
+ * -> out [T, with_angle ? 7 : 6] */
+int ud3d_bbox_decode(const float* raw, int ld_raw, const float* centers, int T, int with_angle,
+                     float* out, void* stream);
+/* out[t, j] = src[t, cols[j]]  (per-dataset class column gather, encoder.py:191-194) */
+int ud3d_gather_columns(const float* src, int ld_src, const int32_t* cols, int n_cols, int T,
+                        float* out, void* stream);
+
+/* ------------------------------------------------------------------ post-processing
+ * softmax over classes, drop the last (no_obj) column, top-k over the flattened [T*C] scores,
+ * sorted descending (unidet3d.py:504-515).  logits [T, C+1]; k <= 1024 and k <= T*C.
+ * scores_out[k], labels_out[k] (= idx % C), query_out[k] (= idx / C); ws >= T*C*4 bytes. */
+int ud3d_topk_scores(const float* logits, int T, int C_plus1, int k, float* scores_out,
+                     int32_t* labels_out, int32_t* query_out, void* ws, size_t ws_bytes, void* stream);
+/* multi-class 3D NMS (unidet3d.py:595-650): boxes [n,box_dim] (6 or 7), n <= 1024, already in
+ * descending score order.  mode 0: mmcv nms3d (rotated BEV IoU), 1: mmcv nms3d_normal (axis-aligned
+ * BEV), 2: mmdet3d aligned_3d_nms (3-D IoU).  keep_out[n]: kept input indices, ascending class then
+ * descending score; *n_keep device int32.  ws >= ud3d_nms_workspace_bytes(n). */
+size_t ud3d_nms_workspace_bytes(int n);
+int ud3d_nms_multiclass(const float* boxes, int box_dim, const float* scores, const int32_t* labels, int n,
+                        int mode, float iou_thr, float score_thr, int32_t* keep_out, int32_t* n_keep,
+                        void* ws, size_t ws_bytes, void* stream);
+/* trim_bboxes_by_superpoints (unidet3d.py:540-593, get_face_distances :652-677):
+ * points [n_pts,ld_pts>=3], sp int64 [n_pts], boxes [m,box_dim]; box_index (optional int32 [m]) selects
+ * rows of `boxes`.  out [m,6] = (centre, size) of the tight AABB of the voted points.
+ * ws >= ud3d_trim_workspace_bytes(n_sp). */
+size_t ud3d_trim_workspace_bytes(int n_sp);
+int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pts, int n_sp,
+                    const float* boxes, int box_dim, const int32_t* box_index, int m,
+                    float low_thr, float up_thr, float* out, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIDET3D_B200_H_ */

@@ -1,0 +1,306 @@
+"""GPU parity tests of every C-ABI op against the CPU oracle (bit-exact for integer work,
+<= 1e-3 relative (max-abs error over max-abs reference) for floating point; most ops land ~1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import voxelize as ovox, rulebook as orb, nms as onms, postprocess as opost, encoder as oenc
+from oracle.spconv import sparse_conv, weight_to_koc
+from oracle.pool import scatter_mean
+from unidet3d_b200.synthetic import make_scene, SCENE_PRESETS
+
+DEV = "cuda"
+
+
+def relerr(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def _scenes(preset, B, seed0=0):
+    n, v, a, c = SCENE_PRESETS[preset]
+    return [make_scene(seed0 + i, n, a, c) for i in range(B)], v
+
+
+# ------------------------------------------------------------------ voxelise + grid + rulebooks
+@pytest.mark.parametrize("preset,B", [("tiny", 3), ("small20k", 2)])
+def test_voxelize_and_rulebooks_bit_exact(preset, B):
+    from unidet3d_b200 import ops
+    scenes, vs = _scenes(preset, B)
+    pts = [s[0] for s in scenes]
+    ref_coords, ref_feats, ref_inv, ref_shape = ovox.voxelize(pts, vs)
+    ref_bc, ref_bf = ovox.point_coords(pts, vs)
+    offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device=DEV)
+    P = torch.as_tensor(np.concatenate(pts)).to(DEV)
+    coords, feats, stats, maxc = ops.point_coords(P, offs, vs)
+    assert np.array_equal(coords.cpu().numpy(), ref_bc)
+    assert relerr(feats, ref_bf) < 1e-6
+    shape = np.maximum(maxc.cpu().numpy() + 1, 128)
+    assert np.array_equal(shape, ref_shape)
+    dims = [B] + [int(x) + 1 for x in maxc.cpu().numpy()]
+    grid = ops.Grid(dims, DEV)
+    n1 = int(grid.build(coords).item())
+    assert n1 == len(ref_coords)
+    inv = grid.rank(coords)
+    assert np.array_equal(inv.cpu().numpy().astype(np.int64), ref_inv)
+    vox = grid.coords(n1)
+    assert np.array_equal(vox.cpu().numpy(), ref_coords)
+    vf = ops.voxel_mean(feats, inv, n1)
+    assert relerr(vf, ref_feats) < 1e-5
+    # SubM table (canonical order) + tile mask
+    table, mask = ops.rulebook_subm3(vox, grid, canonical=True)
+    ref_table = orb.subm3_table(ref_coords, ref_shape)
+    assert np.array_equal(table.cpu().numpy(), ref_table)
+    m = mask.cpu().numpy().view(np.uint32)
+    for t in range(len(m)):
+        act = (ref_table[:, t * 128:(t + 1) * 128] >= 0).any(1)
+        assert m[t] == sum(1 << k for k in range(27) if act[k])
+    # non-canonical row order
+    perm = torch.randperm(n1, device=DEV)
+    table_p, _ = ops.rulebook_subm3(vox[perm].contiguous(), grid, canonical=False)
+    assert np.array_equal(table_p.cpu().numpy(), orb.subm3_table(ref_coords[perm.cpu().numpy()], ref_shape))
+    # strided pyramid, 4 levels down
+    c, s, rc, rs = vox, [int(x) for x in shape], ref_coords, ref_shape
+    for lvl in range(4):
+        parents = ops.down2_parents(c, s)
+        out_shape = [(x - 2) // 2 + 1 for x in s]
+        cg = ops.Grid([B] + [max(1, min(o, (d + 1) // 2)) for o, d in zip(out_shape, dims[1:])], DEV)
+        dims = cg.dims
+        nc = int(cg.build(parents).item())
+        ref_cc, ref_child, ref_up, ref_os = orb.down2(rc, rs)
+        assert nc == len(ref_cc) and list(ref_os) == out_shape
+        cc = cg.coords(nc)
+        assert np.array_equal(cc.cpu().numpy(), ref_cc)
+        child, up, cm, um = ops.rulebook_down2(c, parents, nc, cg)
+        assert np.array_equal(child.cpu().numpy(), ref_child)
+        assert np.array_equal(up.cpu().numpy(), ref_up)
+        um_np = um.cpu().numpy().view(np.uint32)
+        for t in range(len(um_np)):
+            act = (ref_up[:, t * 128:(t + 1) * 128] >= 0).any(1)
+            assert um_np[t] == sum(1 << k for k in range(8) if act[k])
+        c, s, rc, rs = cc, out_shape, ref_cc, ref_os
+
+
+def test_down2_drops_odd_boundary():
+    from unidet3d_b200 import ops
+    rng = np.random.default_rng(0)
+    shape = [9, 7, 6]
+    cc = np.unique(rng.integers(0, shape, (200, 3)), axis=0)
+    coords = np.concatenate([np.zeros((len(cc), 1), np.int64), cc], 1).astype(np.int32)
+    coords = coords[rng.permutation(len(coords))]
+    c = torch.as_tensor(coords).to(DEV)
+    parents = ops.down2_parents(c, shape)
+    cg = ops.Grid([1, 4, 3, 3], DEV)
+    nc = int(cg.build(parents).item())
+    ref_cc, ref_child, ref_up, _ = orb.down2(coords, shape)
+    assert nc == len(ref_cc)
+    child, up, _, _ = ops.rulebook_down2(c, parents, nc, cg)
+    assert np.array_equal(child.cpu().numpy(), ref_child) and np.array_equal(up.cpu().numpy(), ref_up)
+    assert (ref_up < 0).all(0).any()          # some fine rows really are dropped
+
+
+# ------------------------------------------------------------------ gather-GEMM
+def _rand_table(rng, K, n_out, n_in, density=0.4):
+    t = rng.integers(0, n_in, (K, n_out)).astype(np.int32)
+    t[rng.random((K, n_out)) > density] = -1
+    return t
+
+
+@pytest.mark.parametrize("c_in,c_out,K,n_in,n_out", [
+    (32, 32, 27, 700, 700), (64, 64, 27, 300, 300), (6, 32, 27, 500, 500), (96, 96, 27, 260, 260),
+    (128, 128, 27, 130, 130), (160, 160, 27, 200, 200), (64, 32, 8, 400, 900), (32, 64, 8, 900, 300),
+    (320, 160, 27, 150, 150), (8, 40, 27, 333, 333), (192, 96, 1, 257, 257)])
+def test_gemm_sparse_conv(c_in, c_out, K, n_in, n_out):
+    from unidet3d_b200 import ops
+    rng = np.random.default_rng(c_in * 1000 + c_out)
+    g = torch.Generator().manual_seed(c_in + c_out)
+    x = torch.randn(n_in, c_in, generator=g)
+    w = torch.randn(c_out, K, c_in, generator=g) / (c_in * 3) ** 0.5
+    table = _rand_table(rng, K, n_out, n_in)
+    scale, shift = torch.rand(c_in, generator=g) + 0.5, torch.randn(c_in, generator=g) * 0.2
+    res = torch.randn(n_out, c_out, generator=g)
+    w_koc = w.permute(1, 2, 0).contiguous()
+    ref = sparse_conv(torch.relu(x * scale + shift), table, w_koc) + res
+    xd, td = x.to(DEV), torch.as_tensor(table).to(DEV)
+    pw = ops.PackedWeight(w.to(DEV))
+    kw = dict(table=td, in_scale=scale.to(DEV), in_shift=shift.to(DEV), in_relu=True, residual=res.to(DEV))
+    out = ops.gemm(xd, pw, **kw)
+    out_simt = ops.gemm_simt(xd, w.to(DEV), **kw)
+    assert relerr(out_simt, ref) < 1e-5
+    assert relerr(out, ref) < 2e-4, relerr(out, ref)
+    # no prologue, no residual
+    ref2 = sparse_conv(x, table, w_koc)
+    assert relerr(ops.gemm(xd, pw, table=td), ref2) < 2e-4
+
+
+def test_gemm_strided_views_and_tile_mask():
+    """concat-free U-Net plumbing: read/write column slices of wider buffers; per-tile offset skipping."""
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    rng = np.random.default_rng(3)
+    n, c = 515, 32
+    buf = torch.randn(n, 2 * c, generator=g).to(DEV)
+    w = (torch.randn(c, 27, c, generator=g) / 10).to(DEV)
+    table = _rand_table(rng, 27, n, n, 0.3)
+    table[5] = -1
+    table[20, 128:256] = -1
+    mask = np.zeros((n + 127) // 128, np.uint32)
+    for t in range(len(mask)):
+        act = (table[:, t * 128:(t + 1) * 128] >= 0).any(1)
+        mask[t] = sum(1 << k for k in range(27) if act[k])
+    td, md = torch.as_tensor(table).to(DEV), torch.as_tensor(mask.view(np.int32)).to(DEV)
+    pw = ops.PackedWeight(w)
+    ref = sparse_conv(buf[:, c:].cpu(), table, w.cpu().permute(1, 2, 0).contiguous())
+    outbuf = torch.zeros(n, 2 * c, device=DEV)
+    ops.gemm(buf[:, c:], pw, table=td, tile_mask=md, out=outbuf[:, :c])
+    assert relerr(outbuf[:, :c], ref) < 2e-4
+    assert float(outbuf[:, c:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("T,c_in,c_out,act", [(300, 256, 768, None), (1000, 256, 1024, "gelu"), (257, 1024, 256, None),
+                                              (129, 32, 256, "relu"), (64, 256, 19, None), (500, 256, 100, None),
+                                              (77, 256, 8, None)])
+def test_gemm_dense_linear(T, c_in, c_out, act):
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(T, c_in, generator=g)
+    w = torch.randn(c_out, c_in, generator=g) / c_in ** 0.5
+    b = torch.randn(c_out, generator=g)
+    res = torch.randn(T, c_out, generator=g)
+    y = x @ w.t() + b
+    y = torch.relu(y) if act == "relu" else torch.nn.functional.gelu(y) if act == "gelu" else y
+    y = y + res
+    out = ops.gemm(x.to(DEV), ops.PackedWeight(w.to(DEV)), bias=b.to(DEV), act=act, residual=res.to(DEV))
+    assert relerr(out, y) < 2e-4, relerr(out, y)
+
+
+# ------------------------------------------------------------------ pooling / LN / attention / heads
+def test_segmented_mean():
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    n_vox, n_pts, n_seg = 5000, 40000, 700
+    feats = torch.randn(n_vox, 32, generator=g)
+    inv = torch.randint(0, n_vox, (n_pts,), generator=g)
+    seg = torch.randint(0, n_seg - 3, (n_pts,), generator=g)       # last ids never occur -> zero rows
+    seg = torch.sort(seg)[0][torch.randperm(n_pts, generator=g)] if False else seg
+    scale, shift = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.3
+    ref = scatter_mean(torch.relu(feats * scale + shift)[inv], seg, n_seg)
+    out = ops.segmented_mean(feats.to(DEV), seg.to(DEV), n_seg, gather=inv.int().to(DEV), scale=scale.to(DEV),
+                             shift=shift.to(DEV), relu=True)
+    assert relerr(out, ref) < 1e-5
+    assert float(out[-3:].abs().max()) == 0.0
+    # superpoint centres: C=3 of a [n,6] matrix, runs of equal ids
+    pts = torch.randn(n_pts, 6, generator=g)
+    seg2 = torch.sort(seg)[0]
+    ref2 = scatter_mean(pts[:, :3], seg2, n_seg)
+    out2 = ops.segmented_mean(pts.to(DEV), seg2.to(DEV), n_seg, channels=3)
+    assert relerr(out2, ref2) < 1e-5
+
+
+def test_layernorm():
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    for C in (256, 128, 64):
+        x, r = torch.randn(333, C, generator=g) * 3, torch.randn(333, C, generator=g)
+        gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+        ref = torch.nn.functional.layer_norm(x + r, (C,), gam, bet, 1e-5)
+        out = ops.layernorm(x.to(DEV), gam.to(DEV), bet.to(DEV), residual=r.to(DEV))
+        assert relerr(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("lens", [[37, 21, 50], [300, 1], [1000, 64, 65, 129]])
+def test_attention(lens):
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(sum(lens))
+    H, d = 8, 256
+    Tt = sum(lens)
+    qkv = torch.randn(Tt, 3 * d, generator=g) * 1.5
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32)
+    ref = []
+    for i, T in enumerate(lens):
+        s = qkv[cu[i]:cu[i + 1]]
+        q, k, v = [s[:, j * d:(j + 1) * d].view(T, H, 32).transpose(0, 1) for j in range(3)]
+        a = torch.softmax(q @ k.transpose(1, 2) / 32 ** 0.5, -1) @ v
+        ref.append(a.transpose(0, 1).reshape(T, d))
+    ref = torch.cat(ref)
+    out = ops.attention(qkv.to(DEV), cu.to(DEV), max(lens), H)
+    assert relerr(out, ref) < 1e-4, relerr(out, ref)
+
+
+def test_bbox_decode_and_gather_columns():
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    raw = torch.randn(100, 8, generator=g) * 0.5
+    cen = torch.randn(100, 3, generator=g)
+    for ang in (False, True):
+        b = torch.hstack((torch.exp(raw[:, :6]), raw[:, 6:]))
+        ref = oenc.bbox_pred_to_bbox(cen, b if ang else b[:, :6])
+        out = ops.bbox_decode(raw.to(DEV), cen.to(DEV), ang)
+        assert relerr(out, ref) < 1e-5
+    src = torch.randn(50, 100, generator=g)
+    cols = torch.tensor([5, 99, 0, 17], dtype=torch.int32)
+    assert torch.equal(ops.gather_columns(src.to(DEV), cols.to(DEV)).cpu(), src[:, cols.long()])
+
+
+# ------------------------------------------------------------------ post-processing
+@pytest.mark.parametrize("T,C,k", [(90, 5, 300), (2000, 18, 1000), (4096, 84, 1000), (60, 17, 1000)])
+def test_topk(T, C, k):
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(T)
+    logits = torch.randn(T, C + 1, generator=g) * 2
+    _, rs, rl, rq = opost.topk_candidates(logits, torch.zeros(T, 6), k)
+    s, l, q = ops.topk_scores(logits.to(DEV), k)
+    assert np.allclose(s.cpu().numpy(), rs.numpy(), rtol=1e-5, atol=0)
+    # identical selection wherever scores are not within rounding of each other
+    same = (l.cpu().long() == rl) & (q.cpu().long() == rq)
+    assert same.float().mean() > 0.995
+    assert torch.all(s[:-1] >= s[1:])
+
+
+def _rand_boxes(rng, n, yaw):
+    b = np.concatenate([rng.uniform(0, 5, (n, 3)), rng.uniform(0.3, 1.6, (n, 3))], 1)
+    if yaw:
+        b = np.concatenate([b, rng.uniform(-3.2, 3.2, (n, 1))], 1)
+    return b.astype(np.float32)
+
+
+@pytest.mark.parametrize("mode,yaw", [(0, True), (1, False), (2, False)])
+def test_nms_multiclass(mode, yaw):
+    from unidet3d_b200 import ops
+    rng = np.random.default_rng(mode)
+    n = 1000
+    boxes = _rand_boxes(rng, n, yaw)
+    scores = np.sort(rng.random(n).astype(np.float32))[::-1].copy()
+    scores[-5:] = 0.0                                   # score_thr=0 filters these
+    labels = rng.integers(0, 7, n).astype(np.int32)
+    thr = 0.3
+    rb, rs, rl, ri = opost.multiclass_nms(torch.as_tensor(boxes), torch.as_tensor(scores), torch.as_tensor(labels).long(),
+                                          fast_nms=(mode == 1), iou_thr=thr)
+    keep, nk = ops.nms_multiclass(torch.as_tensor(boxes).to(DEV), torch.as_tensor(scores).to(DEV),
+                                  torch.as_tensor(labels).to(DEV), mode, thr)
+    k = keep[: int(nk.item())].cpu().long()
+    assert len(k) == len(ri) and torch.equal(k, ri)
+
+
+def test_trim_boxes():
+    from unidet3d_b200 import ops
+    rng = np.random.default_rng(4)
+    pts, sp = make_scene(0, 20000, 21.0, 0.5)
+    xyz = torch.as_tensor(pts[:, :3] - pts[:, :3].min(0))
+    n_sp = int(sp.max()) + 1
+    M = 40
+    ext = xyz.max(0).values.numpy()
+    boxes = np.concatenate([rng.uniform(0, 1, (M, 3)) * ext, rng.uniform(0.3, 1.5, (M, 3)), rng.uniform(-3, 3, (M, 1))], 1).astype(np.float32)
+    for bd in (7, 6):
+        b = torch.as_tensor(boxes[:, :bd].copy())
+        ref = opost.trim_bboxes_by_superpoints(torch.as_tensor(sp), xyz, b, 0.18, 0.81)
+        P = torch.as_tensor(pts).to(DEV).clone()
+        P[:, :3] = xyz.to(DEV)
+        out = ops.trim_boxes(P, torch.as_tensor(sp).to(DEV), n_sp, b.to(DEV), 0.18, 0.81).cpu()
+        fin = torch.isfinite(ref)
+        assert torch.equal(torch.isfinite(out), fin)
+        close = torch.isclose(out[fin], ref[fin], rtol=1e-5, atol=1e-6)
+        assert close.float().mean() > 0.98     # a borderline point (|face distance| ~ 1 ulp) may flip a vote

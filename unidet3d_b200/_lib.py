@@ -1,0 +1,92 @@
+"""ctypes binding of libunidet3d_b200.so (the C-ABI in include/unidet3d_b200.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing the
+compute modules raises.  Build it with ``python -m unidet3d_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libunidet3d_b200.so")
+
+c_i32p = C.POINTER(C.c_int32)
+
+
+class GemmArgs(C.Structure):
+    """Mirror of ``ud3d_gemm_args`` (include/unidet3d_b200.h)."""
+    _fields_ = [
+        ("in_", C.c_void_p), ("ld_in", C.c_int32), ("c_in", C.c_int32),
+        ("table", C.c_void_p), ("tile_mask", C.c_void_p),
+        ("K", C.c_int32), ("n_out", C.c_int32),
+        ("w_packed", C.c_void_p),
+        ("out", C.c_void_p), ("ld_out", C.c_int32), ("c_out", C.c_int32),
+        ("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_relu", C.c_int32),
+        ("bias", C.c_void_p),
+        ("act", C.c_int32),
+        ("residual", C.c_void_p), ("ld_res", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); must list EVERY symbol declared in include/unidet3d_b200.h
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+SIGNATURES = {
+    "ud3d_version": (C.c_int, []),
+    "ud3d_last_error": (C.c_char_p, []),
+    "ud3d_launch_count": (C.c_int64, [_i]),
+    "ud3d_point_coords_workspace_bytes": (_sz, [_i]),
+    "ud3d_point_coords": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ud3d_grid_workspace_bytes": (_sz, [c_i32p]),
+    "ud3d_grid_build": (_i, [_vp, _i, c_i32p, _vp, _sz, _vp, _vp]),
+    "ud3d_grid_rank": (_i, [_vp, _i, c_i32p, _vp, _vp, _vp]),
+    "ud3d_grid_coords": (_i, [c_i32p, _vp, _vp, _i, _vp]),
+    "ud3d_voxel_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "ud3d_rulebook_subm3": (_i, [_vp, _i, c_i32p, _vp, _vp, _vp, _vp, _vp]),
+    "ud3d_down2_parents": (_i, [_vp, _i, c_i32p, _vp, _vp]),
+    "ud3d_rulebook_down2": (_i, [_vp, _vp, _i, _i, c_i32p, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ud3d_gemm_packed_weight_bytes": (_sz, [_i, _i, _i]),
+    "ud3d_gemm_pack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ud3d_gemm_fwd": (_i, [C.POINTER(GemmArgs), _vp]),
+    "ud3d_gemm_fwd_simt": (_i, [C.POINTER(GemmArgs), _vp, _vp]),
+    "ud3d_segmented_mean": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "ud3d_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "ud3d_attention_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ud3d_bbox_decode": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
+    "ud3d_gather_columns": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
+    "ud3d_topk_scores": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ud3d_nms_workspace_bytes": (_sz, [_i]),
+    "ud3d_nms_multiclass": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "ud3d_trim_workspace_bytes": (_sz, [_i]),
+    "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _f, _f, _vp, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+class Ud3dError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach prototypes.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Ud3dError(
+            f"{LIB_PATH} not found: the CUDA extension is not built.  Run `python -m unidet3d_b200.build` "
+            "(needs nvcc).  unidet3d_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)           # AttributeError if a declared symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ud3d_last_error().decode("utf-8", "replace")
+        raise Ud3dError(f"{what} failed (code {rc}): {msg}")

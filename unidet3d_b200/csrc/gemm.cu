@@ -1,0 +1,415 @@
+// Gather-GEMM: sparse convolution (SubM / strided / inverse) and dense linear layers on the
+// 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), sm_100a.
+//
+//   out[o,:] = act( sum_k pre(in[table[k][o],:]) @ W_k + bias ) + residual[o,:]
+//
+// Design (one CTA = 128 output rows x N_TILE output channels, 256 threads):
+//   * the K-loop runs over (kernel offset k, 32-channel chunk c).  For each step the 8 warps gather
+//     the 128 input rows of that offset with coalesced 16-byte loads (4 lanes per row), apply the
+//     folded BatchNorm affine + ReLU in registers, split every fp32 value into bf16 hi + lo and
+//     write [hi(32ch) | lo(32ch)] = one 128-byte row into a 128B-swizzled K-major smem tile;
+//   * the matching weight tile (pre-packed on the host side of the ABI into the identical
+//     swizzled image, hi|lo per output channel) is fetched by ONE cp.async.bulk (TMA engine)
+//     onto an mbarrier;
+//   * one thread issues 6 tcgen05.mma (M=128, N=N_TILE, K=16): hi*hi, lo*hi, hi*lo -> fp32
+//     accumulation in TMEM (~2e-5 relative error end to end, vs 1.5e-3 for single-pass TF32);
+//   * 3-stage smem ring: tcgen05.commit -> mbarrier frees a stage, so the gather of step i+1/i+2
+//     overlaps the MMAs of step i; offsets with no active input in the tile are skipped via the
+//     rulebook's per-tile mask;
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> global.
+// HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
+#include "common.cuh"
+
+namespace ud3d {
+
+constexpr int kTileM = UD3D_TILE_M;   // 128
+constexpr int kChunk = 32;            // input channels per K-step
+constexpr int kStages = 3;
+constexpr int kThreads = 256;
+
+struct GemmParams {
+  ud3d_gemm_args a;
+  int n_chunks;
+  int vec_ok;      // 16-byte vector gather allowed
+  int out_vec_ok;  // 16-byte vector epilogue allowed
+};
+
+static inline int pick_ntile(int c_out) {
+  if (c_out <= 32) return 32;
+  if (c_out <= 64) return 64;
+  if (c_out <= 96) return 96;
+  if (c_out <= 128) return 128;
+  if (c_out <= 160) return 160;
+  return 256;
+}
+
+// ---------------------------------------------------------------- weight packing
+// image: [n_tile][k][chunk][N_TILE rows][8 x 16B], row n holds hi(32 ch) | lo(32 ch), 16-byte
+// chunk j stored at physical position j ^ (n & 7)  (Swizzle<3,4,3>, 128B rows)
+__global__ void pack_weight_kernel(const float* __restrict__ w, int K, int c_in, int c_out, int n_tile_sz, int n_tiles,
+                                   int n_chunks, uint4* __restrict__ out) {
+  long long total = (long long)n_tiles * K * n_chunks * n_tile_sz * 8;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(t & 7);
+    long long r = t >> 3;
+    int n = (int)(r % n_tile_sz);
+    r /= n_tile_sz;
+    int c = (int)(r % n_chunks);
+    r /= n_chunks;
+    int k = (int)(r % K);
+    int nt = (int)(r / K);
+    int ng = nt * n_tile_sz + n;
+    int ch0 = c * kChunk + (j & 3) * 8;
+    uint32_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float x[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int ch = ch0 + e * 2 + h;
+        x[h] = (ng < c_out && ch < c_in) ? w[((size_t)ng * K + k) * c_in + ch] : 0.f;
+      }
+      uint32_t hi, lo;
+      split_bf16x2(x[0], x[1], hi, lo);
+      v[e] = (j < 4) ? hi : lo;
+    }
+    size_t tile = ((size_t)nt * K + k) * n_chunks + c;
+    out[tile * n_tile_sz * 8 + (size_t)n * 8 + (j ^ (n & 7))] = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// ---------------------------------------------------------------- the tensor-core kernel
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmParams p) {
+  constexpr int A_BYTES = kTileM * 128;
+  constexpr int B_BYTES = N_TILE * 128;
+  constexpr uint32_t TMEM_COLS = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+  constexpr uint32_t IDESC = umma_idesc_bf16_m128(N_TILE);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * A_BYTES;
+  uint8_t* tail = sB + kStages * B_BYTES;
+  uint64_t* b_full = (uint64_t*)tail;            // [kStages]
+  uint64_t* mma_done = b_full + kStages;         // [kStages]
+  uint64_t* acc_full = mma_done + kStages;       // [1]
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+  float* s_scale = (float*)(tail + 128);
+  const ud3d_gemm_args& a = p.a;
+  const int c_in_pad = p.n_chunks * kChunk;
+  float* s_shift = s_scale + c_in_pad;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * kTileM;
+  const int nt = blockIdx.y;
+  const int n0 = nt * N_TILE;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&mma_done[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (a.in_scale) {
+    for (int c = tid; c < c_in_pad; c += kThreads) {
+      s_scale[c] = c < a.c_in ? a.in_scale[c] : 0.f;
+      s_shift[c] = c < a.c_in ? a.in_shift[c] : 0.f;
+    }
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // gather roles: 4 lanes per row (8 floats each), rows rl and rl+64
+  const int q = tid & 3;
+  const int rl = tid >> 2;
+  const uint32_t tile_mask = a.tile_mask ? a.tile_mask[blockIdx.x] : 0xffffffffu;
+  const uint8_t* wp = (const uint8_t*)a.w_packed + (size_t)nt * a.K * p.n_chunks * B_BYTES;
+  const bool affine = a.in_scale != nullptr;
+  const bool relu = a.in_relu != 0;
+
+  int it = 0;  // CTA-uniform count of issued K-steps
+  for (int k = 0; k < a.K; ++k) {
+    if (a.K <= 32 && !((tile_mask >> k) & 1u)) continue;
+    int idx[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int row = m0 + rl + h * 64;
+      if (row < a.n_out)
+        idx[h] = a.table ? __ldg(a.table + (size_t)k * a.n_out + row) : row;
+      else
+        idx[h] = -1;
+    }
+    if (a.table && !a.tile_mask) {
+      if (!__syncthreads_or((idx[0] >= 0) | (idx[1] >= 0))) continue;
+    }
+    for (int c = 0; c < p.n_chunks; ++c, ++it) {
+      const int s = it % kStages;
+      const uint32_t use = (uint32_t)(it / kStages);
+      if (it >= kStages) mbar_wait(&mma_done[s], (use - 1) & 1);   // stage s free again
+      uint8_t* As = sA + s * A_BYTES;
+      uint8_t* Bs = sB + s * B_BYTES;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&b_full[s], B_BYTES);
+        bulk_copy_g2s(Bs, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
+      }
+      const int ch0 = c * kChunk + q * 8;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[8];
+        if (idx[h] >= 0) {
+          const float* src = a.in + (size_t)idx[h] * a.ld_in + ch0;
+          if (p.vec_ok) {
+            // c_in % 8 == 0: an 8-channel segment is entirely inside or entirely outside the row
+            if (ch0 < a.c_in) {
+              float4 x0 = __ldg((const float4*)src), x1 = __ldg((const float4*)src + 1);
+              v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
+              v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (ch0 + e < a.c_in) ? __ldg(src + e) : 0.f;
+          }
+          if (affine) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
+          }
+          if (relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (!p.vec_ok || affine) {
+            // padded channels must stay exactly zero (shift of a padded channel is 0, but be explicit)
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (ch0 + e >= a.c_in) v[e] = 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+        const int r = rl + h * 64;
+        uint8_t* arow = As + r * 128;
+        *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(&b_full[s], use & 1);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+        // K-steps of 16 bf16 = 32 bytes inside the 128B row: hi at +0,+32 ; lo at +64,+96
+        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 0), IDESC, it > 0);
+        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 32), IDESC, 1);
+        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 64), umma_desc_sw128(b_addr + 0), IDESC, 1);
+        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 96), umma_desc_sw128(b_addr + 32), IDESC, 1);
+        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 64), IDESC, 1);
+        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 96), IDESC, 1);
+        umma_commit(&mma_done[s]);
+      }
+    }
+  }
+  if (tid == 0) umma_commit(acc_full);
+
+  // ------------------------------------------------------------ epilogue (warps 0..3, one row per thread)
+  if (warp < 4) {
+    if (it > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after_sync();
+    }
+    const int row = warp * 32 + lane;
+    const int grow = m0 + row;
+    const bool row_ok = grow < a.n_out;
+    float* orow = a.out + (size_t)(row_ok ? grow : 0) * a.ld_out;
+    const float* rrow = a.residual ? a.residual + (size_t)(row_ok ? grow : 0) * a.ld_res : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+      uint32_t r[32];
+      if (it > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (!row_ok) continue;
+      const int col0 = n0 + c0;
+      if (col0 >= a.c_out) continue;
+      if (p.out_vec_ok && col0 + 32 <= a.c_out) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          if (a.bias) {
+            float4 b = __ldg((const float4*)(a.bias + col0 + j));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          }
+          if (a.act) {
+            v.x = apply_act(v.x, a.act); v.y = apply_act(v.y, a.act);
+            v.z = apply_act(v.z, a.act); v.w = apply_act(v.w, a.act);
+          }
+          if (rrow) {
+            float4 t = __ldg((const float4*)(rrow + col0 + j));
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+          }
+          *(float4*)(orow + col0 + j) = v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int col = col0 + j;
+          if (col < a.c_out) {
+            float v = __uint_as_float(r[j]);
+            if (a.bias) v += __ldg(a.bias + col);
+            v = apply_act(v, a.act);
+            if (rrow) v += __ldg(rrow + col);
+            orow[col] = v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- fp32 CUDA-core cross-check kernel
+// block (32 cols, 8 rows)
+__global__ void gather_gemm_simt_kernel(const ud3d_gemm_args a, const float* __restrict__ w) {
+  int col = blockIdx.y * 32 + threadIdx.x;
+  int row = blockIdx.x * 8 + threadIdx.y;
+  if (row >= a.n_out || col >= a.c_out) return;
+  float acc = 0.f;
+  for (int k = 0; k < a.K; ++k) {
+    int idx = a.table ? a.table[(size_t)k * a.n_out + row] : row;
+    if (idx < 0) continue;
+    const float* src = a.in + (size_t)idx * a.ld_in;
+    const float* wk = w + ((size_t)col * a.K + k) * a.c_in;
+    for (int ci = 0; ci < a.c_in; ++ci) {
+      float v = src[ci];
+      if (a.in_scale) v = fmaf(v, a.in_scale[ci], a.in_shift[ci]);
+      if (a.in_relu) v = fmaxf(v, 0.f);
+      acc = fmaf(v, wk[ci], acc);
+    }
+  }
+  if (a.bias) acc += a.bias[col];
+  acc = apply_act(acc, a.act);
+  if (a.residual) acc += a.residual[(size_t)row * a.ld_res + col];
+  a.out[(size_t)row * a.ld_out + col] = acc;
+}
+
+template <int N_TILE>
+static size_t tc_smem_bytes(int n_chunks) {
+  return 1024 + (size_t)kStages * (kTileM * 128 + N_TILE * 128) + 128 + (size_t)n_chunks * kChunk * 4 * 2;
+}
+
+template <int N_TILE>
+static int launch_tc(const GemmParams& p, int n_tiles, cudaStream_t st) {
+  size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks);
+  static size_t configured = 0;   // largest size this instantiation was configured for
+  if (smem > configured) {
+    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid(cdiv(p.a.n_out, kTileM), n_tiles);
+  gather_gemm_tc_kernel<N_TILE><<<grid, kThreads, smem, st>>>(p);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+static int check_args(const ud3d_gemm_args* a, const char* who) {
+  UD3D_CHECK_ARG(a && a->in && a->out, "%s: NULL in/out", who);
+  UD3D_CHECK_ARG(a->c_in > 0 && a->c_out > 0 && a->K > 0 && a->n_out >= 0, "%s: bad sizes", who);
+  UD3D_CHECK_ARG(a->ld_in >= a->c_in && a->ld_out >= a->c_out, "%s: leading dimension smaller than channel count", who);
+  UD3D_CHECK_ARG(a->table || a->K == 1, "%s: identity gather requires K == 1", who);
+  UD3D_CHECK_ARG(!a->residual || a->ld_res >= a->c_out, "%s: bad ld_res", who);
+  UD3D_CHECK_ARG((a->in_scale == nullptr) == (a->in_shift == nullptr), "%s: in_scale/in_shift must both be set", who);
+  UD3D_CHECK_ARG(!a->tile_mask || a->K <= 32, "%s: tile_mask needs K <= 32", who);
+  return UD3D_OK;
+}
+
+}  // namespace ud3d
+
+using namespace ud3d;
+
+extern "C" {
+
+size_t ud3d_gemm_packed_weight_bytes(int K, int c_in, int c_out) {
+  if (K <= 0 || c_in <= 0 || c_out <= 0) return 0;
+  int nts = pick_ntile(c_out);
+  int n_tiles = cdiv(c_out, nts), n_chunks = cdiv(c_in, kChunk);
+  return (size_t)n_tiles * K * n_chunks * nts * 128;
+}
+
+int ud3d_gemm_pack_weight(const float* w, int K, int c_in, int c_out, void* packed, void* stream) {
+  UD3D_CHECK_ARG(w && packed && K > 0 && c_in > 0 && c_out > 0, "ud3d_gemm_pack_weight: bad argument");
+  UD3D_CHECK_ARG(((uintptr_t)packed & 127) == 0, "ud3d_gemm_pack_weight: packed buffer must be 128-byte aligned");
+  int nts = pick_ntile(c_out);
+  int n_tiles = cdiv(c_out, nts), n_chunks = cdiv(c_in, kChunk);
+  long long total = (long long)n_tiles * K * n_chunks * nts * 8;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, c_in, c_out, nts, n_tiles, n_chunks, (uint4*)packed);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
+  int rc = check_args(args, "ud3d_gemm_fwd");
+  if (rc) return rc;
+  UD3D_CHECK_ARG(args->w_packed && ((uintptr_t)args->w_packed & 127) == 0, "ud3d_gemm_fwd: w_packed NULL or misaligned");
+  if (args->n_out == 0) return UD3D_OK;
+  GemmParams p;
+  p.a = *args;
+  p.n_chunks = cdiv(args->c_in, kChunk);
+  p.vec_ok = (args->ld_in % 4 == 0) && (((uintptr_t)args->in & 15) == 0) && (args->c_in % 8 == 0);
+  p.out_vec_ok = (args->ld_out % 4 == 0) && (((uintptr_t)args->out & 15) == 0) &&
+                 (!args->bias || ((uintptr_t)args->bias & 15) == 0) &&
+                 (!args->residual || ((args->ld_res % 4 == 0) && (((uintptr_t)args->residual & 15) == 0)));
+  int nts = pick_ntile(args->c_out);
+  int n_tiles = cdiv(args->c_out, nts);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (nts) {
+    case 32: return launch_tc<32>(p, n_tiles, st);
+    case 64: return launch_tc<64>(p, n_tiles, st);
+    case 96: return launch_tc<96>(p, n_tiles, st);
+    case 128: return launch_tc<128>(p, n_tiles, st);
+    case 160: return launch_tc<160>(p, n_tiles, st);
+    default: return launch_tc<256>(p, n_tiles, st);
+  }
+}
+
+int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream) {
+  int rc = check_args(args, "ud3d_gemm_fwd_simt");
+  if (rc) return rc;
+  UD3D_CHECK_ARG(w, "ud3d_gemm_fwd_simt: NULL weight");
+  if (args->n_out == 0) return UD3D_OK;
+  dim3 grid(cdiv(args->n_out, 8), cdiv(args->c_out, 32)), block(32, 8);
+  gather_gemm_simt_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(*args, w);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+}  // extern "C"

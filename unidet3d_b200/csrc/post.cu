@@ -1,0 +1,526 @@
+// Post-processing: class softmax + global top-k, batched multi-class 3D NMS (rotated BEV / axis-aligned
+// BEV / axis-aligned 3-D IoU, one launch for all classes, on-device sweep, no host sync), and
+// superpoint box trimming (point-in-box vote + masked AABB) without the reference's
+// [n_pts, n_boxes, 6] temporary.  Reference: unidet3d/unidet3d.py:475-677.
+#include "common.cuh"
+
+#include <float.h>
+
+namespace ud3d {
+
+// ---------------------------------------------------------------- softmax scores (drop last column)
+__global__ void softmax_scores_kernel(const float* __restrict__ logits, int T, int C1, float* __restrict__ scores) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float* l = logits + (size_t)t * C1;
+  float m = -INFINITY;
+  for (int c = 0; c < C1; ++c) m = fmaxf(m, l[c]);
+  float s = 0.f;
+  for (int c = 0; c < C1; ++c) s += expf(l[c] - m);
+  const int C = C1 - 1;
+  for (int c = 0; c < C; ++c) scores[(size_t)t * C + c] = expf(l[c] - m) / s;
+}
+
+// ---------------------------------------------------------------- top-k (k <= 1024), single CTA
+// 64-bit composite key = (score bits << 32) | ~index : descending key order == descending score,
+// ties broken towards the lower flat index; 8 radix-select passes of 8 bits, then a bitonic sort of
+// the k survivors in shared memory.
+__device__ __forceinline__ unsigned long long topk_key(const float* scores, int i) {
+  return ((unsigned long long)__float_as_uint(scores[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)i);
+}
+
+__global__ void __launch_bounds__(1024) topk_select_kernel(const float* __restrict__ scores, int n, int C, int k,
+                                                           float* __restrict__ out_scores, int32_t* __restrict__ out_labels,
+                                                           int32_t* __restrict__ out_query) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix, s_mask;
+  __shared__ int s_remaining;
+  __shared__ unsigned long long cand[1024];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_prefix = 0ull;
+    s_mask = 0ull;
+    s_remaining = k;
+    s_cnt = 0;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix, mask = s_mask;
+    for (int i = tid; i < n; i += 1024) {
+      unsigned long long key = topk_key(scores, i);
+      if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int rem = s_remaining;
+      int d = 255;
+      unsigned int above = 0;
+      for (; d > 0; --d) {
+        if (above + hist[d] >= (unsigned)rem) break;
+        above += hist[d];
+      }
+      s_remaining = rem - (int)above;
+      s_prefix = prefix | ((unsigned long long)d << shift);
+      s_mask = mask | (0xFFull << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned long long kth = s_prefix;   // exact key of the k-th largest element (keys are unique)
+  for (int i = tid; i < n; i += 1024) {
+    unsigned long long key = topk_key(scores, i);
+    if (key >= kth) {
+      int pos = atomicAdd(&s_cnt, 1);
+      if (pos < 1024) cand[pos] = key;
+    }
+  }
+  __syncthreads();
+  const int cnt = min(s_cnt, 1024);
+  if (tid >= cnt) cand[tid] = 0ull;
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= 1024; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      int partner = tid ^ stride;
+      if (partner > tid) {
+        bool desc = (tid & size) == 0;
+        unsigned long long x = cand[tid], y = cand[partner];
+        if ((x < y) == desc) {
+          cand[tid] = y;
+          cand[partner] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < k) {
+    unsigned long long key = cand[tid];
+    int idx = (int)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+    out_scores[tid] = __uint_as_float((uint32_t)(key >> 32));
+    out_labels[tid] = idx % C;
+    out_query[tid] = idx / C;
+  }
+}
+
+// ---------------------------------------------------------------- IoU functions (mmcv iou3d restatement)
+struct P2 {
+  float x, y;
+};
+__device__ __forceinline__ float cross3(P2 p1, P2 p2, P2 p0) { return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y); }
+__device__ __forceinline__ int check_rect_cross(P2 p1, P2 p2, P2 q1, P2 q2) {
+  return fminf(p1.x, p2.x) <= fmaxf(q1.x, q2.x) && fminf(q1.x, q2.x) <= fmaxf(p1.x, p2.x) &&
+         fminf(p1.y, p2.y) <= fmaxf(q1.y, q2.y) && fminf(q1.y, q2.y) <= fmaxf(p1.y, p2.y);
+}
+__device__ __forceinline__ int check_in_box2d(const float* box, P2 p) {
+  const float MARGIN = 1e-2f;
+  float cx = box[0], cy = box[1];
+  float ac = cosf(-box[6]), as = sinf(-box[6]);
+  float rx = (p.x - cx) * ac + (p.y - cy) * (-as);
+  float ry = (p.x - cx) * as + (p.y - cy) * ac;
+  return (fabsf(rx) < box[3] / 2 + MARGIN && fabsf(ry) < box[4] / 2 + MARGIN);
+}
+__device__ __forceinline__ int seg_intersection(P2 p1, P2 p0, P2 q1, P2 q0, P2& ans) {
+  const float EPS = 1e-8f;
+  if (!check_rect_cross(p0, p1, q0, q1)) return 0;
+  float s1 = cross3(q0, p1, p0);
+  float s2 = cross3(p1, q1, p0);
+  float s3 = cross3(p0, q1, q0);
+  float s4 = cross3(q1, p1, q0);
+  if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+  float s5 = cross3(q1, p1, p0);
+  if (fabsf(s5 - s1) > EPS) {
+    ans.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+    ans.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+  } else {
+    float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+    float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+    float D = a0 * b1 - a1 * b0;
+    ans.x = (b0 * c1 - b1 * c0) / D;
+    ans.y = (a1 * c0 - a0 * c1) / D;
+  }
+  return 1;
+}
+__device__ __forceinline__ void box_corners(const float* box, P2* c) {
+  float hx = box[3] / 2, hy = box[4] / 2;
+  float x1 = box[0] - hx, y1 = box[1] - hy, x2 = box[0] + hx, y2 = box[1] + hy;
+  float ac = cosf(box[6]), as = sinf(box[6]);
+  P2 raw[4] = {{x1, y1}, {x2, y1}, {x2, y2}, {x1, y2}};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float nx = (raw[k].x - box[0]) * ac + (raw[k].y - box[1]) * (-as) + box[0];
+    float ny = (raw[k].x - box[0]) * as + (raw[k].y - box[1]) * ac + box[1];
+    c[k].x = nx;
+    c[k].y = ny;
+  }
+  c[4] = c[0];
+}
+__device__ float box_overlap_rot(const float* a, const float* b) {
+  P2 ca[5], cb[5];
+  box_corners(a, ca);
+  box_corners(b, cb);
+  P2 pts[24];
+  float ang[24];
+  P2 center = {0.f, 0.f};
+  int cnt = 0;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      P2 ans;
+      if (seg_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], ans)) {
+        center.x += ans.x;
+        center.y += ans.y;
+        pts[cnt++] = ans;
+      }
+    }
+  for (int k = 0; k < 4; ++k) {
+    if (check_in_box2d(a, cb[k])) {
+      center.x += cb[k].x;
+      center.y += cb[k].y;
+      pts[cnt++] = cb[k];
+    }
+    if (check_in_box2d(b, ca[k])) {
+      center.x += ca[k].x;
+      center.y += ca[k].y;
+      pts[cnt++] = ca[k];
+    }
+  }
+  if (cnt == 0) return 0.f;
+  center.x /= cnt;
+  center.y /= cnt;
+  for (int i = 0; i < cnt; ++i) ang[i] = atan2f(pts[i].y - center.y, pts[i].x - center.x);
+  // bubble sort ascending by angle (stable), as in the reference kernel
+  for (int j = 0; j < cnt - 1; ++j)
+    for (int i = 0; i < cnt - j - 1; ++i)
+      if (ang[i] > ang[i + 1]) {
+        P2 tp = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = tp;
+        float ta = ang[i]; ang[i] = ang[i + 1]; ang[i + 1] = ta;
+      }
+  float area = 0.f;
+  for (int k = 0; k < cnt - 1; ++k) {
+    float ax = pts[k].x - pts[0].x, ay = pts[k].y - pts[0].y;
+    float bx = pts[k + 1].x - pts[0].x, by = pts[k + 1].y - pts[0].y;
+    area += ax * by - ay * bx;
+  }
+  return fabsf(area) / 2.0f;
+}
+// returns true when box j must be suppressed by kept box i
+__device__ __forceinline__ bool nms_suppress(const float* bi, const float* bj, int mode, float thr) {
+  const float EPS = 1e-8f;
+  if (mode == 0) {
+    float sa = bi[3] * bi[4], sb = bj[3] * bj[4];
+    float so = box_overlap_rot(bi, bj);
+    return so / fmaxf(sa + sb - so, EPS) > thr;
+  } else if (mode == 1) {
+    float left = fmaxf(bi[0] - bi[3] / 2, bj[0] - bj[3] / 2), right = fminf(bi[0] + bi[3] / 2, bj[0] + bj[3] / 2);
+    float top = fmaxf(bi[1] - bi[4] / 2, bj[1] - bj[4] / 2), bottom = fminf(bi[1] + bi[4] / 2, bj[1] + bj[4] / 2);
+    float w = fmaxf(right - left, 0.f), hgt = fmaxf(bottom - top, 0.f);
+    float inter = w * hgt;
+    return inter / fmaxf(bi[3] * bi[4] + bj[3] * bj[4] - inter, EPS) > thr;
+  } else {
+    // mmdet3d aligned_3d_nms on corners of (centre,size) boxes (criterion.py:180-198 _bbox_to_loss)
+    float a1[3], a2[3], b1[3], b2[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      a1[d] = bi[d] - bi[3 + d] / 2; a2[d] = bi[d] + bi[3 + d] / 2;
+      b1[d] = bj[d] - bj[3 + d] / 2; b2[d] = bj[d] + bj[3 + d] / 2;
+    }
+    float va = (a2[0] - a1[0]) * (a2[1] - a1[1]) * (a2[2] - a1[2]);
+    float vb = (b2[0] - b1[0]) * (b2[1] - b1[1]) * (b2[2] - b1[2]);
+    float inter = fmaxf(0.f, fminf(a2[0], b2[0]) - fmaxf(a1[0], b1[0])) * fmaxf(0.f, fminf(a2[1], b2[1]) - fmaxf(a1[1], b1[1])) *
+                  fmaxf(0.f, fminf(a2[2], b2[2]) - fmaxf(a1[2], b1[2]));
+    float iou = inter / (va + vb - inter);
+    return !(iou <= thr);   // survivors are `iou <= thr`
+  }
+}
+
+// ---------------------------------------------------------------- NMS stage 1: class-major order
+// input is in descending score order; pos = (#valid with smaller label) + (#valid earlier with same label)
+struct NmsWs {
+  int32_t* sorted_idx;      // [n]
+  int32_t* n_valid;         // [1]
+  float* boxes7;            // [n,7] in sorted order (yaw 0 when box_dim == 6)
+  int32_t* sorted_label;    // [n]
+  unsigned long long* mask; // [n, 16]
+};
+static inline size_t nms_ws_bytes(int n) {
+  return align_up((size_t)n * 4, 256) + 256 + align_up((size_t)n * 28, 256) + align_up((size_t)n * 4, 256) +
+         align_up((size_t)n * 16 * 8, 256);
+}
+static inline NmsWs nms_ws_view(void* ws, int n) {
+  NmsWs v;
+  char* p = (char*)ws;
+  v.sorted_idx = (int32_t*)p; p += align_up((size_t)n * 4, 256);
+  v.n_valid = (int32_t*)p; p += 256;
+  v.boxes7 = (float*)p; p += align_up((size_t)n * 28, 256);
+  v.sorted_label = (int32_t*)p; p += align_up((size_t)n * 4, 256);
+  v.mask = (unsigned long long*)p;
+  return v;
+}
+
+__global__ void __launch_bounds__(1024) nms_order_kernel(const float* __restrict__ boxes, int box_dim,
+                                                         const float* __restrict__ scores,
+                                                         const int32_t* __restrict__ labels, int n, float score_thr,
+                                                         NmsWs w) {
+  __shared__ int s_label[1024];
+  __shared__ unsigned char s_valid[1024];
+  const int i = threadIdx.x;
+  bool valid = i < n && scores[i] > score_thr;
+  s_label[i] = i < n ? labels[i] : 0x7fffffff;
+  s_valid[i] = valid;
+  __syncthreads();
+  if (valid) {
+    int my = s_label[i], pos = 0;
+    for (int j = 0; j < n; ++j) {
+      if (!s_valid[j]) continue;
+      int lj = s_label[j];
+      pos += (lj < my) || (lj == my && j < i);
+    }
+    w.sorted_idx[pos] = i;
+    w.sorted_label[pos] = my;
+    const float* b = boxes + (size_t)i * box_dim;
+    float* o = w.boxes7 + (size_t)pos * 7;
+#pragma unroll
+    for (int d = 0; d < 6; ++d) o[d] = b[d];
+    o[6] = box_dim == 7 ? b[6] : 0.f;
+  }
+  int nv = __syncthreads_count(valid);
+  if (i == 0) *w.n_valid = nv;
+}
+
+// stage 2: suppression bit matrix (64 x 64 blocks, same-class pairs, j > i)
+__global__ void __launch_bounds__(64) nms_mask_kernel(NmsWs w, int n, int mode, float thr) {
+  const int nv = *w.n_valid;
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (rb * 64 >= nv || cb * 64 >= nv || cb < rb) return;
+  __shared__ float sb[64 * 7];
+  __shared__ int sl[64];
+  const int csize = min(nv - cb * 64, 64);
+  if ((int)threadIdx.x < csize) {
+    for (int d = 0; d < 7; ++d) sb[threadIdx.x * 7 + d] = w.boxes7[(size_t)(cb * 64 + threadIdx.x) * 7 + d];
+    sl[threadIdx.x] = w.sorted_label[cb * 64 + threadIdx.x];
+  }
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i >= nv) return;
+  float bi[7];
+  for (int d = 0; d < 7; ++d) bi[d] = w.boxes7[(size_t)i * 7 + d];
+  const int li = w.sorted_label[i];
+  unsigned long long bits = 0ull;
+  const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+  for (int j = start; j < csize; ++j) {
+    if (sl[j] != li) continue;
+    if (nms_suppress(bi, sb + j * 7, mode, thr)) bits |= 1ull << j;
+  }
+  w.mask[(size_t)i * 16 + cb] = bits;
+}
+
+// stage 3: greedy sweep by one warp over the bit matrix staged in shared memory
+__global__ void __launch_bounds__(1024) nms_sweep_kernel(NmsWs w, int32_t* __restrict__ keep_out, int32_t* __restrict__ n_keep) {
+  extern __shared__ unsigned long long smask[];
+  const int nv = *w.n_valid;
+  const int nblk = (nv + 63) / 64;
+  for (int t = threadIdx.x; t < nv * 16; t += blockDim.x) {
+    int i = t >> 4, c = t & 15;
+    smask[t] = (c < nblk && c >= (i >> 6)) ? w.mask[t] : 0ull;
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  unsigned long long removed = 0ull;   // lane c (< 16) owns column block c
+  int kept = 0;
+  for (int i = 0; i < nv; ++i) {
+    unsigned long long r = __shfl_sync(0xffffffffu, removed, i >> 6);
+    if (!((r >> (i & 63)) & 1ull)) {
+      if (lane == 0) keep_out[kept] = w.sorted_idx[i];
+      ++kept;
+      if (lane < 16) removed |= smask[i * 16 + lane];
+    }
+  }
+  if (lane == 0) *n_keep = kept;
+}
+
+// ---------------------------------------------------------------- superpoint trimming
+__global__ void sp_size_kernel(const int64_t* __restrict__ sp, int n_pts, int n_sp, int* __restrict__ size) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pts; p += gridDim.x * blockDim.x) {
+    long long s = sp[p];
+    if (s >= 0 && s < n_sp) atomicAdd(size + s, 1);
+  }
+}
+
+__device__ __forceinline__ bool point_in_box(float px, float py, float pz, const float* b, float c, float s) {
+  // get_face_distances (unidet3d.py:652-677): shift rotated by -yaw about z, then six face distances
+  float sx = px - b[0], sy = py - b[1], sz = pz - b[2];
+  float rx = __fsub_rn(__fmul_rn(sx, c), __fmul_rn(sy, s));
+  float ry = __fadd_rn(__fmul_rn(sx, s), __fmul_rn(sy, c));
+  float cx = b[0] + rx, cy = b[1] + ry, cz = b[2] + sz;
+  float d0 = cx - b[0] + b[3] / 2, d1 = b[0] + b[3] / 2 - cx;
+  float d2 = cy - b[1] + b[4] / 2, d3 = b[1] + b[4] / 2 - cy;
+  float d4 = cz - b[2] + b[5] / 2, d5 = b[2] + b[5] / 2 - cz;
+  return fminf(fminf(fminf(d0, d1), fminf(d2, d3)), fminf(d4, d5)) > 0.f;
+}
+
+// one CTA per box: phase A votes per superpoint in shared memory, phase B masked AABB
+__global__ void __launch_bounds__(256) trim_boxes_kernel(const float* __restrict__ pts, int ld_pts,
+                                                         const int64_t* __restrict__ sp, int n_pts, int n_sp,
+                                                         const float* __restrict__ boxes, int box_dim,
+                                                         const int32_t* __restrict__ box_index,
+                                                         const int* __restrict__ sp_size, float low_thr, float up_thr,
+                                                         float* __restrict__ out) {
+  extern __shared__ int s_cnt[];
+  const int m = blockIdx.x;
+  const float* bsrc = boxes + (size_t)(box_index ? box_index[m] : m) * box_dim;
+  float b[7];
+#pragma unroll
+  for (int d = 0; d < 6; ++d) b[d] = bsrc[d];
+  b[6] = box_dim == 7 ? bsrc[6] : 0.f;
+  const float c = cosf(-b[6]), s = sinf(-b[6]);
+  for (int i = threadIdx.x; i < n_sp; i += blockDim.x) s_cnt[i] = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < n_pts; p += blockDim.x) {
+    const float* q = pts + (size_t)p * ld_pts;
+    if (point_in_box(q[0], q[1], q[2], b, c, s)) {
+      long long id = sp[p];
+      if (id >= 0 && id < n_sp) atomicAdd(&s_cnt[id], 1);
+    }
+  }
+  __syncthreads();
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int p = threadIdx.x; p < n_pts; p += blockDim.x) {
+    const float* q = pts + (size_t)p * ld_pts;
+    long long id = sp[p];
+    bool in = point_in_box(q[0], q[1], q[2], b, c, s);
+    if (id >= 0 && id < n_sp) {
+      float frac = __fdiv_rn((float)s_cnt[id], fmaxf((float)sp_size[id], 1.f));
+      if (frac < low_thr) in = false;
+      if (frac > up_thr) in = true;
+    }
+    if (in) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        mn[d] = fminf(mn[d], q[d]);
+        mx[d] = fmaxf(mx[d], q[d]);
+      }
+    }
+  }
+  __shared__ float r_mn[8][3], r_mx[8][3];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+    if (lane == 0) {
+      r_mn[wp][d] = mn[d];
+      r_mx[wp][d] = mx[d];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int d = threadIdx.x;
+    float a = INFINITY, z = -INFINITY;
+    for (int i = 0; i < 8; ++i) {
+      a = fminf(a, r_mn[i][d]);
+      z = fmaxf(z, r_mx[i][d]);
+    }
+    out[(size_t)m * 6 + d] = (z + a) / 2.f;
+    out[(size_t)m * 6 + 3 + d] = z - a;
+  }
+}
+
+}  // namespace ud3d
+
+using namespace ud3d;
+
+extern "C" {
+
+int ud3d_topk_scores(const float* logits, int T, int C_plus1, int k, float* scores_out, int32_t* labels_out,
+                     int32_t* query_out, void* ws, size_t ws_bytes, void* stream) {
+  UD3D_CHECK_ARG(logits && scores_out && labels_out && query_out && ws, "ud3d_topk_scores: NULL argument");
+  const int C = C_plus1 - 1;
+  UD3D_CHECK_ARG(T > 0 && C > 0 && k > 0 && k <= 1024, "ud3d_topk_scores: need T > 0, C > 0, 0 < k <= 1024");
+  UD3D_CHECK_ARG((long long)T * C >= k, "ud3d_topk_scores: k=%d out of range for %lld scores (torch.topk raises here too)", k,
+                 (long long)T * C);
+  UD3D_CHECK_ARG((long long)T * C < (1ll << 31), "ud3d_topk_scores: too many scores");
+  if (ws_bytes < (size_t)T * C * 4) {
+    set_error("ud3d_topk_scores: workspace too small");
+    return UD3D_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  softmax_scores_kernel<<<cdiv(T, 128), 128, 0, st>>>(logits, T, C_plus1, (float*)ws);
+  UD3D_LAUNCH_CHECK();
+  topk_select_kernel<<<1, 1024, 0, st>>>((const float*)ws, T * C, C, k, scores_out, labels_out, query_out);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+size_t ud3d_nms_workspace_bytes(int n) { return nms_ws_bytes(n > 0 ? n : 1); }
+
+int ud3d_nms_multiclass(const float* boxes, int box_dim, const float* scores, const int32_t* labels, int n, int mode,
+                        float iou_thr, float score_thr, int32_t* keep_out, int32_t* n_keep, void* ws, size_t ws_bytes,
+                        void* stream) {
+  UD3D_CHECK_ARG(boxes && scores && labels && keep_out && n_keep && ws, "ud3d_nms_multiclass: NULL argument");
+  UD3D_CHECK_ARG(n >= 0 && n <= 1024 && (box_dim == 6 || box_dim == 7) && mode >= 0 && mode <= 2,
+                 "ud3d_nms_multiclass: need n <= 1024, box_dim 6|7, mode 0..2");
+  if (ws_bytes < nms_ws_bytes(n > 0 ? n : 1)) {
+    set_error("ud3d_nms_multiclass: workspace too small");
+    return UD3D_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    UD3D_CUDA(cudaMemsetAsync(n_keep, 0, 4, st));
+    return UD3D_OK;
+  }
+  NmsWs w = nms_ws_view(ws, n);
+  nms_order_kernel<<<1, 1024, 0, st>>>(boxes, box_dim, scores, labels, n, score_thr, w);
+  UD3D_LAUNCH_CHECK();
+  int nb = cdiv(n, 64);
+  nms_mask_kernel<<<dim3(nb, nb), 64, 0, st>>>(w, n, mode, iou_thr);
+  UD3D_LAUNCH_CHECK();
+  size_t smem = (size_t)n * 16 * 8;
+  static bool configured = false;
+  if (!configured) {
+    UD3D_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16 * 8));
+    configured = true;
+  }
+  nms_sweep_kernel<<<1, 1024, smem, st>>>(w, keep_out, n_keep);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+size_t ud3d_trim_workspace_bytes(int n_sp) { return align_up((size_t)(n_sp > 0 ? n_sp : 1) * 4, 256); }
+
+int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pts, int n_sp, const float* boxes,
+                    int box_dim, const int32_t* box_index, int m, float low_thr, float up_thr, float* out, void* ws,
+                    size_t ws_bytes, void* stream) {
+  UD3D_CHECK_ARG(points && sp && boxes && out && ws, "ud3d_trim_boxes: NULL argument");
+  UD3D_CHECK_ARG(ld_pts >= 3 && n_pts >= 0 && n_sp > 0 && (box_dim == 6 || box_dim == 7) && m >= 0, "ud3d_trim_boxes: bad sizes");
+  UD3D_CHECK_ARG((size_t)n_sp * 4 <= 200 * 1024, "ud3d_trim_boxes: more than 51200 superpoints per scene is unsupported");
+  if (ws_bytes < ud3d_trim_workspace_bytes(n_sp)) {
+    set_error("ud3d_trim_boxes: workspace too small");
+    return UD3D_EWORKSPACE;
+  }
+  if (m == 0) return UD3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  UD3D_CUDA(cudaMemsetAsync(ws, 0, (size_t)n_sp * 4, st));
+  if (n_pts > 0) {
+    int blocks = cdiv(n_pts, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sp_size_kernel<<<blocks, 256, 0, st>>>(sp, n_pts, n_sp, (int*)ws);
+    UD3D_LAUNCH_CHECK();
+  }
+  size_t smem = (size_t)n_sp * 4;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    UD3D_CUDA(cudaFuncSetAttribute(trim_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  trim_boxes_kernel<<<m, 256, smem, st>>>(points, ld_pts, sp, n_pts, n_sp, boxes, box_dim, box_index, (const int*)ws, low_thr,
+                                         up_thr, out);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+}  // extern "C"

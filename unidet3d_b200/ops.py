@@ -1,0 +1,296 @@
+"""Thin torch-tensor wrappers over the C-ABI (device memory + streams come from PyTorch; every
+kernel is ours).  All functions require CUDA tensors and raise otherwise -- there is no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check
+
+TILE_M = 128
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.Ud3dError(f"{name}: expected a CUDA tensor (unidet3d_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.Ud3dError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.Ud3dError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _dims(d: Sequence[int]):
+    return (C.c_int32 * len(d))(*[int(x) for x in d])
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(_L().ud3d_launch_count(1 if reset else 0))
+
+
+# ------------------------------------------------------------------ voxelisation / grid
+def point_coords(points: torch.Tensor, scene_offsets: torch.Tensor, voxel_size: float):
+    """points fp32 [n,6], scene_offsets int32 [B+1] -> coords int32 [n,4], feats [n,6], stats [B,6], max_coord int32 [3]."""
+    _req(points, torch.float32, "points"), _req(scene_offsets, torch.int32, "scene_offsets")
+    n, B = points.shape[0], scene_offsets.numel() - 1
+    dev = points.device
+    coords = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    feats = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    stats = torch.empty((B, 6), dtype=torch.float32, device=dev)
+    maxc = torch.empty(3, dtype=torch.int32, device=dev)
+    wsb = _L().ud3d_point_coords_workspace_bytes(B)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(_L().ud3d_point_coords(_p(points), n, _p(scene_offsets), B, float(voxel_size), _p(coords), _p(feats),
+                                 _p(stats), _p(maxc), _p(ws), wsb, _stream()), "ud3d_point_coords")
+    return coords, feats, stats, maxc
+
+
+class Grid:
+    """Occupancy grid over the dense (B,X,Y,Z) box: bitmap + popcount prefix (see the C header)."""
+
+    def __init__(self, dims: Sequence[int], device):
+        self.dims = [int(d) for d in dims]
+        self._cd = _dims(self.dims)
+        self.ws_bytes = int(_L().ud3d_grid_workspace_bytes(self._cd))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+        self.n_unique = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def build(self, coords: torch.Tensor):
+        _req(coords, torch.int32, "coords")
+        check(_L().ud3d_grid_build(_p(coords), coords.shape[0], self._cd, _p(self.ws), self.ws_bytes,
+                                   _p(self.n_unique), _stream()), "ud3d_grid_build")
+        return self.n_unique
+
+    def rank(self, coords: torch.Tensor) -> torch.Tensor:
+        _req(coords, torch.int32, "coords")
+        out = torch.empty(coords.shape[0], dtype=torch.int32, device=coords.device)
+        check(_L().ud3d_grid_rank(_p(coords), coords.shape[0], self._cd, _p(self.ws), _p(out), _stream()), "ud3d_grid_rank")
+        return out
+
+    def coords(self, n_unique: int) -> torch.Tensor:
+        out = torch.empty((n_unique, 4), dtype=torch.int32, device=self.ws.device)
+        check(_L().ud3d_grid_coords(self._cd, _p(self.ws), _p(out), n_unique, _stream()), "ud3d_grid_coords")
+        return out
+
+
+def voxel_mean(feats_pts: torch.Tensor, rank: torch.Tensor, n_vox: int) -> torch.Tensor:
+    _req(feats_pts, torch.float32, "feats_pts"), _req(rank, torch.int32, "rank")
+    n, Cc = feats_pts.shape
+    out = torch.empty((n_vox, Cc), dtype=torch.float32, device=feats_pts.device)
+    ws = torch.empty(max(n_vox, 1) * 4, dtype=torch.uint8, device=feats_pts.device)
+    check(_L().ud3d_voxel_mean(_p(feats_pts), _p(rank), n, Cc, n_vox, _p(out), _p(ws), ws.numel(), _stream()), "ud3d_voxel_mean")
+    return out
+
+
+def rulebook_subm3(coords: torch.Tensor, grid: Grid, canonical: bool, with_mask: bool = True):
+    """-> table int32 [27,N], tile_mask uint32-as-int32 [ceil(N/128)] (or None)."""
+    _req(coords, torch.int32, "coords")
+    n = coords.shape[0]
+    dev = coords.device
+    table = torch.empty((27, n), dtype=torch.int32, device=dev)
+    mask = torch.empty((n + TILE_M - 1) // TILE_M, dtype=torch.int32, device=dev) if with_mask else None
+    ror = None if canonical else torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    check(_L().ud3d_rulebook_subm3(_p(coords), n, grid._cd, _p(grid.ws), _p(ror), _p(table), _p(mask), _stream()),
+          "ud3d_rulebook_subm3")
+    return table, mask
+
+
+def down2_parents(coords: torch.Tensor, in_shape: Sequence[int]) -> torch.Tensor:
+    _req(coords, torch.int32, "coords")
+    parents = torch.empty_like(coords)
+    check(_L().ud3d_down2_parents(_p(coords), coords.shape[0], _dims(in_shape), _p(parents), _stream()), "ud3d_down2_parents")
+    return parents
+
+
+def rulebook_down2(coords: torch.Tensor, parents: torch.Tensor, n_coarse: int, coarse_grid: Grid, with_mask: bool = True):
+    n_fine = coords.shape[0]
+    dev = coords.device
+    child = torch.empty((8, n_coarse), dtype=torch.int32, device=dev)
+    up = torch.empty((8, n_fine), dtype=torch.int32, device=dev)
+    cm = torch.empty((n_coarse + TILE_M - 1) // TILE_M, dtype=torch.int32, device=dev) if with_mask else None
+    um = torch.empty((n_fine + TILE_M - 1) // TILE_M, dtype=torch.int32, device=dev) if with_mask else None
+    check(_L().ud3d_rulebook_down2(_p(coords), _p(parents), n_fine, n_coarse, coarse_grid._cd, _p(coarse_grid.ws),
+                                   _p(child), _p(up), _p(cm), _p(um), _stream()), "ud3d_rulebook_down2")
+    return child, up, cm, um
+
+
+# ------------------------------------------------------------------ gather-GEMM
+class PackedWeight:
+    """Weight in the kernel's shared-memory image.  ``w``: [C_out, K, C_in] fp32 (reference layout
+    flattened: spconv [C_out,k,k,k,C_in]; nn.Linear [C_out,C_in] with K=1)."""
+
+    def __init__(self, w: torch.Tensor):
+        if w.dim() == 2:
+            w = w.unsqueeze(1)
+        if w.dim() == 5:
+            w = w.reshape(w.shape[0], -1, w.shape[-1])
+        w = _req(w.detach().to(torch.float32).contiguous(), torch.float32, "weight")
+        self.c_out, self.K, self.c_in = w.shape
+        nbytes = int(_L().ud3d_gemm_packed_weight_bytes(self.K, self.c_in, self.c_out))
+        self.data = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        check(_L().ud3d_gemm_pack_weight(_p(w), self.K, self.c_in, self.c_out, _p(self.data), _stream()), "ud3d_gemm_pack_weight")
+
+
+def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act, residual,
+               w_packed_ptr):
+    a = GemmArgs()
+    a.in_ = x.data_ptr(); a.ld_in = x.stride(0); a.c_in = c_in
+    a.table = table.data_ptr() if table is not None else None
+    a.tile_mask = tile_mask.data_ptr() if tile_mask is not None else None
+    a.K = pw_K; a.n_out = n_out
+    a.w_packed = w_packed_ptr
+    a.out = out.data_ptr(); a.ld_out = out.stride(0); a.c_out = c_out
+    a.in_scale = in_scale.data_ptr() if in_scale is not None else None
+    a.in_shift = in_shift.data_ptr() if in_shift is not None else None
+    a.in_relu = 1 if in_relu else 0
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.act = {None: 0, "none": 0, "relu": 1, "gelu": 2}[act]
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.ld_res = residual.stride(0) if residual is not None else 0
+    return a
+
+
+def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = None, tile_mask=None,
+         n_out: Optional[int] = None, out: Optional[torch.Tensor] = None, in_scale=None, in_shift=None,
+         in_relu: bool = False, bias=None, act=None, residual=None) -> torch.Tensor:
+    """out = act(sum_k pre(x[table[k]]) @ W_k + bias) + residual   (see ud3d_gemm_fwd).
+    ``x``/``out``/``residual`` may be column slices of wider row-major buffers (stride(1) == 1)."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.stride(1) != 1:
+        raise _lib.Ud3dError("gemm: x must be a CUDA fp32 matrix with unit column stride")
+    if n_out is None:
+        n_out = table.shape[1] if table is not None else x.shape[0]
+    if out is None:
+        out = torch.empty((n_out, w.c_out), dtype=torch.float32, device=x.device)
+    assert out.stride(1) == 1 and out.shape[1] == w.c_out and x.shape[1] == w.c_in
+    a = _gemm_args(x, w.K, w.c_in, w.c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act,
+                   residual, w.data.data_ptr())
+    check(_L().ud3d_gemm_fwd(C.byref(a), _stream()), "ud3d_gemm_fwd")
+    return out
+
+
+def gemm_simt(x, w_raw: torch.Tensor, *, table=None, n_out=None, in_scale=None, in_shift=None, in_relu=False,
+              bias=None, act=None, residual=None) -> torch.Tensor:
+    """Diagnostic fp32 CUDA-core version on the unpacked weight [C_out,K,C_in]."""
+    w_raw = w_raw.reshape(w_raw.shape[0], -1, w_raw.shape[-1]).contiguous() if w_raw.dim() != 3 else w_raw.contiguous()
+    c_out, K, c_in = w_raw.shape
+    if n_out is None:
+        n_out = table.shape[1] if table is not None else x.shape[0]
+    out = torch.empty((n_out, c_out), dtype=torch.float32, device=x.device)
+    a = _gemm_args(x, K, c_in, c_out, n_out, table, None, out, in_scale, in_shift, in_relu, bias, act, residual, None)
+    check(_L().ud3d_gemm_fwd_simt(C.byref(a), _p(w_raw), _stream()), "ud3d_gemm_fwd_simt")
+    return out
+
+
+# ------------------------------------------------------------------ pooling / encoder pieces
+def segmented_mean(src: torch.Tensor, seg: torch.Tensor, n_seg: int, *, gather: Optional[torch.Tensor] = None,
+                   channels: Optional[int] = None, scale=None, shift=None, relu: bool = False) -> torch.Tensor:
+    _req(seg, torch.int64, "seg")
+    if not src.is_cuda or src.dtype != torch.float32 or src.stride(1) != 1:
+        raise _lib.Ud3dError("segmented_mean: src must be a CUDA fp32 matrix with unit column stride")
+    Cc = src.shape[1] if channels is None else channels
+    n = seg.shape[0]
+    out = torch.empty((n_seg, Cc), dtype=torch.float32, device=src.device)
+    ws = torch.empty(max(n_seg, 1) * 4, dtype=torch.uint8, device=src.device)
+    check(_L().ud3d_segmented_mean(_p(src), src.stride(0), Cc, _p(gather), _p(seg), n, n_seg, _p(scale), _p(shift),
+                                   1 if relu else 0, _p(out), _p(ws), ws.numel(), _stream()), "ud3d_segmented_mean")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma, beta, residual=None, eps: float = 1e-5, out=None) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_L().ud3d_layernorm(_p(x), _p(residual), _p(gamma), _p(beta), _p(out), x.shape[0], x.shape[1], float(eps),
+                              _stream()), "ud3d_layernorm")
+    return out
+
+
+def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_T: int, num_heads: int) -> torch.Tensor:
+    _req(qkv, torch.float32, "qkv"), _req(cu_seqlens, torch.int32, "cu_seqlens")
+    d = qkv.shape[1] // 3
+    if d != num_heads * 32:
+        raise _lib.Ud3dError("attention: head_dim must be 32")
+    out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
+    check(_L().ud3d_attention_fwd(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, int(max_T), num_heads, _p(out),
+                                  _stream()), "ud3d_attention_fwd")
+    return out
+
+
+def bbox_decode(raw: torch.Tensor, centers: torch.Tensor, with_angle: bool) -> torch.Tensor:
+    _req(centers, torch.float32, "centers")
+    T = raw.shape[0]
+    out = torch.empty((T, 7 if with_angle else 6), dtype=torch.float32, device=raw.device)
+    check(_L().ud3d_bbox_decode(_p(raw), raw.stride(0), _p(centers), T, 1 if with_angle else 0, _p(out), _stream()),
+          "ud3d_bbox_decode")
+    return out
+
+
+def gather_columns(src: torch.Tensor, cols: torch.Tensor) -> torch.Tensor:
+    _req(cols, torch.int32, "cols")
+    T = src.shape[0]
+    out = torch.empty((T, cols.numel()), dtype=torch.float32, device=src.device)
+    check(_L().ud3d_gather_columns(_p(src), src.stride(0), _p(cols), cols.numel(), T, _p(out), _stream()), "ud3d_gather_columns")
+    return out
+
+
+# ------------------------------------------------------------------ post-processing
+def topk_scores(logits: torch.Tensor, k: int):
+    _req(logits, torch.float32, "logits")
+    T, C1 = logits.shape
+    dev = logits.device
+    scores = torch.empty(k, dtype=torch.float32, device=dev)
+    labels = torch.empty(k, dtype=torch.int32, device=dev)
+    query = torch.empty(k, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(T * (C1 - 1), 1) * 4, dtype=torch.uint8, device=dev)
+    check(_L().ud3d_topk_scores(_p(logits), T, C1, k, _p(scores), _p(labels), _p(query), _p(ws), ws.numel(), _stream()),
+          "ud3d_topk_scores")
+    return scores, labels, query
+
+
+NMS_ROTATED_BEV, NMS_ALIGNED_BEV, NMS_ALIGNED_3D = 0, 1, 2
+
+
+def nms_multiclass(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor, mode: int, iou_thr: float,
+                   score_thr: float = 0.0):
+    """-> keep int32 [n] (first n_keep valid), n_keep int32 [1] (device)."""
+    _req(boxes, torch.float32, "boxes"), _req(scores, torch.float32, "scores"), _req(labels, torch.int32, "labels")
+    n = boxes.shape[0]
+    dev = boxes.device
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    n_keep = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = int(_L().ud3d_nms_workspace_bytes(n))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(_L().ud3d_nms_multiclass(_p(boxes), boxes.shape[1], _p(scores), _p(labels), n, mode, float(iou_thr),
+                                   float(score_thr), _p(keep), _p(n_keep), _p(ws), wsb, _stream()), "ud3d_nms_multiclass")
+    return keep, n_keep
+
+
+def trim_boxes(points: torch.Tensor, sp: torch.Tensor, n_sp: int, boxes: torch.Tensor, low_thr: float, up_thr: float,
+               box_index: Optional[torch.Tensor] = None, m: Optional[int] = None) -> torch.Tensor:
+    _req(sp, torch.int64, "sp"), _req(boxes, torch.float32, "boxes")
+    if not points.is_cuda or points.dtype != torch.float32 or points.stride(1) != 1:
+        raise _lib.Ud3dError("trim_boxes: points must be a CUDA fp32 matrix with unit column stride")
+    m = (box_index.numel() if box_index is not None else boxes.shape[0]) if m is None else m
+    out = torch.empty((m, 6), dtype=torch.float32, device=boxes.device)
+    wsb = int(_L().ud3d_trim_workspace_bytes(n_sp))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=boxes.device)
+    check(_L().ud3d_trim_boxes(_p(points), points.stride(0), _p(sp), points.shape[0], n_sp, _p(boxes), boxes.shape[1],
+                               _p(box_index), m, float(low_thr), float(up_thr), _p(out), _p(ws), wsb, _stream()), "ud3d_trim_boxes")
+    return out
