@@ -101,7 +101,7 @@ def make_unet_state_dict(num_planes, block_reps=2, gen=None, p=""):
         sd[key + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
 
     def conv(key, co, k, ci, active):
-        sd[key] = torch.randn(co, k, k, k, ci, generator=g) * (2.0 / (active * ci)) ** 0.5
+        sd[key] = torch.randn(co, k, k, k, ci, generator=g) * (1.0 / (active * ci)) ** 0.5
 
     def block(key, ci, co):
         if ci != co:
@@ -129,7 +129,7 @@ def make_unet_state_dict(num_planes, block_reps=2, gen=None, p=""):
 def make_detector_backbone_state_dict(in_channels=6, num_planes=(32, 64, 96, 128, 160), seed=0):
     g = torch.Generator().manual_seed(seed)
     sd = {"input_conv.0.weight":
-          torch.randn(num_planes[0], 3, 3, 3, in_channels, generator=g) * (2.0 / (11 * in_channels)) ** 0.5}
+          torch.randn(num_planes[0], 3, 3, 3, in_channels, generator=g) * (1.0 / (11 * in_channels)) ** 0.5}
     for k, v in make_unet_state_dict(list(num_planes), 2, g).items():
         sd["unet." + k] = v
     c = num_planes[0]

@@ -200,7 +200,7 @@ def gen_encoder():
     from unidet3d.encoder import UniDet3DEncoder
     torch.manual_seed(7)
     classes = [["chair", "table", "sofa"], ["table", "board"], ["bed", "chair", "oven", "sink"]]
-    cfg = dict(num_layers=2, datasets_classes=classes, in_channels=8, d_model=64, num_heads=4, hidden_dim=128,
+    cfg = dict(num_layers=2, datasets_classes=classes, in_channels=8, d_model=64, num_heads=2, hidden_dim=128,
                dropout=0.0, activation_fn="gelu", datasets=["scannet", "s3dis", "arkitscenes"],
                angles=[False, False, True])
     m = UniDet3DEncoder(**cfg).eval()

@@ -25,7 +25,7 @@ def test_encoder_matches_reference_module(golden_dir):
     g = _load(golden_dir, "encoder_ref.npz")
     sd = {k[3:]: torch.as_tensor(g[k]) for k in g.files if k.startswith("sd.")}
     classes = [["chair", "table", "sofa"], ["table", "board"], ["bed", "chair", "oven", "sink"]]
-    cfg = dict(num_layers=2, num_heads=4, activation_fn="gelu", datasets=["scannet", "s3dis", "arkitscenes"],
+    cfg = dict(num_layers=2, num_heads=2, activation_fn="gelu", datasets=["scannet", "s3dis", "arkitscenes"],
                datasets_classes=classes, angles=[False, False, True])
     x = [torch.as_tensor(g[f"x{i}"]) for i in range(3)]
     c = [torch.as_tensor(g[f"c{i}"]) for i in range(3)]

@@ -1,0 +1,163 @@
+"""UniDet3DEncoder: superpoint transformer encoder + per-dataset heads (reference:
+unidet3d/encoder.py:1-283) on the C-ABI kernels.  Same registry name, constructor arguments,
+``forward`` contract and state_dict keys as the reference.
+
+All scenes of a batch are processed as ONE packed [sum(T_i), d] matrix: every Linear is a single
+tcgen05 GEMM launch with bias / ReLU / GELU / residual fused in the epilogue, LayerNorm is one
+warp-per-row kernel, attention is one varlen launch (scene boundaries in ``cu_seqlens``; the
+reference loops over scenes in Python, encoder.py:36,75,189).
+"""
+from __future__ import annotations
+
+import itertools
+from typing import List
+
+import torch
+from torch import nn
+
+from . import ops
+from .registry import register_model
+
+
+class SelfAttentionLayer(nn.Module):
+    """Parameter tree of encoder.py:8-22."""
+
+    def __init__(self, d_model, num_heads, dropout):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, num_heads, dropout=dropout, batch_first=True)
+        self.norm = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+
+
+class FFN(nn.Module):
+    """Parameter tree of encoder.py:43-61."""
+
+    def __init__(self, d_model, hidden_dim, dropout, activation_fn):
+        super().__init__()
+        self.net = nn.Sequential(nn.Linear(d_model, hidden_dim), nn.ReLU() if activation_fn == "relu" else nn.GELU(),
+                                 nn.Dropout(dropout), nn.Linear(hidden_dim, d_model), nn.Dropout(dropout))
+        self.norm = nn.LayerNorm(d_model)
+        self.activation_fn = activation_fn
+
+
+class PredBBox(nn.Module):
+    """Parameter tree of encoder.py:82-111."""
+
+    def __init__(self, d_model, n_bbox_outs, bbox_init_normal=False):
+        super().__init__()
+        self.linear = nn.Linear(d_model, n_bbox_outs)
+        if bbox_init_normal:
+            nn.init.normal_(self.linear.weight, std=.01)
+
+
+@register_model
+class UniDet3DEncoder(nn.Module):
+    """Encoder for the UniDet3D model (drop-in for the reference class of the same name).
+
+    Extra attribute ``eval_aux_outputs`` (default False): in eval mode the six auxiliary head
+    evaluations, which ``UniDet3D.predict`` never reads (unidet3d.py:498-499), are skipped and
+    ``aux_outputs`` is returned empty; set it to True to get all seven like the reference.
+    """
+
+    def __init__(self, num_layers, datasets_classes, in_channels, d_model, num_heads, hidden_dim, dropout,
+                 activation_fn, datasets, angles, **kwargs):
+        super().__init__()
+        if dropout != 0.0:
+            raise NotImplementedError("dropout > 0 is a training-only feature; the forward path assumes 0.0")
+        if d_model % num_heads or d_model // num_heads != 32:
+            raise NotImplementedError("the attention kernel is specialised for head_dim == 32 (d_model=256, 8 heads)")
+        self.num_layers, self.datasets, self.angles = num_layers, datasets, angles
+        self.d_model, self.num_heads = d_model, num_heads
+        self.input_proj = nn.Sequential(nn.Linear(in_channels, d_model), nn.ReLU(), nn.Linear(d_model, d_model))
+        self.self_attn_layers = nn.ModuleList([SelfAttentionLayer(d_model, num_heads, dropout) for _ in range(num_layers)])
+        self.ffn_layers = nn.ModuleList([FFN(d_model, hidden_dim, dropout, activation_fn) for _ in range(num_layers)])
+        self.out_norm = nn.LayerNorm(d_model)
+        unique_cls = sorted(list(set(itertools.chain.from_iterable(datasets_classes)))) + ["no_obj"]
+        self.outs_cls = nn.Sequential(nn.Linear(d_model, d_model), nn.ReLU(), nn.Linear(d_model, len(unique_cls)))
+        self.datasets_cls_idxs = []
+        for dataset_classes in datasets_classes:
+            self.datasets_cls_idxs.append([unique_cls.index(c) for c in dataset_classes] + [-1])
+        self.n_union = len(unique_cls)
+        self.out_bboxes = PredBBox(d_model, 8)
+        self.activation_fn = activation_fn
+        self.eval_aux_outputs = False
+        self._plan = None
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_plan())
+
+    def invalidate_plan(self):
+        self._plan = None
+
+    def _apply(self, fn, *a, **k):
+        self._plan = None
+        return super()._apply(fn, *a, **k)
+
+    def _get_plan(self):
+        if self._plan is None:
+            f = lambda t: t.detach().float().contiguous()
+            lin = lambda m: (ops.PackedWeight(m.weight), f(m.bias))
+            p = dict(ip0=lin(self.input_proj[0]), ip2=lin(self.input_proj[2]), layers=[])
+            for sa, ff in zip(self.self_attn_layers, self.ffn_layers):
+                p["layers"].append(dict(
+                    qkv=(ops.PackedWeight(sa.attn.in_proj_weight), f(sa.attn.in_proj_bias)),
+                    out=lin(sa.attn.out_proj), n1=(f(sa.norm.weight), f(sa.norm.bias), sa.norm.eps),
+                    f1=lin(ff.net[0]), f2=lin(ff.net[3]), n2=(f(ff.norm.weight), f(ff.norm.bias), ff.norm.eps)))
+            p["on"] = (f(self.out_norm.weight), f(self.out_norm.bias), self.out_norm.eps)
+            p["c0"], p["c2"], p["bb"] = lin(self.outs_cls[0]), lin(self.outs_cls[2]), lin(self.out_bboxes.linear)
+            dev = self.out_norm.weight.device
+            p["cols"] = [torch.tensor([i if i >= 0 else self.n_union - 1 for i in idxs], dtype=torch.int32, device=dev)
+                         for idxs in self.datasets_cls_idxs]
+            self._plan = p
+        return self._plan
+
+    # ------------------------------------------------------------------ heads (encoder.py:165-201)
+    def _forward_head(self, p, H, centers, bounds, ds_idx):
+        nq = ops.layernorm(H, p["on"][0], p["on"][1], eps=p["on"][2])
+        h = ops.gemm(nq, p["c0"][0], bias=p["c0"][1], act="relu")
+        logits = ops.gemm(h, p["c2"][0], bias=p["c2"][1])
+        raw = ops.gemm(nq, p["bb"][0], bias=p["bb"][1])
+        cls_preds, bboxes = [], []
+        for i, j in enumerate(ds_idx):
+            a, b = bounds[i], bounds[i + 1]
+            cls_preds.append(ops.gather_columns(logits[a:b], p["cols"][j]))
+            bboxes.append(ops.bbox_decode(raw[a:b], centers[a:b], bool(self.angles[j])))
+        return cls_preds, bboxes
+
+    def forward(self, x: List[torch.Tensor], sp_centers: List[torch.Tensor], datasets_names: List[str]):
+        """x: list of [T_i, in_channels]; sp_centers: list of [T_i,3]; returns the reference's dict
+        (cls_preds, bboxes, aux_outputs)."""
+        if self.training:
+            raise NotImplementedError("unidet3d_b200.UniDet3DEncoder implements the forward/eval path only (round 1)")
+        p = self._get_plan()
+        lens = [int(t.shape[0]) for t in x]
+        bounds = [0] + list(itertools.accumulate(lens))
+        X = x[0] if len(x) == 1 else torch.cat(x, 0)
+        Cn = sp_centers[0] if len(sp_centers) == 1 else torch.cat(sp_centers, 0)
+        X, Cn = X.contiguous().float(), Cn.contiguous().float()
+        return self.forward_packed(X, Cn, bounds, datasets_names)
+
+    def forward_packed(self, X: torch.Tensor, centers: torch.Tensor, bounds: List[int], datasets_names: List[str]):
+        """Same as ``forward`` on already-packed rows (scene i = rows bounds[i]:bounds[i+1])."""
+        p = self._get_plan()
+        ds_idx = [self.datasets.index(n) for n in datasets_names]
+        cu = torch.tensor(bounds, dtype=torch.int32).to(X.device, non_blocking=True)
+        max_T = max(b - a for a, b in zip(bounds[:-1], bounds[1:])) if len(bounds) > 1 else 0
+        all_heads = self.eval_aux_outputs
+        cls_all, box_all = [], []
+        H = ops.gemm(X, p["ip0"][0], bias=p["ip0"][1], act="relu")
+        H = ops.gemm(H, p["ip2"][0], bias=p["ip2"][1])
+        if all_heads:
+            c, b = self._forward_head(p, H, centers, bounds, ds_idx)
+            cls_all.append(c), box_all.append(b)
+        for li, lp in enumerate(p["layers"]):
+            qkv = ops.gemm(H, lp["qkv"][0], bias=lp["qkv"][1])
+            A = ops.attention(qkv, cu, max_T, self.num_heads)
+            Z = ops.gemm(A, lp["out"][0], bias=lp["out"][1], residual=H)
+            H = ops.layernorm(Z, lp["n1"][0], lp["n1"][1], eps=lp["n1"][2])
+            F1 = ops.gemm(H, lp["f1"][0], bias=lp["f1"][1], act=self.activation_fn)
+            Z = ops.gemm(F1, lp["f2"][0], bias=lp["f2"][1], residual=H)
+            H = ops.layernorm(Z, lp["n2"][0], lp["n2"][1], eps=lp["n2"][2])
+            if all_heads or li == self.num_layers - 1:
+                c, b = self._forward_head(p, H, centers, bounds, ds_idx)
+                cls_all.append(c), box_all.append(b)
+        aux_outputs = [dict(cls_preds=c, bboxes=b) for c, b in zip(cls_all[:-1], box_all[:-1])]
+        return dict(cls_preds=cls_all[-1], bboxes=box_all[-1], aux_outputs=aux_outputs)

@@ -1,0 +1,185 @@
+"""SpConvUNet: the sparse-conv residual U-Net backbone (reference: unidet3d/spconv_unet.py:13-240),
+re-implemented on the tcgen05 gather-GEMM.  Same registry name, constructor arguments and
+state_dict keys/shapes as the reference; no spconv import.
+
+Execution plan (eval mode):
+  * every BatchNorm(eval)+ReLU that precedes a conv is folded into that conv's operand load
+    (``in_scale``/``in_shift``/``in_relu``), every residual add into the conv epilogue, and the skip
+    concat ``[identity | decoder]`` is never materialised: the encoder-side block and the inverse
+    conv write straight into the two column halves of one [N, 2c] buffer;
+  * => each feature map is read once and written once per conv.
+"""
+from __future__ import annotations
+
+import functools
+from collections import OrderedDict
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .registry import register_model
+from .rulebook import Pyramid, build_pyramid
+from .structures import SparseConvTensor
+
+
+class SparseConvWeight(nn.Module):
+    """Parameter holder with the spconv-2.x layout ``[C_out, k, k, k, C_in]`` (no bias)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size):
+        super().__init__()
+        k = kernel_size
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, k
+        w = torch.empty(out_channels, k, k, k, in_channels)
+        nn.init.kaiming_uniform_(w.view(out_channels, -1), a=5 ** 0.5)
+        self.weight = nn.Parameter(w)
+
+
+def fold_bn(bn: nn.Module):
+    """Eval-mode BatchNorm -> per-channel (scale, shift): y = x*scale + shift."""
+    inv = torch.rsqrt(bn.running_var.detach().float() + bn.eps)
+    scale = bn.weight.detach().float() * inv
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+class ResidualBlock(nn.Module):
+    """Parameter tree of the reference block (spconv_unet.py:13-72); executed by SpConvUNet."""
+
+    def __init__(self, in_channels, out_channels, norm_fn, indice_key=None, normalize_before=True):
+        super().__init__()
+        if not normalize_before:
+            raise NotImplementedError("only normalize_before=True is supported (the reference configs use it)")
+        if in_channels == out_channels:
+            self.i_branch = nn.Sequential(nn.Identity())
+        else:
+            self.i_branch = nn.Sequential(SparseConvWeight(in_channels, out_channels, 1))
+        self.conv_branch = nn.Sequential(
+            norm_fn(in_channels), nn.ReLU(), SparseConvWeight(in_channels, out_channels, 3),
+            norm_fn(out_channels), nn.ReLU(), SparseConvWeight(out_channels, out_channels, 3))
+        self.in_channels, self.out_channels = in_channels, out_channels
+
+
+@register_model
+class SpConvUNet(nn.Module):
+    """SpConv U-Net model (drop-in for the reference class of the same name).
+
+    Args mirror unidet3d/spconv_unet.py:108-115.  The reference's recursion passes ``norm_fn``
+    positionally into ``use_sync_bn`` (:166-173); any truthy value selects SyncBatchNorm there.  Here
+    both variants hold plain BatchNorm statistics (identical state_dict keys; eval math identical).
+    """
+
+    def __init__(self, num_planes, use_sync_bn=True, block_reps=2, block=ResidualBlock, indice_key_id=1,
+                 normalize_before=True, return_blocks=False):
+        super().__init__()
+        self.return_blocks = return_blocks
+        self.num_planes = list(num_planes)
+        self.block_reps = block_reps
+        self.indice_key_id = indice_key_id
+        norm_fn = functools.partial(nn.BatchNorm1d, eps=1e-4, momentum=0.1)
+        if isinstance(block, str):
+            assert block in ("residual",), f"only the residual block is implemented, got {block}"
+            block = ResidualBlock
+        c = num_planes[0]
+        self.blocks = nn.Sequential(OrderedDict(
+            (f"block{i}", block(c, c, norm_fn, normalize_before=normalize_before, indice_key=f"subm{indice_key_id}"))
+            for i in range(block_reps)))
+        if len(num_planes) > 1:
+            if not normalize_before:
+                raise NotImplementedError("only normalize_before=True is supported")
+            self.conv = nn.Sequential(norm_fn(c), nn.ReLU(), SparseConvWeight(c, num_planes[1], 2))
+            self.u = SpConvUNet(num_planes[1:], use_sync_bn, block_reps, block, indice_key_id=indice_key_id + 1,
+                                normalize_before=normalize_before, return_blocks=return_blocks)
+            self.deconv = nn.Sequential(norm_fn(num_planes[1]), nn.ReLU(), SparseConvWeight(num_planes[1], c, 2))
+            self.blocks_tail = nn.Sequential(OrderedDict(
+                (f"block{i}", block(c * (2 - i), c, norm_fn, indice_key=f"subm{indice_key_id}",
+                                    normalize_before=normalize_before)) for i in range(block_reps)))
+        self._plan = None
+        self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_plan())
+
+    # ------------------------------------------------------------------ plan (packed weights, folded BN)
+    def invalidate_plan(self):
+        self._plan = None
+        if hasattr(self, "u"):
+            self.u.invalidate_plan()
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_plan()
+        return super()._apply(fn, *a, **k)
+
+    @staticmethod
+    def _block_plan(blk: ResidualBlock):
+        cb = blk.conv_branch
+        p = dict(bn0=fold_bn(cb[0]), w0=ops.PackedWeight(cb[2].weight), bn1=fold_bn(cb[3]), w1=ops.PackedWeight(cb[5].weight))
+        if isinstance(blk.i_branch[0], SparseConvWeight):
+            p["wi"] = ops.PackedWeight(blk.i_branch[0].weight)
+        return p
+
+    def _get_plan(self):
+        if self._plan is None:
+            p = dict(blocks=[self._block_plan(b) for b in self.blocks])
+            if len(self.num_planes) > 1:
+                p["down_bn"] = fold_bn(self.conv[0]); p["down_w"] = ops.PackedWeight(self.conv[2].weight)
+                p["up_bn"] = fold_bn(self.deconv[0]); p["up_w"] = ops.PackedWeight(self.deconv[2].weight)
+                p["tail"] = [self._block_plan(b) for b in self.blocks_tail]
+            self._plan = p
+        return self._plan
+
+    # ------------------------------------------------------------------ execution
+    @staticmethod
+    def _run_block(bp, x, lv, out=None):
+        """x + SubM3(BN.SubM3(BN.x))   (or SubM1(x) + ... when channel counts differ)."""
+        identity = ops.gemm(x, bp["wi"]) if "wi" in bp else x
+        y = ops.gemm(x, bp["w0"], table=lv.subm, tile_mask=lv.subm_mask, in_scale=bp["bn0"][0], in_shift=bp["bn0"][1],
+                     in_relu=True)
+        return ops.gemm(y, bp["w1"], table=lv.subm, tile_mask=lv.subm_mask, in_scale=bp["bn1"][0], in_shift=bp["bn1"][1],
+                        in_relu=True, residual=identity, out=out)
+
+    def _forward_level(self, x: torch.Tensor, pyr: Pyramid, l: int, outputs: list) -> torch.Tensor:
+        plan = self._get_plan()
+        lv = pyr.levels[l]
+        c = self.num_planes[0]
+        has_sub = len(self.num_planes) > 1
+        cat = torch.empty((lv.n, 2 * c), dtype=torch.float32, device=x.device) if has_sub else None
+        nb = len(plan["blocks"])
+        for i, bp in enumerate(plan["blocks"]):
+            dst = cat[:, :c] if (has_sub and i == nb - 1) else None
+            x = self._run_block(bp, x, lv, out=dst)
+        if has_sub:
+            nxt = pyr.levels[l + 1]
+            d = ops.gemm(x, plan["down_w"], table=lv.child, tile_mask=lv.child_mask, n_out=nxt.n,
+                         in_scale=plan["down_bn"][0], in_shift=plan["down_bn"][1], in_relu=True)
+            d = self.u._forward_level(d, pyr, l + 1, outputs)
+            ops.gemm(d, plan["up_w"], table=lv.up, tile_mask=lv.up_mask, n_out=lv.n, in_scale=plan["up_bn"][0],
+                     in_shift=plan["up_bn"][1], in_relu=True, out=cat[:, c:])
+            x = cat
+            for bp in plan["tail"]:
+                x = self._run_block(bp, x, lv)
+        outputs.append((l, x))
+        return x
+
+    def n_levels(self):
+        return len(self.num_planes)
+
+    def forward(self, input: SparseConvTensor, previous_outputs: Optional[List] = None):
+        if self.training:
+            raise NotImplementedError("unidet3d_b200.SpConvUNet implements the forward/eval path only (round 1)")
+        if input.pyramid is None or len(input.pyramid) < self.n_levels():
+            input.pyramid = build_pyramid(input.indices, input.spatial_shape, input.batch_size, self.n_levels(),
+                                          canonical=input.canonical, extents=input.extents)
+        pyr = input.pyramid
+        x = input.features
+        if not (x.is_cuda and x.dtype == torch.float32):
+            raise RuntimeError("SpConvUNet needs CUDA fp32 features (no CPU fallback)")
+        outs: list = []
+        y = self._forward_level(x.contiguous() if x.stride(1) != 1 else x, pyr, 0, outs)
+        output = input.replace_feature(y)
+        if self.return_blocks:
+            if previous_outputs is None:
+                previous_outputs = []
+            for l, f in outs:       # deepest level first, like the reference's recursion (spconv_unet.py:233-238)
+                lv = pyr.levels[l]
+                previous_outputs.append(output if l == 0 else SparseConvTensor(f, lv.coords, lv.shape, input.batch_size))
+            return output, previous_outputs
+        return output
