@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/sec of the UniDet3D forward hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload scannet_b8|s3dis_1|joint_b8]
+
+A "step" is one pass of the hot path (voxelise -> input conv -> SpConvUNet -> superpoint pool ->
+encoder -> last head -> top-k -> NMS -> superpoint trim) over ONE BATCH of synthetic scenes.
+Default workload = BASELINE.json configs[1]: unidet3d_1xb8_scannet, 8 synthetic 100k-point
+ScanNet-shaped scenes per batch (voxel 0.02 m, ~33k voxels/scene, 19-way head), random-init
+weights of the reference architecture (no datasets / checkpoints offline).
+
+* ``value``    : scenes/s with the batch already resident in HBM (device-timed, CUDA events);
+* ``e2e``      : scenes/s through the public API ``UniDet3D.forward_scenes`` with HOST buffers --
+                 pinned H2D of points+superpoints and D2H of the detections inside the timed region;
+* ``roofline`` : the dominant kernel (tcgen05 gather-GEMM, the 49 sparse convs): algorithmic bytes
+                 (BASELINE.md section 3 model) / measured launch time vs measured HBM peak;
+* ``cpu_baseline`` / ``--impl reference``: the CPU oracle (oracle/detector.py) on the host cores.
+Multi-GPU: scenes shard one batch per GPU, no data-path collective (weak scaling); one process per
+GPU under torchrun, device-timed, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (preset, batch, datasets)
+    "scannet_b8": ("scannet100k", 8, ("scannet",)),
+    "s3dis_1": ("s3dis500k", 1, ("scannet",)),
+    "small_1": ("small20k", 1, ("scannet",)),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="scannet_b8")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def make_workload(name, rank):
+    from unidet3d_b200 import configs
+    from unidet3d_b200.synthetic import make_scene, SCENE_PRESETS
+    if name == "joint_b8":
+        preset, batch, datasets = "scannet100k", 8, configs.JOINT
+    else:
+        preset, batch, datasets = WORKLOADS[name]
+    n, voxel, area, sp_cell = SCENE_PRESETS[preset]
+    scenes = [make_scene(rank * batch + i, n, area, sp_cell) for i in range(batch)]
+    cfg = configs.model_cfg(datasets, voxel_size=voxel)
+    names = [datasets[i % len(datasets)] for i in range(batch)]
+    return cfg, scenes, names, preset
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/ud3d_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])), mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def conv_work_model(pyr, planes, in_channels=6):
+    """Algorithmic FLOPs / bytes of the 49 sparse convs for THIS input:
+    FLOPs = 2*P*Cin*Cout; bytes = 4*Nin*Cin + 4*Nout*Cout + 4*K*Cin*Cout + 4*K*Nout (tables)."""
+    flops = bytes_ = 0
+    launches = 0
+    L = len(planes)
+
+    def add(P, n_in, n_out, cin, cout, K):
+        nonlocal flops, bytes_, launches
+        flops += 2 * P * cin * cout
+        bytes_ += 4 * n_in * cin + 4 * n_out * cout + 4 * K * cin * cout + 4 * K * n_out
+        launches += 1
+
+    Ps = [int((lv.subm >= 0).sum().item()) for lv in pyr.levels]
+    Pd = [int((lv.child >= 0).sum().item()) if lv.child is not None else 0 for lv in pyr.levels]
+    n = [lv.n for lv in pyr.levels]
+    add(Ps[0], n[0], n[0], in_channels, planes[0], 27)
+    for l in range(L):
+        c = planes[l]
+        for _ in range(4):
+            add(Ps[l], n[l], n[l], c, c, 27)                     # blocks: 2 x (SubM3, SubM3)
+        if l < L - 1:
+            c1 = planes[l + 1]
+            add(Pd[l], n[l], n[l + 1], c, c1, 8)                 # down
+            add(Pd[l], n[l + 1], n[l], c1, c, 8)                 # up (same pairs reversed)
+            add(n[l], n[l], n[l], 2 * c, c, 1)                   # tail block0 i_branch (1x1)
+            add(Ps[l], n[l], n[l], 2 * c, c, 27)                 # tail block0 conv0
+            for _ in range(3):
+                add(Ps[l], n[l], n[l], c, c, 27)                 # tail block0 conv1, block1 x2
+    return flops, bytes_, launches
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle restatement of the reference forward on the host cores (the reference's own
+    native stack -- spconv / MinkowskiEngine / mmcv -- cannot be installed offline)."""
+    if rank != 0:
+        return
+    from oracle import detector as odet
+    from unidet3d_b200 import configs
+    from unidet3d_b200.synthetic import make_model_state_dict
+    cfg, scenes, names, preset = make_workload(args.workload, 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_model_state_dict(cfg, 0)
+    det_sd = {k: v for k, v in sd.items() if not k.startswith("decoder.")}
+    enc_sd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
+    ocfg = configs.oracle_cfg(cfg)
+    sample = 1                                  # scenes per step: bounded sample of the batch
+    pts, sps = [s[0] for s in scenes], [s[1] for s in scenes]
+    times = []
+    for it in range(args.warmup + args.steps):
+        i = it % len(scenes)
+        t0 = time.perf_counter()
+        odet.forward_scenes(det_sd, enc_sd, ocfg, pts[i:i + sample], sps[i:i + sample], names[i:i + sample])
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    val = sample * len(times) / total
+    line = {"impl": "reference", "metric": "scenes/sec", "value": val, "unit": "scenes/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "preset": preset, "sample": f"{sample} scene/step (bounded sample of the batch)"},
+            "cpu_baseline": {"value": val, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{len(times)} x {sample} scene of {preset}"},
+            "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (unidet3d_b200 has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import unidet3d_b200 as u
+    from unidet3d_b200 import ops
+    from unidet3d_b200.synthetic import make_model_state_dict
+
+    cfg, scenes, names, preset = make_workload(args.workload, rank)
+    model = u.MODELS.build(cfg).eval()
+    model.load_state_dict(make_model_state_dict(cfg, 0), strict=False)
+    model.to(dev)
+    pts, sps = [s[0] for s in scenes], [s[1] for s in scenes]
+    batch = len(scenes)
+    W, K = max(args.warmup, 3), args.steps
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.zero_()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident arm (value)
+    d_pts = [torch.as_tensor(p).to(dev) for p in pts]
+    d_sps = [torch.as_tensor(s).to(dev) for s in sps]
+    for _ in range(W):
+        model.forward_scenes(d_pts, d_sps, names)
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    if rank == 0:
+        sampler.start()
+    ops.launch_count(reset=True)
+    evs = []
+    for _ in range(K):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model.forward_scenes(d_pts, d_sps, names)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = ops.launch_count()
+    t_dev = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+
+    # ---------------------------------------------------------------- end-to-end arm (host buffers)
+    h_pts = [torch.as_tensor(p).pin_memory() for p in pts]
+    h_sps = [torch.as_tensor(s).pin_memory() for s in sps]
+    for _ in range(2):
+        model.forward_scenes(h_pts, h_sps, names)
+    barrier()
+    evs = []
+    d2h = 0
+    for _ in range(K):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = model.forward_scenes(h_pts, h_sps, names)
+        e1.record()
+        evs.append((e0, e1))
+        d2h = sum(b.numel() * 4 + l.numel() * 8 + s.numel() * 4 for b, l, s in res) + 4 * batch + 16 + 4 * 5
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_e2e = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    h2d = sum(p.numel() * 4 for p in h_pts) + sum(s.numel() * 8 for s in h_sps) + 4 * (batch + 1)
+
+    # ---------------------------------------------------------------- dominant kernel: the 49 sparse convs
+    offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device=dev)
+    x, inverse = model.collate(torch.cat(d_pts), offs, batch)
+    planes = cfg["backbone"]["num_planes"]
+    flops, abytes, n_conv = conv_work_model(x.pyramid, planes)
+    plan = model._get_plan()
+    lv0 = x.pyramid.levels[0]
+
+    def backbone_only():
+        f = ops.gemm(x.features, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask)
+        return model.unet(x.replace_feature(f))
+
+    for _ in range(3):
+        backbone_only()
+    torch.cuda.synchronize()
+    ops.launch_count(reset=True)
+    reps = max(3, min(K, 10))
+    evs = []
+    for _ in range(reps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        backbone_only()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    conv_launches = ops.launch_count() // reps
+    t_conv = sum(a.elapsed_time(b) for a, b in evs) / 1e3 / reps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    achieved = abytes / conv_launches / (t_conv / conv_launches) / 1e9
+    roof = {"bound": "hbm", "kernel": "gather_gemm_tc_kernel (49 sparse convs of the backbone)",
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "peak_source": peak_src, "launches_per_step": conv_launches, "avg_launch_us": 1e6 * t_conv / conv_launches,
+            "algorithmic_bytes_per_launch": abytes / conv_launches,
+            "algorithmic_tflops": flops / t_conv / 1e12,
+            "tensor_frac_bf16x3": 3 * flops / t_conv / 1e12 / tf_peak,
+            "backbone_ms_per_batch": 1e3 * t_conv}
+
+    # ---------------------------------------------------------------- aggregate over ranks
+    t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+    value = world * batch * K / t_dev
+    e2e = world * batch * K / t_e2e
+    line = {"metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "preset": preset, "batch_per_gpu": batch,
+                       "points_per_scene": int(pts[0].shape[0]), "voxels_per_level": [lv.n for lv in x.pyramid.levels],
+                       "superpoints": int(sum(int(s.max()) + 1 for s in sps)), "datasets": list(cfg["decoder"]["datasets"]),
+                       "precision": "fp32 storage; bf16 hi/lo 3-term split on tcgen05, fp32 accumulate",
+                       "l2": "flushed between timed iterations (256 MiB memset)", "parallelism": f"scene-sharded dp{world}"},
+            "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * t_e2e / K},
+            "gpu_launches": launches, "roofline": roof, "clocks": clocks}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, scenes, names, preset)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, scenes, names, preset):
+    """Oracle ("port" of the reference math) on the host cores: one scene of the same workload."""
+    from oracle import detector as odet
+    from unidet3d_b200 import configs
+    from unidet3d_b200.synthetic import make_model_state_dict
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = make_model_state_dict(cfg, 0)
+    det_sd = {k: v for k, v in sd.items() if not k.startswith("decoder.")}
+    enc_sd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
+    ocfg = configs.oracle_cfg(cfg)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        odet.forward_scenes(det_sd, enc_sd, ocfg, [scenes[n % len(scenes)][0]], [scenes[n % len(scenes)][1]], names[:1])
+        n += 1
+        if time.perf_counter() - t0 > 10 or n >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} scene(s) of {preset} (1 scene per pass)"}
+
+
+if __name__ == "__main__":
+    main()

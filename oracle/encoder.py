@@ -106,33 +106,4 @@ def encoder_forward(sd, cfg, x, sp_centers, datasets_names, all_heads=True):
     return dict(cls_preds=cls_preds[-1], bboxes=bboxes[-1], aux_outputs=aux, feats=feats)
 
 
-def make_encoder_state_dict(num_layers, in_channels, d_model, hidden_dim, n_cls_out, seed=0):
-    """Random weights with the reference's key names, torch-default-like init scales."""
-    g = torch.Generator().manual_seed(seed)
-    sd = {}
-
-    def lin(key, o, i, wscale=None):
-        s = wscale if wscale is not None else 1.0 / math.sqrt(i)
-        sd[key + ".weight"] = (torch.rand(o, i, generator=g) * 2 - 1) * s
-        sd[key + ".bias"] = (torch.rand(o, generator=g) * 2 - 1) * s
-
-    def ln(key, c):
-        sd[key + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
-        sd[key + ".bias"] = 0.1 * torch.randn(c, generator=g)
-
-    lin("input_proj.0", d_model, in_channels)
-    lin("input_proj.2", d_model, d_model)
-    for i in range(num_layers):
-        p = f"self_attn_layers.{i}"
-        sd[p + ".attn.in_proj_weight"] = (torch.rand(3 * d_model, d_model, generator=g) * 2 - 1) * math.sqrt(6.0 / (4 * d_model))
-        sd[p + ".attn.in_proj_bias"] = 0.02 * torch.randn(3 * d_model, generator=g)
-        lin(p + ".attn.out_proj", d_model, d_model)
-        ln(p + ".norm", d_model)
-        lin(f"ffn_layers.{i}.net.0", hidden_dim, d_model)
-        lin(f"ffn_layers.{i}.net.3", d_model, hidden_dim)
-        ln(f"ffn_layers.{i}.norm", d_model)
-    ln("out_norm", d_model)
-    lin("outs_cls.0", d_model, d_model)
-    lin("outs_cls.2", n_cls_out, d_model)
-    lin("out_bboxes.linear", 8, d_model)
-    return sd
+from unidet3d_b200.synthetic import make_encoder_state_dict  # noqa: E402,F401  (shared synthetic weights)

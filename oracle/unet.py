@@ -85,57 +85,4 @@ def backbone_forward(det_sd, coords, feats, spatial_shape):
     return x, levels
 
 
-# --------------------------------------------------------------------------
-# synthetic, reference-layout weights
-# --------------------------------------------------------------------------
-def make_unet_state_dict(num_planes, block_reps=2, gen=None, p=""):
-    """Random non-trivial weights with the reference's key names / shapes."""
-    g = gen or torch.Generator().manual_seed(0)
-    sd = {}
-
-    def bn(key, c):
-        sd[key + ".weight"] = torch.rand(c, generator=g) + 0.5
-        sd[key + ".bias"] = torch.randn(c, generator=g) * 0.1
-        sd[key + ".running_mean"] = torch.randn(c, generator=g) * 0.1
-        sd[key + ".running_var"] = torch.rand(c, generator=g) + 0.5
-        sd[key + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
-
-    def conv(key, co, k, ci, active):
-        sd[key] = torch.randn(co, k, k, k, ci, generator=g) * (1.0 / (active * ci)) ** 0.5
-
-    def block(key, ci, co):
-        if ci != co:
-            conv(key + ".i_branch.0.weight", co, 1, ci, 1)
-        bn(key + ".conv_branch.0", ci)
-        conv(key + ".conv_branch.2.weight", co, 3, ci, 11)
-        bn(key + ".conv_branch.3", co)
-        conv(key + ".conv_branch.5.weight", co, 3, co, 11)
-
-    c = num_planes[0]
-    for i in range(block_reps):
-        block(p + f"blocks.block{i}", c, c)
-    if len(num_planes) > 1:
-        c1 = num_planes[1]
-        bn(p + "conv.0", c)
-        conv(p + "conv.2.weight", c1, 2, c, 4)
-        sd.update(make_unet_state_dict(num_planes[1:], block_reps, g, p + "u."))
-        bn(p + "deconv.0", c1)
-        conv(p + "deconv.2.weight", c, 2, c1, 1)
-        for i in range(block_reps):
-            block(p + f"blocks_tail.block{i}", c * (2 - i), c)
-    return sd
-
-
-def make_detector_backbone_state_dict(in_channels=6, num_planes=(32, 64, 96, 128, 160), seed=0):
-    g = torch.Generator().manual_seed(seed)
-    sd = {"input_conv.0.weight":
-          torch.randn(num_planes[0], 3, 3, 3, in_channels, generator=g) * (1.0 / (11 * in_channels)) ** 0.5}
-    for k, v in make_unet_state_dict(list(num_planes), 2, g).items():
-        sd["unet." + k] = v
-    c = num_planes[0]
-    sd["output_layer.0.weight"] = torch.rand(c, generator=g) + 0.5
-    sd["output_layer.0.bias"] = torch.randn(c, generator=g) * 0.1
-    sd["output_layer.0.running_mean"] = torch.randn(c, generator=g) * 0.1
-    sd["output_layer.0.running_var"] = torch.rand(c, generator=g) + 0.5
-    sd["output_layer.0.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
-    return sd
+from unidet3d_b200.synthetic import make_unet_state_dict, make_detector_backbone_state_dict  # noqa: E402,F401  (shared synthetic weights)

@@ -59,7 +59,7 @@ SIGNATURES = {
     "ud3d_nms_workspace_bytes": (_sz, [_i]),
     "ud3d_nms_multiclass": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "ud3d_trim_workspace_bytes": (_sz, [_i]),
-    "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _f, _f, _vp, _vp, _sz, _vp]),
+    "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _f, _f, _vp, _vp, _sz, _vp]),
 }
 
 _lib = None

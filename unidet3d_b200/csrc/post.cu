@@ -366,10 +366,12 @@ __global__ void __launch_bounds__(256) trim_boxes_kernel(const float* __restrict
                                                          const int64_t* __restrict__ sp, int n_pts, int n_sp,
                                                          const float* __restrict__ boxes, int box_dim,
                                                          const int32_t* __restrict__ box_index,
+                                                         const int32_t* __restrict__ m_dev,
                                                          const int* __restrict__ sp_size, float low_thr, float up_thr,
                                                          float* __restrict__ out) {
   extern __shared__ int s_cnt[];
   const int m = blockIdx.x;
+  if (m_dev && m >= *m_dev) return;
   const float* bsrc = boxes + (size_t)(box_index ? box_index[m] : m) * box_dim;
   float b[7];
 #pragma unroll
@@ -493,8 +495,8 @@ int ud3d_nms_multiclass(const float* boxes, int box_dim, const float* scores, co
 size_t ud3d_trim_workspace_bytes(int n_sp) { return align_up((size_t)(n_sp > 0 ? n_sp : 1) * 4, 256); }
 
 int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pts, int n_sp, const float* boxes,
-                    int box_dim, const int32_t* box_index, int m, float low_thr, float up_thr, float* out, void* ws,
-                    size_t ws_bytes, void* stream) {
+                    int box_dim, const int32_t* box_index, int m, const int32_t* m_dev, float low_thr, float up_thr,
+                    float* out, void* ws, size_t ws_bytes, void* stream) {
   UD3D_CHECK_ARG(points && sp && boxes && out && ws, "ud3d_trim_boxes: NULL argument");
   UD3D_CHECK_ARG(ld_pts >= 3 && n_pts >= 0 && n_sp > 0 && (box_dim == 6 || box_dim == 7) && m >= 0, "ud3d_trim_boxes: bad sizes");
   UD3D_CHECK_ARG((size_t)n_sp * 4 <= 200 * 1024, "ud3d_trim_boxes: more than 51200 superpoints per scene is unsupported");
@@ -517,7 +519,7 @@ int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pt
     UD3D_CUDA(cudaFuncSetAttribute(trim_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  trim_boxes_kernel<<<m, 256, smem, st>>>(points, ld_pts, sp, n_pts, n_sp, boxes, box_dim, box_index, (const int*)ws, low_thr,
+  trim_boxes_kernel<<<m, 256, smem, st>>>(points, ld_pts, sp, n_pts, n_sp, boxes, box_dim, box_index, m_dev, (const int*)ws, low_thr,
                                          up_thr, out);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;

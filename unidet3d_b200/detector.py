@@ -124,7 +124,7 @@ class UniDet3D(nn.Module):
         trimmed = None
         if self.use_superpoints[ds]:
             trimmed = ops.trim_boxes(points_scene, sp_scene, n_sp, cand, float(cfg["low_sp_thr"]),
-                                     float(cfg["up_sp_thr"]), box_index=keep, m=k)
+                                     float(cfg["up_sp_thr"]), box_index=keep, m=k, m_dev=n_keep)
         return dict(cand=cand, scores=scores, labels=labels, keep=keep, n_keep=n_keep, trimmed=trimmed,
                     with_yaw=with_yaw, ds=ds)
 

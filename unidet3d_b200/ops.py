@@ -273,7 +273,7 @@ def nms_multiclass(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tens
     _req(boxes, torch.float32, "boxes"), _req(scores, torch.float32, "scores"), _req(labels, torch.int32, "labels")
     n = boxes.shape[0]
     dev = boxes.device
-    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    keep = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)   # tail beyond n_keep stays a valid index
     n_keep = torch.zeros(1, dtype=torch.int32, device=dev)
     wsb = int(_L().ud3d_nms_workspace_bytes(n))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
@@ -283,7 +283,8 @@ def nms_multiclass(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tens
 
 
 def trim_boxes(points: torch.Tensor, sp: torch.Tensor, n_sp: int, boxes: torch.Tensor, low_thr: float, up_thr: float,
-               box_index: Optional[torch.Tensor] = None, m: Optional[int] = None) -> torch.Tensor:
+               box_index: Optional[torch.Tensor] = None, m: Optional[int] = None,
+               m_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(sp, torch.int64, "sp"), _req(boxes, torch.float32, "boxes")
     if not points.is_cuda or points.dtype != torch.float32 or points.stride(1) != 1:
         raise _lib.Ud3dError("trim_boxes: points must be a CUDA fp32 matrix with unit column stride")
@@ -292,5 +293,5 @@ def trim_boxes(points: torch.Tensor, sp: torch.Tensor, n_sp: int, boxes: torch.T
     wsb = int(_L().ud3d_trim_workspace_bytes(n_sp))
     ws = torch.empty(wsb, dtype=torch.uint8, device=boxes.device)
     check(_L().ud3d_trim_boxes(_p(points), points.stride(0), _p(sp), points.shape[0], n_sp, _p(boxes), boxes.shape[1],
-                               _p(box_index), m, float(low_thr), float(up_thr), _p(out), _p(ws), wsb, _stream()), "ud3d_trim_boxes")
+                               _p(box_index), m, _p(m_dev), float(low_thr), float(up_thr), _p(out), _p(ws), wsb, _stream()), "ud3d_trim_boxes")
     return out

@@ -20,7 +20,8 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["make_scene", "make_batch", "SCENE_PRESETS"]
+__all__ = ["make_scene", "make_batch", "SCENE_PRESETS", "make_unet_state_dict",
+           "make_detector_backbone_state_dict", "make_encoder_state_dict", "make_model_state_dict"]
 
 # name -> (n_points, voxel_size, surface area m^2, superpoint cell m)
 SCENE_PRESETS = {
@@ -105,3 +106,108 @@ def make_batch(preset: str = "scannet100k", batch_size: int = 8, seed0: int = 0)
     n_points, voxel, area, sp_cell = SCENE_PRESETS[preset]
     scenes = [make_scene(seed0 + i, n_points, area, sp_cell) for i in range(batch_size)]
     return scenes, voxel
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic, reference-layout weights: there are no checkpoints offline.
+# Keys / shapes follow the reference modules (unidet3d/spconv_unet.py, unidet3d/encoder.py,
+# unidet3d/unidet3d.py:95-111); BatchNorm statistics are non-trivial so folding bugs show.
+# ----------------------------------------------------------------------------------------------
+import math  # noqa: E402
+
+import torch  # noqa: E402
+
+def make_unet_state_dict(num_planes, block_reps=2, gen=None, p=""):
+    """Random non-trivial weights with the reference's key names / shapes."""
+    g = gen or torch.Generator().manual_seed(0)
+    sd = {}
+
+    def bn(key, c):
+        sd[key + ".weight"] = torch.rand(c, generator=g) + 0.5
+        sd[key + ".bias"] = torch.randn(c, generator=g) * 0.1
+        sd[key + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+        sd[key + ".running_var"] = torch.rand(c, generator=g) + 0.5
+        sd[key + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    def conv(key, co, k, ci, active):
+        sd[key] = torch.randn(co, k, k, k, ci, generator=g) * (1.0 / (active * ci)) ** 0.5
+
+    def block(key, ci, co):
+        if ci != co:
+            conv(key + ".i_branch.0.weight", co, 1, ci, 1)
+        bn(key + ".conv_branch.0", ci)
+        conv(key + ".conv_branch.2.weight", co, 3, ci, 11)
+        bn(key + ".conv_branch.3", co)
+        conv(key + ".conv_branch.5.weight", co, 3, co, 11)
+
+    c = num_planes[0]
+    for i in range(block_reps):
+        block(p + f"blocks.block{i}", c, c)
+    if len(num_planes) > 1:
+        c1 = num_planes[1]
+        bn(p + "conv.0", c)
+        conv(p + "conv.2.weight", c1, 2, c, 4)
+        sd.update(make_unet_state_dict(num_planes[1:], block_reps, g, p + "u."))
+        bn(p + "deconv.0", c1)
+        conv(p + "deconv.2.weight", c, 2, c1, 1)
+        for i in range(block_reps):
+            block(p + f"blocks_tail.block{i}", c * (2 - i), c)
+    return sd
+
+
+def make_detector_backbone_state_dict(in_channels=6, num_planes=(32, 64, 96, 128, 160), seed=0):
+    g = torch.Generator().manual_seed(seed)
+    sd = {"input_conv.0.weight":
+          torch.randn(num_planes[0], 3, 3, 3, in_channels, generator=g) * (1.0 / (11 * in_channels)) ** 0.5}
+    for k, v in make_unet_state_dict(list(num_planes), 2, g).items():
+        sd["unet." + k] = v
+    c = num_planes[0]
+    sd["output_layer.0.weight"] = torch.rand(c, generator=g) + 0.5
+    sd["output_layer.0.bias"] = torch.randn(c, generator=g) * 0.1
+    sd["output_layer.0.running_mean"] = torch.randn(c, generator=g) * 0.1
+    sd["output_layer.0.running_var"] = torch.rand(c, generator=g) + 0.5
+    sd["output_layer.0.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return sd
+
+
+def make_encoder_state_dict(num_layers, in_channels, d_model, hidden_dim, n_cls_out, seed=0):
+    """Random weights with the reference's key names, torch-default-like init scales."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def lin(key, o, i, wscale=None):
+        s = wscale if wscale is not None else 1.0 / math.sqrt(i)
+        sd[key + ".weight"] = (torch.rand(o, i, generator=g) * 2 - 1) * s
+        sd[key + ".bias"] = (torch.rand(o, generator=g) * 2 - 1) * s
+
+    def ln(key, c):
+        sd[key + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        sd[key + ".bias"] = 0.1 * torch.randn(c, generator=g)
+
+    lin("input_proj.0", d_model, in_channels)
+    lin("input_proj.2", d_model, d_model)
+    for i in range(num_layers):
+        p = f"self_attn_layers.{i}"
+        sd[p + ".attn.in_proj_weight"] = (torch.rand(3 * d_model, d_model, generator=g) * 2 - 1) * math.sqrt(6.0 / (4 * d_model))
+        sd[p + ".attn.in_proj_bias"] = 0.02 * torch.randn(3 * d_model, generator=g)
+        lin(p + ".attn.out_proj", d_model, d_model)
+        ln(p + ".norm", d_model)
+        lin(f"ffn_layers.{i}.net.0", hidden_dim, d_model)
+        lin(f"ffn_layers.{i}.net.3", d_model, hidden_dim)
+        ln(f"ffn_layers.{i}.norm", d_model)
+    ln("out_norm", d_model)
+    lin("outs_cls.0", d_model, d_model)
+    lin("outs_cls.2", n_cls_out, d_model)
+    lin("out_bboxes.linear", 8, d_model)
+    return sd
+
+
+def make_model_state_dict(cfg, seed=0):
+    """Full detector state_dict (``input_conv``, ``unet.*``, ``output_layer``, ``decoder.*``) for a model cfg
+    from unidet3d_b200.configs.model_cfg."""
+    d = cfg["decoder"]
+    sd = make_detector_backbone_state_dict(cfg["in_channels"], cfg["backbone"]["num_planes"], seed)
+    n_union = len(set(sum(d["datasets_classes"], []))) + 1
+    enc = make_encoder_state_dict(d["num_layers"], d["in_channels"], d["d_model"], d["hidden_dim"], n_union, seed)
+    sd.update({"decoder." + k: v for k, v in enc.items()})
+    return sd
