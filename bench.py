@@ -53,6 +53,17 @@ def parse():
     return ap.parse_args()
 
 
+def host_threads():
+    """Threads for the CPU arm: the cores this process may run on, capped at 32 -- beyond that the
+    oracle's many small torch ops (per-offset mm / index_add_) slow down from OpenMP fork/join on the
+    shared 128-core GPU hosts (measured: 128 threads -> ~1000x slower than 8)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get("UD3D_CPU_THREADS", 32))))
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -161,7 +172,7 @@ def run_reference(args, rank, world):
     from unidet3d_b200 import configs
     from unidet3d_b200.synthetic import make_model_state_dict
     cfg, scenes, names, preset = make_workload(args.workload, 0)
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     sd = make_model_state_dict(cfg, 0)
     det_sd = {k: v for k, v in sd.items() if not k.startswith("decoder.")}
     enc_sd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
@@ -336,33 +347,29 @@ def main():
                     "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": launches, "roofline": roof, "clocks": clocks}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg, scenes, names, preset)
+        line["cpu_baseline"] = cpu_baseline(cfg, scenes, names, preset, args.workload)
     print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
 
-def cpu_baseline(cfg, scenes, names, preset):
-    """Oracle ("port" of the reference math) on the host cores: one scene of the same workload."""
-    from oracle import detector as odet
-    from unidet3d_b200 import configs
-    from unidet3d_b200.synthetic import make_model_state_dict
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = make_model_state_dict(cfg, 0)
-    det_sd = {k: v for k, v in sd.items() if not k.startswith("decoder.")}
-    enc_sd = {k[len("decoder."):]: v for k, v in sd.items() if k.startswith("decoder.")}
-    ocfg = configs.oracle_cfg(cfg)
-    t0 = time.perf_counter()
-    n = 0
-    while True:
-        odet.forward_scenes(det_sd, enc_sd, ocfg, [scenes[n % len(scenes)][0]], [scenes[n % len(scenes)][1]], names[:1])
-        n += 1
-        if time.perf_counter() - t0 > 10 or n >= 3:
-            break
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} scene(s) of {preset} (1 scene per pass)"}
+def cpu_baseline(cfg, scenes, names, preset, workload="scannet_b8", budget_s=150):
+    """Oracle ("port" of the reference math) on the host cores, in a child process with a hard time
+    budget (a pathological host must not stall the bench): `--impl reference` with 2 steps of 1 scene."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--workload", workload]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1")
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=budget_s, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"value": None, "unit": "scenes/s", "cores": host_threads(), "kind": "port",
+                "sample": "failed: " + (r.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+    except subprocess.TimeoutExpired:
+        return {"value": None, "unit": "scenes/s", "cores": host_threads(), "kind": "port",
+                "sample": f"timed out after {budget_s}s (3 x 1 scene of {preset})"}
 
 
 if __name__ == "__main__":
