@@ -184,8 +184,8 @@ int ud3d_nms_multiclass(const float* boxes, int box_dim, const float* scores, co
  * points [n_pts,ld_pts>=3], sp int64 [n_pts], boxes [m,box_dim]; box_index (optional int32 [m]) selects
  * rows of `boxes`.  out [m,6] = (centre, size) of the tight AABB of the voted points.
  * m_dev (optional device int32): only the first min(m, *m_dev) boxes are processed (lets the NMS
- * count stay on the device).  ws >= ud3d_trim_workspace_bytes(n_sp). */
-size_t ud3d_trim_workspace_bytes(int n_sp);
+ * count stay on the device).  ws >= ud3d_trim_workspace_bytes(n_sp, n_pts, m). */
+size_t ud3d_trim_workspace_bytes(int n_sp, int n_pts, int m);
 int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pts, int n_sp,
                     const float* boxes, int box_dim, const int32_t* box_index, int m, const int32_t* m_dev,
                     float low_thr, float up_thr, float* out, void* ws, size_t ws_bytes, void* stream);

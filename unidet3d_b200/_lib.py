@@ -58,7 +58,7 @@ SIGNATURES = {
     "ud3d_topk_scores": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ud3d_nms_workspace_bytes": (_sz, [_i]),
     "ud3d_nms_multiclass": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
-    "ud3d_trim_workspace_bytes": (_sz, [_i]),
+    "ud3d_trim_workspace_bytes": (_sz, [_i, _i, _i]),
     "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _f, _f, _vp, _vp, _sz, _vp]),
 }
 

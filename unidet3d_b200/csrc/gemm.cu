@@ -3,7 +3,7 @@
 //
 //   out[o,:] = act( sum_k pre(in[table[k][o],:]) @ W_k + bias ) + residual[o,:]
 //
-// Design (one CTA = 128 output rows x N_TILE output channels, 256 threads):
+// Design (one CTA = 128 output rows x N_TILE output channels, 10 warps, warp-specialised):
 //   * the K-loop runs over (kernel offset k, 32-channel chunk c).  For each step the 8 warps gather
 //     the 128 input rows of that offset with coalesced 16-byte loads (4 lanes per row), apply the
 //     folded BatchNorm affine + ReLU in registers, split every fp32 value into bf16 hi + lo and
@@ -13,9 +13,11 @@
 //     onto an mbarrier;
 //   * one thread issues 6 tcgen05.mma (M=128, N=N_TILE, K=16): hi*hi, lo*hi, hi*lo -> fp32
 //     accumulation in TMEM (~2e-5 relative error end to end, vs 1.5e-3 for single-pass TF32);
-//   * 3-stage smem ring: tcgen05.commit -> mbarrier frees a stage, so the gather of step i+1/i+2
-//     overlaps the MMAs of step i; offsets with no active input in the tile are skipped via the
-//     rulebook's per-tile mask;
+//   * roles: warps 0-7 gather/transform A (loads of step t+1 in flight while step t is stored),
+//     warp 8 issues the weight bulk copies, warp 9 issues the MMAs; a 3-4 stage smem ring linked only
+//     by mbarriers (a_full / b_full / empty via tcgen05.commit) -- no block barrier in the mainloop;
+//     the tile's rulebook slice is staged in smem first; offsets with no active input in the tile
+//     are skipped (rulebook tile mask); launches that cannot fill 148 SMs are split along K;
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> global.
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
 #include "common.cuh"
@@ -24,8 +26,6 @@ namespace ud3d {
 
 constexpr int kTileM = UD3D_TILE_M;   // 128
 constexpr int kChunk = 32;            // input channels per K-step
-constexpr int kStages = 3;
-constexpr int kThreads = 256;
 
 struct GemmParams {
   ud3d_gemm_args a;
@@ -85,8 +85,24 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+constexpr int kProducerWarps = 8;                 // warps 0..7 gather A (warps 0..3 also run the epilogue)
+constexpr int kWarpB = 8;                         // warp 8: weight-tile bulk copies
+constexpr int kWarpMma = 9;                       // warp 9: tcgen05.mma issue
+constexpr int kThreadsTc = 32 * 10;
+
+template <int N_TILE> struct TcCfg {
+  static constexpr int kStages = N_TILE <= 64 ? 4 : 3;
+};
+
+// Raw gathered operand of one K-step for this thread: 2 rows x 8 channels
+struct GatherRegs {
+  float4 v[2][2];
+  int ok[2];
+};
+
 template <int N_TILE>
-__global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p) {
+  constexpr int STAGES = TcCfg<N_TILE>::kStages;
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = N_TILE * 128;
   constexpr uint32_t TMEM_COLS = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
@@ -95,32 +111,39 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmPara
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * A_BYTES;
-  uint8_t* tail = sB + kStages * B_BYTES;
-  uint64_t* b_full = (uint64_t*)tail;            // [kStages]
-  uint64_t* mma_done = b_full + kStages;         // [kStages]
-  uint64_t* acc_full = mma_done + kStages;       // [1]
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* tail = sB + STAGES * B_BYTES;
+  uint64_t* a_full = (uint64_t*)tail;            // [STAGES] count = producer warps
+  uint64_t* b_full = a_full + STAGES;            // [STAGES] count = 1 (+tx bytes)
+  uint64_t* empty = b_full + STAGES;             // [STAGES] count = 1 (tcgen05.commit)
+  uint64_t* acc_full = empty + STAGES;           // [1]
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
-  float* s_scale = (float*)(tail + 128);
+  uint32_t* s_mask = tmem_slot + 1;
+  uint8_t* s_actk = (uint8_t*)(tail + 128);      // [32] active kernel offsets, ascending
+  float* s_scale = (float*)(tail + 192);
   const ud3d_gemm_args& a = p.a;
   const int c_in_pad = p.n_chunks * kChunk;
   float* s_shift = s_scale + c_in_pad;
+  int32_t* s_tbl = (int32_t*)(s_shift + c_in_pad);   // [K][128] table slice of this tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * kTileM;
   const int nt = blockIdx.y;
   const int n0 = nt * N_TILE;
+  const bool has_table = a.table != nullptr;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&a_full[s], kProducerWarps);
       mbar_init(&b_full[s], 1);
-      mbar_init(&mma_done[s], 1);
+      mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
     fence_mbar_init();
+    *s_mask = 0u;
   }
   if (a.in_scale) {
-    for (int c = tid; c < c_in_pad; c += kThreads) {
+    for (int c = tid; c < c_in_pad; c += kThreadsTc) {
       s_scale[c] = c < a.c_in ? a.in_scale[c] : 0.f;
       s_shift[c] = c < a.c_in ? a.in_shift[c] : 0.f;
     }
@@ -129,64 +152,91 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmPara
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  // stage the tile's slice of the rulebook in shared memory (one coalesced pass, removes the
+  // dependent table -> row load chain from the mainloop)
+  uint32_t mybits = 0;
+  if (has_table) {
+    for (int i = tid; i < a.K * kTileM; i += kThreadsTc) {
+      int k = i >> 7, r = i & 127;
+      int row = m0 + r;
+      int v = row < a.n_out ? __ldg(a.table + (size_t)k * a.n_out + row) : -1;
+      s_tbl[i] = v;
+      if (v >= 0) mybits |= 1u << k;
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (has_table && !a.tile_mask) {
+    mybits = __reduce_or_sync(0xffffffffu, mybits);
+    if (lane == 0 && mybits) atomicOr(s_mask, mybits);
+  }
+  __syncthreads();
   const uint32_t tmem_base = *tmem_slot;
-
-  // gather roles: 4 lanes per row (8 floats each), rows rl and rl+64
-  const int q = tid & 3;
-  const int rl = tid >> 2;
-  const uint32_t tile_mask = a.tile_mask ? a.tile_mask[blockIdx.x] : 0xffffffffu;
+  uint32_t mask = has_table ? (a.tile_mask ? a.tile_mask[blockIdx.x] : *s_mask) : 1u;
+  if (tid == 0) {
+    int n = 0;
+    for (int k = 0; k < 32; ++k)
+      if ((mask >> k) & 1u) s_actk[n++] = (uint8_t)k;
+  }
+  __syncthreads();
+  const int nact = __popc(mask);
+  const int nsteps_all = nact * p.n_chunks;
+  // split-K: this CTA handles steps [t_begin, t_end) of the tile's active (offset, chunk) sequence
+  const int t_begin = (int)((long long)nsteps_all * blockIdx.z / gridDim.z);
+  const int t_end = (int)((long long)nsteps_all * (blockIdx.z + 1) / gridDim.z);
+  const int nsteps = t_end - t_begin;
   const uint8_t* wp = (const uint8_t*)a.w_packed + (size_t)nt * a.K * p.n_chunks * B_BYTES;
-  const bool affine = a.in_scale != nullptr;
-  const bool relu = a.in_relu != 0;
 
-  int it = 0;  // CTA-uniform count of issued K-steps
-  for (int k = 0; k < a.K; ++k) {
-    if (a.K <= 32 && !((tile_mask >> k) & 1u)) continue;
-    int idx[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int row = m0 + rl + h * 64;
-      if (row < a.n_out)
-        idx[h] = a.table ? __ldg(a.table + (size_t)k * a.n_out + row) : row;
-      else
-        idx[h] = -1;
-    }
-    if (a.table && !a.tile_mask) {
-      if (!__syncthreads_or((idx[0] >= 0) | (idx[1] >= 0))) continue;
-    }
-    for (int c = 0; c < p.n_chunks; ++c, ++it) {
-      const int s = it % kStages;
-      const uint32_t use = (uint32_t)(it / kStages);
-      if (it >= kStages) mbar_wait(&mma_done[s], (use - 1) & 1);   // stage s free again
-      uint8_t* As = sA + s * A_BYTES;
-      uint8_t* Bs = sB + s * B_BYTES;
-      if (tid == 0) {
-        mbar_arrive_expect_tx(&b_full[s], B_BYTES);
-        bulk_copy_g2s(Bs, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
-      }
+  if (warp < kProducerWarps) {
+    // =========================================================== A producers (gather + transform)
+    const int q = tid & 3;
+    const int rl = tid >> 2;
+    const bool affine = a.in_scale != nullptr;
+    const bool relu = a.in_relu != 0;
+
+    auto issue_loads = [&](int t, GatherRegs& g) {
+      const int tt = t_begin + t;
+      const int kslot = tt / p.n_chunks;
+      const int c = tt - kslot * p.n_chunks;
+      const int k = s_actk[kslot];
       const int ch0 = c * kChunk + q * 8;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float v[8];
-        if (idx[h] >= 0) {
-          const float* src = a.in + (size_t)idx[h] * a.ld_in + ch0;
+        const int r = rl + h * 64;
+        int idx;
+        if (has_table) idx = s_tbl[k * kTileM + r];
+        else idx = (m0 + r < a.n_out) ? m0 + r : -1;
+        g.ok[h] = idx >= 0 && ch0 < a.c_in;
+        if (g.ok[h]) {
+          const float* src = a.in + (size_t)idx * a.ld_in + ch0;
           if (p.vec_ok) {
-            // c_in % 8 == 0: an 8-channel segment is entirely inside or entirely outside the row
-            if (ch0 < a.c_in) {
-              float4 x0 = __ldg((const float4*)src), x1 = __ldg((const float4*)src + 1);
-              v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w;
-              v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            }
+            g.v[h][0] = __ldg((const float4*)src);
+            g.v[h][1] = __ldg((const float4*)src + 1);
           } else {
+            float e[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (ch0 + e < a.c_in) ? __ldg(src + e) : 0.f;
+            for (int j = 0; j < 8; ++j) e[j] = (ch0 + j < a.c_in) ? __ldg(src + j) : 0.f;
+            g.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
+            g.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
           }
+        }
+      }
+    };
+    auto store_step = [&](int t, const GatherRegs& g) {
+      const int s = t % STAGES;
+      const uint32_t use = (uint32_t)(t / STAGES);
+      const int tt = t_begin + t;
+      const int c = tt % p.n_chunks;
+      const int ch0 = c * kChunk + q * 8;
+      if (t >= STAGES) mbar_wait(&empty[s], (use - 1) & 1);
+      uint8_t* As = sA + s * A_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[8];
+        if (g.ok[h]) {
+          v[0] = g.v[h][0].x; v[1] = g.v[h][0].y; v[2] = g.v[h][0].z; v[3] = g.v[h][0].w;
+          v[4] = g.v[h][1].x; v[5] = g.v[h][1].y; v[6] = g.v[h][1].z; v[7] = g.v[h][1].w;
           if (affine) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
@@ -195,11 +245,10 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmPara
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
-          if (!p.vec_ok || affine) {
-            // padded channels must stay exactly zero (shift of a padded channel is 0, but be explicit)
+          if (!p.vec_ok) {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-              if (ch0 + e >= a.c_in) v[e] = 0.f;
+              if (ch0 + e >= a.c_in) v[e] = 0.f;     // padded channels stay exactly zero
           }
         } else {
 #pragma unroll
@@ -213,40 +262,81 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmPara
         *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
-      fence_proxy_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(&b_full[s], use & 1);
-        tc_fence_after_sync();
-        const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+      fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[s]);
+    };
+
+    // software pipeline: the global loads of step t+1 are in flight while step t is converted/stored
+    GatherRegs g0, g1;
+    if (nsteps > 0) issue_loads(0, g0);
+    for (int t = 0; t < nsteps; t += 2) {
+      if (t + 1 < nsteps) issue_loads(t + 1, g1);
+      store_step(t, g0);
+      if (t + 1 < nsteps) {
+        if (t + 2 < nsteps) issue_loads(t + 2, g0);
+        store_step(t + 1, g1);
+      }
+    }
+  } else if (warp == kWarpB) {
+    // =========================================================== B producer: one bulk copy per step
+    for (int t = 0; t < nsteps; ++t) {
+      const int s = t % STAGES;
+      const uint32_t use = (uint32_t)(t / STAGES);
+      if (t >= STAGES) mbar_wait(&empty[s], (use - 1) & 1);
+      if (lane == 0) {
+        const int tt = t_begin + t;
+        const int kslot = tt / p.n_chunks;
+        const int c = tt - kslot * p.n_chunks;
+        const int k = s_actk[kslot];
+        mbar_arrive_expect_tx(&b_full[s], B_BYTES);
+        bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================================================== MMA issuer
+    for (int t = 0; t < nsteps; ++t) {
+      const int s = t % STAGES;
+      const uint32_t use = (uint32_t)(t / STAGES);
+      mbar_wait(&a_full[s], use & 1);
+      mbar_wait(&b_full[s], use & 1);
+      tc_fence_after_sync();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
         // K-steps of 16 bf16 = 32 bytes inside the 128B row: hi at +0,+32 ; lo at +64,+96
-        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 0), IDESC, it > 0);
+        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 0), IDESC, t > 0);
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 32), IDESC, 1);
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 64), umma_desc_sw128(b_addr + 0), IDESC, 1);
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 96), umma_desc_sw128(b_addr + 32), IDESC, 1);
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 64), IDESC, 1);
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 96), IDESC, 1);
-        umma_commit(&mma_done[s]);
+        umma_commit(&empty[s]);            // stage s reusable once these MMAs have read it
       }
+      __syncwarp();
     }
+    if (lane == 0) umma_commit(acc_full);
+    __syncwarp();
   }
-  if (tid == 0) umma_commit(acc_full);
 
   // ------------------------------------------------------------ epilogue (warps 0..3, one row per thread)
   if (warp < 4) {
-    if (it > 0) {
+    if (nsteps > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
     }
     const int row = warp * 32 + lane;
     const int grow = m0 + row;
     const bool row_ok = grow < a.n_out;
+    const bool split = gridDim.z > 1;
+    const bool lead = blockIdx.z == 0;       // the split that adds bias / residual
     float* orow = a.out + (size_t)(row_ok ? grow : 0) * a.ld_out;
-    const float* rrow = a.residual ? a.residual + (size_t)(row_ok ? grow : 0) * a.ld_res : nullptr;
+    const float* rrow = (a.residual && lead) ? a.residual + (size_t)(row_ok ? grow : 0) * a.ld_res : nullptr;
+    const float* bias = lead ? a.bias : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
       uint32_t r[32];
-      if (it > 0) {
+      if (nsteps > 0) {
         tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
       } else {
@@ -256,13 +346,25 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmPara
       if (!row_ok) continue;
       const int col0 = n0 + c0;
       if (col0 >= a.c_out) continue;
-      if (p.out_vec_ok && col0 + 32 <= a.c_out) {
+      if (split) {
+        // partial sums of a split-K launch: fp32 red.add into the pre-zeroed output (act == 0 enforced)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int col = col0 + j;
+          if (col < a.c_out) {
+            float v = __uint_as_float(r[j]);
+            if (bias) v += __ldg(bias + col);
+            if (rrow) v += __ldg(rrow + col);
+            atomicAdd(orow + col, v);
+          }
+        }
+      } else if (p.out_vec_ok && col0 + 32 <= a.c_out) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                  __uint_as_float(r[j + 3]));
-          if (a.bias) {
-            float4 b = __ldg((const float4*)(a.bias + col0 + j));
+          if (bias) {
+            float4 b = __ldg((const float4*)(bias + col0 + j));
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
           }
           if (a.act) {
@@ -281,7 +383,7 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const GemmPara
           int col = col0 + j;
           if (col < a.c_out) {
             float v = __uint_as_float(r[j]);
-            if (a.bias) v += __ldg(a.bias + col);
+            if (bias) v += __ldg(bias + col);
             v = apply_act(v, a.act);
             if (rrow) v += __ldg(rrow + col);
             orow[col] = v;
@@ -321,20 +423,21 @@ __global__ void gather_gemm_simt_kernel(const ud3d_gemm_args a, const float* __r
 }
 
 template <int N_TILE>
-static size_t tc_smem_bytes(int n_chunks) {
-  return 1024 + (size_t)kStages * (kTileM * 128 + N_TILE * 128) + 128 + (size_t)n_chunks * kChunk * 4 * 2;
+static size_t tc_smem_bytes(int n_chunks, int K, bool has_table) {
+  return 1024 + (size_t)TcCfg<N_TILE>::kStages * (kTileM * 128 + N_TILE * 128) + 192 + (size_t)n_chunks * kChunk * 4 * 2 +
+         (has_table ? (size_t)K * kTileM * 4 : 0);
 }
 
 template <int N_TILE>
-static int launch_tc(const GemmParams& p, int n_tiles, cudaStream_t st) {
-  size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks);
+static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
+  size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr);
   static size_t configured = 0;   // largest size this instantiation was configured for
   if (smem > configured) {
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid(cdiv(p.a.n_out, kTileM), n_tiles);
-  gather_gemm_tc_kernel<N_TILE><<<grid, kThreads, smem, st>>>(p);
+  dim3 grid(cdiv(p.a.n_out, kTileM), n_tiles, splits);
+  gather_gemm_tc_kernel<N_TILE><<<grid, kThreadsTc, smem, st>>>(p);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }
@@ -346,7 +449,7 @@ static int check_args(const ud3d_gemm_args* a, const char* who) {
   UD3D_CHECK_ARG(a->table || a->K == 1, "%s: identity gather requires K == 1", who);
   UD3D_CHECK_ARG(!a->residual || a->ld_res >= a->c_out, "%s: bad ld_res", who);
   UD3D_CHECK_ARG((a->in_scale == nullptr) == (a->in_shift == nullptr), "%s: in_scale/in_shift must both be set", who);
-  UD3D_CHECK_ARG(!a->tile_mask || a->K <= 32, "%s: tile_mask needs K <= 32", who);
+  UD3D_CHECK_ARG(!a->table || a->K <= 32, "%s: a gather table supports at most 32 kernel offsets", who);
   return UD3D_OK;
 }
 
@@ -391,13 +494,29 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   int nts = pick_ntile(args->c_out);
   int n_tiles = cdiv(args->c_out, nts);
   cudaStream_t st = (cudaStream_t)stream;
+  // split-K for launches that cannot fill the 148 SMs (deep U-Net levels: 5..91 row tiles x 100+ K-steps):
+  // the (offset, chunk) sequence is cut across gridDim.z CTAs that red.add fp32 partials into the output
+  int splits = 1;
+  {
+    long long ctas = (long long)cdiv(args->n_out, kTileM) * n_tiles;
+    int max_steps = args->K * p.n_chunks;
+    if (args->act == 0 && ctas < 120 && max_steps >= 16 && (const float*)args->out != args->in &&
+        (const float*)args->out != args->residual) {
+      splits = (int)(296 / ctas);
+      if (splits > max_steps / 6) splits = max_steps / 6;
+      if (splits > 16) splits = 16;
+      if (splits < 1) splits = 1;
+    }
+    if (splits > 1)
+      UD3D_CUDA(cudaMemset2DAsync(args->out, (size_t)args->ld_out * 4, 0, (size_t)args->c_out * 4, (size_t)args->n_out, st));
+  }
   switch (nts) {
-    case 32: return launch_tc<32>(p, n_tiles, st);
-    case 64: return launch_tc<64>(p, n_tiles, st);
-    case 96: return launch_tc<96>(p, n_tiles, st);
-    case 128: return launch_tc<128>(p, n_tiles, st);
-    case 160: return launch_tc<160>(p, n_tiles, st);
-    default: return launch_tc<256>(p, n_tiles, st);
+    case 32: return launch_tc<32>(p, n_tiles, splits, st);
+    case 64: return launch_tc<64>(p, n_tiles, splits, st);
+    case 96: return launch_tc<96>(p, n_tiles, splits, st);
+    case 128: return launch_tc<128>(p, n_tiles, splits, st);
+    case 160: return launch_tc<160>(p, n_tiles, splits, st);
+    default: return launch_tc<256>(p, n_tiles, splits, st);
   }
 }
 

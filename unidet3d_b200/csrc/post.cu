@@ -342,18 +342,111 @@ __global__ void __launch_bounds__(1024) nms_sweep_kernel(NmsWs w, int32_t* __res
 }
 
 // ---------------------------------------------------------------- superpoint trimming
+// reference: trim_bboxes_by_superpoints (unidet3d.py:540-593).  Three phases, all data-parallel:
+//   A  vote:   every (point, box) pair is tested once; inside -> red.add cnt[box][sp(point)]
+//   B  decide: one warp per (box, superpoint) pair with cnt > 0 walks that superpoint's points
+//              (CSR built once per scene) and applies  in = (inside && frac >= low) || frac > up,
+//              warp-reduces the AABB and issues 6 atomics per pair
+//   C  finalise: centre / size.
+// Pairs with cnt == 0 have frac = 0 < low_thr, so none of their points can be selected: skipping
+// them is exact.  Nothing of size n_pts x n_boxes is ever materialised (the reference builds a
+// [n_pts, n_boxes, 6] fp32 tensor = 2.4 GB at 100k x 1000).
+struct TrimWs {
+  int* sp_size;     // [n_sp]
+  int* sp_start;    // [n_sp + 1]
+  int* cursor;      // [n_sp]
+  int* sp_points;   // [n_pts]
+  int* cnt;         // [m, n_sp]
+  int* aabb;        // [m, 6] ordered-int encoded min xyz / max xyz
+};
+static inline size_t trim_ws_bytes(int n_sp, int n_pts, int m) {
+  return align_up((size_t)n_sp * 4, 256) + align_up((size_t)(n_sp + 1) * 4, 256) + align_up((size_t)n_sp * 4, 256) +
+         align_up((size_t)n_pts * 4, 256) + align_up((size_t)m * n_sp * 4, 256) + align_up((size_t)m * 24, 256);
+}
+static inline TrimWs trim_ws_view(void* ws, int n_sp, int n_pts, int m) {
+  TrimWs v;
+  char* p = (char*)ws;
+  v.sp_size = (int*)p; p += align_up((size_t)n_sp * 4, 256);
+  v.sp_start = (int*)p; p += align_up((size_t)(n_sp + 1) * 4, 256);
+  v.cursor = (int*)p; p += align_up((size_t)n_sp * 4, 256);
+  v.sp_points = (int*)p; p += align_up((size_t)n_pts * 4, 256);
+  v.cnt = (int*)p; p += align_up((size_t)m * n_sp * 4, 256);
+  v.aabb = (int*)p;
+  return v;
+}
+
 __global__ void sp_size_kernel(const int64_t* __restrict__ sp, int n_pts, int n_sp, int* __restrict__ size) {
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pts; p += gridDim.x * blockDim.x) {
     long long s = sp[p];
     if (s >= 0 && s < n_sp) atomicAdd(size + s, 1);
   }
 }
+// single CTA exclusive scan of sp_size -> sp_start (+ cursor copy)
+__global__ void __launch_bounds__(1024) sp_scan_kernel(const int* __restrict__ size, int n_sp, int* __restrict__ start,
+                                                       int* __restrict__ cursor) {
+  __shared__ int sh[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n_sp; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = i < n_sp ? size[i] : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) sh[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = sh[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      sh[lane] = t;
+    }
+    __syncthreads();
+    int incl = x + (w > 0 ? sh[w - 1] : 0) + carry;
+    if (i < n_sp) {
+      start[i] = incl - v;
+      cursor[i] = incl - v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[n_sp] = carry;
+}
+__global__ void sp_fill_kernel(const int64_t* __restrict__ sp, int n_pts, int n_sp, int* cursor, int* __restrict__ sp_points) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pts; p += gridDim.x * blockDim.x) {
+    long long s = sp[p];
+    if (s >= 0 && s < n_sp) sp_points[atomicAdd(cursor + s, 1)] = p;
+  }
+}
 
-__device__ __forceinline__ bool point_in_box(float px, float py, float pz, const float* b, float c, float s) {
+struct BoxP {
+  float b[6];
+  float c, s;   // cos(-yaw), sin(-yaw)
+};
+__device__ __forceinline__ BoxP load_box(const float* __restrict__ boxes, int box_dim, const int32_t* __restrict__ box_index,
+                                         int m) {
+  const float* src = boxes + (size_t)(box_index ? box_index[m] : m) * box_dim;
+  BoxP q;
+#pragma unroll
+  for (int d = 0; d < 6; ++d) q.b[d] = src[d];
+  float yaw = box_dim == 7 ? src[6] : 0.f;
+  q.c = cosf(-yaw);
+  q.s = sinf(-yaw);
+  return q;
+}
+__device__ __forceinline__ bool point_in_box(float px, float py, float pz, const BoxP& q) {
   // get_face_distances (unidet3d.py:652-677): shift rotated by -yaw about z, then six face distances
+  const float* b = q.b;
   float sx = px - b[0], sy = py - b[1], sz = pz - b[2];
-  float rx = __fsub_rn(__fmul_rn(sx, c), __fmul_rn(sy, s));
-  float ry = __fadd_rn(__fmul_rn(sx, s), __fmul_rn(sy, c));
+  float rx = __fsub_rn(__fmul_rn(sx, q.c), __fmul_rn(sy, q.s));
+  float ry = __fadd_rn(__fmul_rn(sx, q.s), __fmul_rn(sy, q.c));
   float cx = b[0] + rx, cy = b[1] + ry, cz = b[2] + sz;
   float d0 = cx - b[0] + b[3] / 2, d1 = b[0] + b[3] / 2 - cx;
   float d2 = cy - b[1] + b[4] / 2, d3 = b[1] + b[4] / 2 - cy;
@@ -361,75 +454,91 @@ __device__ __forceinline__ bool point_in_box(float px, float py, float pz, const
   return fminf(fminf(fminf(d0, d1), fminf(d2, d3)), fminf(d4, d5)) > 0.f;
 }
 
-// one CTA per box: phase A votes per superpoint in shared memory, phase B masked AABB
-__global__ void __launch_bounds__(256) trim_boxes_kernel(const float* __restrict__ pts, int ld_pts,
-                                                         const int64_t* __restrict__ sp, int n_pts, int n_sp,
-                                                         const float* __restrict__ boxes, int box_dim,
-                                                         const int32_t* __restrict__ box_index,
-                                                         const int32_t* __restrict__ m_dev,
-                                                         const int* __restrict__ sp_size, float low_thr, float up_thr,
-                                                         float* __restrict__ out) {
-  extern __shared__ int s_cnt[];
-  const int m = blockIdx.x;
-  if (m_dev && m >= *m_dev) return;
-  const float* bsrc = boxes + (size_t)(box_index ? box_index[m] : m) * box_dim;
-  float b[7];
-#pragma unroll
-  for (int d = 0; d < 6; ++d) b[d] = bsrc[d];
-  b[6] = box_dim == 7 ? bsrc[6] : 0.f;
-  const float c = cosf(-b[6]), s = sinf(-b[6]);
-  for (int i = threadIdx.x; i < n_sp; i += blockDim.x) s_cnt[i] = 0;
+constexpr int kTrimBoxGroup = 32;
+// phase A: grid (point chunks, box groups)
+__global__ void __launch_bounds__(256) trim_vote_kernel(const float* __restrict__ pts, int ld_pts, const int64_t* __restrict__ sp,
+                                                        int n_pts, int n_sp, const float* __restrict__ boxes, int box_dim,
+                                                        const int32_t* __restrict__ box_index, int m,
+                                                        const int32_t* __restrict__ m_dev, int* __restrict__ cnt) {
+  const int mm = m_dev ? min(m, *m_dev) : m;
+  const int b0 = blockIdx.y * kTrimBoxGroup;
+  if (b0 >= mm) return;
+  const int nb = min(kTrimBoxGroup, mm - b0);
+  __shared__ BoxP sbox[kTrimBoxGroup];
+  if ((int)threadIdx.x < nb) sbox[threadIdx.x] = load_box(boxes, box_dim, box_index, b0 + threadIdx.x);
   __syncthreads();
-  for (int p = threadIdx.x; p < n_pts; p += blockDim.x) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pts; p += gridDim.x * blockDim.x) {
     const float* q = pts + (size_t)p * ld_pts;
-    if (point_in_box(q[0], q[1], q[2], b, c, s)) {
-      long long id = sp[p];
-      if (id >= 0 && id < n_sp) atomicAdd(&s_cnt[id], 1);
-    }
+    const float x = q[0], y = q[1], z = q[2];
+    const long long id = sp[p];
+    if (id < 0 || id >= n_sp) continue;
+    for (int j = 0; j < nb; ++j)
+      if (point_in_box(x, y, z, sbox[j])) atomicAdd(cnt + (size_t)(b0 + j) * n_sp + id, 1);
   }
-  __syncthreads();
-  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int p = threadIdx.x; p < n_pts; p += blockDim.x) {
-    const float* q = pts + (size_t)p * ld_pts;
-    long long id = sp[p];
-    bool in = point_in_box(q[0], q[1], q[2], b, c, s);
-    if (id >= 0 && id < n_sp) {
-      float frac = __fdiv_rn((float)s_cnt[id], fmaxf((float)sp_size[id], 1.f));
-      if (frac < low_thr) in = false;
-      if (frac > up_thr) in = true;
-    }
-    if (in) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        mn[d] = fminf(mn[d], q[d]);
-        mx[d] = fmaxf(mx[d], q[d]);
+}
+
+__device__ __forceinline__ int f2ord(float f) {   // monotone float -> int
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void trim_init_kernel(int* aabb, int m) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m * 6) aabb[i] = (i % 6) < 3 ? f2ord(INFINITY) : f2ord(-INFINITY);
+}
+
+// phase B: one warp per (box, superpoint) entry of cnt
+__global__ void __launch_bounds__(256) trim_decide_kernel(const float* __restrict__ pts, int ld_pts, int n_sp,
+                                                          const float* __restrict__ boxes, int box_dim,
+                                                          const int32_t* __restrict__ box_index, int m,
+                                                          const int32_t* __restrict__ m_dev, const int* __restrict__ cnt,
+                                                          const int* __restrict__ sp_size, const int* __restrict__ sp_start,
+                                                          const int* __restrict__ sp_points, float low_thr, float up_thr,
+                                                          int* aabb) {
+  const int mm = m_dev ? min(m, *m_dev) : m;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)mm * n_sp;
+  for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < total;
+       e += ((long long)gridDim.x * blockDim.x) >> 5) {
+    const int c = cnt[e];
+    if (c == 0) continue;                       // frac = 0 < low_thr: no point of this superpoint is selected
+    const int b = (int)(e / n_sp), s = (int)(e % n_sp);
+    const float frac = __fdiv_rn((float)c, fmaxf((float)sp_size[s], 1.f));
+    const bool del = frac < low_thr, add = frac > up_thr;
+    if (del && !add) continue;
+    const BoxP q = load_box(boxes, box_dim, box_index, b);
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const int beg = sp_start[s], end = sp_start[s + 1];
+    for (int i = beg + lane; i < end; i += 32) {
+      const float* pp = pts + (size_t)sp_points[i] * ld_pts;
+      const float x = pp[0], y = pp[1], z = pp[2];
+      bool in = add || point_in_box(x, y, z, q);
+      if (in) {
+        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+        mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
       }
     }
-  }
-  __shared__ float r_mn[8][3], r_mx[8][3];
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
 #pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    for (int o = 16; o > 0; o >>= 1) {
-      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
-      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    for (int d = 0; d < 3; ++d) {
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+        mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+      }
     }
-    if (lane == 0) {
-      r_mn[wp][d] = mn[d];
-      r_mx[wp][d] = mx[d];
-    }
+    if (lane < 3) atomicMin(aabb + b * 6 + lane, f2ord(mn[lane]));
+    else if (lane < 6) atomicMax(aabb + b * 6 + lane, f2ord(mx[lane - 3]));
   }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    int d = threadIdx.x;
-    float a = INFINITY, z = -INFINITY;
-    for (int i = 0; i < 8; ++i) {
-      a = fminf(a, r_mn[i][d]);
-      z = fmaxf(z, r_mx[i][d]);
-    }
-    out[(size_t)m * 6 + d] = (z + a) / 2.f;
-    out[(size_t)m * 6 + 3 + d] = z - a;
-  }
+}
+
+__global__ void trim_final_kernel(const int* __restrict__ aabb, int m, const int32_t* __restrict__ m_dev, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int mm = m_dev ? min(m, *m_dev) : m;
+  if (i >= mm * 3) return;
+  int b = i / 3, d = i % 3;
+  float a = ord2f(aabb[b * 6 + d]), z = ord2f(aabb[b * 6 + 3 + d]);
+  out[(size_t)b * 6 + d] = (z + a) / 2.f;
+  out[(size_t)b * 6 + 3 + d] = z - a;
 }
 
 }  // namespace ud3d
@@ -492,35 +601,49 @@ int ud3d_nms_multiclass(const float* boxes, int box_dim, const float* scores, co
   return UD3D_OK;
 }
 
-size_t ud3d_trim_workspace_bytes(int n_sp) { return align_up((size_t)(n_sp > 0 ? n_sp : 1) * 4, 256); }
+size_t ud3d_trim_workspace_bytes(int n_sp, int n_pts, int m) {
+  return trim_ws_bytes(n_sp > 0 ? n_sp : 1, n_pts > 0 ? n_pts : 1, m > 0 ? m : 1);
+}
 
 int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pts, int n_sp, const float* boxes,
                     int box_dim, const int32_t* box_index, int m, const int32_t* m_dev, float low_thr, float up_thr,
                     float* out, void* ws, size_t ws_bytes, void* stream) {
   UD3D_CHECK_ARG(points && sp && boxes && out && ws, "ud3d_trim_boxes: NULL argument");
   UD3D_CHECK_ARG(ld_pts >= 3 && n_pts >= 0 && n_sp > 0 && (box_dim == 6 || box_dim == 7) && m >= 0, "ud3d_trim_boxes: bad sizes");
-  UD3D_CHECK_ARG((size_t)n_sp * 4 <= 200 * 1024, "ud3d_trim_boxes: more than 51200 superpoints per scene is unsupported");
-  if (ws_bytes < ud3d_trim_workspace_bytes(n_sp)) {
+  UD3D_CHECK_ARG((long long)m * n_sp < (1ll << 31), "ud3d_trim_boxes: m * n_sp too large");
+  if (ws_bytes < ud3d_trim_workspace_bytes(n_sp, n_pts, m)) {
     set_error("ud3d_trim_boxes: workspace too small");
     return UD3D_EWORKSPACE;
   }
   if (m == 0) return UD3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  UD3D_CUDA(cudaMemsetAsync(ws, 0, (size_t)n_sp * 4, st));
+  TrimWs w = trim_ws_view(ws, n_sp, n_pts > 0 ? n_pts : 1, m);
+  UD3D_CUDA(cudaMemsetAsync(w.sp_size, 0, (size_t)n_sp * 4, st));
+  UD3D_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)m * n_sp * 4, st));
+  trim_init_kernel<<<cdiv(m * 6, 256), 256, 0, st>>>(w.aabb, m);
+  UD3D_LAUNCH_CHECK();
   if (n_pts > 0) {
-    int blocks = cdiv(n_pts, 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    sp_size_kernel<<<blocks, 256, 0, st>>>(sp, n_pts, n_sp, (int*)ws);
+    int pblocks = cdiv(n_pts, 256);
+    if (pblocks > 148 * 8) pblocks = 148 * 8;
+    sp_size_kernel<<<pblocks, 256, 0, st>>>(sp, n_pts, n_sp, w.sp_size);
+    UD3D_LAUNCH_CHECK();
+    sp_scan_kernel<<<1, 1024, 0, st>>>(w.sp_size, n_sp, w.sp_start, w.cursor);
+    UD3D_LAUNCH_CHECK();
+    sp_fill_kernel<<<pblocks, 256, 0, st>>>(sp, n_pts, n_sp, w.cursor, w.sp_points);
+    UD3D_LAUNCH_CHECK();
+    int vb = cdiv(n_pts, 256);
+    if (vb > 296) vb = 296;
+    trim_vote_kernel<<<dim3(vb, cdiv(m, kTrimBoxGroup)), 256, 0, st>>>(points, ld_pts, sp, n_pts, n_sp, boxes, box_dim, box_index, m,
+                                                                   m_dev, w.cnt);
+    UD3D_LAUNCH_CHECK();
+    long long warps = (long long)m * n_sp;
+    long long db = (warps * 32 + 255) / 256;
+    if (db > 148 * 16) db = 148 * 16;
+    trim_decide_kernel<<<(int)db, 256, 0, st>>>(points, ld_pts, n_sp, boxes, box_dim, box_index, m, m_dev, w.cnt, w.sp_size,
+                                                w.sp_start, w.sp_points, low_thr, up_thr, w.aabb);
     UD3D_LAUNCH_CHECK();
   }
-  size_t smem = (size_t)n_sp * 4;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    UD3D_CUDA(cudaFuncSetAttribute(trim_boxes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  trim_boxes_kernel<<<m, 256, smem, st>>>(points, ld_pts, sp, n_pts, n_sp, boxes, box_dim, box_index, m_dev, (const int*)ws, low_thr,
-                                         up_thr, out);
+  trim_final_kernel<<<cdiv(m * 3, 256), 256, 0, st>>>(w.aabb, m, m_dev, out);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

@@ -170,12 +170,32 @@ class UniDet3D(nn.Module):
         ds_idx = [self.decoder.datasets.index(n) for n in datasets_names]
         out = self.decoder.forward_packed(pooled, sp_centers, [int(v) for v in sp_off], datasets_names)
 
-        per_scene = []
+        # per-scene post-processing is independent: fan the scenes out over side streams so the
+        # single-CTA stages (top-k select, NMS order / sweep) of different scenes overlap
+        per_scene = [None] * B
+        cur = torch.cuda.current_stream()
+        if B > 1:
+            if getattr(self, "_post_streams", None) is None or len(self._post_streams) < min(B, 8):
+                self._post_streams = [torch.cuda.Stream(device=dev) for _ in range(min(B, 8))]
+            fork = torch.cuda.Event()
+            fork.record(cur)
         for i in range(B):
             a, b = int(pt_off[i]), int(pt_off[i + 1])
-            sp_local = sp_b[a:b] - int(sp_off[i]) if sp_off[i] else sp_b[a:b]
-            per_scene.append(self.predict_by_feat_scene(out["cls_preds"][i], out["bboxes"][i], pts[a:b], sp_local,
-                                                        n_sps[i], ds_idx[i]))
+
+            def run(i=i, a=a, b=b):
+                sp_local = sp_b[a:b] - int(sp_off[i]) if sp_off[i] else sp_b[a:b]
+                return self.predict_by_feat_scene(out["cls_preds"][i], out["bboxes"][i], pts[a:b], sp_local, n_sps[i],
+                                                  ds_idx[i])
+            if B > 1:
+                st = self._post_streams[i % len(self._post_streams)]
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    per_scene[i] = run()
+            else:
+                per_scene[i] = run()
+        if B > 1:
+            for st in self._post_streams[:min(B, len(self._post_streams))]:
+                cur.wait_stream(st)
         # one D2H round-trip for the whole batch
         n_keeps = torch.cat([r["n_keep"] for r in per_scene]).cpu().tolist()
         results = []

@@ -290,7 +290,7 @@ def trim_boxes(points: torch.Tensor, sp: torch.Tensor, n_sp: int, boxes: torch.T
         raise _lib.Ud3dError("trim_boxes: points must be a CUDA fp32 matrix with unit column stride")
     m = (box_index.numel() if box_index is not None else boxes.shape[0]) if m is None else m
     out = torch.empty((m, 6), dtype=torch.float32, device=boxes.device)
-    wsb = int(_L().ud3d_trim_workspace_bytes(n_sp))
+    wsb = int(_L().ud3d_trim_workspace_bytes(n_sp, points.shape[0], m))
     ws = torch.empty(wsb, dtype=torch.uint8, device=boxes.device)
     check(_L().ud3d_trim_boxes(_p(points), points.stride(0), _p(sp), points.shape[0], n_sp, _p(boxes), boxes.shape[1],
                                _p(box_index), m, _p(m_dev), float(low_thr), float(up_thr), _p(out), _p(ws), wsb, _stream()), "ud3d_trim_boxes")
