@@ -286,8 +286,12 @@ def main():
     lv0 = x.pyramid.levels[0]
 
     def backbone_only():
-        f = ops.gemm(x.features, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask)
-        return model.unet(x.replace_feature(f))
+        bn0 = model.unet.first_bn()
+        f_act = torch.empty((lv0.n, plan["w_in"].c_out), dtype=torch.float32, device=dev)
+        f = ops.gemm(x.features, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask, acts=[(f_act, bn0[0], bn0[1])])
+        y = x.replace_feature(f)
+        y.features_act = f_act
+        return model.unet(y)
 
     for _ in range(3):
         backbone_only()

@@ -126,15 +126,30 @@ typedef struct {
   const uint32_t* tile_mask;   /* optional [ceil(n_out/128)] */
   int32_t K; int32_t n_out;
   const void* w_packed;        /* from ud3d_gemm_pack_weight */
-  float* out; int32_t ld_out; int32_t c_out;
+  float* out; int32_t ld_out; int32_t c_out;   /* always a valid buffer (scratch when no_raw) */
   const float* in_scale; const float* in_shift; int32_t in_relu;  /* in_scale NULL => no affine */
   const float* bias;           /* [c_out] or NULL */
   int32_t act;                 /* 0 none, 1 relu, 2 gelu(erf) */
   const float* residual; int32_t ld_res;
+  /* operand-form feature maps (see ud3d_act_split):
+   * in_split != 0: `in` holds the split-bf16 operand form of the ALREADY ACTIVATED input (ld_in, c_in in
+   * channels = 4-byte units as for fp32; c_in % 32 == 0); it is gathered with cp.async straight into the
+   * swizzled tile, no per-use conversion.  in_scale must be NULL.
+   * out_act[i] != NULL: additionally store relu(result * act_scale[i] + act_shift[i]) in operand form
+   * (the consumer conv's folded BatchNorm+ReLU, applied ONCE per element instead of once per use);
+   * c_out % 32 == 0.  no_raw != 0: skip the fp32 store to `out` (still used as scratch by split-K). */
+  int32_t in_split; int32_t no_raw;
+  float* out_act[2]; int32_t ld_act[2]; const float* act_scale[2]; const float* act_shift[2];
 } ud3d_gemm_args;
 size_t ud3d_gemm_packed_weight_bytes(int K, int c_in, int c_out);
 int ud3d_gemm_pack_weight(const float* w, int K, int c_in, int c_out, void* packed, void* stream);
 int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream);
+/* operand form of a feature map: per row, per 32-channel chunk, 64 bytes of bf16 "hi" followed by 64 bytes of
+ * bf16 "lo" (x ~= hi + lo), i.e. the same 4 bytes per element as fp32 and exactly the 128-byte row of the
+ * kernel's shared-memory tile.  out_split[r, c] = split(relu?(raw[r, c] * scale[c] + shift[c])); scale may be
+ * NULL (identity).  c % 32 == 0; ld in 4-byte units. */
+int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scale, const float* shift, int relu,
+                   float* out_split, int ld_out, void* stream);
 /* same contract, plain fp32 CUDA-core kernel on the unpacked weight w [C_out,K,C_in]
  * (diagnostic cross-check of the tensor-core path; not used by the product path) */
 int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream);

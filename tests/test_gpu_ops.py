@@ -304,3 +304,61 @@ def test_trim_boxes():
         assert torch.equal(torch.isfinite(out), fin)
         close = torch.isclose(out[fin], ref[fin], rtol=1e-5, atol=1e-6)
         assert close.float().mean() > 0.98     # a borderline point (|face distance| ~ 1 ulp) may flip a vote
+
+
+# ------------------------------------------------------------------ operand-form (pre-split) feature maps
+def split_encode(x):
+    """fp32 [N,C] -> operand form [N,C] (bytes: per 32-ch chunk 32 bf16 hi then 32 bf16 lo)."""
+    N, C = x.shape
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    packed = torch.cat([hi.view(N, C // 32, 32), lo.view(N, C // 32, 32)], dim=2).contiguous()
+    return packed.view(torch.float32).view(N, C)
+
+
+def split_decode(s):
+    N, C = s.shape
+    b = s.contiguous().view(torch.bfloat16).view(N, C // 32, 64).float()
+    return (b[:, :, :32] + b[:, :, 32:]).reshape(N, C)
+
+
+def test_act_split_roundtrip():
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(777, 96, generator=g) * 3
+    sc, sh = torch.rand(96, generator=g) + 0.5, torch.randn(96, generator=g)
+    out = ops.act_split(x.to(DEV), sc.to(DEV), sh.to(DEV), relu=True)
+    ref = torch.relu(x * sc + sh)
+    assert torch.equal(out.cpu().view(torch.int32), split_encode(ref).view(torch.int32)) or relerr(split_decode(out.cpu()), ref) < 1e-5
+    assert relerr(split_decode(out.cpu()), ref) < 2e-5
+
+
+@pytest.mark.parametrize("c_in,c_out,K,n", [(32, 32, 27, 1500), (64, 64, 27, 700), (64, 32, 27, 900), (128, 128, 27, 300),
+                                            (160, 160, 27, 140), (32, 64, 8, 2000), (96, 64, 8, 500)])
+def test_gemm_operand_form_in_and_out(c_in, c_out, K, n):
+    """pre-activated split input (cp.async gather) + operand-form outputs for two consumer BatchNorms,
+    with and without split-K (small n -> gridDim.z > 1)."""
+    from unidet3d_b200 import ops
+    rng = np.random.default_rng(n + c_in)
+    g = torch.Generator().manual_seed(n + c_out)
+    x = torch.relu(torch.randn(n, c_in, generator=g))
+    w = torch.randn(c_out, K, c_in, generator=g) / (c_in * 3) ** 0.5
+    table = _rand_table(rng, K, n, n, 0.35)
+    res = torch.randn(n, c_out, generator=g)
+    ref = sparse_conv(x, table, w.permute(1, 2, 0).contiguous()) + res
+    s1, h1 = torch.rand(c_out, generator=g) + 0.5, torch.randn(c_out, generator=g) * 0.3
+    s2, h2 = torch.rand(c_out, generator=g) + 0.5, torch.randn(c_out, generator=g) * 0.3
+    xs = split_encode(x).to(DEV)
+    a1 = torch.zeros(n, c_out, device=DEV)
+    wide = torch.zeros(n, 2 * c_out, device=DEV)
+    out = ops.gemm(xs, ops.PackedWeight(w.to(DEV)), table=torch.as_tensor(table).to(DEV), in_split=True,
+                   residual=res.to(DEV), acts=[(a1, s1.to(DEV), h1.to(DEV)), (wide[:, c_out:], s2.to(DEV), h2.to(DEV))])
+    assert relerr(out, ref) < 2e-4, relerr(out, ref)
+    assert relerr(split_decode(a1.cpu()), torch.relu(ref * s1 + h1)) < 2e-4
+    assert relerr(split_decode(wide[:, c_out:].cpu().contiguous()), torch.relu(ref * s2 + h2)) < 2e-4
+    assert float(wide[:, :c_out].abs().max()) == 0.0
+    # no_raw: only the operand-form output is produced
+    a3 = torch.zeros(n, c_out, device=DEV)
+    ops.gemm(xs, ops.PackedWeight(w.to(DEV)), table=torch.as_tensor(table).to(DEV), in_split=True, no_raw=True,
+             acts=[(a3, s1.to(DEV), h1.to(DEV))])
+    assert relerr(split_decode(a3.cpu()), torch.relu((ref - res) * s1 + h1)) < 2e-4

@@ -27,6 +27,9 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p),
         ("act", C.c_int32),
         ("residual", C.c_void_p), ("ld_res", C.c_int32),
+        ("in_split", C.c_int32), ("no_raw", C.c_int32),
+        ("out_act", C.c_void_p * 2), ("ld_act", C.c_int32 * 2),
+        ("act_scale", C.c_void_p * 2), ("act_shift", C.c_void_p * 2),
     ]
 
 
@@ -49,6 +52,7 @@ SIGNATURES = {
     "ud3d_gemm_packed_weight_bytes": (_sz, [_i, _i, _i]),
     "ud3d_gemm_pack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ud3d_gemm_fwd": (_i, [C.POINTER(GemmArgs), _vp]),
+    "ud3d_act_split": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "ud3d_gemm_fwd_simt": (_i, [C.POINTER(GemmArgs), _vp, _vp]),
     "ud3d_segmented_mean": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "ud3d_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),

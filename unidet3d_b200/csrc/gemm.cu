@@ -189,7 +189,52 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   const uint8_t* wp = (const uint8_t*)a.w_packed + (size_t)nt * a.K * p.n_chunks * B_BYTES;
 
   if (warp < kProducerWarps) {
-    // =========================================================== A producers (gather + transform)
+    // =========================================================== A producers
+    if (a.in_split) {
+      // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
+      //      zero-fill for missing neighbours; D steps of copies in flight per thread, no ALU work
+      constexpr int D = STAGES - 1;
+      const uint8_t* in_bytes = (const uint8_t*)a.in;
+      const size_t row_bytes = (size_t)a.ld_in * 4;
+      const int j = tid & 7;
+      auto issue_copy = [&](int t) {
+        const int s = t % STAGES;
+        const uint32_t use = (uint32_t)(t / STAGES);
+        if (t >= STAGES) mbar_wait(&empty[s], (use - 1) & 1);
+        const int tt = t_begin + t;
+        const int kslot = tt / p.n_chunks;
+        const int c = tt - kslot * p.n_chunks;
+        const int k = s_actk[kslot];
+        const uint32_t as_addr = smem_u32(sA + s * A_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (tid >> 3) + 32 * i;
+          int idx;
+          if (has_table) idx = s_tbl[k * kTileM + r];
+          else idx = (m0 + r < a.n_out) ? m0 + r : -1;
+          const uint8_t* src = in_bytes + (idx >= 0 ? (size_t)idx * row_bytes + (size_t)c * 128 + j * 16 : 0);
+          cp_async_16_zfill(as_addr + r * 128 + ((j ^ (r & 7)) << 4), src, idx >= 0 ? 16u : 0u);
+        }
+        cp_async_commit();
+      };
+      auto publish = [&](int t) {          // copies of step t have landed (wait_group done by the caller)
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[t % STAGES]);
+      };
+      for (int t = 0; t < nsteps; ++t) {
+        issue_copy(t);
+        if (t >= D) {
+          cp_async_wait<D>();
+          publish(t - D);
+        }
+      }
+      // drain
+      if constexpr (D >= 3) { if (nsteps >= 3) { cp_async_wait<2>(); publish(nsteps - 3); } }
+      if constexpr (D >= 2) { if (nsteps >= 2) { cp_async_wait<1>(); publish(nsteps - 2); } }
+      if (nsteps >= 1) { cp_async_wait<0>(); publish(nsteps - 1); }
+    } else {
+    // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers
     const int q = tid & 3;
     const int rl = tid >> 2;
     const bool affine = a.in_scale != nullptr;
@@ -278,6 +323,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
         store_step(t + 1, g1);
       }
     }
+    }  // fp32-input producer
   } else if (warp == kWarpB) {
     // =========================================================== B producer: one bulk copy per step
     for (int t = 0; t < nsteps; ++t) {
@@ -347,7 +393,8 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       const int col0 = n0 + c0;
       if (col0 >= a.c_out) continue;
       if (split) {
-        // partial sums of a split-K launch: fp32 red.add into the pre-zeroed output (act == 0 enforced)
+        // partial sums of a split-K launch: fp32 red.add into the pre-zeroed output (act == 0 enforced;
+        // operand-form outputs are produced afterwards by act_split kernels on the host side of this call)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           int col = col0 + j;
@@ -358,36 +405,66 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
             atomicAdd(orow + col, v);
           }
         }
-      } else if (p.out_vec_ok && col0 + 32 <= a.c_out) {
+        continue;
+      }
+      // final fp32 values of this thread's 32 columns
+      float v[32];
+      const bool full = col0 + 32 <= a.c_out;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3]));
-          if (bias) {
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.out_vec_ok && full) {
+        if (bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
             float4 b = __ldg((const float4*)(bias + col0 + j));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
           }
-          if (a.act) {
-            v.x = apply_act(v.x, a.act); v.y = apply_act(v.y, a.act);
-            v.z = apply_act(v.z, a.act); v.w = apply_act(v.w, a.act);
-          }
-          if (rrow) {
+        }
+        if (a.act) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+        }
+        if (rrow) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
             float4 t = __ldg((const float4*)(rrow + col0 + j));
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
           }
-          *(float4*)(orow + col0 + j) = v;
+        }
+        if (!a.no_raw) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *(float4*)(orow + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           int col = col0 + j;
           if (col < a.c_out) {
-            float v = __uint_as_float(r[j]);
-            if (bias) v += __ldg(bias + col);
-            v = apply_act(v, a.act);
-            if (rrow) v += __ldg(rrow + col);
-            orow[col] = v;
+            if (bias) v[j] += __ldg(bias + col);
+            v[j] = apply_act(v[j], a.act);
+            if (rrow) v[j] += __ldg(rrow + col);
+            if (!a.no_raw) orow[col] = v[j];
           }
+        }
+      }
+      // operand-form outputs for the consumer convs: relu(v * scale + shift) -> bf16 hi | lo, one 128-byte row-chunk
+#pragma unroll
+      for (int oi = 0; oi < 2; ++oi) {
+        if (!a.out_act[oi]) continue;      // (c_out % 32 == 0 enforced on the host: `full` holds)
+        const float* sc = a.act_scale[oi] + col0;
+        const float* sh = a.act_shift[oi] + col0;
+        uint4* dst = (uint4*)((uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float x0 = fmaxf(fmaf(v[j], __ldg(sc + j), __ldg(sh + j)), 0.f);
+          float x1 = fmaxf(fmaf(v[j + 1], __ldg(sc + j + 1), __ldg(sh + j + 1)), 0.f);
+          split_bf16x2(x0, x1, hi[j >> 1], lo[j >> 1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dst[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          dst[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
         }
       }
     }
@@ -395,6 +472,50 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------- fp32 -> operand form (one warp per 4 row-chunks)
+__global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict__ raw, int ld_raw, int n, int c,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        int relu, float* __restrict__ out, int ld_out) {
+  // thread -> (row, chunk, 8-channel segment q): reads 32 B, writes 16 B hi + 16 B lo
+  const int chunks = c / kChunk;
+  const long long total = (long long)n * chunks * 4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(t & 3);
+    const long long rc = t >> 2;
+    const int ch = (int)(rc % chunks);
+    const int row = (int)(rc / chunks);
+    const int ch0 = ch * kChunk + q * 8;
+    const float* src = raw + (size_t)row * ld_raw + ch0;
+    float4 x0 = *(const float4*)src, x1 = *((const float4*)src + 1);
+    float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    if (scale) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], __ldg(scale + ch0 + e), __ldg(shift + ch0 + e));
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+    uint4* dst = (uint4*)((uint8_t*)(out + (size_t)row * ld_out) + (size_t)ch * 128);
+    dst[q] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[4 + q] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+static int launch_act_split(const float* raw, int ld_raw, int n, int c, const float* scale, const float* shift, int relu,
+                            float* out, int ld_out, cudaStream_t st) {
+  long long total = (long long)n * (c / kChunk) * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  act_split_kernel<<<blocks, 256, 0, st>>>(raw, ld_raw, n, c, scale, shift, relu, out, ld_out);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
 }
 
 // ---------------------------------------------------------------- fp32 CUDA-core cross-check kernel
@@ -450,6 +571,18 @@ static int check_args(const ud3d_gemm_args* a, const char* who) {
   UD3D_CHECK_ARG(!a->residual || a->ld_res >= a->c_out, "%s: bad ld_res", who);
   UD3D_CHECK_ARG((a->in_scale == nullptr) == (a->in_shift == nullptr), "%s: in_scale/in_shift must both be set", who);
   UD3D_CHECK_ARG(!a->table || a->K <= 32, "%s: a gather table supports at most 32 kernel offsets", who);
+  if (a->in_split) {
+    UD3D_CHECK_ARG(!a->in_scale && !a->in_relu, "%s: in_split input is already activated (no in_scale / in_relu)", who);
+    UD3D_CHECK_ARG(a->c_in % 32 == 0 && a->ld_in % 32 == 0 && ((uintptr_t)a->in & 15) == 0,
+                   "%s: in_split needs c_in %% 32 == 0, ld_in %% 32 == 0, 16-byte aligned", who);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (!a->out_act[i]) continue;
+    UD3D_CHECK_ARG(a->act_scale[i] && a->act_shift[i], "%s: out_act needs act_scale / act_shift", who);
+    UD3D_CHECK_ARG(a->c_out % 32 == 0 && a->ld_act[i] % 4 == 0 && a->ld_act[i] >= a->c_out &&
+                       ((uintptr_t)a->out_act[i] & 15) == 0,
+                   "%s: out_act needs c_out %% 32 == 0 and a 16-byte aligned buffer", who);
+  }
   return UD3D_OK;
 }
 
@@ -510,14 +643,39 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
     if (splits > 1)
       UD3D_CUDA(cudaMemset2DAsync(args->out, (size_t)args->ld_out * 4, 0, (size_t)args->c_out * 4, (size_t)args->n_out, st));
   }
+  if (splits > 1) p.a.no_raw = 0;
+  int rc2;
   switch (nts) {
-    case 32: return launch_tc<32>(p, n_tiles, splits, st);
-    case 64: return launch_tc<64>(p, n_tiles, splits, st);
-    case 96: return launch_tc<96>(p, n_tiles, splits, st);
-    case 128: return launch_tc<128>(p, n_tiles, splits, st);
-    case 160: return launch_tc<160>(p, n_tiles, splits, st);
-    default: return launch_tc<256>(p, n_tiles, splits, st);
+    case 32: rc2 = launch_tc<32>(p, n_tiles, splits, st); break;
+    case 64: rc2 = launch_tc<64>(p, n_tiles, splits, st); break;
+    case 96: rc2 = launch_tc<96>(p, n_tiles, splits, st); break;
+    case 128: rc2 = launch_tc<128>(p, n_tiles, splits, st); break;
+    case 160: rc2 = launch_tc<160>(p, n_tiles, splits, st); break;
+    default: rc2 = launch_tc<256>(p, n_tiles, splits, st); break;
   }
+  if (rc2) return rc2;
+  if (splits > 1) {
+    // the complete sums exist only now: derive the operand-form outputs from the fp32 result
+    for (int i = 0; i < 2; ++i) {
+      if (!args->out_act[i]) continue;
+      UD3D_CHECK_ARG(args->ld_out % 4 == 0 && ((uintptr_t)args->out & 15) == 0, "ud3d_gemm_fwd: split-K + out_act needs an aligned `out`");
+      int rc3 = launch_act_split(args->out, args->ld_out, args->n_out, args->c_out, args->act_scale[i], args->act_shift[i], 1,
+                                 args->out_act[i], args->ld_act[i], st);
+      if (rc3) return rc3;
+    }
+  }
+  return UD3D_OK;
+}
+
+int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scale, const float* shift, int relu,
+                   float* out_split, int ld_out, void* stream) {
+  UD3D_CHECK_ARG(raw && out_split && n >= 0 && c > 0, "ud3d_act_split: bad argument");
+  UD3D_CHECK_ARG(c % 32 == 0 && ld_raw % 4 == 0 && ld_out % 4 == 0 && ld_raw >= c && ld_out >= c &&
+                     (((uintptr_t)raw | (uintptr_t)out_split) & 15) == 0,
+                 "ud3d_act_split: need c %% 32 == 0 and 16-byte aligned rows");
+  UD3D_CHECK_ARG((scale == nullptr) == (shift == nullptr), "ud3d_act_split: scale/shift must both be set");
+  if (n == 0) return UD3D_OK;
+  return launch_act_split(raw, ld_raw, n, c, scale, shift, relu, out_split, ld_out, (cudaStream_t)stream);
 }
 
 int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream) {

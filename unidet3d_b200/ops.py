@@ -149,7 +149,7 @@ class PackedWeight:
 
 
 def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act, residual,
-               w_packed_ptr):
+               w_packed_ptr, in_split=False, no_raw=False, acts=None):
     a = GemmArgs()
     a.in_ = x.data_ptr(); a.ld_in = x.stride(0); a.c_in = c_in
     a.table = table.data_ptr() if table is not None else None
@@ -164,14 +164,23 @@ def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_
     a.act = {None: 0, "none": 0, "relu": 1, "gelu": 2}[act]
     a.residual = residual.data_ptr() if residual is not None else None
     a.ld_res = residual.stride(0) if residual is not None else 0
+    a.in_split = 1 if in_split else 0
+    a.no_raw = 1 if no_raw else 0
+    for i, (buf, sc, sh) in enumerate(acts or ()):
+        a.out_act[i] = buf.data_ptr(); a.ld_act[i] = buf.stride(0)
+        a.act_scale[i] = sc.data_ptr(); a.act_shift[i] = sh.data_ptr()
     return a
 
 
 def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = None, tile_mask=None,
          n_out: Optional[int] = None, out: Optional[torch.Tensor] = None, in_scale=None, in_shift=None,
-         in_relu: bool = False, bias=None, act=None, residual=None) -> torch.Tensor:
+         in_relu: bool = False, bias=None, act=None, residual=None, in_split: bool = False, no_raw: bool = False,
+         acts=None) -> torch.Tensor:
     """out = act(sum_k pre(x[table[k]]) @ W_k + bias) + residual   (see ud3d_gemm_fwd).
-    ``x``/``out``/``residual`` may be column slices of wider row-major buffers (stride(1) == 1)."""
+    ``x``/``out``/``residual`` may be column slices of wider row-major buffers (stride(1) == 1).
+    ``in_split``: x is an operand-form (pre-activated, bf16 hi|lo) feature map, see ``act_split``.
+    ``acts``: up to two (buffer, scale, shift): also store relu(out*scale+shift) in operand form.
+    ``no_raw``: the fp32 result itself is not needed (``out`` is then scratch)."""
     if not x.is_cuda or x.dtype != torch.float32 or x.stride(1) != 1:
         raise _lib.Ud3dError("gemm: x must be a CUDA fp32 matrix with unit column stride")
     if n_out is None:
@@ -180,8 +189,20 @@ def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = No
         out = torch.empty((n_out, w.c_out), dtype=torch.float32, device=x.device)
     assert out.stride(1) == 1 and out.shape[1] == w.c_out and x.shape[1] == w.c_in
     a = _gemm_args(x, w.K, w.c_in, w.c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act,
-                   residual, w.data.data_ptr())
+                   residual, w.data.data_ptr(), in_split, no_raw, acts)
     check(_L().ud3d_gemm_fwd(C.byref(a), _stream()), "ud3d_gemm_fwd")
+    return out
+
+
+def act_split(raw: torch.Tensor, scale=None, shift=None, relu: bool = True, out: Optional[torch.Tensor] = None):
+    """fp32 [n,c] -> operand form [n,c] (same bytes; bf16 hi|lo per 32-channel chunk) of relu(raw*scale+shift)."""
+    if not raw.is_cuda or raw.dtype != torch.float32 or raw.stride(1) != 1:
+        raise _lib.Ud3dError("act_split: raw must be a CUDA fp32 matrix with unit column stride")
+    n, c = raw.shape
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=raw.device)
+    check(_L().ud3d_act_split(_p(raw), raw.stride(0), n, c, _p(scale), _p(shift), 1 if relu else 0, _p(out), out.stride(0),
+                              _stream()), "ud3d_act_split")
     return out
 
 

@@ -108,6 +108,11 @@ class SpConvUNet(nn.Module):
         self.invalidate_plan()
         return super()._apply(fn, *a, **k)
 
+    def first_bn(self):
+        """Folded (scale, shift) of ``blocks.block0.conv_branch.0``: lets the producer of the input
+        feature map emit its operand-form copy directly (``SparseConvTensor.features_act``)."""
+        return self._get_plan()["blocks"][0]["bn0"]
+
     @staticmethod
     def _block_plan(blk: ResidualBlock):
         cb = blk.conv_branch
@@ -127,37 +132,81 @@ class SpConvUNet(nn.Module):
         return self._plan
 
     # ------------------------------------------------------------------ execution
+    # Feature maps travel between convs in "operand form": relu(bn(x)) already applied (the CONSUMER's
+    # folded BatchNorm), split into bf16 hi|lo -- the exact bytes of the tensor-core tile, gathered by
+    # cp.async with no per-use conversion.  A conv epilogue emits one operand-form copy per consumer
+    # BatchNorm (at most two) plus the raw fp32 map only where it is needed as a residual / output.
     @staticmethod
-    def _run_block(bp, x, lv, out=None):
-        """x + SubM3(BN.SubM3(BN.x))   (or SubM1(x) + ... when channel counts differ)."""
-        identity = ops.gemm(x, bp["wi"]) if "wi" in bp else x
-        y = ops.gemm(x, bp["w0"], table=lv.subm, tile_mask=lv.subm_mask, in_scale=bp["bn0"][0], in_shift=bp["bn0"][1],
-                     in_relu=True)
-        return ops.gemm(y, bp["w1"], table=lv.subm, tile_mask=lv.subm_mask, in_scale=bp["bn1"][0], in_shift=bp["bn1"][1],
-                        in_relu=True, residual=identity, out=out)
+    def _conv(x_act, w, table, mask, n_out, *, residual=None, raw=None, want_raw=True, acts=()):
+        """x_act: operand-form input.  acts: sequence of (buffer|None, (scale, shift)).  Returns (raw, [act bufs])."""
+        dev = x_act.device
+        bufs = []
+        for buf, bn in acts:
+            if buf is None:
+                buf = torch.empty((n_out, w.c_out), dtype=torch.float32, device=dev)
+            bufs.append((buf, bn[0], bn[1]))
+        out = ops.gemm(x_act, w, table=table, tile_mask=mask, n_out=n_out, in_split=True, residual=residual, out=raw,
+                       no_raw=not want_raw, acts=bufs)
+        return (out if want_raw else None), [b[0] for b in bufs]
 
-    def _forward_level(self, x: torch.Tensor, pyr: Pyramid, l: int, outputs: list) -> torch.Tensor:
+    def _run_block(self, bp, x_raw, x_act, lv, *, out_raw=None, want_raw=True, out_acts=()):
+        """ResidualBlock (spconv_unet.py:74-91) with equal channel counts: x + SubM3(BN.SubM3(BN.x)).
+        x_act = operand form of relu(bn0(x))."""
+        _, (y_act,) = self._conv(x_act, bp["w0"], lv.subm, lv.subm_mask, lv.n, want_raw=False, acts=[(None, bp["bn1"])])
+        return self._conv(y_act, bp["w1"], lv.subm, lv.subm_mask, lv.n, residual=x_raw, raw=out_raw, want_raw=want_raw,
+                          acts=out_acts)
+
+    def _forward_level(self, x_raw, x_act, pyr: Pyramid, l: int, outputs: list, out_bn=None):
+        """x_raw: fp32 [N_l, c]; x_act: operand form of relu(blocks.block0.bn0(x)).
+        out_bn: folded BN of the parent's ``deconv.0`` (None at the top level).
+        Returns (raw fp32 level output, operand-form output for the parent or None)."""
         plan = self._get_plan()
         lv = pyr.levels[l]
         c = self.num_planes[0]
+        dev = x_raw.device
+        blocks = plan["blocks"]
         has_sub = len(self.num_planes) > 1
-        cat = torch.empty((lv.n, 2 * c), dtype=torch.float32, device=x.device) if has_sub else None
-        nb = len(plan["blocks"])
-        for i, bp in enumerate(plan["blocks"]):
-            dst = cat[:, :c] if (has_sub and i == nb - 1) else None
-            x = self._run_block(bp, x, lv, out=dst)
-        if has_sub:
-            nxt = pyr.levels[l + 1]
-            d = ops.gemm(x, plan["down_w"], table=lv.child, tile_mask=lv.child_mask, n_out=nxt.n,
-                         in_scale=plan["down_bn"][0], in_shift=plan["down_bn"][1], in_relu=True)
-            d = self.u._forward_level(d, pyr, l + 1, outputs)
-            ops.gemm(d, plan["up_w"], table=lv.up, tile_mask=lv.up_mask, n_out=lv.n, in_scale=plan["up_bn"][0],
-                     in_shift=plan["up_bn"][1], in_relu=True, out=cat[:, c:])
-            x = cat
-            for bp in plan["tail"]:
-                x = self._run_block(bp, x, lv)
-        outputs.append((l, x))
-        return x
+        out_acts_final = [(None, out_bn)] if out_bn is not None else []
+        if not has_sub:
+            raw, act = x_raw, x_act
+            for i, bp in enumerate(blocks):
+                last = i == len(blocks) - 1
+                acts = out_acts_final if last else [(None, blocks[i + 1]["bn0"])]
+                raw, a = self._run_block(bp, raw, act, lv, out_acts=acts)
+                act = a[0] if a else None
+            outputs.append((l, raw))
+            return raw, act
+        tail = plan["tail"]
+        cat_raw = torch.empty((lv.n, 2 * c), dtype=torch.float32, device=dev)     # [identity | decoder], never concatenated
+        cat_act = torch.empty((lv.n, 2 * c), dtype=torch.float32, device=dev)     # operand form under tail.block0.bn0
+        t_sc, t_sh = tail[0]["bn0"]
+        raw, act = x_raw, x_act
+        a_down = None
+        for i, bp in enumerate(blocks):
+            last = i == len(blocks) - 1
+            if last:
+                raw, (a_down, _) = self._run_block(bp, raw, act, lv, out_raw=cat_raw[:, :c],
+                                                   out_acts=[(None, plan["down_bn"]), (cat_act[:, :c], (t_sc[:c], t_sh[:c]))])
+            else:
+                raw, (act,) = self._run_block(bp, raw, act, lv, out_acts=[(None, blocks[i + 1]["bn0"])])
+        nxt = pyr.levels[l + 1]
+        sub_bn0 = self.u._get_plan()["blocks"][0]["bn0"]
+        d_raw, (d_act,) = self._conv(a_down, plan["down_w"], lv.child, lv.child_mask, nxt.n, acts=[(None, sub_bn0)])
+        _, u_act = self.u._forward_level(d_raw, d_act, pyr, l + 1, outputs, out_bn=plan["up_bn"])
+        self._conv(u_act, plan["up_w"], lv.up, lv.up_mask, lv.n, raw=cat_raw[:, c:],
+                   acts=[(cat_act[:, c:], (t_sc[c:], t_sh[c:]))])
+        # tail block 0: SubM1(cat) + SubM3(BN.SubM3(BN.cat))   (in 2c -> c, spconv_unet.py:36-38)
+        r = ops.gemm(cat_raw, tail[0]["wi"])
+        _, (y_act,) = self._conv(cat_act, tail[0]["w0"], lv.subm, lv.subm_mask, lv.n, want_raw=False, acts=[(None, tail[0]["bn1"])])
+        raw, (act,) = self._conv(y_act, tail[0]["w1"], lv.subm, lv.subm_mask, lv.n, residual=r,
+                                 acts=[(None, tail[1]["bn0"])] if len(tail) > 1 else out_acts_final)
+        for i in range(1, len(tail)):
+            last = i == len(tail) - 1
+            acts = out_acts_final if last else [(None, tail[i + 1]["bn0"])]
+            raw, a = self._run_block(tail[i], raw, act, lv, out_acts=acts)
+            act = a[0] if a else None
+        outputs.append((l, raw))
+        return raw, act
 
     def n_levels(self):
         return len(self.num_planes)
@@ -173,7 +222,12 @@ class SpConvUNet(nn.Module):
         if not (x.is_cuda and x.dtype == torch.float32):
             raise RuntimeError("SpConvUNet needs CUDA fp32 features (no CPU fallback)")
         outs: list = []
-        y = self._forward_level(x.contiguous() if x.stride(1) != 1 else x, pyr, 0, outs)
+        x = x.contiguous() if x.stride(1) != 1 else x
+        x_act = getattr(input, "features_act", None)       # operand form under blocks.block0.bn0, if the caller has it
+        if x_act is None:
+            bn0 = self._get_plan()["blocks"][0]["bn0"]
+            x_act = ops.act_split(x, bn0[0], bn0[1], relu=True)
+        y, _ = self._forward_level(x, x_act, pyr, 0, outs)
         output = input.replace_feature(y)
         if self.return_blocks:
             if previous_outputs is None:

@@ -26,6 +26,7 @@ class SparseConvTensor:
         self.pyramid = pyramid          # rulebook cache (plays the role of spconv's indice_dict)
         self.canonical = canonical      # rows already in ascending (b,x,y,z) order
         self.extents = None if extents is None else [int(e) for e in extents]   # max coord + 1 (<= spatial_shape)
+        self.features_act = None        # optional operand-form copy of `features` for the first consumer conv
 
     def replace_feature(self, new_features: torch.Tensor) -> "SparseConvTensor":
         t = SparseConvTensor(new_features, self.indices, self.spatial_shape, self.batch_size, self.pyramid,
