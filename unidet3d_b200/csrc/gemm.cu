@@ -90,8 +90,13 @@ constexpr int kWarpB = 8;                         // warp 8: weight-tile bulk co
 constexpr int kWarpMma = 9;                       // warp 9: tcgen05.mma issue
 constexpr int kThreadsTc = 32 * 10;
 
+// Ring depth S and copies-in-flight D per instantiation.  A stage cycles fill (L2 latency L) -> MMA round
+// trip (M: a_full arrive -> issue -> tcgen05.commit -> empty) -> refill, so steady-state step time per CTA is
+// ~max(L / D, M / (S - D)): D = S / 2 balances the two (measured: D = S - 1 makes every step pay the full
+// ~1400-cycle MMA round trip).  S is the largest depth that keeps 2 CTAs/SM (1 CTA/SM for N_TILE >= 160).
 template <int N_TILE> struct TcCfg {
-  static constexpr int kStages = N_TILE <= 64 ? 4 : 3;
+  static constexpr int kStages = N_TILE <= 64 ? 4 : N_TILE <= 128 ? 3 : N_TILE == 160 ? 5 : 4;
+  static constexpr int kInFlight = kStages / 2;
 };
 
 // Raw gathered operand of one K-step for this thread: 2 rows x 8 channels
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     if (a.in_split) {
       // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
       //      zero-fill for missing neighbours; D steps of copies in flight per thread, no ALU work
-      constexpr int D = STAGES - 1;
+      constexpr int D = TcCfg<N_TILE>::kInFlight;
       const uint8_t* in_bytes = (const uint8_t*)a.in;
       const size_t row_bytes = (size_t)a.ld_in * 4;
       const int j = tid & 7;

@@ -98,11 +98,14 @@ class UniDet3D(nn.Module):
         batch_offsets[i]:batch_offsets[i+1] belong to scene i)."""
         plan = self._get_plan()
         lv0 = x.pyramid.levels[0]
-        bn0 = self.unet.first_bn()
-        f_act = torch.empty((lv0.n, plan["w_in"].c_out), dtype=torch.float32, device=x.features.device)
-        f = ops.gemm(x.features, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask, acts=[(f_act, bn0[0], bn0[1])])
-        x = x.replace_feature(f)
-        x.features_act = f_act          # operand form for the U-Net's first conv, emitted by the input conv epilogue
+        if self.unet.operand_form_ok():
+            bn0 = self.unet.first_bn()
+            f_act = torch.empty((lv0.n, plan["w_in"].c_out), dtype=torch.float32, device=x.features.device)
+            f = ops.gemm(x.features, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask, acts=[(f_act, bn0[0], bn0[1])])
+            x = x.replace_feature(f)
+            x.features_act = f_act      # operand form for the U-Net's first conv, emitted by the input conv epilogue
+        else:
+            x = x.replace_feature(ops.gemm(x.features, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask))
         x, _ = self.unet(x) if self.unet.return_blocks else (self.unet(x), None)
         pooled = ops.segmented_mean(x.features, superpoints, int(batch_offsets[-1]), gather=inverse_mapping,
                                     scale=plan["out_bn"][0], shift=plan["out_bn"][1], relu=True)

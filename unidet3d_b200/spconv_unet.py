@@ -208,6 +208,42 @@ class SpConvUNet(nn.Module):
         outputs.append((l, raw))
         return raw, act
 
+    # ---- fallback executor: fp32 feature maps, BN+ReLU folded into every consumer's operand load
+    #      (used when a level's channel count is not a multiple of 32, e.g. tiny test models)
+    @staticmethod
+    def _run_block_fp32(bp, x, lv, out=None):
+        identity = ops.gemm(x, bp["wi"]) if "wi" in bp else x
+        y = ops.gemm(x, bp["w0"], table=lv.subm, tile_mask=lv.subm_mask, in_scale=bp["bn0"][0], in_shift=bp["bn0"][1],
+                     in_relu=True)
+        return ops.gemm(y, bp["w1"], table=lv.subm, tile_mask=lv.subm_mask, in_scale=bp["bn1"][0], in_shift=bp["bn1"][1],
+                        in_relu=True, residual=identity, out=out)
+
+    def _forward_level_fp32(self, x: torch.Tensor, pyr: Pyramid, l: int, outputs: list) -> torch.Tensor:
+        plan = self._get_plan()
+        lv = pyr.levels[l]
+        c = self.num_planes[0]
+        has_sub = len(self.num_planes) > 1
+        cat = torch.empty((lv.n, 2 * c), dtype=torch.float32, device=x.device) if has_sub else None
+        nb = len(plan["blocks"])
+        for i, bp in enumerate(plan["blocks"]):
+            dst = cat[:, :c] if (has_sub and i == nb - 1) else None
+            x = self._run_block_fp32(bp, x, lv, out=dst)
+        if has_sub:
+            nxt = pyr.levels[l + 1]
+            d = ops.gemm(x, plan["down_w"], table=lv.child, tile_mask=lv.child_mask, n_out=nxt.n,
+                         in_scale=plan["down_bn"][0], in_shift=plan["down_bn"][1], in_relu=True)
+            d = self.u._forward_level_fp32(d, pyr, l + 1, outputs)
+            ops.gemm(d, plan["up_w"], table=lv.up, tile_mask=lv.up_mask, n_out=lv.n, in_scale=plan["up_bn"][0],
+                     in_shift=plan["up_bn"][1], in_relu=True, out=cat[:, c:])
+            x = cat
+            for bp in plan["tail"]:
+                x = self._run_block_fp32(bp, x, lv)
+        outputs.append((l, x))
+        return x
+
+    def operand_form_ok(self):
+        return all(c % 32 == 0 for c in self.num_planes)
+
     def n_levels(self):
         return len(self.num_planes)
 
@@ -223,11 +259,14 @@ class SpConvUNet(nn.Module):
             raise RuntimeError("SpConvUNet needs CUDA fp32 features (no CPU fallback)")
         outs: list = []
         x = x.contiguous() if x.stride(1) != 1 else x
-        x_act = getattr(input, "features_act", None)       # operand form under blocks.block0.bn0, if the caller has it
-        if x_act is None:
-            bn0 = self._get_plan()["blocks"][0]["bn0"]
-            x_act = ops.act_split(x, bn0[0], bn0[1], relu=True)
-        y, _ = self._forward_level(x, x_act, pyr, 0, outs)
+        if self.operand_form_ok():
+            x_act = getattr(input, "features_act", None)   # operand form under blocks.block0.bn0, if the caller has it
+            if x_act is None:
+                bn0 = self._get_plan()["blocks"][0]["bn0"]
+                x_act = ops.act_split(x, bn0[0], bn0[1], relu=True)
+            y, _ = self._forward_level(x, x_act, pyr, 0, outs)
+        else:
+            y = self._forward_level_fp32(x, pyr, 0, outs)
         output = input.replace_feature(y)
         if self.return_blocks:
             if previous_outputs is None:
