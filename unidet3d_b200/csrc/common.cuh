@@ -137,15 +137,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU box
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// bounded wait: a protocol bug traps instead of hanging the GPU box (slow path kept out of line)
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) {
-      printf("ud3d: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+    if (++spins > (1u << 22)) {
+      printf("ud3d: mbarrier wait timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // generic-proxy smem writes -> visible to the async proxy (tensor core / bulk copy engine)
 __device__ __forceinline__ void fence_proxy_async_smem() {

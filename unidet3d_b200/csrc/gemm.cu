@@ -193,168 +193,181 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   const int nsteps = t_end - t_begin;
   const uint8_t* wp = (const uint8_t*)a.w_packed + (size_t)nt * a.K * p.n_chunks * B_BYTES;
 
+  // (kslot, chunk) of this CTA's first step: the only integer division of the mainloop
+  const int kslot0 = t_begin / p.n_chunks;
+  const int chunk0 = t_begin - kslot0 * p.n_chunks;
+
   if (warp < kProducerWarps) {
     // =========================================================== A producers
     if (a.in_split) {
       // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
       //      zero-fill for missing neighbours; D steps of copies in flight per thread, no ALU work
       constexpr int D = TcCfg<N_TILE>::kInFlight;
-      const uint8_t* in_bytes = (const uint8_t*)a.in;
       const size_t row_bytes = (size_t)a.ld_in * 4;
       const int j = tid & 7;
-      auto issue_copy = [&](int t) {
-        const int s = t % STAGES;
-        const uint32_t use = (uint32_t)(t / STAGES);
-        if (t >= STAGES) mbar_wait(&empty[s], (use - 1) & 1);
-        const int tt = t_begin + t;
-        const int kslot = tt / p.n_chunks;
-        const int c = tt - kslot * p.n_chunks;
-        const int k = s_actk[kslot];
-        const uint32_t as_addr = smem_u32(sA + s * A_BYTES);
+      const int rbase = tid >> 3;
+      const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
+      const uint32_t sA_addr = smem_u32(sA);
+      uint32_t dst_off[4];
+      int ident[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rbase + 32 * i;
+        dst_off[i] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+        ident[i] = (m0 + r < a.n_out) ? m0 + r : -1;
+      }
+      int kslot = kslot0, c = chunk0, s = 0, pub_s = 0;
+      uint32_t use = 0;
+      for (int t = 0; t < nsteps; ++t) {
+        if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+        const int32_t* trow = s_tbl + (int)s_actk[kslot] * kTileM + rbase;
+        const uint8_t* sb = src_base + c * 128;
+        const uint32_t as_addr = sA_addr + s * A_BYTES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int r = (tid >> 3) + 32 * i;
-          int idx;
-          if (has_table) idx = s_tbl[k * kTileM + r];
-          else idx = (m0 + r < a.n_out) ? m0 + r : -1;
-          const uint8_t* src = in_bytes + (idx >= 0 ? (size_t)idx * row_bytes + (size_t)c * 128 + j * 16 : 0);
-          cp_async_16_zfill(as_addr + r * 128 + ((j ^ (r & 7)) << 4), src, idx >= 0 ? 16u : 0u);
+          const int idx = has_table ? trow[32 * i] : ident[i];
+          cp_async_16_zfill(as_addr + dst_off[i], sb + (size_t)(idx < 0 ? 0 : idx) * row_bytes, idx >= 0 ? 16u : 0u);
         }
         cp_async_commit();
-      };
-      auto publish = [&](int t) {          // copies of step t have landed (wait_group done by the caller)
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[t % STAGES]);
-      };
-      for (int t = 0; t < nsteps; ++t) {
-        issue_copy(t);
+        if (++c == p.n_chunks) { c = 0; ++kslot; }
+        if (++s == STAGES) { s = 0; ++use; }
         if (t >= D) {
-          cp_async_wait<D>();
-          publish(t - D);
+          cp_async_wait<D>();             // the copies of step t - D have landed
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[pub_s]);
+          if (++pub_s == STAGES) pub_s = 0;
         }
       }
-      // drain
-      if constexpr (D >= 3) { if (nsteps >= 3) { cp_async_wait<2>(); publish(nsteps - 3); } }
-      if constexpr (D >= 2) { if (nsteps >= 2) { cp_async_wait<1>(); publish(nsteps - 2); } }
-      if (nsteps >= 1) { cp_async_wait<0>(); publish(nsteps - 1); }
+      // drain the last min(D, nsteps) steps
+#pragma unroll
+      for (int d = D - 1; d >= 0; --d) {
+        if (nsteps > d) {
+          if (d == 2) cp_async_wait<2>();
+          else if (d == 1) cp_async_wait<1>();
+          else cp_async_wait<0>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[pub_s]);
+          if (++pub_s == STAGES) pub_s = 0;
+        }
+      }
     } else {
-    // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers
-    const int q = tid & 3;
-    const int rl = tid >> 2;
-    const bool affine = a.in_scale != nullptr;
-    const bool relu = a.in_relu != 0;
-
-    auto issue_loads = [&](int t, GatherRegs& g) {
-      const int tt = t_begin + t;
-      const int kslot = tt / p.n_chunks;
-      const int c = tt - kslot * p.n_chunks;
-      const int k = s_actk[kslot];
-      const int ch0 = c * kChunk + q * 8;
+      // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers (4 lanes per row, 8 channels each)
+      const int q = tid & 3;
+      const int rl = tid >> 2;
+      const bool affine = a.in_scale != nullptr;
+      const bool relu = a.in_relu != 0;
+      int ident[2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int r = rl + h * 64;
-        int idx;
-        if (has_table) idx = s_tbl[k * kTileM + r];
-        else idx = (m0 + r < a.n_out) ? m0 + r : -1;
-        g.ok[h] = idx >= 0 && ch0 < a.c_in;
-        if (g.ok[h]) {
-          const float* src = a.in + (size_t)idx * a.ld_in + ch0;
-          if (p.vec_ok) {
-            g.v[h][0] = __ldg((const float4*)src);
-            g.v[h][1] = __ldg((const float4*)src + 1);
+      for (int h = 0; h < 2; ++h) ident[h] = (m0 + rl + h * 64 < a.n_out) ? m0 + rl + h * 64 : -1;
+
+      auto issue_loads = [&](int kslot, int c, GatherRegs& g) {
+        const int32_t* trow = s_tbl + (int)s_actk[kslot] * kTileM + rl;
+        const int ch0 = c * kChunk + q * 8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int idx = has_table ? trow[h * 64] : ident[h];
+          g.ok[h] = idx >= 0 && ch0 < a.c_in;
+          if (g.ok[h]) {
+            const float* src = a.in + (size_t)idx * a.ld_in + ch0;
+            if (p.vec_ok) {
+              g.v[h][0] = __ldg((const float4*)src);
+              g.v[h][1] = __ldg((const float4*)src + 1);
+            } else {
+              float e[8];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) e[jj] = (ch0 + jj < a.c_in) ? __ldg(src + jj) : 0.f;
+              g.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
+              g.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
+            }
+          }
+        }
+      };
+      auto store_step = [&](int s, uint32_t use, int c, const GatherRegs& g) {
+        const int ch0 = c * kChunk + q * 8;
+        if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+        uint8_t* As = sA + s * A_BYTES;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[8];
+          if (g.ok[h]) {
+            v[0] = g.v[h][0].x; v[1] = g.v[h][0].y; v[2] = g.v[h][0].z; v[3] = g.v[h][0].w;
+            v[4] = g.v[h][1].x; v[5] = g.v[h][1].y; v[6] = g.v[h][1].z; v[7] = g.v[h][1].w;
+            if (affine) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
+            }
+            if (relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (!p.vec_ok) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if (ch0 + e >= a.c_in) v[e] = 0.f;     // padded channels stay exactly zero
+            }
           } else {
-            float e[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = (ch0 + j < a.c_in) ? __ldg(src + j) : 0.f;
-            g.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
-            g.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
           }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+          const int r = rl + h * 64;
+          uint8_t* arow = As + r * 128;
+          *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-      }
-    };
-    auto store_step = [&](int t, const GatherRegs& g) {
-      const int s = t % STAGES;
-      const uint32_t use = (uint32_t)(t / STAGES);
-      const int tt = t_begin + t;
-      const int c = tt % p.n_chunks;
-      const int ch0 = c * kChunk + q * 8;
-      if (t >= STAGES) mbar_wait(&empty[s], (use - 1) & 1);
-      uint8_t* As = sA + s * A_BYTES;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[8];
-        if (g.ok[h]) {
-          v[0] = g.v[h][0].x; v[1] = g.v[h][0].y; v[2] = g.v[h][0].z; v[3] = g.v[h][0].w;
-          v[4] = g.v[h][1].x; v[5] = g.v[h][1].y; v[6] = g.v[h][1].z; v[7] = g.v[h][1].w;
-          if (affine) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
-          }
-          if (relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          if (!p.vec_ok) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (ch0 + e >= a.c_in) v[e] = 0.f;     // padded channels stay exactly zero
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        }
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-        const int r = rl + h * 64;
-        uint8_t* arow = As + r * 128;
-        *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[s]);
-    };
+        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[s]);
+      };
 
-    // software pipeline: the global loads of step t+1 are in flight while step t is converted/stored
-    GatherRegs g0, g1;
-    if (nsteps > 0) issue_loads(0, g0);
-    for (int t = 0; t < nsteps; t += 2) {
-      if (t + 1 < nsteps) issue_loads(t + 1, g1);
-      store_step(t, g0);
-      if (t + 1 < nsteps) {
-        if (t + 2 < nsteps) issue_loads(t + 2, g0);
-        store_step(t + 1, g1);
+      // software pipeline: the global loads of step t+1 are in flight while step t is converted/stored
+      GatherRegs g0, g1;
+      int lk = kslot0, lc = chunk0;        // (kslot, chunk) of the next loads to issue
+      int sc = chunk0;                     // chunk of the next step to store
+      int s = 0;
+      uint32_t use = 0;
+      auto adv_load = [&]() { if (++lc == p.n_chunks) { lc = 0; ++lk; } };
+      auto adv_store = [&]() { if (++sc == p.n_chunks) sc = 0; if (++s == STAGES) { s = 0; ++use; } };
+      if (nsteps > 0) { issue_loads(lk, lc, g0); adv_load(); }
+      for (int t = 0; t < nsteps; t += 2) {
+        if (t + 1 < nsteps) { issue_loads(lk, lc, g1); adv_load(); }
+        store_step(s, use, sc, g0); adv_store();
+        if (t + 1 < nsteps) {
+          if (t + 2 < nsteps) { issue_loads(lk, lc, g0); adv_load(); }
+          store_step(s, use, sc, g1); adv_store();
+        }
       }
     }
-    }  // fp32-input producer
   } else if (warp == kWarpB) {
     // =========================================================== B producer: one bulk copy per step
+    int kslot = kslot0, c = chunk0, s = 0;
+    uint32_t use = 0;
     for (int t = 0; t < nsteps; ++t) {
-      const int s = t % STAGES;
-      const uint32_t use = (uint32_t)(t / STAGES);
-      if (t >= STAGES) mbar_wait(&empty[s], (use - 1) & 1);
+      if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
       if (lane == 0) {
-        const int tt = t_begin + t;
-        const int kslot = tt / p.n_chunks;
-        const int c = tt - kslot * p.n_chunks;
         const int k = s_actk[kslot];
         mbar_arrive_expect_tx(&b_full[s], B_BYTES);
         bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
       }
       __syncwarp();
+      if (++c == p.n_chunks) { c = 0; ++kslot; }
+      if (++s == STAGES) { s = 0; ++use; }
     }
   } else {
     // =========================================================== MMA issuer
+    int s = 0;
+    uint32_t use = 0;
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     for (int t = 0; t < nsteps; ++t) {
-      const int s = t % STAGES;
-      const uint32_t use = (uint32_t)(t / STAGES);
-      mbar_wait(&a_full[s], use & 1);
-      mbar_wait(&b_full[s], use & 1);
+      mbar_wait(&a_full[s], use & 1u);
+      mbar_wait(&b_full[s], use & 1u);
       tc_fence_after_sync();
       if (lane == 0) {
-        const uint32_t a_addr = smem_u32(sA + s * A_BYTES), b_addr = smem_u32(sB + s * B_BYTES);
+        const uint32_t a_addr = sA_addr + s * A_BYTES, b_addr = sB_addr + s * B_BYTES;
         // K-steps of 16 bf16 = 32 bytes inside the 128B row: hi at +0,+32 ; lo at +64,+96
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 0), IDESC, t > 0);
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 32), IDESC, 1);
@@ -365,6 +378,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
         umma_commit(&empty[s]);            // stage s reusable once these MMAs have read it
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ++use; }
     }
     if (lane == 0) umma_commit(acc_full);
     __syncwarp();
