@@ -237,8 +237,9 @@ def main():
     # ---------------------------------------------------------------- device-resident arm (value)
     d_pts = [torch.as_tensor(p).to(dev) for p in pts]
     d_sps = [torch.as_tensor(s).to(dev) for s in sps]
+    n_sps = [int(s.max()) + 1 for s in sps]
     for _ in range(W):
-        model.forward_scenes(d_pts, d_sps, names)
+        model.forward_scenes(d_pts, d_sps, names, n_sps)
     barrier()
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     if rank == 0:
@@ -249,7 +250,7 @@ def main():
         flush_l2()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        model.forward_scenes(d_pts, d_sps, names)
+        model.forward_scenes(d_pts, d_sps, names, n_sps)
         e1.record()
         evs.append((e0, e1))
     barrier()

@@ -140,6 +140,8 @@ typedef struct {
    * c_out % 32 == 0.  no_raw != 0: skip the fp32 store to `out` (still used as scratch by split-K). */
   int32_t in_split; int32_t no_raw;
   float* out_act[2]; int32_t ld_act[2]; const float* act_scale[2]; const float* act_shift[2];
+  int32_t act_norelu;          /* bit i set: out_act[i] = split(result * scale + shift) without the ReLU;
+                                  act_scale[i] == NULL means identity (scale 1, shift 0) */
 } ud3d_gemm_args;
 size_t ud3d_gemm_packed_weight_bytes(int K, int c_in, int c_out);
 int ud3d_gemm_pack_weight(const float* w, int K, int c_in, int c_out, void* packed, void* stream);
@@ -168,11 +170,18 @@ int ud3d_segmented_mean(const float* src, int ld_src, int C, const int32_t* gath
  * LayerNorm(eps) of (x + residual) per row (encoder.py:38-39,77-78,189); C % 32 == 0, C <= 1024 */
 int ud3d_layernorm(const float* x, const float* residual, const float* gamma, const float* beta,
                    float* out, int rows, int C, float eps, void* stream);
+/* same, additionally (out_split != NULL) storing the result in operand form (ud3d_act_split layout) for the
+ * consumer GEMMs; out may be NULL when only the operand form is needed.  C in {128, 256}. */
+int ud3d_layernorm_split(const float* x, const float* residual, const float* gamma, const float* beta,
+                         float* out, float* out_split, int rows, int C, float eps, void* stream);
 /* multi-head self-attention core of nn.MultiheadAttention (encoder.py:37) on packed projections:
  * qkv [T_total, 3*d] (q|k|v, heads contiguous, head_dim = 32), cu_seqlens int32 [B+1] scene
  * boundaries (no cross-scene attention, no mask/padding), out [T_total, d] = softmax(QK^T/sqrt(32))V */
 int ud3d_attention_fwd(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
                        float* out, void* stream);
+/* same with the output stored in operand form (one head = one 32-channel chunk) for the out-projection GEMM */
+int ud3d_attention_fwd_split(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
+                             float* out_split, void* stream);
 /* PredBBox exp + _bbox_pred_to_bbox (encoder.py:109-111,241-283): raw [T,ld_raw>=8], centres [T,3]
  * -> out [T, with_angle ? 7 : 6] */
 int ud3d_bbox_decode(const float* raw, int ld_raw, const float* centers, int T, int with_angle,

@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("in_split", C.c_int32), ("no_raw", C.c_int32),
         ("out_act", C.c_void_p * 2), ("ld_act", C.c_int32 * 2),
         ("act_scale", C.c_void_p * 2), ("act_shift", C.c_void_p * 2),
+        ("act_norelu", C.c_int32),
     ]
 
 
@@ -57,6 +58,8 @@ SIGNATURES = {
     "ud3d_segmented_mean": (_i, [_vp, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "ud3d_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ud3d_attention_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ud3d_attention_fwd_split": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ud3d_layernorm_split": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ud3d_bbox_decode": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "ud3d_gather_columns": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "ud3d_topk_scores": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

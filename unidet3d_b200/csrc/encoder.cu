@@ -70,7 +70,8 @@ __global__ void segmented_norm_kernel(float* out, const float* __restrict__ cnt,
 template <int PER_LANE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float* __restrict__ out, int rows, int C, float eps) {
+                                                        float* __restrict__ out, float* __restrict__ out_split, int rows,
+                                                        int C, float eps) {
   const int lane = threadIdx.x & 31;
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -106,7 +107,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.y = (v[j * 4 + 1] - mean) * rstd * g.y + b.y;
     o.z = (v[j * 4 + 2] - mean) * rstd * g.z + b.z;
     o.w = (v[j * 4 + 3] - mean) * rstd * g.w + b.w;
-    *(float4*)(out + (size_t)row * C + c) = o;
+    if (out) *(float4*)(out + (size_t)row * C + c) = o;
+    if (out_split) {
+      // operand form: chunk = c / 32, 4 channels at (c % 32): hi 8 bytes, lo 8 bytes (+64)
+      uint32_t h0, l0, h1, l1;
+      split_bf16x2(o.x, o.y, h0, l0);
+      split_bf16x2(o.z, o.w, h1, l1);
+      uint8_t* d = (uint8_t*)(out_split + (size_t)row * C) + (c >> 5) * 128 + (c & 31) * 2;
+      *(uint2*)d = make_uint2(h0, h1);
+      *(uint2*)(d + 64) = make_uint2(l0, l1);
+    }
   }
 }
 
@@ -150,6 +160,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+template <bool SPLIT_OUT>
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu,
                                                         int num_heads, float* __restrict__ out) {
   const int b = blockIdx.z, h = blockIdx.y;
@@ -306,8 +317,25 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 #pragma unroll
   for (int dn = 0; dn < 4; ++dn) {
     const int col = h * kHeadDim + dn * 8 + 2 * t;
-    if (r0 < T) *(float2*)(out + (size_t)(t0 + r0) * d_model + col) = make_float2(o[dn][0] * inv0, o[dn][1] * inv0);
-    if (r1 < T) *(float2*)(out + (size_t)(t0 + r1) * d_model + col) = make_float2(o[dn][2] * inv1, o[dn][3] * inv1);
+    if constexpr (SPLIT_OUT) {
+      // operand form: head h == 32-channel chunk h; hi pair at (dn*8+2t)*2 bytes, lo pair +64
+      uint32_t hi, lo;
+      if (r0 < T) {
+        split_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0, hi, lo);
+        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r0) * d_model) + h * 128 + (dn * 8 + 2 * t) * 2;
+        *(uint32_t*)d = hi;
+        *(uint32_t*)(d + 64) = lo;
+      }
+      if (r1 < T) {
+        split_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1, hi, lo);
+        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r1) * d_model) + h * 128 + (dn * 8 + 2 * t) * 2;
+        *(uint32_t*)d = hi;
+        *(uint32_t*)(d + 64) = lo;
+      }
+    } else {
+      if (r0 < T) *(float2*)(out + (size_t)(t0 + r0) * d_model + col) = make_float2(o[dn][0] * inv0, o[dn][1] * inv0);
+      if (r1 < T) *(float2*)(out + (size_t)(t0 + r1) * d_model + col) = make_float2(o[dn][2] * inv1, o[dn][3] * inv1);
+    }
   }
 }
 
@@ -383,34 +411,61 @@ int ud3d_segmented_mean(const float* src, int ld_src, int C, const int32_t* gath
   return UD3D_OK;
 }
 
-int ud3d_layernorm(const float* x, const float* residual, const float* gamma, const float* beta, float* out, int rows,
-                   int C, float eps, void* stream) {
-  UD3D_CHECK_ARG(x && gamma && beta && out, "ud3d_layernorm: NULL argument");
-  UD3D_CHECK_ARG(C > 0 && C % 32 == 0 && C <= 1024 && rows >= 0, "ud3d_layernorm: need C %% 32 == 0, C <= 1024");
+static int layernorm_impl(const float* x, const float* residual, const float* gamma, const float* beta, float* out,
+                          float* out_split, int rows, int C, float eps, void* stream, const char* who) {
+  UD3D_CHECK_ARG(x && gamma && beta && (out || out_split), "%s: NULL argument", who);
+  UD3D_CHECK_ARG(C > 0 && C % 32 == 0 && C <= 1024 && rows >= 0, "%s: need C %% 32 == 0, C <= 1024", who);
   if (rows == 0) return UD3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = cdiv(rows, 8);
-  bool vec = (C % 128 == 0) && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)residual) & 15) == 0;
+  bool vec = (C % 128 == 0) &&
+             (((uintptr_t)x | (uintptr_t)out | (uintptr_t)out_split | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)residual) & 15) == 0;
   if (vec && C == 256)
-    layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, residual, gamma, beta, out, rows, C, eps);
+    layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, residual, gamma, beta, out, out_split, rows, C, eps);
   else if (vec && C == 128)
-    layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, residual, gamma, beta, out, rows, C, eps);
-  else
+    layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, residual, gamma, beta, out, out_split, rows, C, eps);
+  else {
+    UD3D_CHECK_ARG(!out_split, "%s: operand-form output needs C in {128, 256} and 16-byte aligned pointers", who);
     layernorm_generic_kernel<<<blocks, 256, 0, st>>>(x, residual, gamma, beta, out, rows, C, eps);
+  }
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_layernorm(const float* x, const float* residual, const float* gamma, const float* beta, float* out, int rows,
+                   int C, float eps, void* stream) {
+  UD3D_CHECK_ARG(out, "ud3d_layernorm: NULL out");
+  return layernorm_impl(x, residual, gamma, beta, out, nullptr, rows, C, eps, stream, "ud3d_layernorm");
+}
+
+int ud3d_layernorm_split(const float* x, const float* residual, const float* gamma, const float* beta, float* out,
+                         float* out_split, int rows, int C, float eps, void* stream) {
+  return layernorm_impl(x, residual, gamma, beta, out, out_split, rows, C, eps, stream, "ud3d_layernorm_split");
+}
+
+static int attention_impl(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads, float* out,
+                          bool split, void* stream) {
+  UD3D_CHECK_ARG(qkv && cu_seqlens && out, "ud3d_attention_fwd: NULL argument");
+  UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd: bad sizes");
+  UD3D_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)out) & 15) == 0, "ud3d_attention_fwd: pointers must be 16-byte aligned");
+  if (max_T == 0) return UD3D_OK;
+  dim3 grid(cdiv(max_T, kAttQ), num_heads, B);
+  if (split)
+    attention_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, cu_seqlens, num_heads, out);
+  else
+    attention_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, cu_seqlens, num_heads, out);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }
 
 int ud3d_attention_fwd(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads, float* out,
                        void* stream) {
-  UD3D_CHECK_ARG(qkv && cu_seqlens && out, "ud3d_attention_fwd: NULL argument");
-  UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd: bad sizes");
-  UD3D_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)out) & 15) == 0, "ud3d_attention_fwd: pointers must be 16-byte aligned");
-  if (max_T == 0) return UD3D_OK;
-  dim3 grid(cdiv(max_T, kAttQ), num_heads, B);
-  attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, cu_seqlens, num_heads, out);
-  UD3D_LAUNCH_CHECK();
-  return UD3D_OK;
+  return attention_impl(qkv, cu_seqlens, B, max_T, num_heads, out, false, stream);
+}
+
+int ud3d_attention_fwd_split(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
+                             float* out_split, void* stream) {
+  return attention_impl(qkv, cu_seqlens, B, max_T, num_heads, out_split, true, stream);
 }
 
 int ud3d_bbox_decode(const float* raw, int ld_raw, const float* centers, int T, int with_angle, float* out, void* stream) {

@@ -470,14 +470,22 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
 #pragma unroll
       for (int oi = 0; oi < 2; ++oi) {
         if (!a.out_act[oi]) continue;      // (c_out % 32 == 0 enforced on the host: `full` holds)
-        const float* sc = a.act_scale[oi] + col0;
-        const float* sh = a.act_shift[oi] + col0;
+        const float* sc = a.act_scale[oi] ? a.act_scale[oi] + col0 : nullptr;
+        const float* sh = a.act_scale[oi] ? a.act_shift[oi] + col0 : nullptr;
+        const bool do_relu = !((a.act_norelu >> oi) & 1);
         uint4* dst = (uint4*)((uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4);
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float x0 = fmaxf(fmaf(v[j], __ldg(sc + j), __ldg(sh + j)), 0.f);
-          float x1 = fmaxf(fmaf(v[j + 1], __ldg(sc + j + 1), __ldg(sh + j + 1)), 0.f);
+          float x0 = v[j], x1 = v[j + 1];
+          if (sc) {
+            x0 = fmaf(x0, __ldg(sc + j), __ldg(sh + j));
+            x1 = fmaf(x1, __ldg(sc + j + 1), __ldg(sh + j + 1));
+          }
+          if (do_relu) {
+            x0 = fmaxf(x0, 0.f);
+            x1 = fmaxf(x1, 0.f);
+          }
           split_bf16x2(x0, x1, hi[j >> 1], lo[j >> 1]);
         }
 #pragma unroll
@@ -597,7 +605,7 @@ static int check_args(const ud3d_gemm_args* a, const char* who) {
   }
   for (int i = 0; i < 2; ++i) {
     if (!a->out_act[i]) continue;
-    UD3D_CHECK_ARG(a->act_scale[i] && a->act_shift[i], "%s: out_act needs act_scale / act_shift", who);
+    UD3D_CHECK_ARG((a->act_scale[i] == nullptr) == (a->act_shift[i] == nullptr), "%s: act_scale / act_shift must both be set or both NULL", who);
     UD3D_CHECK_ARG(a->c_out % 32 == 0 && a->ld_act[i] % 4 == 0 && a->ld_act[i] >= a->c_out &&
                        ((uintptr_t)a->out_act[i] & 15) == 0,
                    "%s: out_act needs c_out %% 32 == 0 and a 16-byte aligned buffer", who);
@@ -678,7 +686,8 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
     for (int i = 0; i < 2; ++i) {
       if (!args->out_act[i]) continue;
       UD3D_CHECK_ARG(args->ld_out % 4 == 0 && ((uintptr_t)args->out & 15) == 0, "ud3d_gemm_fwd: split-K + out_act needs an aligned `out`");
-      int rc3 = launch_act_split(args->out, args->ld_out, args->n_out, args->c_out, args->act_scale[i], args->act_shift[i], 1,
+      int rc3 = launch_act_split(args->out, args->ld_out, args->n_out, args->c_out, args->act_scale[i], args->act_shift[i],
+                                 !((args->act_norelu >> i) & 1),
                                  args->out_act[i], args->ld_act[i], st);
       if (rc3) return rc3;
     }

@@ -81,6 +81,7 @@ class UniDet3DEncoder(nn.Module):
         self.out_bboxes = PredBBox(d_model, 8)
         self.activation_fn = activation_fn
         self.eval_aux_outputs = False
+        self._split_ok = False
         self._plan = None
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_plan())
 
@@ -111,10 +112,18 @@ class UniDet3DEncoder(nn.Module):
 
     # ------------------------------------------------------------------ heads (encoder.py:165-201)
     def _forward_head(self, p, H, centers, bounds, ds_idx):
-        nq = ops.layernorm(H, p["on"][0], p["on"][1], eps=p["on"][2])
-        h = ops.gemm(nq, p["c0"][0], bias=p["c0"][1], act="relu")
-        logits = ops.gemm(h, p["c2"][0], bias=p["c2"][1])
-        raw = ops.gemm(nq, p["bb"][0], bias=p["bb"][1])
+        """H: fp32 [sum T, d].  LayerNorm -> operand form; cls MLP and box Linear read it with cp.async."""
+        if self._split_ok:
+            _, nq_s = ops.layernorm_split(H, p["on"][0], p["on"][1], eps=p["on"][2], want_raw=False)
+            h_s = torch.empty_like(H)
+            ops.gemm(nq_s, p["c0"][0], bias=p["c0"][1], act="relu", in_split=True, no_raw=True, acts=[(h_s, None, None, False)])
+            logits = ops.gemm(h_s, p["c2"][0], bias=p["c2"][1], in_split=True)
+            raw = ops.gemm(nq_s, p["bb"][0], bias=p["bb"][1], in_split=True)
+        else:
+            nq = ops.layernorm(H, p["on"][0], p["on"][1], eps=p["on"][2])
+            h = ops.gemm(nq, p["c0"][0], bias=p["c0"][1], act="relu")
+            logits = ops.gemm(h, p["c2"][0], bias=p["c2"][1])
+            raw = ops.gemm(nq, p["bb"][0], bias=p["bb"][1])
         cls_preds, bboxes = [], []
         for i, j in enumerate(ds_idx):
             a, b = bounds[i], bounds[i + 1]
@@ -143,21 +152,49 @@ class UniDet3DEncoder(nn.Module):
         max_T = max(b - a for a, b in zip(bounds[:-1], bounds[1:])) if len(bounds) > 1 else 0
         all_heads = self.eval_aux_outputs
         cls_all, box_all = [], []
-        H = ops.gemm(X, p["ip0"][0], bias=p["ip0"][1], act="relu")
-        H = ops.gemm(H, p["ip2"][0], bias=p["ip2"][1])
-        if all_heads:
-            c, b = self._forward_head(p, H, centers, bounds, ds_idx)
-            cls_all.append(c), box_all.append(b)
-        for li, lp in enumerate(p["layers"]):
-            qkv = ops.gemm(H, lp["qkv"][0], bias=lp["qkv"][1])
-            A = ops.attention(qkv, cu, max_T, self.num_heads)
-            Z = ops.gemm(A, lp["out"][0], bias=lp["out"][1], residual=H)
-            H = ops.layernorm(Z, lp["n1"][0], lp["n1"][1], eps=lp["n1"][2])
-            F1 = ops.gemm(H, lp["f1"][0], bias=lp["f1"][1], act=self.activation_fn)
-            Z = ops.gemm(F1, lp["f2"][0], bias=lp["f2"][1], residual=H)
-            H = ops.layernorm(Z, lp["n2"][0], lp["n2"][1], eps=lp["n2"][2])
-            if all_heads or li == self.num_layers - 1:
+        d = self.d_model
+        hidden = self.ffn_layers[0].net[0].out_features if self.num_layers else d
+        self._split_ok = (d in (128, 256)) and hidden % 32 == 0
+        if self._split_ok:
+            # operand-form dataflow: every GEMM input is written once in tensor-core tile form by its producer
+            # (GEMM / LayerNorm / attention epilogue) and gathered with cp.async -- no per-use conversion
+            n = X.shape[0]
+            t_s = torch.empty((n, d), dtype=torch.float32, device=X.device)
+            ops.gemm(X, p["ip0"][0], bias=p["ip0"][1], act="relu", no_raw=True, acts=[(t_s, None, None, False)])
+            H_s = torch.empty((n, d), dtype=torch.float32, device=X.device)
+            H = ops.gemm(t_s, p["ip2"][0], bias=p["ip2"][1], in_split=True, acts=[(H_s, None, None, False)])
+            if all_heads:
                 c, b = self._forward_head(p, H, centers, bounds, ds_idx)
                 cls_all.append(c), box_all.append(b)
+            for li, lp in enumerate(p["layers"]):
+                qkv = ops.gemm(H_s, lp["qkv"][0], bias=lp["qkv"][1], in_split=True)
+                A_s = ops.attention(qkv, cu, max_T, self.num_heads, split_out=True)
+                Z = ops.gemm(A_s, lp["out"][0], bias=lp["out"][1], residual=H, in_split=True)
+                H, H_s = ops.layernorm_split(Z, lp["n1"][0], lp["n1"][1], eps=lp["n1"][2])
+                F_s = torch.empty((n, hidden), dtype=torch.float32, device=X.device)
+                ops.gemm(H_s, lp["f1"][0], bias=lp["f1"][1], act=self.activation_fn, in_split=True, no_raw=True,
+                         acts=[(F_s, None, None, False)])
+                Z = ops.gemm(F_s, lp["f2"][0], bias=lp["f2"][1], residual=H, in_split=True)
+                H, H_s = ops.layernorm_split(Z, lp["n2"][0], lp["n2"][1], eps=lp["n2"][2])
+                if all_heads or li == self.num_layers - 1:
+                    c, b = self._forward_head(p, H, centers, bounds, ds_idx)
+                    cls_all.append(c), box_all.append(b)
+        else:
+            H = ops.gemm(X, p["ip0"][0], bias=p["ip0"][1], act="relu")
+            H = ops.gemm(H, p["ip2"][0], bias=p["ip2"][1])
+            if all_heads:
+                c, b = self._forward_head(p, H, centers, bounds, ds_idx)
+                cls_all.append(c), box_all.append(b)
+            for li, lp in enumerate(p["layers"]):
+                qkv = ops.gemm(H, lp["qkv"][0], bias=lp["qkv"][1])
+                A = ops.attention(qkv, cu, max_T, self.num_heads)
+                Z = ops.gemm(A, lp["out"][0], bias=lp["out"][1], residual=H)
+                H = ops.layernorm(Z, lp["n1"][0], lp["n1"][1], eps=lp["n1"][2])
+                F1 = ops.gemm(H, lp["f1"][0], bias=lp["f1"][1], act=self.activation_fn)
+                Z = ops.gemm(F1, lp["f2"][0], bias=lp["f2"][1], residual=H)
+                H = ops.layernorm(Z, lp["n2"][0], lp["n2"][1], eps=lp["n2"][2])
+                if all_heads or li == self.num_layers - 1:
+                    c, b = self._forward_head(p, H, centers, bounds, ds_idx)
+                    cls_all.append(c), box_all.append(b)
         aux_outputs = [dict(cls_preds=c, bboxes=b) for c, b in zip(cls_all[:-1], box_all[:-1])]
         return dict(cls_preds=cls_all[-1], bboxes=box_all[-1], aux_outputs=aux_outputs)

@@ -166,9 +166,15 @@ def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_
     a.ld_res = residual.stride(0) if residual is not None else 0
     a.in_split = 1 if in_split else 0
     a.no_raw = 1 if no_raw else 0
-    for i, (buf, sc, sh) in enumerate(acts or ()):
+    norelu = 0
+    for i, spec in enumerate(acts or ()):
+        buf, sc, sh = spec[0], spec[1], spec[2]
         a.out_act[i] = buf.data_ptr(); a.ld_act[i] = buf.stride(0)
-        a.act_scale[i] = sc.data_ptr(); a.act_shift[i] = sh.data_ptr()
+        a.act_scale[i] = sc.data_ptr() if sc is not None else None
+        a.act_shift[i] = sh.data_ptr() if sh is not None else None
+        if len(spec) > 3 and not spec[3]:
+            norelu |= 1 << i
+    a.act_norelu = norelu
     return a
 
 
@@ -179,7 +185,8 @@ def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = No
     """out = act(sum_k pre(x[table[k]]) @ W_k + bias) + residual   (see ud3d_gemm_fwd).
     ``x``/``out``/``residual`` may be column slices of wider row-major buffers (stride(1) == 1).
     ``in_split``: x is an operand-form (pre-activated, bf16 hi|lo) feature map, see ``act_split``.
-    ``acts``: up to two (buffer, scale, shift): also store relu(out*scale+shift) in operand form.
+    ``acts``: up to two (buffer, scale, shift[, relu=True]): also store relu?(out*scale+shift) in operand
+    form (scale/shift None = identity).
     ``no_raw``: the fp32 result itself is not needed (``out`` is then scratch)."""
     if not x.is_cuda or x.dtype != torch.float32 or x.stride(1) != 1:
         raise _lib.Ud3dError("gemm: x must be a CUDA fp32 matrix with unit column stride")
@@ -243,14 +250,26 @@ def layernorm(x: torch.Tensor, gamma, beta, residual=None, eps: float = 1e-5, ou
     return out
 
 
-def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_T: int, num_heads: int) -> torch.Tensor:
+def layernorm_split(x: torch.Tensor, gamma, beta, residual=None, eps: float = 1e-5, want_raw: bool = True):
+    """-> (fp32 result or None, operand-form result)."""
+    _req(x, torch.float32, "x")
+    out = torch.empty_like(x) if want_raw else None
+    out_s = torch.empty_like(x)
+    check(_L().ud3d_layernorm_split(_p(x), _p(residual), _p(gamma), _p(beta), _p(out), _p(out_s), x.shape[0], x.shape[1],
+                                    float(eps), _stream()), "ud3d_layernorm_split")
+    return out, out_s
+
+
+def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_T: int, num_heads: int, split_out: bool = False) -> torch.Tensor:
+    """softmax(QK^T/sqrt(32))V per scene; ``split_out``: result in operand form for the out-projection GEMM."""
     _req(qkv, torch.float32, "qkv"), _req(cu_seqlens, torch.int32, "cu_seqlens")
     d = qkv.shape[1] // 3
     if d != num_heads * 32:
         raise _lib.Ud3dError("attention: head_dim must be 32")
     out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
-    check(_L().ud3d_attention_fwd(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, int(max_T), num_heads, _p(out),
-                                  _stream()), "ud3d_attention_fwd")
+    fn = _L().ud3d_attention_fwd_split if split_out else _L().ud3d_attention_fwd
+    check(fn(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, int(max_T), num_heads, _p(out), _stream()),
+          "ud3d_attention_fwd")
     return out
 
 
