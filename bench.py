@@ -328,18 +328,15 @@ def main():
             "backbone_ms_per_batch": 1e3 * t_conv}
 
     # ---------------------------------------------------------------- aggregate over ranks
-    t = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev, t_e2e = t.tolist()
+    from unidet3d_b200 import sharding
+    t_dev, t_e2e = sharding.aggregate_times([t_dev, t_e2e], device=dev)
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
             dist.destroy_process_group()
         return
-    value = world * batch * K / t_dev
-    e2e = world * batch * K / t_e2e
+    value = sharding.whole_job_throughput(batch * K, world, t_dev)
+    e2e = sharding.whole_job_throughput(batch * K, world, t_e2e)
     line = {"metric": "scenes/sec", "value": value, "unit": "scenes/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
