@@ -22,6 +22,8 @@
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ud3d {
 
 constexpr int kTileM = UD3D_TILE_M;   // 128
@@ -105,7 +107,7 @@ struct GatherRegs {
   int ok[2];
 };
 
-template <int N_TILE>
+template <int N_TILE, int D_INFLIGHT = TcCfg<N_TILE>::kInFlight>
 __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p) {
   constexpr int STAGES = TcCfg<N_TILE>::kStages;
   constexpr int A_BYTES = kTileM * 128;
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     if (a.in_split) {
       // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
       //      zero-fill for missing neighbours; D steps of copies in flight per thread, no ALU work
-      constexpr int D = TcCfg<N_TILE>::kInFlight;
+      constexpr int D = D_INFLIGHT;
       const size_t row_bytes = (size_t)a.ld_in * 4;
       const int j = tid & 7;
       const int rbase = tid >> 3;
@@ -219,7 +221,10 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       int kslot = kslot0, c = chunk0, s = 0, pub_s = 0;
       uint32_t use = 0;
       for (int t = 0; t < nsteps; ++t) {
-        if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+        if (use) {                         // one poller per warp (256 spinning threads starve the MMA / TMA warps)
+          if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+          __syncwarp();
+        }
         const int32_t* trow = s_tbl + (int)s_actk[kslot] * kTileM + rbase;
         const uint8_t* sb = src_base + c * 128;
         const uint32_t as_addr = sA_addr + s * A_BYTES;
@@ -286,7 +291,10 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       };
       auto store_step = [&](int s, uint32_t use, int c, const GatherRegs& g) {
         const int ch0 = c * kChunk + q * 8;
-        if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+        if (use) {
+          if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+          __syncwarp();
+        }
         uint8_t* As = sA + s * A_BYTES;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -347,8 +355,8 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     int kslot = kslot0, c = chunk0, s = 0;
     uint32_t use = 0;
     for (int t = 0; t < nsteps; ++t) {
-      if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
       if (lane == 0) {
+        if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
         const int k = s_actk[kslot];
         mbar_arrive_expect_tx(&b_full[s], B_BYTES);
         bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
@@ -363,10 +371,10 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     uint32_t use = 0;
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     for (int t = 0; t < nsteps; ++t) {
-      mbar_wait(&a_full[s], use & 1u);
-      mbar_wait(&b_full[s], use & 1u);
-      tc_fence_after_sync();
       if (lane == 0) {
+        mbar_wait(&a_full[s], use & 1u);
+        mbar_wait(&b_full[s], use & 1u);
+        tc_fence_after_sync();
         const uint32_t a_addr = sA_addr + s * A_BYTES, b_addr = sB_addr + s * B_BYTES;
         // K-steps of 16 bf16 = 32 bytes inside the 128B row: hi at +0,+32 ; lo at +64,+96
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 0), IDESC, t > 0);
@@ -576,18 +584,33 @@ static size_t tc_smem_bytes(int n_chunks, int K, bool has_table) {
          (has_table ? (size_t)K * kTileM * 4 : 0);
 }
 
-template <int N_TILE>
-static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
+template <int N_TILE, int D>
+static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
   size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr);
   static size_t configured = 0;   // largest size this instantiation was configured for
   if (smem > configured) {
-    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid(cdiv(p.a.n_out, kTileM), n_tiles, splits);
-  gather_gemm_tc_kernel<N_TILE><<<grid, kThreadsTc, smem, st>>>(p);
+  gather_gemm_tc_kernel<N_TILE, D><<<grid, kThreadsTc, smem, st>>>(p);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
+}
+
+template <int N_TILE>
+static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
+  // tuning knob (experiments): UD3D_GEMM_D overrides the number of cp.async steps in flight for N_TILE <= 64
+  static int d_override = -1;
+  if (d_override < 0) {
+    const char* e = getenv("UD3D_GEMM_D");
+    d_override = e ? atoi(e) : 0;
+  }
+  if constexpr (N_TILE <= 64) {
+    if (d_override == 1) return launch_tc_d<N_TILE, 1>(p, n_tiles, splits, st);
+    if (d_override == 3) return launch_tc_d<N_TILE, 3>(p, n_tiles, splits, st);
+  }
+  return launch_tc_d<N_TILE, TcCfg<N_TILE>::kInFlight>(p, n_tiles, splits, st);
 }
 
 static int check_args(const ud3d_gemm_args* a, const char* who) {
