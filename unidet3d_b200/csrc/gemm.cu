@@ -34,7 +34,12 @@ struct GemmParams {
   int n_chunks;
   int vec_ok;      // 16-byte vector gather allowed
   int out_vec_ok;  // 16-byte vector epilogue allowed
+  long long* trace;   // debug: clock64 timestamps of one CTA (ud3d_debug_set_trace), else nullptr
+  int trace_block;
 };
+
+static long long* g_trace = nullptr;
+static int g_trace_block = 0;
 
 static inline int pick_ntile(int c_out) {
   if (c_out <= 32) return 32;
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   const int nt = blockIdx.y;
   const int n0 = nt * N_TILE;
   const bool has_table = a.table != nullptr;
+  if (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1019] = clock64();
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -220,11 +226,14 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       }
       int kslot = kslot0, c = chunk0, s = 0, pub_s = 0;
       uint32_t use = 0;
+      long long* tr = (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) ? p.trace : nullptr;
+      if (tr) { tr[1023] = nsteps; tr[1022] = clock64(); }
       for (int t = 0; t < nsteps; ++t) {
         if (use) {                         // one poller per warp (256 spinning threads starve the MMA / TMA warps)
           if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
           __syncwarp();
         }
+        if (tr && t < 64) tr[t * 8 + 0] = clock64();
         const int32_t* trow = s_tbl + (int)s_actk[kslot] * kTileM + rbase;
         const uint8_t* sb = src_base + c * 128;
         const uint32_t as_addr = sA_addr + s * A_BYTES;
@@ -234,13 +243,16 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
           cp_async_16_zfill(as_addr + dst_off[i], sb + (size_t)(idx < 0 ? 0 : idx) * row_bytes, idx >= 0 ? 16u : 0u);
         }
         cp_async_commit();
+        if (tr && t < 64) tr[t * 8 + 1] = clock64();
         if (++c == p.n_chunks) { c = 0; ++kslot; }
         if (++s == STAGES) { s = 0; ++use; }
         if (t >= D) {
           cp_async_wait<D>();             // the copies of step t - D have landed
+          if (tr && t - D < 64) tr[(t - D) * 8 + 2] = clock64();
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[pub_s]);
+          if (tr && t - D < 64) tr[(t - D) * 8 + 3] = clock64();
           if (++pub_s == STAGES) pub_s = 0;
         }
       }
@@ -372,8 +384,11 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
     for (int t = 0; t < nsteps; ++t) {
       if (lane == 0) {
+        long long* tr = (p.trace && (int)blockIdx.x == p.trace_block) ? p.trace : nullptr;
         mbar_wait(&a_full[s], use & 1u);
+        if (tr && t < 64) tr[t * 8 + 4] = clock64();
         mbar_wait(&b_full[s], use & 1u);
+        if (tr && t < 64) tr[t * 8 + 5] = clock64();
         tc_fence_after_sync();
         const uint32_t a_addr = sA_addr + s * A_BYTES, b_addr = sB_addr + s * B_BYTES;
         // K-steps of 16 bf16 = 32 bytes inside the 128B row: hi at +0,+32 ; lo at +64,+96
@@ -384,6 +399,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 64), IDESC, 1);
         umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 96), IDESC, 1);
         umma_commit(&empty[s]);            // stage s reusable once these MMAs have read it
+        if (tr && t < 64) tr[t * 8 + 6] = clock64();
       }
       __syncwarp();
       if (++s == STAGES) { s = 0; ++use; }
@@ -398,6 +414,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       mbar_wait(acc_full, 0);
       tc_fence_after_sync();
     }
+    if (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1021] = clock64();
     const int row = warp * 32 + lane;
     const int grow = m0 + row;
     const bool row_ok = grow < a.n_out;
@@ -504,6 +521,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       }
     }
   }
+  if (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1020] = clock64();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
@@ -670,6 +688,8 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   GemmParams p;
   p.a = *args;
   p.n_chunks = cdiv(args->c_in, kChunk);
+  p.trace = g_trace;
+  p.trace_block = g_trace_block;
   p.vec_ok = (args->ld_in % 4 == 0) && (((uintptr_t)args->in & 15) == 0) && (args->c_in % 8 == 0);
   p.out_vec_ok = (args->ld_out % 4 == 0) && (((uintptr_t)args->out & 15) == 0) &&
                  (!args->bias || ((uintptr_t)args->bias & 15) == 0) &&
@@ -727,6 +747,14 @@ int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scal
   UD3D_CHECK_ARG((scale == nullptr) == (shift == nullptr), "ud3d_act_split: scale/shift must both be set");
   if (n == 0) return UD3D_OK;
   return launch_act_split(raw, ld_raw, n, c, scale, shift, relu, out_split, ld_out, (cudaStream_t)stream);
+}
+
+/* debug only (not declared in the public header): record clock64 timestamps of one CTA of subsequent
+ * ud3d_gemm_fwd launches into `buf` (device, >= 1024 int64), or stop with buf = NULL */
+int ud3d_debug_set_trace(long long* buf, int block) {
+  g_trace = buf;
+  g_trace_block = block;
+  return UD3D_OK;
 }
 
 int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream) {
