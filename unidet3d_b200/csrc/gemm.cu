@@ -22,7 +22,9 @@
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
 #include "common.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
+#include <string.h>
 
 namespace ud3d {
 
@@ -34,6 +36,7 @@ struct GemmParams {
   int n_chunks;
   int vec_ok;      // 16-byte vector gather allowed
   int out_vec_ok;  // 16-byte vector epilogue allowed
+  int use_tma;     // operand-form input gathered by TMA tile::gather4 (else cp.async)
   long long* trace;   // debug: clock64 timestamps of one CTA (ud3d_debug_set_trace), else nullptr
   int trace_block;
 };
@@ -113,7 +116,7 @@ struct GatherRegs {
 };
 
 template <int N_TILE, int D_INFLIGHT = TcCfg<N_TILE>::kInFlight>
-__global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_a) {
   constexpr int STAGES = TcCfg<N_TILE>::kStages;
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = N_TILE * 128;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&a_full[s], kProducerWarps);
+      mbar_init(&a_full[s], p.use_tma ? 1 : kProducerWarps);
       mbar_init(&b_full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -169,12 +172,23 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   // dependent table -> row load chain from the mainloop)
   uint32_t mybits = 0;
   if (has_table) {
-    for (int i = tid; i < a.K * kTileM; i += kThreadsTc) {
-      int k = i >> 7, r = i & 127;
-      int row = m0 + r;
-      int v = row < a.n_out ? __ldg(a.table + (size_t)k * a.n_out + row) : -1;
-      s_tbl[i] = v;
-      if (v >= 0) mybits |= 1u << k;
+    // all loads of a thread are issued back to back (one L2 round trip for the whole slice)
+    constexpr int kPer = (32 * kTileM + kThreadsTc - 1) / kThreadsTc;   // 13
+    int vals[kPer];
+    const int total = a.K * kTileM;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + j * kThreadsTc;
+      const int k = i >> 7, row = m0 + (i & 127);
+      vals[j] = (i < total && row < a.n_out) ? __ldg(a.table + (size_t)k * a.n_out + row) : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + j * kThreadsTc;
+      if (i < total) {
+        s_tbl[i] = vals[j];
+        if (vals[j] >= 0) mybits |= 1u << (i >> 7);
+      }
     }
   }
   tc_fence_before_sync();
@@ -207,7 +221,9 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
 
   if (warp < kProducerWarps) {
     // =========================================================== A producers
-    if (a.in_split) {
+    if (p.use_tma) {
+      // operand-form input gathered by the TMA warp (tile::gather4): nothing to do here
+    } else if (a.in_split) {
       // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
       //      zero-fill for missing neighbours; D steps of copies in flight per thread, no ALU work
       constexpr int D = D_INFLIGHT;
@@ -363,17 +379,30 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       }
     }
   } else if (warp == kWarpB) {
-    // =========================================================== B producer: one bulk copy per step
+    // =========================================================== TMA warp: weight tile (bulk copy) and, for
+    // operand-form inputs, the A tile: 32 lanes x one tile::gather4 (4 rows x 128 B, hardware 128B swizzle,
+    // rows with index -1 are out of bounds and arrive zero-filled) = 128 rows per step, no LSU traffic
     int kslot = kslot0, c = chunk0, s = 0;
     uint32_t use = 0;
+    const uint32_t sA_addr = smem_u32(sA);
     for (int t = 0; t < nsteps; ++t) {
+      const int k = s_actk[kslot];
       if (lane == 0) {
         if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-        const int k = s_actk[kslot];
         mbar_arrive_expect_tx(&b_full[s], B_BYTES);
         bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
+        if (p.use_tma) mbar_arrive_expect_tx(&a_full[s], A_BYTES);
       }
       __syncwarp();
+      if (p.use_tma) {
+        int r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = 4 * lane + i;
+          r[i] = has_table ? s_tbl[k * kTileM + row] : ((m0 + row < a.n_out) ? m0 + row : -1);
+        }
+        tma_gather4(sA_addr + s * A_BYTES + lane * 512, &tmap_a, c * 64, r[0], r[1], r[2], r[3], &a_full[s]);
+      }
       if (++c == p.n_chunks) { c = 0; ++kslot; }
       if (++s == STAGES) { s = 0; ++use; }
     }
@@ -602,6 +631,48 @@ static size_t tc_smem_bytes(int n_chunks, int K, bool has_table) {
          (has_table ? (size_t)K * kTileM * 4 : 0);
 }
 
+// ---- TMA descriptor of the operand-form input: 2-D tensor of bf16 [rows, c_in*2], row pitch ld_in*4 bytes,
+//      box = 64 elements (128 B = one 32-channel chunk, hi|lo) x 1 row, 128B swizzle, zero fill out of bounds
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+static int make_tmap_a(CUtensorMap* tm, const ud3d_gemm_args& a) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return UD3D_ECUDA;
+  }
+  static int box_rows = -1;
+  if (box_rows < 0) {
+    const char* e = getenv("UD3D_GATHER4_BOXROWS");
+    box_rows = e ? atoi(e) : 1;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)a.c_in * 2, (cuuint64_t)1 << 30};     // rows: upper bound only (indices come from the rulebook)
+  cuuint64_t gstride[1] = {(cuuint64_t)a.ld_in * 4};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.in, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return UD3D_ECUDA;
+  }
+  return UD3D_OK;
+}
+
 template <int N_TILE, int D>
 static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
   size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr);
@@ -610,8 +681,14 @@ static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  alignas(64) CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  if (p.use_tma) {
+    int rc = make_tmap_a(&tm, p.a);
+    if (rc) return rc;
+  }
   dim3 grid(cdiv(p.a.n_out, kTileM), n_tiles, splits);
-  gather_gemm_tc_kernel<N_TILE, D><<<grid, kThreadsTc, smem, st>>>(p);
+  gather_gemm_tc_kernel<N_TILE, D><<<grid, kThreadsTc, smem, st>>>(p, tm);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }
@@ -690,6 +767,14 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   p.n_chunks = cdiv(args->c_in, kChunk);
   p.trace = g_trace;
   p.trace_block = g_trace_block;
+  {
+    static int tma_mode = -1;   // UD3D_GATHER=ldgsts selects the cp.async gather instead of TMA tile::gather4
+    if (tma_mode < 0) {
+      const char* e = getenv("UD3D_GATHER");
+      tma_mode = (e && e[0] == 'l') ? 0 : 1;
+    }
+    p.use_tma = (args->in_split && tma_mode) ? 1 : 0;
+  }
   p.vec_ok = (args->ld_in % 4 == 0) && (((uintptr_t)args->in & 15) == 0) && (args->c_in % 8 == 0);
   p.out_vec_ok = (args->ld_out % 4 == 0) && (((uintptr_t)args->out & 15) == 0) &&
                  (!args->bias || ((uintptr_t)args->bias & 15) == 0) &&
