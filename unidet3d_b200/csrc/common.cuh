@@ -162,15 +162,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                : "memory");
 }
 
-// TMA tile::gather4: four rows (row coordinates r0..r3, column coordinate c0 in elements) of a 2-D tensor map
-// -> four consecutive box-rows at smem_dst, completion bytes on an mbarrier (PTX ISA 8.6, sm_100)
-__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const void* tmap, int c0, int r0, int r1, int r2, int r3,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-      ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
-      : "memory");
-}
 // 16-byte async copy global -> shared (LDGSTS, L2-only caching); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes) : "memory");

@@ -22,7 +22,6 @@
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
 #include "common.cuh"
 
-#include <cuda.h>      // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,7 +35,6 @@ struct GemmParams {
   int n_chunks;
   int vec_ok;      // 16-byte vector gather allowed
   int out_vec_ok;  // 16-byte vector epilogue allowed
-  int use_tma;     // operand-form input gathered by TMA tile::gather4 (else cp.async)
   long long* trace;   // debug: clock64 timestamps of one CTA (ud3d_debug_set_trace), else nullptr
   int trace_block;
 };
@@ -116,7 +114,7 @@ struct GatherRegs {
 };
 
 template <int N_TILE, int D_INFLIGHT = TcCfg<N_TILE>::kInFlight>
-__global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_a) {
+__global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p) {
   constexpr int STAGES = TcCfg<N_TILE>::kStages;
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = N_TILE * 128;
@@ -150,7 +148,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&a_full[s], p.use_tma ? 1 : kProducerWarps);
+      mbar_init(&a_full[s], kProducerWarps);
       mbar_init(&b_full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -221,9 +219,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
 
   if (warp < kProducerWarps) {
     // =========================================================== A producers
-    if (p.use_tma) {
-      // operand-form input gathered by the TMA warp (tile::gather4): nothing to do here
-    } else if (a.in_split) {
+    if (a.in_split) {
       // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
       //      zero-fill for missing neighbours; D steps of copies in flight per thread, no ALU work
       constexpr int D = D_INFLIGHT;
@@ -379,61 +375,60 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       }
     }
   } else if (warp == kWarpB) {
-    // =========================================================== TMA warp: weight tile (bulk copy) and, for
-    // operand-form inputs, the A tile: 32 lanes x one tile::gather4 (4 rows x 128 B, hardware 128B swizzle,
-    // rows with index -1 are out of bounds and arrive zero-filled) = 128 rows per step, no LSU traffic
+    // =========================================================== B producer: one bulk copy (TMA engine) per step
     int kslot = kslot0, c = chunk0, s = 0;
     uint32_t use = 0;
-    const uint32_t sA_addr = smem_u32(sA);
-    for (int t = 0; t < nsteps; ++t) {
-      const int k = s_actk[kslot];
-      if (lane == 0) {
+    if (lane == 0) {
+      for (int t = 0; t < nsteps; ++t) {
         if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+        const int k = s_actk[kslot];
         mbar_arrive_expect_tx(&b_full[s], B_BYTES);
         bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
-        if (p.use_tma) mbar_arrive_expect_tx(&a_full[s], A_BYTES);
+        if (++c == p.n_chunks) { c = 0; ++kslot; }
+        if (++s == STAGES) { s = 0; ++use; }
       }
-      __syncwarp();
-      if (p.use_tma) {
-        int r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = 4 * lane + i;
-          r[i] = has_table ? s_tbl[k * kTileM + row] : ((m0 + row < a.n_out) ? m0 + row : -1);
-        }
-        tma_gather4(sA_addr + s * A_BYTES + lane * 512, &tmap_a, c * 64, r[0], r[1], r[2], r[3], &a_full[s]);
-      }
-      if (++c == p.n_chunks) { c = 0; ++kslot; }
-      if (++s == STAGES) { s = 0; ++use; }
     }
+    __syncwarp();
   } else {
-    // =========================================================== MMA issuer
-    int s = 0;
-    uint32_t use = 0;
-    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-    for (int t = 0; t < nsteps; ++t) {
-      if (lane == 0) {
-        long long* tr = (p.trace && (int)blockIdx.x == p.trace_block) ? p.trace : nullptr;
-        mbar_wait(&a_full[s], use & 1u);
-        if (tr && t < 64) tr[t * 8 + 4] = clock64();
-        mbar_wait(&b_full[s], use & 1u);
-        if (tr && t < 64) tr[t * 8 + 5] = clock64();
-        tc_fence_after_sync();
-        const uint32_t a_addr = sA_addr + s * A_BYTES, b_addr = sB_addr + s * B_BYTES;
-        // K-steps of 16 bf16 = 32 bytes inside the 128B row: hi at +0,+32 ; lo at +64,+96
-        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 0), IDESC, t > 0);
-        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 32), IDESC, 1);
-        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 64), umma_desc_sw128(b_addr + 0), IDESC, 1);
-        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 96), umma_desc_sw128(b_addr + 32), IDESC, 1);
-        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 0), umma_desc_sw128(b_addr + 64), IDESC, 1);
-        umma_bf16(tmem_base, umma_desc_sw128(a_addr + 32), umma_desc_sw128(b_addr + 96), IDESC, 1);
-        umma_commit(&empty[s]);            // stage s reusable once these MMAs have read it
-        if (tr && t < 64) tr[t * 8 + 6] = clock64();
+    // =========================================================== MMA issuer (one lane; the other 31 idle at the
+    // final barrier).  A single thread's dependent instruction chain is the latency of this role, so the
+    // smem descriptors of every stage are built once and each K-step only adds the +32/+64/+96-byte offsets.
+    if (lane == 0) {
+      uint64_t adesc[STAGES], bdesc[STAGES];
+#pragma unroll
+      for (int i = 0; i < STAGES; ++i) {
+        adesc[i] = umma_desc_sw128(smem_u32(sA + i * A_BYTES));
+        bdesc[i] = umma_desc_sw128(smem_u32(sB + i * B_BYTES));
       }
-      __syncwarp();
-      if (++s == STAGES) { s = 0; ++use; }
+      long long* tr = (p.trace && (int)blockIdx.x == p.trace_block) ? p.trace : nullptr;
+      uint32_t use = 0;
+      int t = 0;
+      while (t < nsteps) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+          if (t < nsteps) {
+            mbar_wait(&a_full[s], use & 1u);
+            if (tr && t < 64) tr[t * 8 + 4] = clock64();
+            mbar_wait(&b_full[s], use & 1u);
+            if (tr && t < 64) tr[t * 8 + 5] = clock64();
+            tc_fence_after_sync();
+            const uint64_t ad = adesc[s], bd = bdesc[s];
+            // start-address field is in 16-byte units: +2 = 32 B (second K=16 slice), +4 = lo half, +6 = lo second slice
+            umma_bf16(tmem_base, ad + 0, bd + 0, IDESC, t > 0);
+            umma_bf16(tmem_base, ad + 2, bd + 2, IDESC, 1);
+            umma_bf16(tmem_base, ad + 4, bd + 0, IDESC, 1);
+            umma_bf16(tmem_base, ad + 6, bd + 2, IDESC, 1);
+            umma_bf16(tmem_base, ad + 0, bd + 4, IDESC, 1);
+            umma_bf16(tmem_base, ad + 2, bd + 6, IDESC, 1);
+            umma_commit(&empty[s]);            // stage s reusable once these MMAs have read it
+            if (tr && t < 64) tr[t * 8 + 6] = clock64();
+            ++t;
+          }
+        }
+        ++use;
+      }
+      umma_commit(acc_full);
     }
-    if (lane == 0) umma_commit(acc_full);
     __syncwarp();
   }
 
@@ -631,48 +626,6 @@ static size_t tc_smem_bytes(int n_chunks, int K, bool has_table) {
          (has_table ? (size_t)K * kTileM * 4 : 0);
 }
 
-// ---- TMA descriptor of the operand-form input: 2-D tensor of bf16 [rows, c_in*2], row pitch ld_in*4 bytes,
-//      box = 64 elements (128 B = one 32-channel chunk, hi|lo) x 1 row, 128B swizzle, zero fill out of bounds
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-static int make_tmap_a(CUtensorMap* tm, const ud3d_gemm_args& a) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) {
-    set_error("cuTensorMapEncodeTiled is not available from the driver");
-    return UD3D_ECUDA;
-  }
-  static int box_rows = -1;
-  if (box_rows < 0) {
-    const char* e = getenv("UD3D_GATHER4_BOXROWS");
-    box_rows = e ? atoi(e) : 1;
-  }
-  cuuint64_t gdim[2] = {(cuuint64_t)a.c_in * 2, (cuuint64_t)1 << 30};     // rows: upper bound only (indices come from the rulebook)
-  cuuint64_t gstride[1] = {(cuuint64_t)a.ld_in * 4};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)a.in, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return UD3D_ECUDA;
-  }
-  return UD3D_OK;
-}
-
 template <int N_TILE, int D>
 static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
   size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr);
@@ -681,14 +634,8 @@ static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  alignas(64) CUtensorMap tm;
-  memset(&tm, 0, sizeof(tm));
-  if (p.use_tma) {
-    int rc = make_tmap_a(&tm, p.a);
-    if (rc) return rc;
-  }
   dim3 grid(cdiv(p.a.n_out, kTileM), n_tiles, splits);
-  gather_gemm_tc_kernel<N_TILE, D><<<grid, kThreadsTc, smem, st>>>(p, tm);
+  gather_gemm_tc_kernel<N_TILE, D><<<grid, kThreadsTc, smem, st>>>(p);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }
@@ -767,14 +714,6 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   p.n_chunks = cdiv(args->c_in, kChunk);
   p.trace = g_trace;
   p.trace_block = g_trace_block;
-  {
-    static int tma_mode = -1;   // UD3D_GATHER=ldgsts selects the cp.async gather instead of TMA tile::gather4
-    if (tma_mode < 0) {
-      const char* e = getenv("UD3D_GATHER");
-      tma_mode = (e && e[0] == 'l') ? 0 : 1;
-    }
-    p.use_tma = (args->in_split && tma_mode) ? 1 : 0;
-  }
   p.vec_ok = (args->ld_in % 4 == 0) && (((uintptr_t)args->in & 15) == 0) && (args->c_in % 8 == 0);
   p.out_vec_ok = (args->ld_out % 4 == 0) && (((uintptr_t)args->out & 15) == 0) &&
                  (!args->bias || ((uintptr_t)args->bias & 15) == 0) &&
