@@ -182,6 +182,10 @@ int ud3d_attention_fwd(const float* qkv, const int32_t* cu_seqlens, int B, int m
 /* same with the output stored in operand form (one head = one 32-channel chunk) for the out-projection GEMM */
 int ud3d_attention_fwd_split(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
                              float* out_split, void* stream);
+/* both the packed q|k|v projection and the output in operand form (the QKV GEMM writes it with out_act):
+ * K/V tiles stream through cp.async as raw 128-byte rows, no per-tile conversion */
+int ud3d_attention_fwd_opform(const float* qkv_split, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
+                              float* out_split, void* stream);
 /* PredBBox exp + _bbox_pred_to_bbox (encoder.py:109-111,241-283): raw [T,ld_raw>=8], centres [T,3]
  * -> out [T, with_angle ? 7 : 6] */
 int ud3d_bbox_decode(const float* raw, int ld_raw, const float* centers, int T, int with_angle,

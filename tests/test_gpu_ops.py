@@ -362,3 +362,25 @@ def test_gemm_operand_form_in_and_out(c_in, c_out, K, n):
     ops.gemm(xs, ops.PackedWeight(w.to(DEV)), table=torch.as_tensor(table).to(DEV), in_split=True, no_raw=True,
              acts=[(a3, s1.to(DEV), h1.to(DEV))])
     assert relerr(split_decode(a3.cpu()), torch.relu((ref - res) * s1 + h1)) < 2e-4
+
+
+@pytest.mark.parametrize("lens", [[37, 21, 50], [300, 1], [1000, 64, 65, 129, 128], [1700, 1650]])
+def test_attention_operand_form(lens):
+    """q|k|v and the output in operand form (what the encoder uses): cp.async K/V ring + ldmatrix.trans path."""
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(sum(lens) + 1)
+    H, d = 8, 256
+    Tt = sum(lens)
+    qkv = torch.randn(Tt, 3 * d, generator=g) * 1.5
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32)
+    ref = []
+    for i, T in enumerate(lens):
+        s = qkv[cu[i]:cu[i + 1]]
+        q, k, v = [s[:, j * d:(j + 1) * d].view(T, H, 32).transpose(0, 1) for j in range(3)]
+        a = torch.softmax(q @ k.transpose(1, 2) / 32 ** 0.5, -1) @ v
+        ref.append(a.transpose(0, 1).reshape(T, d))
+    ref = torch.cat(ref)
+    out_s = ops.attention(split_encode(qkv).to(DEV), cu.to(DEV), max(lens), H, split_in=True)
+    assert relerr(split_decode(out_s.cpu()), ref) < 1e-4, relerr(split_decode(out_s.cpu()), ref)
+    out_s2 = ops.attention(qkv.to(DEV), cu.to(DEV), max(lens), H, split_out=True)
+    assert relerr(split_decode(out_s2.cpu()), ref) < 1e-4

@@ -339,6 +339,200 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- attention on operand-form q|k|v
+// Input: the QKV projection already in operand form (per token, per head: 64 B bf16 hi | 64 B bf16 lo for each of
+// q, k, v; written once by the QKV GEMM epilogue).  CTA = 128 queries of one (scene, head), 8 warps x 16 rows;
+// K/V tiles of 64 keys stream through a 2-stage cp.async ring as raw 128-byte rows (XOR-swizzled 16-byte chunks:
+// conflict-free fragment loads, V fragments via ldmatrix.trans) -- no per-tile conversion, loads overlap the MMAs.
+constexpr int kAtt2Q = 128, kAtt2KV = 64;
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t smem_addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_addr));
+}
+
+__global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __restrict__ qkv, const int32_t* __restrict__ cu,
+                                                               int num_heads, uint8_t* __restrict__ out) {
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int t0 = cu[b];
+  const int T = cu[b + 1] - t0;
+  const int q0 = blockIdx.x * kAtt2Q;
+  if (q0 >= T) return;
+  const int d_model = num_heads * kHeadDim;
+  const size_t ldb = (size_t)3 * d_model * 4;          // bytes per token row of qkv
+  const size_t ldo = (size_t)d_model * 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  __shared__ __align__(128) uint8_t sK[2][kAtt2KV * 128];
+  __shared__ __align__(128) uint8_t sV[2][kAtt2KV * 128];
+
+  auto load_tile = [&](int stage, int kv0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = tid + 256 * i;
+      const int which = id >> 9, rem = id & 511;
+      const int key = rem >> 3, j = rem & 7;
+      const int kr = kv0 + key;
+      const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + j * 16;
+      uint8_t* dst = (which ? sV[stage] : sK[stage]) + key * 128 + ((j ^ (key & 7)) << 4);
+      cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
+    }
+    cp_async_commit();
+  };
+
+  // ---- Q fragments straight from the operand form
+  uint32_t qh[2][4], ql[2][4];
+  {
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {
+        const int row = (part & 1) ? r1 : r0;
+        const int col = ks * 16 + 2 * t + ((part >> 1) ? 8 : 0);
+        uint32_t vh = 0, vl = 0;
+        if (row < T) {
+          const uint8_t* qp = qkv + (size_t)(t0 + row) * ldb + (size_t)h * 128 + col * 2;
+          vh = *(const uint32_t*)qp;
+          vl = *(const uint32_t*)(qp + 64);
+        }
+        qh[ks][part] = vh;
+        ql[ks][part] = vl;
+      }
+    }
+  }
+  const float qscale = 1.44269504088896340736f * 0.17677669529663688110f;   // log2(e) / sqrt(32)
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+  const int n_tiles = (T + kAtt2KV - 1) / kAtt2KV;
+  load_tile(0, 0);
+  for (int it = 0; it < n_tiles; ++it) {
+    const int stage = it & 1;
+    const int kv0 = it * kAtt2KV;
+    if (it + 1 < n_tiles) {
+      load_tile(stage ^ 1, kv0 + kAtt2KV);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const uint8_t* Ks = sK[stage];
+    const uint32_t Vs = smem_u32(sV[stage]);
+
+    // ---- S = Q K^T  (16 x 64 per warp)
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+      const uint8_t* krow = Ks + (nt * 8 + g) * 128;      // key & 7 == g
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t bh0 = *(const uint32_t*)(krow + (((2 * ks) ^ g) << 4) + 4 * t);
+        const uint32_t bh1 = *(const uint32_t*)(krow + (((2 * ks + 1) ^ g) << 4) + 4 * t);
+        const uint32_t bl0 = *(const uint32_t*)(krow + (((4 + 2 * ks) ^ g) << 4) + 4 * t);
+        const uint32_t bl1 = *(const uint32_t*)(krow + (((5 + 2 * ks) ^ g) << 4) + 4 * t);
+        mma_bf16_16816(s[nt], qh[ks], bh0, bh1);
+        mma_bf16_16816(s[nt], ql[ks], bh0, bh1);
+        mma_bf16_16816(s[nt], qh[ks], bl0, bl1);
+      }
+    }
+    // ---- scale, mask keys >= T, online softmax
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int kc = kv0 + nt * 8 + 2 * t;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[nt][j] *= qscale;
+      if (kc >= T) s[nt][0] = s[nt][2] = -INFINITY;
+      if (kc + 1 >= T) s[nt][1] = s[nt][3] = -INFINITY;
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+    float alpha[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      float m_new = fmaxf(m_run[r], mx[r]);
+      alpha[r] = exp2f(m_run[r] - m_new);
+      m_run[r] = m_new;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = exp2f(s[nt][0] - m_run[0]);
+      s[nt][1] = exp2f(s[nt][1] - m_run[0]);
+      s[nt][2] = exp2f(s[nt][2] - m_run[1]);
+      s[nt][3] = exp2f(s[nt][3] - m_run[1]);
+      rs[0] += s[nt][0] + s[nt][1];
+      rs[1] += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 1);
+      rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
+      l_run[r] = l_run[r] * alpha[r] + rs[r];
+    }
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn) {
+      o[dn][0] *= alpha[0]; o[dn][1] *= alpha[0];
+      o[dn][2] *= alpha[1]; o[dn][3] *= alpha[1];
+    }
+    // ---- O += P V : V fragments by ldmatrix.trans from the row-major (key, dim) tile
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t ph[4], pl[4];
+      split_bf16x2(s[2 * j][0], s[2 * j][1], ph[0], pl[0]);
+      split_bf16x2(s[2 * j][2], s[2 * j][3], ph[1], pl[1]);
+      split_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
+      split_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
+      // lane -> (matrix = lane >> 3, row = lane & 7): matrices {keys 0-7, keys 8-15} x {dim tile dn, dn + 1}
+      const int key = 16 * j + (lane & 7) + ((lane >> 3) & 1) * 8;
+      const uint32_t vrow = Vs + key * 128;
+      const int csel = lane >> 4;
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {
+        uint32_t vh[4], vl[4];
+        ldmatrix_x4_trans(vh, vrow + (((2 * dp + csel) ^ (key & 7)) << 4));
+        ldmatrix_x4_trans(vl, vrow + (((4 + 2 * dp + csel) ^ (key & 7)) << 4));
+        mma_bf16_16816(o[2 * dp], ph, vh[0], vh[1]);
+        mma_bf16_16816(o[2 * dp], pl, vh[0], vh[1]);
+        mma_bf16_16816(o[2 * dp], ph, vl[0], vl[1]);
+        mma_bf16_16816(o[2 * dp + 1], ph, vh[2], vh[3]);
+        mma_bf16_16816(o[2 * dp + 1], pl, vh[2], vh[3]);
+        mma_bf16_16816(o[2 * dp + 1], ph, vl[2], vl[3]);
+      }
+    }
+    __syncthreads();   // everyone is done with this stage before it is refilled
+  }
+  // ---- finalize: operand-form output (head h == chunk h)
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+  const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
+#pragma unroll
+  for (int dn = 0; dn < 4; ++dn) {
+    uint32_t hi, lo;
+    if (r0 < T) {
+      split_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0, hi, lo);
+      uint8_t* d = out + (size_t)(t0 + r0) * ldo + h * 128 + (dn * 8 + 2 * t) * 2;
+      *(uint32_t*)d = hi;
+      *(uint32_t*)(d + 64) = lo;
+    }
+    if (r1 < T) {
+      split_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1, hi, lo);
+      uint8_t* d = out + (size_t)(t0 + r1) * ldo + h * 128 + (dn * 8 + 2 * t) * 2;
+      *(uint32_t*)d = hi;
+      *(uint32_t*)(d + 64) = lo;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- box decode / column gather
 __global__ void bbox_decode_kernel(const float* __restrict__ raw, int ld_raw, const float* __restrict__ centers, int T,
                                    int with_angle, float* __restrict__ out) {
@@ -466,6 +660,18 @@ int ud3d_attention_fwd(const float* qkv, const int32_t* cu_seqlens, int B, int m
 int ud3d_attention_fwd_split(const float* qkv, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
                              float* out_split, void* stream) {
   return attention_impl(qkv, cu_seqlens, B, max_T, num_heads, out_split, true, stream);
+}
+
+int ud3d_attention_fwd_opform(const float* qkv_split, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
+                              float* out_split, void* stream) {
+  UD3D_CHECK_ARG(qkv_split && cu_seqlens && out_split, "ud3d_attention_fwd_opform: NULL argument");
+  UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd_opform: bad sizes");
+  UD3D_CHECK_ARG((((uintptr_t)qkv_split | (uintptr_t)out_split) & 15) == 0, "ud3d_attention_fwd_opform: pointers must be 16-byte aligned");
+  if (max_T == 0) return UD3D_OK;
+  dim3 grid(cdiv(max_T, kAtt2Q), num_heads, B);
+  attention_opform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads, (uint8_t*)out_split);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
 }
 
 int ud3d_bbox_decode(const float* raw, int ld_raw, const float* centers, int T, int with_angle, float* out, void* stream) {

@@ -167,8 +167,9 @@ class UniDet3DEncoder(nn.Module):
                 c, b = self._forward_head(p, H, centers, bounds, ds_idx)
                 cls_all.append(c), box_all.append(b)
             for li, lp in enumerate(p["layers"]):
-                qkv = ops.gemm(H_s, lp["qkv"][0], bias=lp["qkv"][1], in_split=True)
-                A_s = ops.attention(qkv, cu, max_T, self.num_heads, split_out=True)
+                qkv_s = torch.empty((n, 3 * d), dtype=torch.float32, device=X.device)
+                ops.gemm(H_s, lp["qkv"][0], bias=lp["qkv"][1], in_split=True, no_raw=True, acts=[(qkv_s, None, None, False)])
+                A_s = ops.attention(qkv_s, cu, max_T, self.num_heads, split_in=True)
                 Z = ops.gemm(A_s, lp["out"][0], bias=lp["out"][1], residual=H, in_split=True)
                 H, H_s = ops.layernorm_split(Z, lp["n1"][0], lp["n1"][1], eps=lp["n1"][2])
                 F_s = torch.empty((n, hidden), dtype=torch.float32, device=X.device)
