@@ -31,7 +31,7 @@ def test_argument_errors_are_reported_not_crashing():
     rc = lib.ud3d_gemm_fwd(None, None)
     assert rc == -1 and b"NULL" in lib.ud3d_last_error()
     assert lib.ud3d_gemm_packed_weight_bytes(27, 32, 32) == 27 * 32 * 128
-    assert lib.ud3d_gemm_packed_weight_bytes(1, 256, 768) == 3 * 8 * 256 * 128
+    assert lib.ud3d_gemm_packed_weight_bytes(1, 256, 768) == 768 * 8 * 128
 
 
 def test_no_cpu_fallback():

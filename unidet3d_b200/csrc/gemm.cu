@@ -48,7 +48,14 @@ static inline int pick_ntile(int c_out) {
   if (c_out <= 96) return 96;
   if (c_out <= 128) return 128;
   if (c_out <= 160) return 160;
-  return 256;
+  // wide dense GEMMs: tuning knob UD3D_NTILE_WIDE (128 keeps 2 CTAs/SM, 256 halves the A re-reads); the packed
+  // weight image depends on it, so it is read once per process
+  static int wide = 0;
+  if (!wide) {
+    const char* e = getenv("UD3D_NTILE_WIDE");
+    wide = (e && atoi(e) == 256) ? 256 : 128;
+  }
+  return wide;
 }
 
 // ---------------------------------------------------------------- weight packing
@@ -100,11 +107,12 @@ constexpr int kThreadsTc = 32 * 10;
 
 // Ring depth S and copies-in-flight D per instantiation.  A stage cycles fill (L2 latency L) -> MMA round
 // trip (M: a_full arrive -> issue -> tcgen05.commit -> empty) -> refill, so steady-state step time per CTA is
-// ~max(L / D, M / (S - D)): D = S / 2 balances the two (measured: D = S - 1 makes every step pay the full
-// ~1400-cycle MMA round trip).  S is the largest depth that keeps 2 CTAs/SM (1 CTA/SM for N_TILE >= 160).
+// bounded by  D * T >= L  and  (S - D - 1) * T >= M  (a stage published at iteration t + D must be free again at
+// t + S).  Traced on B200: L ~ M ~ 1000 cycles, so D = 1 with S = 4 (T >= M / 2) beats D = 2 (T >= M) and
+// D = 3 (every step pays the full round trip).  S is the largest depth that keeps 2 CTAs/SM (1 for N_TILE >= 160).
 template <int N_TILE> struct TcCfg {
   static constexpr int kStages = N_TILE <= 64 ? 4 : N_TILE <= 128 ? 3 : N_TILE == 160 ? 5 : 4;
-  static constexpr int kInFlight = kStages / 2;
+  static constexpr int kInFlight = N_TILE == 160 ? 2 : 1;
 };
 
 // Raw gathered operand of one K-step for this thread: 2 rows x 8 channels
