@@ -218,6 +218,24 @@ int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pt
                     const float* boxes, int box_dim, const int32_t* box_index, int m, const int32_t* m_dev,
                     float low_thr, float up_thr, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ fused per-scene post-processing
+ * predict_by_feat for one scene (unidet3d.py:475-538) as ONE host call: softmax/top-k -> candidate box gather ->
+ * multi-class NMS -> (optional) superpoint trimming, ~13 kernel launches issued back to back from C++ on `stream`
+ * (lets several scenes run concurrently on different streams without per-launch interpreter overhead).
+ * Outputs (all device, caller-owned): scores[k], labels[k], cand[k,box_dim] (candidate boxes in score order),
+ * keep[k] + n_keep[1] (kept candidate indices: ascending class, descending score), trimmed[k,6] (row j = trimmed box
+ * of candidate keep[j]; only when use_trim). */
+typedef struct {
+  const float* logits; int32_t ld_logits; int32_t T; int32_t C1;
+  const float* boxes; int32_t box_dim;
+  int32_t k; int32_t nms_mode; float iou_thr; float score_thr;
+  int32_t use_trim; const float* points; int32_t ld_pts; const int64_t* sp; int32_t n_pts; int32_t n_sp;
+  float low_thr; float up_thr;
+  float* scores; int32_t* labels; float* cand; int32_t* keep; int32_t* n_keep; float* trimmed;
+} ud3d_post_args;
+size_t ud3d_postprocess_workspace_bytes(const ud3d_post_args* args);
+int ud3d_postprocess_scene(const ud3d_post_args* args, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

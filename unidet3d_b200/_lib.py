@@ -34,6 +34,19 @@ class GemmArgs(C.Structure):
     ]
 
 
+class PostArgs(C.Structure):
+    """Mirror of ``ud3d_post_args``."""
+    _fields_ = [
+        ("logits", C.c_void_p), ("ld_logits", C.c_int32), ("T", C.c_int32), ("C1", C.c_int32),
+        ("boxes", C.c_void_p), ("box_dim", C.c_int32),
+        ("k", C.c_int32), ("nms_mode", C.c_int32), ("iou_thr", C.c_float), ("score_thr", C.c_float),
+        ("use_trim", C.c_int32), ("points", C.c_void_p), ("ld_pts", C.c_int32), ("sp", C.c_void_p),
+        ("n_pts", C.c_int32), ("n_sp", C.c_int32), ("low_thr", C.c_float), ("up_thr", C.c_float),
+        ("scores", C.c_void_p), ("labels", C.c_void_p), ("cand", C.c_void_p), ("keep", C.c_void_p),
+        ("n_keep", C.c_void_p), ("trimmed", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list EVERY symbol declared in include/unidet3d_b200.h
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -67,6 +80,8 @@ SIGNATURES = {
     "ud3d_nms_workspace_bytes": (_sz, [_i]),
     "ud3d_nms_multiclass": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "ud3d_trim_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ud3d_postprocess_workspace_bytes": (_sz, [C.POINTER(PostArgs)]),
+    "ud3d_postprocess_scene": (_i, [C.POINTER(PostArgs), _vp, _sz, _vp]),
     "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _f, _f, _vp, _vp, _sz, _vp]),
 }
 

@@ -9,10 +9,10 @@
 namespace ud3d {
 
 // ---------------------------------------------------------------- softmax scores (drop last column)
-__global__ void softmax_scores_kernel(const float* __restrict__ logits, int T, int C1, float* __restrict__ scores) {
+__global__ void softmax_scores_kernel(const float* __restrict__ logits, int ld, int T, int C1, float* __restrict__ scores) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= T) return;
-  const float* l = logits + (size_t)t * C1;
+  const float* l = logits + (size_t)t * ld;
   float m = -INFINITY;
   for (int c = 0; c < C1; ++c) m = fmaxf(m, l[c]);
   float s = 0.f;
@@ -541,6 +541,14 @@ __global__ void trim_final_kernel(const int* __restrict__ aabb, int m, const int
   out[(size_t)b * 6 + 3 + d] = z - a;
 }
 
+__global__ void gather_rows_kernel(const float* __restrict__ src, int dim, const int32_t* __restrict__ idx, int n,
+                                   float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * dim) return;
+  int r = i / dim, c = i % dim;
+  out[i] = src[(size_t)idx[r] * dim + c];
+}
+
 }  // namespace ud3d
 
 using namespace ud3d;
@@ -560,7 +568,7 @@ int ud3d_topk_scores(const float* logits, int T, int C_plus1, int k, float* scor
     return UD3D_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  softmax_scores_kernel<<<cdiv(T, 128), 128, 0, st>>>(logits, T, C_plus1, (float*)ws);
+  softmax_scores_kernel<<<cdiv(T, 128), 128, 0, st>>>(logits, C_plus1, T, C_plus1, (float*)ws);
   UD3D_LAUNCH_CHECK();
   topk_select_kernel<<<1, 1024, 0, st>>>((const float*)ws, T * C, C, k, scores_out, labels_out, query_out);
   UD3D_LAUNCH_CHECK();
@@ -645,6 +653,54 @@ int ud3d_trim_boxes(const float* points, int ld_pts, const int64_t* sp, int n_pt
   }
   trim_final_kernel<<<cdiv(m * 3, 256), 256, 0, st>>>(w.aabb, m, m_dev, out);
   UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+size_t ud3d_postprocess_workspace_bytes(const ud3d_post_args* a) {
+  if (!a) return 0;
+  size_t b = align_up((size_t)(a->T > 0 ? a->T : 1) * (a->C1 > 1 ? a->C1 - 1 : 1) * 4, 256);   // scores
+  b += align_up((size_t)a->k * 4, 256);                                                        // query
+  b += align_up(ud3d_nms_workspace_bytes(a->k), 256);
+  if (a->use_trim) b += align_up(ud3d_trim_workspace_bytes(a->n_sp, a->n_pts, a->k), 256);
+  return b;
+}
+
+int ud3d_postprocess_scene(const ud3d_post_args* a, void* ws, size_t ws_bytes, void* stream) {
+  UD3D_CHECK_ARG(a && ws, "ud3d_postprocess_scene: NULL argument");
+  UD3D_CHECK_ARG(a->logits && a->boxes && a->scores && a->labels && a->cand && a->keep && a->n_keep, "ud3d_postprocess_scene: NULL buffer");
+  UD3D_CHECK_ARG(!a->use_trim || (a->points && a->sp && a->trimmed), "ud3d_postprocess_scene: trim needs points / sp / trimmed");
+  UD3D_CHECK_ARG(a->ld_logits >= a->C1 && a->T > 0 && a->C1 > 1 && a->k > 0 && a->k <= 1024, "ud3d_postprocess_scene: bad sizes");
+  UD3D_CHECK_ARG((long long)a->T * (a->C1 - 1) >= a->k, "ud3d_postprocess_scene: k=%d out of range for %lld scores", a->k,
+                 (long long)a->T * (a->C1 - 1));
+  if (ws_bytes < ud3d_postprocess_workspace_bytes(a)) {
+    set_error("ud3d_postprocess_scene: workspace too small");
+    return UD3D_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* p = (char*)ws;
+  float* scores_all = (float*)p;
+  p += align_up((size_t)a->T * (a->C1 - 1) * 4, 256);
+  int32_t* query = (int32_t*)p;
+  p += align_up((size_t)a->k * 4, 256);
+  void* nms_ws = p;
+  size_t nms_bytes = align_up(ud3d_nms_workspace_bytes(a->k), 256);
+  p += nms_bytes;
+  const int C = a->C1 - 1;
+  softmax_scores_kernel<<<cdiv(a->T, 128), 128, 0, st>>>(a->logits, a->ld_logits, a->T, a->C1, scores_all);
+  UD3D_LAUNCH_CHECK();
+  topk_select_kernel<<<1, 1024, 0, st>>>(scores_all, a->T * C, C, a->k, a->scores, a->labels, query);
+  UD3D_LAUNCH_CHECK();
+  gather_rows_kernel<<<cdiv(a->k * a->box_dim, 256), 256, 0, st>>>(a->boxes, a->box_dim, query, a->k, a->cand);
+  UD3D_LAUNCH_CHECK();
+  int rc = ud3d_nms_multiclass(a->cand, a->box_dim, a->scores, a->labels, a->k, a->nms_mode, a->iou_thr, a->score_thr, a->keep,
+                               a->n_keep, nms_ws, nms_bytes, stream);
+  if (rc) return rc;
+  if (a->use_trim) {
+    size_t tb = ud3d_trim_workspace_bytes(a->n_sp, a->n_pts, a->k);
+    rc = ud3d_trim_boxes(a->points, a->ld_pts, a->sp, a->n_pts, a->n_sp, a->cand, a->box_dim, a->keep, a->k, a->n_keep, a->low_thr,
+                         a->up_thr, a->trimmed, p, tb, stream);
+    if (rc) return rc;
+  }
   return UD3D_OK;
 }
 

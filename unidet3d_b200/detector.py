@@ -121,18 +121,46 @@ class UniDet3D(nn.Module):
         -> (boxes [<=k, 6|7] padded, scores, labels, keep idx, n_keep tensor)."""
         cfg = self.test_cfg
         k = int(cfg["topk_insts"])
-        scores, labels, query = ops.topk_scores(cls_preds, k)
-        # boxes of the selected queries, ordered like the candidates (a 1000-row gather: plumbing)
-        cand = pred_bboxes.index_select(0, query.long())
-        with_yaw = cand.shape[1] == 7
-        keep, n_keep = ops.nms_multiclass(cand, scores, labels, self._nms_mode(ds, with_yaw),
-                                          float(cfg["iou_thr"][ds]), float(cfg["score_thr"]))
-        trimmed = None
-        if self.use_superpoints[ds]:
-            trimmed = ops.trim_boxes(points_scene, sp_scene, n_sp, cand, float(cfg["low_sp_thr"]),
-                                     float(cfg["up_sp_thr"]), box_index=keep, m=k, m_dev=n_keep)
-        return dict(cand=cand, scores=scores, labels=labels, keep=keep, n_keep=n_keep, trimmed=trimmed,
-                    with_yaw=with_yaw, ds=ds)
+        with_yaw = pred_bboxes.shape[1] == 7
+        trim = bool(self.use_superpoints[ds])
+        r = ops.postprocess_scene(cls_preds, pred_bboxes, k, self._nms_mode(ds, with_yaw), float(cfg["iou_thr"][ds]),
+                                  float(cfg["score_thr"]), points=points_scene if trim else None,
+                                  sp=sp_scene if trim else None, n_sp=n_sp, low_thr=float(cfg["low_sp_thr"]),
+                                  up_thr=float(cfg["up_sp_thr"]))
+        r.update(with_yaw=with_yaw, ds=ds)
+        return r
+
+    def postprocess_batch(self, out, pts, sp_b, pt_off, sp_off, n_sps, ds_idx):
+        """Per-scene top-k / NMS / trim for a whole batch; returns the per-scene device-side result dicts."""
+        B = len(ds_idx)
+        dev = pts.device
+        # per-scene post-processing is independent: fan the scenes out over side streams so the
+        # single-CTA stages (top-k select, NMS order / sweep) of different scenes overlap
+        per_scene = [None] * B
+        cur = torch.cuda.current_stream()
+        if B > 1:
+            if getattr(self, "_post_streams", None) is None or len(self._post_streams) < min(B, 8):
+                self._post_streams = [torch.cuda.Stream(device=dev) for _ in range(min(B, 8))]
+            fork = torch.cuda.Event()
+            fork.record(cur)
+        for i in range(B):
+            a, b = int(pt_off[i]), int(pt_off[i + 1])
+
+            def run(i=i, a=a, b=b):
+                sp_local = sp_b[a:b] - int(sp_off[i]) if sp_off[i] else sp_b[a:b]
+                return self.predict_by_feat_scene(out["cls_preds"][i], out["bboxes"][i], pts[a:b], sp_local, n_sps[i],
+                                                  ds_idx[i])
+            if B > 1:
+                st = self._post_streams[i % len(self._post_streams)]
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    per_scene[i] = run()
+            else:
+                per_scene[i] = run()
+        if B > 1:
+            for st in self._post_streams[:min(B, len(self._post_streams))]:
+                cur.wait_stream(st)
+        return per_scene
 
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
@@ -183,32 +211,7 @@ class UniDet3D(nn.Module):
         ds_idx = [self.decoder.datasets.index(n) for n in datasets_names]
         out = self.decoder.forward_packed(pooled, sp_centers, [int(v) for v in sp_off], datasets_names)
 
-        # per-scene post-processing is independent: fan the scenes out over side streams so the
-        # single-CTA stages (top-k select, NMS order / sweep) of different scenes overlap
-        per_scene = [None] * B
-        cur = torch.cuda.current_stream()
-        if B > 1:
-            if getattr(self, "_post_streams", None) is None or len(self._post_streams) < min(B, 8):
-                self._post_streams = [torch.cuda.Stream(device=dev) for _ in range(min(B, 8))]
-            fork = torch.cuda.Event()
-            fork.record(cur)
-        for i in range(B):
-            a, b = int(pt_off[i]), int(pt_off[i + 1])
-
-            def run(i=i, a=a, b=b):
-                sp_local = sp_b[a:b] - int(sp_off[i]) if sp_off[i] else sp_b[a:b]
-                return self.predict_by_feat_scene(out["cls_preds"][i], out["bboxes"][i], pts[a:b], sp_local, n_sps[i],
-                                                  ds_idx[i])
-            if B > 1:
-                st = self._post_streams[i % len(self._post_streams)]
-                st.wait_event(fork)
-                with torch.cuda.stream(st):
-                    per_scene[i] = run()
-            else:
-                per_scene[i] = run()
-        if B > 1:
-            for st in self._post_streams[:min(B, len(self._post_streams))]:
-                cur.wait_stream(st)
+        per_scene = self.postprocess_batch(out, pts, sp_b, pt_off, sp_off, n_sps, ds_idx)
         # one D2H round-trip for the whole batch
         n_keeps = torch.cat([r["n_keep"] for r in per_scene]).cpu().tolist()
         results = []

@@ -337,3 +337,41 @@ def trim_boxes(points: torch.Tensor, sp: torch.Tensor, n_sp: int, boxes: torch.T
     check(_L().ud3d_trim_boxes(_p(points), points.stride(0), _p(sp), points.shape[0], n_sp, _p(boxes), boxes.shape[1],
                                _p(box_index), m, _p(m_dev), float(low_thr), float(up_thr), _p(out), _p(ws), wsb, _stream()), "ud3d_trim_boxes")
     return out
+
+
+def postprocess_scene(logits: torch.Tensor, boxes: torch.Tensor, k: int, nms_mode: int, iou_thr: float, score_thr: float,
+                      points: Optional[torch.Tensor] = None, sp: Optional[torch.Tensor] = None, n_sp: int = 0,
+                      low_thr: float = 0.0, up_thr: float = 1.0):
+    """predict_by_feat for one scene in ONE host call (see ud3d_postprocess_scene).  ``points``/``sp`` given =>
+    superpoint trimming.  Returns dict(scores, labels, cand, keep, n_keep, trimmed|None), all on the device."""
+    from ._lib import PostArgs
+    if not logits.is_cuda or logits.dtype != torch.float32 or logits.stride(1) != 1:
+        raise _lib.Ud3dError("postprocess_scene: logits must be a CUDA fp32 matrix with unit column stride")
+    _req(boxes, torch.float32, "boxes")
+    dev = logits.device
+    T, C1 = logits.shape
+    use_trim = points is not None
+    a = PostArgs()
+    a.logits = logits.data_ptr(); a.ld_logits = logits.stride(0); a.T = T; a.C1 = C1
+    a.boxes = boxes.data_ptr(); a.box_dim = boxes.shape[1]
+    a.k = k; a.nms_mode = nms_mode; a.iou_thr = float(iou_thr); a.score_thr = float(score_thr)
+    a.use_trim = 1 if use_trim else 0
+    if use_trim:
+        _req(sp, torch.int64, "sp")
+        a.points = points.data_ptr(); a.ld_pts = points.stride(0); a.sp = sp.data_ptr()
+        a.n_pts = points.shape[0]; a.n_sp = int(n_sp); a.low_thr = float(low_thr); a.up_thr = float(up_thr)
+    # one allocation for all outputs: scores | labels | keep | n_keep | cand | trimmed
+    bd = boxes.shape[1]
+    buf = torch.empty(k * (3 + bd + 6) + 8, dtype=torch.float32, device=dev)
+    scores = buf[:k]
+    labels = buf[k:2 * k].view(torch.int32)
+    keep = buf[2 * k:3 * k].view(torch.int32)
+    n_keep = buf[3 * k:3 * k + 1].view(torch.int32)
+    cand = buf[3 * k + 8:3 * k + 8 + k * bd].view(k, bd)
+    trimmed = buf[3 * k + 8 + k * bd:].view(k, 6) if use_trim else None
+    a.scores = scores.data_ptr(); a.labels = labels.data_ptr(); a.cand = cand.data_ptr(); a.keep = keep.data_ptr()
+    a.n_keep = n_keep.data_ptr(); a.trimmed = trimmed.data_ptr() if use_trim else None
+    wsb = int(_L().ud3d_postprocess_workspace_bytes(C.byref(a)))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    check(_L().ud3d_postprocess_scene(C.byref(a), _p(ws), wsb, _stream()), "ud3d_postprocess_scene")
+    return dict(scores=scores, labels=labels, cand=cand, keep=keep, n_keep=n_keep, trimmed=trimmed, _buf=buf)
