@@ -55,19 +55,38 @@ __global__ void __launch_bounds__(1024) topk_select_kernel(const float* __restri
       if ((key & mask) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      int rem = s_remaining;
-      int d = 255;
-      unsigned int above = 0;
-      for (; d > 0; --d) {
-        if (above + hist[d] >= (unsigned)rem) break;
-        above += hist[d];
+    if (tid < 32) {
+      // suffix scan over the 256 bins by one warp: lane l owns bins [8l, 8l+8)
+      const int rem = s_remaining;
+      unsigned int loc[8], tot = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        loc[j] = hist[tid * 8 + j];
+        tot += loc[j];
       }
-      s_remaining = rem - (int)above;
-      s_prefix = prefix | ((unsigned long long)d << shift);
-      s_mask = mask | (0xFFull << shift);
+      // inclusive suffix sum over lanes (higher lanes = larger digits)
+      unsigned int suf = tot;
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int y = __shfl_down_sync(0xffffffffu, suf, o);
+        if (tid + o < 32) suf += y;
+      }
+      const unsigned int above = suf - tot;           // elements in bins owned by higher lanes
+      const bool mine = above < (unsigned)rem && suf >= (unsigned)rem;
+      if (mine) {
+        int d = 7;
+        unsigned int a = above;
+        for (; d > 0; --d) {
+          if (a + loc[d] >= (unsigned)rem) break;
+          a += loc[d];
+        }
+        const bool exact = a + loc[d] == (unsigned)rem;   // the whole bin is selected: no finer digit needed
+        s_remaining = exact ? 0 : rem - (int)a;
+        s_prefix = prefix | ((unsigned long long)(tid * 8 + d) << shift);
+        s_mask = mask | (0xFFull << shift);
+      }
     }
     __syncthreads();
+    if (s_remaining == 0) break;
   }
   const unsigned long long kth = s_prefix;   // exact key of the k-th largest element (keys are unique)
   for (int i = tid; i < n; i += 1024) {
@@ -259,33 +278,77 @@ static inline NmsWs nms_ws_view(void* ws, int n) {
   return v;
 }
 
+constexpr int kNmsMaxLabel = 2048;   // labels must be in [0, kNmsMaxLabel)
+
 __global__ void __launch_bounds__(1024) nms_order_kernel(const float* __restrict__ boxes, int box_dim,
                                                          const float* __restrict__ scores,
                                                          const int32_t* __restrict__ labels, int n, float score_thr,
                                                          NmsWs w) {
-  __shared__ int s_label[1024];
-  __shared__ unsigned char s_valid[1024];
-  const int i = threadIdx.x;
-  bool valid = i < n && scores[i] > score_thr;
-  s_label[i] = i < n ? labels[i] : 0x7fffffff;
-  s_valid[i] = valid;
+  // stable counting sort by class of the score-sorted candidates: class histogram -> exclusive scan -> rank of each
+  // element among the earlier elements of its class (warp match + a running per-class counter, warps in order)
+  __shared__ int s_hist[kNmsMaxLabel];
+  __shared__ int s_run[kNmsMaxLabel];
+  __shared__ int s_part[32];
+  const int i = threadIdx.x, lane = i & 31, wp = i >> 5;
+  for (int c = i; c < kNmsMaxLabel; c += 1024) {
+    s_hist[c] = 0;
+    s_run[c] = 0;
+  }
   __syncthreads();
-  if (valid) {
-    int my = s_label[i], pos = 0;
-    for (int j = 0; j < n; ++j) {
-      if (!s_valid[j]) continue;
-      int lj = s_label[j];
-      pos += (lj < my) || (lj == my && j < i);
+  const int lab = i < n ? labels[i] : -1;
+  const bool valid = i < n && scores[i] > score_thr && lab >= 0 && lab < kNmsMaxLabel;
+  if (valid) atomicAdd(&s_hist[lab], 1);
+  __syncthreads();
+  // exclusive scan of the histogram (2 entries per thread)
+  int h0 = s_hist[2 * i], h1 = s_hist[2 * i + 1];
+  int x = h0 + h1;
+  int incl = x;
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s_part[wp] = incl;
+  __syncthreads();
+  if (wp == 0) {
+    int t = s_part[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
     }
+    s_part[lane] = t;
+  }
+  __syncthreads();
+  const int base = incl - x + (wp > 0 ? s_part[wp - 1] : 0);
+  const int nv = s_part[31];
+  __syncthreads();
+  s_hist[2 * i] = base;            // class start offsets
+  s_hist[2 * i + 1] = base + h0;
+  __syncthreads();
+  // rank within class, warps processed in order
+  const unsigned same = __match_any_sync(0xffffffffu, valid ? lab : -1 - lane);
+  const int intra = __popc(same & ((1u << lane) - 1u));
+  int rank = 0;
+  for (int ww = 0; ww < 32; ++ww) {
+    if (wp == ww) {
+      const int r0 = valid ? s_run[lab] : 0;          // every lane reads before any lane of the warp updates
+      __syncwarp();
+      if (valid) {
+        rank = r0 + intra;
+        if (intra == 0) s_run[lab] = r0 + __popc(same);   // the first lane of each label group advances the counter
+      }
+    }
+    __syncthreads();
+  }
+  if (valid) {
+    const int pos = s_hist[lab] + rank;
     w.sorted_idx[pos] = i;
-    w.sorted_label[pos] = my;
+    w.sorted_label[pos] = lab;
     const float* b = boxes + (size_t)i * box_dim;
     float* o = w.boxes7 + (size_t)pos * 7;
 #pragma unroll
     for (int d = 0; d < 6; ++d) o[d] = b[d];
     o[6] = box_dim == 7 ? b[6] : 0.f;
   }
-  int nv = __syncthreads_count(valid);
   if (i == 0) *w.n_valid = nv;
 }
 
@@ -316,29 +379,90 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(NmsWs w, int n, int mode, 
   w.mask[(size_t)i * 16 + cb] = bits;
 }
 
-// stage 3: greedy sweep by one warp over the bit matrix staged in shared memory
+// stage 3: greedy sweep.  Boxes only suppress boxes of their own class, and the class-major order makes every class a
+// contiguous segment, so the segments are swept independently: warp w takes segments w, w+32, ... (bit matrix staged
+// in shared memory); kept flags are then compacted in order (ascending class, descending score).
 __global__ void __launch_bounds__(1024) nms_sweep_kernel(NmsWs w, int32_t* __restrict__ keep_out, int32_t* __restrict__ n_keep) {
   extern __shared__ unsigned long long smask[];
+  __shared__ unsigned char s_keep[1024];
+  __shared__ int s_segstart[1025];
+  __shared__ int s_nseg;
+  __shared__ int s_part[32];
   const int nv = *w.n_valid;
   const int nblk = (nv + 63) / 64;
-  for (int t = threadIdx.x; t < nv * 16; t += blockDim.x) {
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  for (int t = tid; t < nv * 16; t += blockDim.x) {
     int i = t >> 4, c = t & 15;
     smask[t] = (c < nblk && c >= (i >> 6)) ? w.mask[t] : 0ull;
   }
+  s_keep[tid] = 0;
+  if (tid == 0) s_nseg = 0;
   __syncthreads();
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  unsigned long long removed = 0ull;   // lane c (< 16) owns column block c
-  int kept = 0;
-  for (int i = 0; i < nv; ++i) {
-    unsigned long long r = __shfl_sync(0xffffffffu, removed, i >> 6);
-    if (!((r >> (i & 63)) & 1ull)) {
-      if (lane == 0) keep_out[kept] = w.sorted_idx[i];
-      ++kept;
-      if (lane < 16) removed |= smask[i * 16 + lane];
+  // segment starts: positions where the label changes (ordered list via warp-aggregated append is not needed:
+  // flag + ordered scan)
+  const bool is_start = tid < nv && (tid == 0 || w.sorted_label[tid] != w.sorted_label[tid - 1]);
+  {
+    int f = is_start ? 1 : 0, incl = f;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_part[wp] = incl;
+    __syncthreads();
+    if (wp == 0) {
+      int t = s_part[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_part[lane] = t;
+    }
+    __syncthreads();
+    const int pos = incl - f + (wp > 0 ? s_part[wp - 1] : 0);
+    if (is_start) s_segstart[pos] = tid;
+    if (tid == 0) {
+      s_nseg = s_part[31];
+    }
+    __syncthreads();
+    if (tid == 0) s_segstart[s_nseg] = nv;
+    __syncthreads();
+  }
+  const int nseg = s_nseg;
+  for (int sg = wp; sg < nseg; sg += 32) {
+    const int st = s_segstart[sg], en = s_segstart[sg + 1];
+    const int w0 = st >> 6;
+    unsigned long long removed = 0ull;     // lane j owns 64-bit word w0 + j of the removed set
+    for (int i = st; i < en; ++i) {
+      const unsigned long long r = __shfl_sync(0xffffffffu, removed, (i >> 6) - w0);
+      if (!((r >> (i & 63)) & 1ull)) {
+        if (lane == 0) s_keep[i] = 1;
+        if (w0 + lane < 16) removed |= smask[i * 16 + w0 + lane];
+      }
     }
   }
-  if (lane == 0) *n_keep = kept;
+  __syncthreads();
+  // ordered compaction of the kept flags
+  {
+    int f = (tid < nv && s_keep[tid]) ? 1 : 0, incl = f;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_part[wp] = incl;
+    __syncthreads();
+    if (wp == 0) {
+      int t = s_part[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_part[lane] = t;
+    }
+    __syncthreads();
+    const int pos = incl - f + (wp > 0 ? s_part[wp - 1] : 0);
+    if (f) keep_out[pos] = w.sorted_idx[tid];
+    if (tid == 0) *n_keep = s_part[31];
+  }
 }
 
 // ---------------------------------------------------------------- superpoint trimming
