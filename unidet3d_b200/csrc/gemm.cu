@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
       }
       int kslot = kslot0, c = chunk0, s = 0, pub_s = 0;
       uint32_t use = 0;
+      uint32_t dirty = 0xFFFFFFFFu;        // bit (stage*4 + i): this thread's chunk i of the stage may hold non-zero data
       long long* tr = (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) ? p.trace : nullptr;
       if (tr) { tr[1023] = nsteps; tr[1022] = clock64(); }
       for (int t = 0; t < nsteps; ++t) {
@@ -260,7 +261,16 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int idx = has_table ? trow[32 * i] : ident[i];
-          cp_async_16_zfill(as_addr + dst_off[i], sb + (size_t)(idx < 0 ? 0 : idx) * row_bytes, idx >= 0 ? 16u : 0u);
+          const uint32_t bit = 1u << (s * 4 + i);
+          if (idx >= 0) {
+            cp_async_16(as_addr + dst_off[i], sb + (size_t)idx * row_bytes);
+            dirty |= bit;
+          } else if (dirty & bit) {
+            // missing neighbour: the chunk must read as zero.  It only needs a store when the previous use of this
+            // stage left data there (~60 % of all (row, offset) slots are missing: most of them cost nothing)
+            st_shared_zero16(as_addr + dst_off[i]);
+            dirty &= ~bit;
+          }
         }
         cp_async_commit();
         if (tr && t < 64) tr[t * 8 + 1] = clock64();
