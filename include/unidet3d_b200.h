@@ -149,7 +149,8 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream);
 /* operand form of a feature map: per row, per 32-channel chunk, 64 bytes of bf16 "hi" followed by 64 bytes of
  * bf16 "lo" (x ~= hi + lo), i.e. the same 4 bytes per element as fp32 and exactly the 128-byte row of the
  * kernel's shared-memory tile.  out_split[r, c] = split(relu?(raw[r, c] * scale[c] + shift[c])); scale may be
- * NULL (identity).  c % 32 == 0; ld in 4-byte units. */
+ * NULL (identity).  ld in 4-byte units; when c is not a multiple of 32 the last chunk is zero-padded
+ * (ld_out >= roundup(c, 32)). */
 int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scale, const float* shift, int relu,
                    float* out_split, int ld_out, void* stream);
 /* same contract, plain fp32 CUDA-core kernel on the unpacked weight w [C_out,K,C_in]

@@ -100,6 +100,100 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// One thread's 32 consecutive output columns [col0, col0+32) of row `grow`: bias / activation / residual, fp32 store
+// and/or operand-form stores (or the red.add of a split-K partial).  r = raw fp32 accumulator bits.
+__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], int grow, int col0,
+                                                     bool split, bool lead) {
+  const ud3d_gemm_args& a = p.a;
+  if (col0 >= a.c_out) return;
+  float* orow = a.out + (size_t)grow * a.ld_out;
+  const float* rrow = (a.residual && lead) ? a.residual + (size_t)grow * a.ld_res : nullptr;
+  const float* bias = lead ? a.bias : nullptr;
+  if (split) {
+    // partial sums of a split-K launch: fp32 red.add into the pre-zeroed output (act == 0 enforced;
+    // operand-form outputs are produced afterwards by act_split kernels on the host side of this call)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      int col = col0 + j;
+      if (col < a.c_out) {
+        float v = __uint_as_float(r[j]);
+        if (bias) v += __ldg(bias + col);
+        if (rrow) v += __ldg(rrow + col);
+        atomicAdd(orow + col, v);
+      }
+    }
+    return;
+  }
+  // final fp32 values of this thread's 32 columns
+  float v[32];
+  const bool full = col0 + 32 <= a.c_out;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.out_vec_ok && full) {
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 b = __ldg((const float4*)(bias + col0 + j));
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (a.act) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
+    }
+    if (rrow) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 t = __ldg((const float4*)(rrow + col0 + j));
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    }
+    if (!a.no_raw) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *(float4*)(orow + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      int col = col0 + j;
+      if (col < a.c_out) {
+        if (bias) v[j] += __ldg(bias + col);
+        v[j] = apply_act(v[j], a.act);
+        if (rrow) v[j] += __ldg(rrow + col);
+        if (!a.no_raw) orow[col] = v[j];
+      }
+    }
+  }
+  // operand-form outputs for the consumer convs: relu(v * scale + shift) -> bf16 hi | lo, one 128-byte row-chunk
+#pragma unroll
+  for (int oi = 0; oi < 2; ++oi) {
+    if (!a.out_act[oi]) continue;      // (c_out % 32 == 0 enforced on the host: `full` holds)
+    const float* sc = a.act_scale[oi] ? a.act_scale[oi] + col0 : nullptr;
+    const float* sh = a.act_scale[oi] ? a.act_shift[oi] + col0 : nullptr;
+    const bool do_relu = !((a.act_norelu >> oi) & 1);
+    uint4* dst = (uint4*)((uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4);
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float x0 = v[j], x1 = v[j + 1];
+      if (sc) {
+        x0 = fmaf(x0, __ldg(sc + j), __ldg(sh + j));
+        x1 = fmaf(x1, __ldg(sc + j + 1), __ldg(sh + j + 1));
+      }
+      if (do_relu) {
+        x0 = fmaxf(x0, 0.f);
+        x1 = fmaxf(x1, 0.f);
+      }
+      split_bf16x2(x0, x1, hi[j >> 1], lo[j >> 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dst[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      dst[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+    }
+  }
+}
+
 constexpr int kProducerWarps = 8;                 // warps 0..7 gather A (warps 0..3 also run the epilogue)
 constexpr int kWarpB = 8;                         // warp 8: weight-tile bulk copies
 constexpr int kWarpMma = 9;                       // warp 9: tcgen05.mma issue
@@ -462,9 +556,6 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     const bool row_ok = grow < a.n_out;
     const bool split = gridDim.z > 1;
     const bool lead = blockIdx.z == 0;       // the split that adds bias / residual
-    float* orow = a.out + (size_t)(row_ok ? grow : 0) * a.ld_out;
-    const float* rrow = (a.residual && lead) ? a.residual + (size_t)(row_ok ? grow : 0) * a.ld_res : nullptr;
-    const float* bias = lead ? a.bias : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < N_TILE; c0 += 32) {
       uint32_t r[32];
@@ -476,91 +567,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       if (!row_ok) continue;
-      const int col0 = n0 + c0;
-      if (col0 >= a.c_out) continue;
-      if (split) {
-        // partial sums of a split-K launch: fp32 red.add into the pre-zeroed output (act == 0 enforced;
-        // operand-form outputs are produced afterwards by act_split kernels on the host side of this call)
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int col = col0 + j;
-          if (col < a.c_out) {
-            float v = __uint_as_float(r[j]);
-            if (bias) v += __ldg(bias + col);
-            if (rrow) v += __ldg(rrow + col);
-            atomicAdd(orow + col, v);
-          }
-        }
-        continue;
-      }
-      // final fp32 values of this thread's 32 columns
-      float v[32];
-      const bool full = col0 + 32 <= a.c_out;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.out_vec_ok && full) {
-        if (bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b = __ldg((const float4*)(bias + col0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
-        }
-        if (a.act) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
-        }
-        if (rrow) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 t = __ldg((const float4*)(rrow + col0 + j));
-            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-          }
-        }
-        if (!a.no_raw) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *(float4*)(orow + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int col = col0 + j;
-          if (col < a.c_out) {
-            if (bias) v[j] += __ldg(bias + col);
-            v[j] = apply_act(v[j], a.act);
-            if (rrow) v[j] += __ldg(rrow + col);
-            if (!a.no_raw) orow[col] = v[j];
-          }
-        }
-      }
-      // operand-form outputs for the consumer convs: relu(v * scale + shift) -> bf16 hi | lo, one 128-byte row-chunk
-#pragma unroll
-      for (int oi = 0; oi < 2; ++oi) {
-        if (!a.out_act[oi]) continue;      // (c_out % 32 == 0 enforced on the host: `full` holds)
-        const float* sc = a.act_scale[oi] ? a.act_scale[oi] + col0 : nullptr;
-        const float* sh = a.act_scale[oi] ? a.act_shift[oi] + col0 : nullptr;
-        const bool do_relu = !((a.act_norelu >> oi) & 1);
-        uint4* dst = (uint4*)((uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4);
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float x0 = v[j], x1 = v[j + 1];
-          if (sc) {
-            x0 = fmaf(x0, __ldg(sc + j), __ldg(sh + j));
-            x1 = fmaf(x1, __ldg(sc + j + 1), __ldg(sh + j + 1));
-          }
-          if (do_relu) {
-            x0 = fmaxf(x0, 0.f);
-            x1 = fmaxf(x1, 0.f);
-          }
-          split_bf16x2(x0, x1, hi[j >> 1], lo[j >> 1]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dst[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-          dst[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-        }
-      }
+      epilogue_store_chunk(p, r, grow, n0 + c0, split, lead);
     }
   }
   if (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1020] = clock64();
@@ -569,12 +576,406 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------- persistent gather-GEMM
+// One CTA per SM loops over work items (row tile, column tile, K-split).  Compared with the one-tile-per-CTA kernel
+// the smem ring never drains: the producers run ahead into the next tile while the MMA warp finishes the current one and
+// the epilogue warps drain the previous accumulator (two TMEM accumulator buffers); the next tile's rulebook slice is
+// prefetched during the current tile; barrier init / TMEM alloc happen once per SM instead of once per tile.
+//   warps 0-3  : epilogue (TMEM -> registers -> global), accumulator buffer i & 1
+//   warps 4-11 : A producers (cp.async operand-form gather, or fp32 gather + transform)
+//   warp 12    : weight tiles (cp.async.bulk)          warp 13 : tcgen05.mma issue
+constexpr int kPThreads = 32 * 14;
+constexpr int kPProdWarp0 = 4, kPProdThreads = 256, kPWarpB = 12;
+template <int N_TILE> struct PCfg {
+  static constexpr int kStages = N_TILE <= 64 ? 8 : N_TILE <= 128 ? 6 : N_TILE == 160 ? 5 : 4;
+  static constexpr int kInFlight = kStages >= 8 ? 3 : kStages >= 5 ? 2 : 1;
+  static constexpr uint32_t kAccCols = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+};
+
+struct WorkItem {
+  int m0, nt, z, nsteps, kslot0, chunk0;
+  uint32_t mask;       // active offsets of the row tile (bit k)
+};
+
+__device__ __forceinline__ WorkItem get_work(const GemmParams& p, int w, int n_ntiles, int splits) {
+  WorkItem wi;
+  wi.z = w % splits;
+  const int t = w / splits;
+  wi.nt = t % n_ntiles;
+  const int mt = t / n_ntiles;
+  wi.m0 = mt * kTileM;
+  const uint32_t all = p.a.K >= 32 ? 0xffffffffu : ((1u << p.a.K) - 1u);
+  wi.mask = p.a.table ? (p.a.tile_mask ? (p.a.tile_mask[mt] & all) : all) : 1u;
+  const int nsteps_all = __popc(wi.mask) * p.n_chunks;
+  const int tb = (int)((long long)nsteps_all * wi.z / splits);
+  const int te = (int)((long long)nsteps_all * (wi.z + 1) / splits);
+  wi.nsteps = te - tb;
+  wi.kslot0 = tb / p.n_chunks;
+  wi.chunk0 = tb - wi.kslot0 * p.n_chunks;
+  return wi;
+}
+// mask with its kslot0 lowest set bits removed: __ffs() then enumerates this split's offsets in order
+__device__ __forceinline__ uint32_t skip_bits(uint32_t mask, int n) {
+  for (int i = 0; i < n; ++i) mask &= mask - 1;
+  return mask;
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kPThreads, 1) gather_gemm_persistent_kernel(const GemmParams p, int n_work, int n_ntiles,
+                                                                              int splits) {
+  constexpr int STAGES = PCfg<N_TILE>::kStages;
+  constexpr int D = PCfg<N_TILE>::kInFlight;
+  constexpr int A_BYTES = kTileM * 128;
+  constexpr int B_BYTES = N_TILE * 128;
+  constexpr uint32_t ACC_COLS = PCfg<N_TILE>::kAccCols;
+  constexpr uint32_t IDESC = umma_idesc_bf16_m128(N_TILE);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* tail = sB + STAGES * B_BYTES;
+  uint64_t* a_full = (uint64_t*)tail;            // [STAGES] count = 8 producer warps
+  uint64_t* b_full = a_full + STAGES;            // [STAGES] count = 1 (+tx)
+  uint64_t* empty = b_full + STAGES;             // [STAGES] count = 1 (tcgen05.commit)
+  uint64_t* acc_full = empty + STAGES;           // [2] count = 1 (tcgen05.commit)
+  uint64_t* acc_empty = acc_full + 2;            // [2] count = 4 epilogue warps
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  float* s_scale = (float*)(tail + 256);
+  const ud3d_gemm_args& a = p.a;
+  const int c_in_pad = p.n_chunks * kChunk;
+  float* s_shift = s_scale + c_in_pad;
+  int32_t* s_tbl = (int32_t*)(s_shift + c_in_pad);   // [2][K][128] rulebook slices (current / next work item)
+  const int tbl_stride = a.K * kTileM;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_table = a.table != nullptr;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&a_full[s], 8);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (a.in_scale) {
+    for (int c = tid; c < c_in_pad; c += kPThreads) {
+      s_scale[c] = c < a.c_in ? a.in_scale[c] : 0.f;
+      s_shift[c] = c < a.c_in ? a.in_shift[c] : 0.f;
+    }
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 2 * ACC_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint8_t* w_all = (const uint8_t*)a.w_packed;
+
+  if (warp < 4) {
+    // =========================================================== epilogue warps
+    int n_used = 0;       // non-empty work items so far: accumulator buffer / phase bookkeeping (same rule as the MMA warp)
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      const WorkItem wi = get_work(p, w, n_ntiles, splits);
+      const int buf = n_used & 1;
+      const uint32_t use = (uint32_t)(n_used >> 1);
+      if (wi.nsteps > 0) {
+        if (lane == 0) mbar_wait(&acc_full[buf], use & 1u);
+        __syncwarp();
+        tc_fence_after_sync();
+      }
+      const int grow = wi.m0 + warp * 32 + lane;
+      const bool row_ok = grow < a.n_out;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t r[32];
+        if (wi.nsteps > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * ACC_COLS + (uint32_t)c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (row_ok) epilogue_store_chunk(p, r, grow, wi.nt * N_TILE + c0, splits > 1, wi.z == 0);
+      }
+      if (wi.nsteps > 0) {
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);     // accumulator buffer may be overwritten
+        ++n_used;
+      }
+    }
+  } else if (warp < kPWarpB) {
+    // =========================================================== A producers (256 threads)
+    const int ptid = tid - kPProdWarp0 * 32;
+    int s = 0;
+    uint32_t use = 0;
+    // rulebook slice of a work item -> registers (issued early) -> shared memory buffer
+    constexpr int kPer = (32 * kTileM + kPProdThreads - 1) / kPProdThreads;   // 16
+    int tv[kPer];
+    auto tbl_load = [&](int w) {
+      const int m0w = ((w / splits) / n_ntiles) * kTileM;
+      const int total = a.K * kTileM;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = ptid + j * kPProdThreads;
+        const int row = m0w + (i & 127);
+        tv[j] = (i < total && row < a.n_out) ? __ldg(a.table + (size_t)(i >> 7) * a.n_out + row) : -1;
+      }
+    };
+    auto tbl_store = [&](int b) {
+      const int total = a.K * kTileM;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = ptid + j * kPProdThreads;
+        if (i < total) s_tbl[b * tbl_stride + i] = tv[j];
+      }
+    };
+    if (has_table && (int)blockIdx.x < n_work) {
+      tbl_load(blockIdx.x);
+      tbl_store(0);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    if (a.in_split) {
+      // ---- operand-form input: cp.async 16 B per lane, D steps in flight, ring continues across work items
+      const size_t row_bytes = (size_t)a.ld_in * 4;
+      const int j = ptid & 7;
+      const int rbase = ptid >> 3;
+      const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
+      const uint32_t sA_addr = smem_u32(sA);
+      uint32_t dst_off[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rbase + 32 * i;
+        dst_off[i] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+      }
+      int pub_s = 0, pending = 0;      // pending = committed-but-unpublished steps (<= D)
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const WorkItem wi = get_work(p, w, n_ntiles, splits);
+        const int32_t* tb = s_tbl + (it & 1) * tbl_stride;
+        const int wn = w + gridDim.x;
+        if (has_table && wn < n_work) tbl_load(wn);             // in flight during this work item
+        uint32_t rem = skip_bits(wi.mask, wi.kslot0);
+        int k = __ffs(rem) - 1, c = wi.chunk0;
+        for (int t = 0; t < wi.nsteps; ++t) {
+          if (use) {
+            if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+            __syncwarp();
+          }
+          const int32_t* trow = tb + k * kTileM + rbase;
+          const uint8_t* sb = src_base + c * 128;
+          const uint32_t as_addr = sA_addr + s * A_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int idx;
+            if (has_table) idx = trow[32 * i];
+            else idx = (wi.m0 + rbase + 32 * i < a.n_out) ? wi.m0 + rbase + 32 * i : -1;
+            cp_async_16_zfill(as_addr + dst_off[i], sb + (size_t)(idx < 0 ? 0 : idx) * row_bytes, idx >= 0 ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (++c == p.n_chunks) { c = 0; rem &= rem - 1; k = __ffs(rem) - 1; }
+          if (++s == STAGES) { s = 0; ++use; }
+          if (pending == D) {
+            cp_async_wait<D>();             // the oldest unpublished step has landed
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[pub_s]);
+            if (++pub_s == STAGES) pub_s = 0;
+          } else {
+            ++pending;
+          }
+        }
+        if (has_table && wn < n_work) tbl_store((it + 1) & 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // next slice visible to all producers
+      }
+      // drain
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      for (int i = 0; i < pending; ++i) {
+        if (lane == 0) mbar_arrive(&a_full[pub_s]);
+        if (++pub_s == STAGES) pub_s = 0;
+      }
+    } else {
+      // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers (4 lanes per row, 8 channels each)
+      const int q = ptid & 3;
+      const int rl = ptid >> 2;
+      const bool affine = a.in_scale != nullptr;
+      const bool relu = a.in_relu != 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const WorkItem wi = get_work(p, w, n_ntiles, splits);
+        const int32_t* tb = s_tbl + (it & 1) * tbl_stride;
+        const int wn = w + gridDim.x;
+        if (has_table && wn < n_work) tbl_load(wn);
+        auto issue_loads = [&](int k, int c, GatherRegs& g) {
+          const int ch0 = c * kChunk + q * 8;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = rl + h * 64;
+            int idx;
+            if (has_table) idx = tb[k * kTileM + r];
+            else idx = (wi.m0 + r < a.n_out) ? wi.m0 + r : -1;
+            g.ok[h] = idx >= 0 && ch0 < a.c_in;
+            if (g.ok[h]) {
+              const float* src = a.in + (size_t)idx * a.ld_in + ch0;
+              if (p.vec_ok) {
+                g.v[h][0] = __ldg((const float4*)src);
+                g.v[h][1] = __ldg((const float4*)src + 1);
+              } else {
+                float e[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) e[jj] = (ch0 + jj < a.c_in) ? __ldg(src + jj) : 0.f;
+                g.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
+                g.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
+              }
+            }
+          }
+        };
+        auto store_step = [&](int c, const GatherRegs& g) {
+          const int ch0 = c * kChunk + q * 8;
+          if (use) {
+            if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+            __syncwarp();
+          }
+          uint8_t* As = sA + s * A_BYTES;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[8];
+            if (g.ok[h]) {
+              v[0] = g.v[h][0].x; v[1] = g.v[h][0].y; v[2] = g.v[h][0].z; v[3] = g.v[h][0].w;
+              v[4] = g.v[h][1].x; v[5] = g.v[h][1].y; v[6] = g.v[h][1].z; v[7] = g.v[h][1].w;
+              if (affine) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
+              }
+              if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              if (!p.vec_ok) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (ch0 + e >= a.c_in) v[e] = 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+            const int r = rl + h * 64;
+            uint8_t* arow = As + r * 128;
+            *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[s]);
+          if (++s == STAGES) { s = 0; ++use; }
+        };
+        GatherRegs g0, g1;
+        uint32_t rem = skip_bits(wi.mask, wi.kslot0);
+        int lk = __ffs(rem) - 1, lc = wi.chunk0, sc = wi.chunk0;
+        auto adv_load = [&]() { if (++lc == p.n_chunks) { lc = 0; rem &= rem - 1; lk = __ffs(rem) - 1; } };
+        auto adv_store = [&]() { if (++sc == p.n_chunks) sc = 0; };
+        if (wi.nsteps > 0) { issue_loads(lk, lc, g0); adv_load(); }
+        for (int t = 0; t < wi.nsteps; t += 2) {
+          if (t + 1 < wi.nsteps) { issue_loads(lk, lc, g1); adv_load(); }
+          store_step(sc, g0); adv_store();
+          if (t + 1 < wi.nsteps) {
+            if (t + 2 < wi.nsteps) { issue_loads(lk, lc, g0); adv_load(); }
+            store_step(sc, g1); adv_store();
+          }
+        }
+        if (has_table && wn < n_work) tbl_store((it + 1) & 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+    }
+  } else if (warp == kPWarpB) {
+    // =========================================================== B producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t use = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const WorkItem wi = get_work(p, w, n_ntiles, splits);
+        const uint8_t* wp = w_all + (size_t)wi.nt * a.K * p.n_chunks * B_BYTES;
+        uint32_t rem = skip_bits(wi.mask, wi.kslot0);
+        int k = __ffs(rem) - 1, c = wi.chunk0;
+        for (int t = 0; t < wi.nsteps; ++t) {
+          if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&b_full[s], B_BYTES);
+          bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
+          if (++c == p.n_chunks) { c = 0; rem &= rem - 1; k = __ffs(rem) - 1; }
+          if (++s == STAGES) { s = 0; ++use; }
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      uint64_t adesc[STAGES], bdesc[STAGES];
+#pragma unroll
+      for (int i = 0; i < STAGES; ++i) {
+        adesc[i] = umma_desc_sw128(smem_u32(sA + i * A_BYTES));
+        bdesc[i] = umma_desc_sw128(smem_u32(sB + i * B_BYTES));
+      }
+      int s = 0, n_used = 0;
+      uint32_t use = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const WorkItem wi = get_work(p, w, n_ntiles, splits);
+        if (wi.nsteps == 0) continue;            // (the epilogue writes zeros for an empty item)
+        const int buf = n_used & 1;
+        const uint32_t ause = (uint32_t)(n_used >> 1);
+        ++n_used;
+        if (ause) mbar_wait(&acc_empty[buf], (ause & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
+        for (int t = 0; t < wi.nsteps; ++t) {
+          mbar_wait(&a_full[s], use & 1u);
+          mbar_wait(&b_full[s], use & 1u);
+          tc_fence_after_sync();
+          uint64_t ad = adesc[0], bd = bdesc[0];
+#pragma unroll
+          for (int i = 1; i < STAGES; ++i)
+            if (s == i) { ad = adesc[i]; bd = bdesc[i]; }
+          umma_bf16(d_tmem, ad + 0, bd + 0, IDESC, t > 0);
+          umma_bf16(d_tmem, ad + 2, bd + 2, IDESC, 1);
+          umma_bf16(d_tmem, ad + 4, bd + 0, IDESC, 1);
+          umma_bf16(d_tmem, ad + 6, bd + 2, IDESC, 1);
+          umma_bf16(d_tmem, ad + 0, bd + 4, IDESC, 1);
+          umma_bf16(d_tmem, ad + 2, bd + 6, IDESC, 1);
+          umma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ++use; }
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 2 * ACC_COLS);
+}
+
 // ---------------------------------------------------------------- fp32 -> operand form (one warp per 4 row-chunks)
 __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict__ raw, int ld_raw, int n, int c,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
-                                                        int relu, float* __restrict__ out, int ld_out) {
-  // thread -> (row, chunk, 8-channel segment q): reads 32 B, writes 16 B hi + 16 B lo
-  const int chunks = c / kChunk;
+                                                        int relu, float* __restrict__ out, int ld_out, int vec) {
+  // thread -> (row, chunk, 8-channel segment q): reads 32 B, writes 16 B hi + 16 B lo.  c need not be a multiple of 32:
+  // the channels of the last chunk beyond c are written as zeros (e.g. the 6-channel voxel features -> one 32-ch chunk)
+  const int chunks = (c + kChunk - 1) / kChunk;
   const long long total = (long long)n * chunks * 4;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(t & 3);
@@ -583,11 +984,18 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
     const int row = (int)(rc / chunks);
     const int ch0 = ch * kChunk + q * 8;
     const float* src = raw + (size_t)row * ld_raw + ch0;
-    float4 x0 = *(const float4*)src, x1 = *((const float4*)src + 1);
-    float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float v[8];
+    if (vec) {
+      float4 x0 = *(const float4*)src, x1 = *((const float4*)src + 1);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (ch0 + e < c) ? src[e] : 0.f;
+    }
     if (scale) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], __ldg(scale + ch0 + e), __ldg(shift + ch0 + e));
+      for (int e = 0; e < 8; ++e)
+        if (ch0 + e < c) v[e] = fmaf(v[e], __ldg(scale + ch0 + e), __ldg(shift + ch0 + e));
     }
     if (relu) {
 #pragma unroll
@@ -604,11 +1012,12 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
 
 static int launch_act_split(const float* raw, int ld_raw, int n, int c, const float* scale, const float* shift, int relu,
                             float* out, int ld_out, cudaStream_t st) {
-  long long total = (long long)n * (c / kChunk) * 4;
+  long long total = (long long)n * cdiv(c, kChunk) * 4;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  act_split_kernel<<<blocks, 256, 0, st>>>(raw, ld_raw, n, c, scale, shift, relu, out, ld_out);
+  int vec = (c % 8 == 0) && (ld_raw % 4 == 0) && (((uintptr_t)raw & 15) == 0);
+  act_split_kernel<<<blocks, 256, 0, st>>>(raw, ld_raw, n, c, scale, shift, relu, out, ld_out, vec);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }
@@ -659,16 +1068,40 @@ static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_
 }
 
 template <int N_TILE>
-static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
-  // tuning knob (experiments): UD3D_GEMM_D overrides the number of cp.async steps in flight for N_TILE <= 64
-  static int d_override = -1;
-  if (d_override < 0) {
-    const char* e = getenv("UD3D_GEMM_D");
-    d_override = e ? atoi(e) : 0;
+static int launch_persistent(const GemmParams& p, int n_ntiles, int splits, cudaStream_t st) {
+  const bool has_table = p.a.table != nullptr;
+  size_t smem = 1024 + (size_t)PCfg<N_TILE>::kStages * (kTileM * 128 + N_TILE * 128) + 256 + (size_t)p.n_chunks * kChunk * 4 * 2 +
+                (has_table ? (size_t)2 * p.a.K * kTileM * 4 : 0);
+  if (smem > 227 * 1024) return 1;     // does not fit (very wide c_in): caller falls back to the per-tile kernel
+  static size_t configured = 0;
+  if (smem > configured) {
+    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_persistent_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
   }
-  if constexpr (N_TILE <= 64) {
-    if (d_override == 1) return launch_tc_d<N_TILE, 1>(p, n_tiles, splits, st);
-    if (d_override == 3) return launch_tc_d<N_TILE, 3>(p, n_tiles, splits, st);
+  static int n_sms = 0;
+  if (!n_sms) {
+    int dev = 0;
+    UD3D_CUDA(cudaGetDevice(&dev));
+    UD3D_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int n_work = cdiv(p.a.n_out, kTileM) * n_ntiles * splits;
+  const int grid = n_work < n_sms ? n_work : n_sms;
+  gather_gemm_persistent_kernel<N_TILE><<<grid, kPThreads, smem, st>>>(p, n_work, n_ntiles, splits);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+template <int N_TILE>
+static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
+  // UD3D_GEMM_KERNEL=tile selects the one-tile-per-CTA kernel (default: persistent)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("UD3D_GEMM_KERNEL");
+    mode = (e && e[0] == 't') ? 0 : 1;
+  }
+  if (mode == 1) {
+    int rc = launch_persistent<N_TILE>(p, n_tiles, splits, st);
+    if (rc <= 0) return rc;
   }
   return launch_tc_d<N_TILE, TcCfg<N_TILE>::kInFlight>(p, n_tiles, splits, st);
 }
@@ -783,9 +1216,8 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
 int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scale, const float* shift, int relu,
                    float* out_split, int ld_out, void* stream) {
   UD3D_CHECK_ARG(raw && out_split && n >= 0 && c > 0, "ud3d_act_split: bad argument");
-  UD3D_CHECK_ARG(c % 32 == 0 && ld_raw % 4 == 0 && ld_out % 4 == 0 && ld_raw >= c && ld_out >= c &&
-                     (((uintptr_t)raw | (uintptr_t)out_split) & 15) == 0,
-                 "ud3d_act_split: need c %% 32 == 0 and 16-byte aligned rows");
+  UD3D_CHECK_ARG(ld_out % 4 == 0 && ld_raw >= c && ld_out >= cdiv(c, 32) * 32 && ((uintptr_t)out_split & 15) == 0,
+                 "ud3d_act_split: out_split needs ld_out >= roundup(c, 32) and 16-byte aligned rows");
   UD3D_CHECK_ARG((scale == nullptr) == (shift == nullptr), "ud3d_act_split: scale/shift must both be set");
   if (n == 0) return UD3D_OK;
   return launch_act_split(raw, ld_raw, n, c, scale, shift, relu, out_split, ld_out, (cudaStream_t)stream);

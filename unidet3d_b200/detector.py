@@ -101,7 +101,11 @@ class UniDet3D(nn.Module):
         if self.unet.operand_form_ok():
             bn0 = self.unet.first_bn()
             f_act = torch.empty((lv0.n, plan["w_in"].c_out), dtype=torch.float32, device=x.features.device)
-            f = ops.gemm(x.features, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask, acts=[(f_act, bn0[0], bn0[1])])
+            # the 6-channel voxel features go through the operand form too (one zero-padded 32-channel chunk): the
+            # 27-offset gather then is the cp.async path instead of 24-byte scalar row loads
+            vox_s = ops.act_split(x.features, relu=False)
+            f = ops.gemm(vox_s, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask, in_split=True,
+                         acts=[(f_act, bn0[0], bn0[1])])
             x = x.replace_feature(f)
             x.features_act = f_act      # operand form for the U-Net's first conv, emitted by the input conv epilogue
         else:

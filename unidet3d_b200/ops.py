@@ -194,8 +194,9 @@ def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = No
         n_out = table.shape[1] if table is not None else x.shape[0]
     if out is None:
         out = torch.empty((n_out, w.c_out), dtype=torch.float32, device=x.device)
-    assert out.stride(1) == 1 and out.shape[1] == w.c_out and x.shape[1] == w.c_in
-    a = _gemm_args(x, w.K, w.c_in, w.c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act,
+    c_in = w.c_in if not in_split else (w.c_in + 31) // 32 * 32     # operand form pads the last chunk with zeros
+    assert out.stride(1) == 1 and out.shape[1] == w.c_out and x.shape[1] == c_in
+    a = _gemm_args(x, w.K, c_in, w.c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act,
                    residual, w.data.data_ptr(), in_split, no_raw, acts)
     check(_L().ud3d_gemm_fwd(C.byref(a), _stream()), "ud3d_gemm_fwd")
     return out
@@ -207,7 +208,7 @@ def act_split(raw: torch.Tensor, scale=None, shift=None, relu: bool = True, out:
         raise _lib.Ud3dError("act_split: raw must be a CUDA fp32 matrix with unit column stride")
     n, c = raw.shape
     if out is None:
-        out = torch.empty((n, c), dtype=torch.float32, device=raw.device)
+        out = torch.empty((n, (c + 31) // 32 * 32), dtype=torch.float32, device=raw.device)
     check(_L().ud3d_act_split(_p(raw), raw.stride(0), n, c, _p(scale), _p(shift), 1 if relu else 0, _p(out), out.stride(0),
                               _stream()), "ud3d_act_split")
     return out
