@@ -581,14 +581,17 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
 // the smem ring never drains: the producers run ahead into the next tile while the MMA warp finishes the current one and
 // the epilogue warps drain the previous accumulator (two TMEM accumulator buffers); the next tile's rulebook slice is
 // prefetched during the current tile; barrier init / TMEM alloc happen once per SM instead of once per tile.
-//   warps 0-3  : epilogue (TMEM -> registers -> global), accumulator buffer i & 1
-//   warps 4-11 : A producers (cp.async operand-form gather, or fp32 gather + transform)
-//   warp 12    : weight tiles (cp.async.bulk)          warp 13 : tcgen05.mma issue
-constexpr int kPThreads = 32 * 14;
-constexpr int kPProdWarp0 = 4, kPProdThreads = 256, kPWarpB = 12;
+//   warps 0-3  : epilogue (TMEM -> registers -> global), two accumulator buffers
+//   warps 4-19 : A producers in two groups of 8 warps that take alternate K-steps (a step is one dependent chain
+//                wait -> index -> address -> 4 x LDGSTS -> commit -> wait_group -> proxy fence -> arrive per warp, ~550
+//                cycles: two chains in flight per SM double the step rate)
+//   warp 20    : weight tiles (cp.async.bulk)          warp 21 : tcgen05.mma issue
+constexpr int kPGroups = 2;                       // producer groups: group g gathers the K-steps with (global step) % 2 == g
+constexpr int kPProdWarp0 = 4, kPProdThreads = 256 * kPGroups, kPWarpB = kPProdWarp0 + 8 * kPGroups;
+constexpr int kPThreads = 32 * (kPWarpB + 2);     // 4 epilogue + 16 producer + B + MMA warps = 704 threads
 template <int N_TILE> struct PCfg {
-  static constexpr int kStages = N_TILE <= 64 ? 8 : N_TILE <= 128 ? 6 : N_TILE == 160 ? 5 : 4;
-  static constexpr int kInFlight = kStages >= 8 ? 3 : kStages >= 5 ? 2 : 1;
+  static constexpr int kStages = N_TILE <= 64 ? 8 : N_TILE <= 128 ? 6 : 4;       // even: a stage always belongs to one group
+  static constexpr int kInFlight = kStages >= 6 ? 2 : 1;                         // cp.async steps in flight per group (< S/2)
   static constexpr uint32_t kAccCols = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
 };
 
@@ -621,7 +624,7 @@ __device__ __forceinline__ uint32_t skip_bits(uint32_t mask, int n) {
 }
 
 template <int N_TILE>
-__global__ void __launch_bounds__(kPThreads, 1) gather_gemm_persistent_kernel(const GemmParams p, int n_work, int n_ntiles,
+__global__ void __launch_bounds__(32 * 22, 1) gather_gemm_persistent_kernel(const GemmParams p, int n_work, int n_ntiles,
                                                                               int splits) {
   constexpr int STAGES = PCfg<N_TILE>::kStages;
   constexpr int D = PCfg<N_TILE>::kInFlight;
@@ -713,12 +716,12 @@ __global__ void __launch_bounds__(kPThreads, 1) gather_gemm_persistent_kernel(co
       }
     }
   } else if (warp < kPWarpB) {
-    // =========================================================== A producers (256 threads)
-    const int ptid = tid - kPProdWarp0 * 32;
-    int s = 0;
-    uint32_t use = 0;
+    // =========================================================== A producers (2 groups x 256 threads)
+    const int ptid = tid - kPProdWarp0 * 32;       // 0..511: rulebook-slice loading
+    const int grp = ptid >> 8;                     // producer group
+    const int gtid = ptid & 255;                   // thread within the group: row / chunk assignment
     // rulebook slice of a work item -> registers (issued early) -> shared memory buffer
-    constexpr int kPer = (32 * kTileM + kPProdThreads - 1) / kPProdThreads;   // 16
+    constexpr int kPer = (32 * kTileM + kPProdThreads - 1) / kPProdThreads;   // 8
     int tv[kPer];
     auto tbl_load = [&](int w) {
       const int m0w = ((w / splits) / n_ntiles) * kTileM;
@@ -742,13 +745,14 @@ __global__ void __launch_bounds__(kPThreads, 1) gather_gemm_persistent_kernel(co
       tbl_load(blockIdx.x);
       tbl_store(0);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    uint32_t g = 0;                                // global K-step index of this CTA (same sequence in every role)
 
     if (a.in_split) {
-      // ---- operand-form input: cp.async 16 B per lane, D steps in flight, ring continues across work items
+      // ---- operand-form input: cp.async 16 B per lane, D steps in flight per group, ring continues across work items
       const size_t row_bytes = (size_t)a.ld_in * 4;
-      const int j = ptid & 7;
-      const int rbase = ptid >> 3;
+      const int j = gtid & 7;
+      const int rbase = gtid >> 3;
       const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
       const uint32_t sA_addr = smem_u32(sA);
       uint32_t dst_off[4];
@@ -757,7 +761,8 @@ __global__ void __launch_bounds__(kPThreads, 1) gather_gemm_persistent_kernel(co
         const int r = rbase + 32 * i;
         dst_off[i] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
       }
-      int pub_s = 0, pending = 0;      // pending = committed-but-unpublished steps (<= D)
+      uint32_t pub_g = grp;            // global index of this group's next step to publish
+      int pending = 0;                 // committed-but-unpublished steps of this group (<= D)
       int it = 0;
       for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
         const WorkItem wi = get_work(p, w, n_ntiles, splits);
@@ -766,49 +771,52 @@ __global__ void __launch_bounds__(kPThreads, 1) gather_gemm_persistent_kernel(co
         if (has_table && wn < n_work) tbl_load(wn);             // in flight during this work item
         uint32_t rem = skip_bits(wi.mask, wi.kslot0);
         int k = __ffs(rem) - 1, c = wi.chunk0;
-        for (int t = 0; t < wi.nsteps; ++t) {
-          if (use) {
-            if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-            __syncwarp();
-          }
-          const int32_t* trow = tb + k * kTileM + rbase;
-          const uint8_t* sb = src_base + c * 128;
-          const uint32_t as_addr = sA_addr + s * A_BYTES;
+        for (int t = 0; t < wi.nsteps; ++t, ++g) {
+          if ((g & 1u) == (uint32_t)grp) {
+            const int s = (int)(g % STAGES);
+            const uint32_t use = g / STAGES;
+            if (use) {
+              if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+              __syncwarp();
+            }
+            const int32_t* trow = tb + k * kTileM + rbase;
+            const uint8_t* sb = src_base + c * 128;
+            const uint32_t as_addr = sA_addr + s * A_BYTES;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int idx;
-            if (has_table) idx = trow[32 * i];
-            else idx = (wi.m0 + rbase + 32 * i < a.n_out) ? wi.m0 + rbase + 32 * i : -1;
-            cp_async_16_zfill(as_addr + dst_off[i], sb + (size_t)(idx < 0 ? 0 : idx) * row_bytes, idx >= 0 ? 16u : 0u);
+            for (int i = 0; i < 4; ++i) {
+              int idx;
+              if (has_table) idx = trow[32 * i];
+              else idx = (wi.m0 + rbase + 32 * i < a.n_out) ? wi.m0 + rbase + 32 * i : -1;
+              cp_async_16_zfill(as_addr + dst_off[i], sb + (size_t)(idx < 0 ? 0 : idx) * row_bytes, idx >= 0 ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (pending == D) {
+              cp_async_wait<D>();             // this group's oldest unpublished step has landed
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&a_full[pub_g % STAGES]);
+              pub_g += 2;
+            } else {
+              ++pending;
+            }
           }
-          cp_async_commit();
           if (++c == p.n_chunks) { c = 0; rem &= rem - 1; k = __ffs(rem) - 1; }
-          if (++s == STAGES) { s = 0; ++use; }
-          if (pending == D) {
-            cp_async_wait<D>();             // the oldest unpublished step has landed
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[pub_s]);
-            if (++pub_s == STAGES) pub_s = 0;
-          } else {
-            ++pending;
-          }
         }
         if (has_table && wn < n_work) tbl_store((it + 1) & 1);
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // next slice visible to all producers
+        asm volatile("bar.sync 1, 512;" ::: "memory");          // next slice visible to all producers
       }
       // drain
       cp_async_wait<0>();
       fence_proxy_async_smem();
       __syncwarp();
       for (int i = 0; i < pending; ++i) {
-        if (lane == 0) mbar_arrive(&a_full[pub_s]);
-        if (++pub_s == STAGES) pub_s = 0;
+        if (lane == 0) mbar_arrive(&a_full[pub_g % STAGES]);
+        pub_g += 2;
       }
     } else {
       // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers (4 lanes per row, 8 channels each)
-      const int q = ptid & 3;
-      const int rl = ptid >> 2;
+      const int q = gtid & 3;
+      const int rl = gtid >> 2;
       const bool affine = a.in_scale != nullptr;
       const bool relu = a.in_relu != 0;
       int it = 0;
@@ -817,89 +825,79 @@ __global__ void __launch_bounds__(kPThreads, 1) gather_gemm_persistent_kernel(co
         const int32_t* tb = s_tbl + (it & 1) * tbl_stride;
         const int wn = w + gridDim.x;
         if (has_table && wn < n_work) tbl_load(wn);
-        auto issue_loads = [&](int k, int c, GatherRegs& g) {
-          const int ch0 = c * kChunk + q * 8;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int r = rl + h * 64;
-            int idx;
-            if (has_table) idx = tb[k * kTileM + r];
-            else idx = (wi.m0 + r < a.n_out) ? wi.m0 + r : -1;
-            g.ok[h] = idx >= 0 && ch0 < a.c_in;
-            if (g.ok[h]) {
-              const float* src = a.in + (size_t)idx * a.ld_in + ch0;
-              if (p.vec_ok) {
-                g.v[h][0] = __ldg((const float4*)src);
-                g.v[h][1] = __ldg((const float4*)src + 1);
-              } else {
-                float e[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) e[jj] = (ch0 + jj < a.c_in) ? __ldg(src + jj) : 0.f;
-                g.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
-                g.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
-              }
-            }
-          }
-        };
-        auto store_step = [&](int c, const GatherRegs& g) {
-          const int ch0 = c * kChunk + q * 8;
-          if (use) {
-            if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-            __syncwarp();
-          }
-          uint8_t* As = sA + s * A_BYTES;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float v[8];
-            if (g.ok[h]) {
-              v[0] = g.v[h][0].x; v[1] = g.v[h][0].y; v[2] = g.v[h][0].z; v[3] = g.v[h][0].w;
-              v[4] = g.v[h][1].x; v[5] = g.v[h][1].y; v[6] = g.v[h][1].z; v[7] = g.v[h][1].w;
-              if (affine) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
-              }
-              if (relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-              }
-              if (!p.vec_ok) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  if (ch0 + e >= a.c_in) v[e] = 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            }
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-            const int r = rl + h * 64;
-            uint8_t* arow = As + r * 128;
-            *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[s]);
-          if (++s == STAGES) { s = 0; ++use; }
-        };
-        GatherRegs g0, g1;
         uint32_t rem = skip_bits(wi.mask, wi.kslot0);
-        int lk = __ffs(rem) - 1, lc = wi.chunk0, sc = wi.chunk0;
-        auto adv_load = [&]() { if (++lc == p.n_chunks) { lc = 0; rem &= rem - 1; lk = __ffs(rem) - 1; } };
-        auto adv_store = [&]() { if (++sc == p.n_chunks) sc = 0; };
-        if (wi.nsteps > 0) { issue_loads(lk, lc, g0); adv_load(); }
-        for (int t = 0; t < wi.nsteps; t += 2) {
-          if (t + 1 < wi.nsteps) { issue_loads(lk, lc, g1); adv_load(); }
-          store_step(sc, g0); adv_store();
-          if (t + 1 < wi.nsteps) {
-            if (t + 2 < wi.nsteps) { issue_loads(lk, lc, g0); adv_load(); }
-            store_step(sc, g1); adv_store();
+        int k = __ffs(rem) - 1, c = wi.chunk0;
+        for (int t = 0; t < wi.nsteps; ++t, ++g) {
+          if ((g & 1u) == (uint32_t)grp) {
+            const int ch0 = c * kChunk + q * 8;
+            GatherRegs gr;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int r = rl + h * 64;
+              int idx;
+              if (has_table) idx = tb[k * kTileM + r];
+              else idx = (wi.m0 + r < a.n_out) ? wi.m0 + r : -1;
+              gr.ok[h] = idx >= 0 && ch0 < a.c_in;
+              if (gr.ok[h]) {
+                const float* src = a.in + (size_t)idx * a.ld_in + ch0;
+                if (p.vec_ok) {
+                  gr.v[h][0] = __ldg((const float4*)src);
+                  gr.v[h][1] = __ldg((const float4*)src + 1);
+                } else {
+                  float e[8];
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) e[jj] = (ch0 + jj < a.c_in) ? __ldg(src + jj) : 0.f;
+                  gr.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
+                  gr.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
+                }
+              }
+            }
+            const int s = (int)(g % STAGES);
+            const uint32_t use = g / STAGES;
+            if (use) {
+              if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+              __syncwarp();
+            }
+            uint8_t* As = sA + s * A_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float v[8];
+              if (gr.ok[h]) {
+                v[0] = gr.v[h][0].x; v[1] = gr.v[h][0].y; v[2] = gr.v[h][0].z; v[3] = gr.v[h][0].w;
+                v[4] = gr.v[h][1].x; v[5] = gr.v[h][1].y; v[6] = gr.v[h][1].z; v[7] = gr.v[h][1].w;
+                if (affine) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
+                }
+                if (relu) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                if (!p.vec_ok) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (ch0 + e >= a.c_in) v[e] = 0.f;
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+              const int r = rl + h * 64;
+              uint8_t* arow = As + r * 128;
+              *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[s]);
           }
+          if (++c == p.n_chunks) { c = 0; rem &= rem - 1; k = __ffs(rem) - 1; }
         }
         if (has_table && wn < n_work) tbl_store((it + 1) & 1);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
     }
   } else if (warp == kPWarpB) {
