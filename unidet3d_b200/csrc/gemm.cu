@@ -22,8 +22,6 @@
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
 #include "common.cuh"
 
-#include <stdlib.h>
-#include <string.h>
 
 namespace ud3d {
 
@@ -48,14 +46,8 @@ static inline int pick_ntile(int c_out) {
   if (c_out <= 96) return 96;
   if (c_out <= 128) return 128;
   if (c_out <= 160) return 160;
-  // wide dense GEMMs: tuning knob UD3D_NTILE_WIDE (128 keeps 2 CTAs/SM, 256 halves the A re-reads); the packed
-  // weight image depends on it, so it is read once per process
-  static int wide = 0;
-  if (!wide) {
-    const char* e = getenv("UD3D_NTILE_WIDE");
-    wide = (e && atoi(e) == 256) ? 256 : 128;
-  }
-  return wide;
+  // wide dense GEMMs (encoder): 128-column tiles keep 2 CTAs/SM (measured 7 % faster end to end than 256)
+  return 128;
 }
 
 // ---------------------------------------------------------------- weight packing
@@ -196,7 +188,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
 
 constexpr int kProducerWarps = 8;                 // warps 0..7 gather A (warps 0..3 also run the epilogue)
 constexpr int kWarpB = 8;                         // warp 8: weight-tile bulk copies
-constexpr int kWarpMma = 9;                       // warp 9: tcgen05.mma issue
+// warp 9: tcgen05.mma issue
 constexpr int kThreadsTc = 32 * 10;
 
 // Ring depth S and copies-in-flight D per instantiation.  A stage cycles fill (L2 latency L) -> MMA round
@@ -576,397 +568,6 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// ---------------------------------------------------------------- persistent gather-GEMM
-// One CTA per SM loops over work items (row tile, column tile, K-split).  Compared with the one-tile-per-CTA kernel
-// the smem ring never drains: the producers run ahead into the next tile while the MMA warp finishes the current one and
-// the epilogue warps drain the previous accumulator (two TMEM accumulator buffers); the next tile's rulebook slice is
-// prefetched during the current tile; barrier init / TMEM alloc happen once per SM instead of once per tile.
-//   warps 0-3  : epilogue (TMEM -> registers -> global), two accumulator buffers
-//   warps 4-19 : A producers in two groups of 8 warps that take alternate K-steps (a step is one dependent chain
-//                wait -> index -> address -> 4 x LDGSTS -> commit -> wait_group -> proxy fence -> arrive per warp, ~550
-//                cycles: two chains in flight per SM double the step rate)
-//   warp 20    : weight tiles (cp.async.bulk)          warp 21 : tcgen05.mma issue
-constexpr int kPGroups = 2;                       // producer groups: group g gathers the K-steps with (global step) % 2 == g
-constexpr int kPProdWarp0 = 4, kPProdThreads = 256 * kPGroups, kPWarpB = kPProdWarp0 + 8 * kPGroups;
-constexpr int kPThreads = 32 * (kPWarpB + 2);     // 4 epilogue + 16 producer + B + MMA warps = 704 threads
-template <int N_TILE> struct PCfg {
-  static constexpr int kStages = N_TILE <= 64 ? 8 : N_TILE <= 128 ? 6 : 4;       // even: a stage always belongs to one group
-  static constexpr int kInFlight = kStages >= 6 ? 2 : 1;                         // cp.async steps in flight per group (< S/2)
-  static constexpr uint32_t kAccCols = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
-};
-
-struct WorkItem {
-  int m0, nt, z, nsteps, kslot0, chunk0;
-  uint32_t mask;       // active offsets of the row tile (bit k)
-};
-
-__device__ __forceinline__ WorkItem get_work(const GemmParams& p, int w, int n_ntiles, int splits) {
-  WorkItem wi;
-  wi.z = w % splits;
-  const int t = w / splits;
-  wi.nt = t % n_ntiles;
-  const int mt = t / n_ntiles;
-  wi.m0 = mt * kTileM;
-  const uint32_t all = p.a.K >= 32 ? 0xffffffffu : ((1u << p.a.K) - 1u);
-  wi.mask = p.a.table ? (p.a.tile_mask ? (p.a.tile_mask[mt] & all) : all) : 1u;
-  const int nsteps_all = __popc(wi.mask) * p.n_chunks;
-  const int tb = (int)((long long)nsteps_all * wi.z / splits);
-  const int te = (int)((long long)nsteps_all * (wi.z + 1) / splits);
-  wi.nsteps = te - tb;
-  wi.kslot0 = tb / p.n_chunks;
-  wi.chunk0 = tb - wi.kslot0 * p.n_chunks;
-  return wi;
-}
-// mask with its kslot0 lowest set bits removed: __ffs() then enumerates this split's offsets in order
-__device__ __forceinline__ uint32_t skip_bits(uint32_t mask, int n) {
-  for (int i = 0; i < n; ++i) mask &= mask - 1;
-  return mask;
-}
-
-template <int N_TILE>
-__global__ void __launch_bounds__(32 * 22, 1) gather_gemm_persistent_kernel(const GemmParams p, int n_work, int n_ntiles,
-                                                                              int splits) {
-  constexpr int STAGES = PCfg<N_TILE>::kStages;
-  constexpr int D = PCfg<N_TILE>::kInFlight;
-  constexpr int A_BYTES = kTileM * 128;
-  constexpr int B_BYTES = N_TILE * 128;
-  constexpr uint32_t ACC_COLS = PCfg<N_TILE>::kAccCols;
-  constexpr uint32_t IDESC = umma_idesc_bf16_m128(N_TILE);
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint8_t* tail = sB + STAGES * B_BYTES;
-  uint64_t* a_full = (uint64_t*)tail;            // [STAGES] count = 8 producer warps
-  uint64_t* b_full = a_full + STAGES;            // [STAGES] count = 1 (+tx)
-  uint64_t* empty = b_full + STAGES;             // [STAGES] count = 1 (tcgen05.commit)
-  uint64_t* acc_full = empty + STAGES;           // [2] count = 1 (tcgen05.commit)
-  uint64_t* acc_empty = acc_full + 2;            // [2] count = 4 epilogue warps
-  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
-  float* s_scale = (float*)(tail + 256);
-  const ud3d_gemm_args& a = p.a;
-  const int c_in_pad = p.n_chunks * kChunk;
-  float* s_shift = s_scale + c_in_pad;
-  int32_t* s_tbl = (int32_t*)(s_shift + c_in_pad);   // [2][K][128] rulebook slices (current / next work item)
-  const int tbl_stride = a.K * kTileM;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool has_table = a.table != nullptr;
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&a_full[s], 8);
-      mbar_init(&b_full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
-    }
-    fence_mbar_init();
-  }
-  if (a.in_scale) {
-    for (int c = tid; c < c_in_pad; c += kPThreads) {
-      s_scale[c] = c < a.c_in ? a.in_scale[c] : 0.f;
-      s_shift[c] = c < a.c_in ? a.in_shift[c] : 0.f;
-    }
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 2 * ACC_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint8_t* w_all = (const uint8_t*)a.w_packed;
-
-  if (warp < 4) {
-    // =========================================================== epilogue warps
-    int n_used = 0;       // non-empty work items so far: accumulator buffer / phase bookkeeping (same rule as the MMA warp)
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-      const WorkItem wi = get_work(p, w, n_ntiles, splits);
-      const int buf = n_used & 1;
-      const uint32_t use = (uint32_t)(n_used >> 1);
-      if (wi.nsteps > 0) {
-        if (lane == 0) mbar_wait(&acc_full[buf], use & 1u);
-        __syncwarp();
-        tc_fence_after_sync();
-      }
-      const int grow = wi.m0 + warp * 32 + lane;
-      const bool row_ok = grow < a.n_out;
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-        uint32_t r[32];
-        if (wi.nsteps > 0) {
-          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + buf * ACC_COLS + (uint32_t)c0, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
-        }
-        if (row_ok) epilogue_store_chunk(p, r, grow, wi.nt * N_TILE + c0, splits > 1, wi.z == 0);
-      }
-      if (wi.nsteps > 0) {
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);     // accumulator buffer may be overwritten
-        ++n_used;
-      }
-    }
-  } else if (warp < kPWarpB) {
-    // =========================================================== A producers (2 groups x 256 threads)
-    const int ptid = tid - kPProdWarp0 * 32;       // 0..511: rulebook-slice loading
-    const int grp = ptid >> 8;                     // producer group
-    const int gtid = ptid & 255;                   // thread within the group: row / chunk assignment
-    // rulebook slice of a work item -> registers (issued early) -> shared memory buffer
-    constexpr int kPer = (32 * kTileM + kPProdThreads - 1) / kPProdThreads;   // 8
-    int tv[kPer];
-    auto tbl_load = [&](int w) {
-      const int m0w = ((w / splits) / n_ntiles) * kTileM;
-      const int total = a.K * kTileM;
-#pragma unroll
-      for (int j = 0; j < kPer; ++j) {
-        const int i = ptid + j * kPProdThreads;
-        const int row = m0w + (i & 127);
-        tv[j] = (i < total && row < a.n_out) ? __ldg(a.table + (size_t)(i >> 7) * a.n_out + row) : -1;
-      }
-    };
-    auto tbl_store = [&](int b) {
-      const int total = a.K * kTileM;
-#pragma unroll
-      for (int j = 0; j < kPer; ++j) {
-        const int i = ptid + j * kPProdThreads;
-        if (i < total) s_tbl[b * tbl_stride + i] = tv[j];
-      }
-    };
-    if (has_table && (int)blockIdx.x < n_work) {
-      tbl_load(blockIdx.x);
-      tbl_store(0);
-    }
-    asm volatile("bar.sync 1, 512;" ::: "memory");
-    uint32_t g = 0;                                // global K-step index of this CTA (same sequence in every role)
-
-    if (a.in_split) {
-      // ---- operand-form input: cp.async 16 B per lane, D steps in flight per group, ring continues across work items
-      const size_t row_bytes = (size_t)a.ld_in * 4;
-      const int j = gtid & 7;
-      const int rbase = gtid >> 3;
-      const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
-      const uint32_t sA_addr = smem_u32(sA);
-      uint32_t dst_off[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = rbase + 32 * i;
-        dst_off[i] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
-      }
-      uint32_t pub_g = grp;            // global index of this group's next step to publish
-      int pending = 0;                 // committed-but-unpublished steps of this group (<= D)
-      int it = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const WorkItem wi = get_work(p, w, n_ntiles, splits);
-        const int32_t* tb = s_tbl + (it & 1) * tbl_stride;
-        const int wn = w + gridDim.x;
-        if (has_table && wn < n_work) tbl_load(wn);             // in flight during this work item
-        uint32_t rem = skip_bits(wi.mask, wi.kslot0);
-        int k = __ffs(rem) - 1, c = wi.chunk0;
-        for (int t = 0; t < wi.nsteps; ++t, ++g) {
-          if ((g & 1u) == (uint32_t)grp) {
-            const int s = (int)(g % STAGES);
-            const uint32_t use = g / STAGES;
-            if (use) {
-              if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-              __syncwarp();
-            }
-            const int32_t* trow = tb + k * kTileM + rbase;
-            const uint8_t* sb = src_base + c * 128;
-            const uint32_t as_addr = sA_addr + s * A_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              int idx;
-              if (has_table) idx = trow[32 * i];
-              else idx = (wi.m0 + rbase + 32 * i < a.n_out) ? wi.m0 + rbase + 32 * i : -1;
-              cp_async_16_zfill(as_addr + dst_off[i], sb + (size_t)(idx < 0 ? 0 : idx) * row_bytes, idx >= 0 ? 16u : 0u);
-            }
-            cp_async_commit();
-            if (pending == D) {
-              cp_async_wait<D>();             // this group's oldest unpublished step has landed
-              fence_proxy_async_smem();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&a_full[pub_g % STAGES]);
-              pub_g += 2;
-            } else {
-              ++pending;
-            }
-          }
-          if (++c == p.n_chunks) { c = 0; rem &= rem - 1; k = __ffs(rem) - 1; }
-        }
-        if (has_table && wn < n_work) tbl_store((it + 1) & 1);
-        asm volatile("bar.sync 1, 512;" ::: "memory");          // next slice visible to all producers
-      }
-      // drain
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      for (int i = 0; i < pending; ++i) {
-        if (lane == 0) mbar_arrive(&a_full[pub_g % STAGES]);
-        pub_g += 2;
-      }
-    } else {
-      // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers (4 lanes per row, 8 channels each)
-      const int q = gtid & 3;
-      const int rl = gtid >> 2;
-      const bool affine = a.in_scale != nullptr;
-      const bool relu = a.in_relu != 0;
-      int it = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
-        const WorkItem wi = get_work(p, w, n_ntiles, splits);
-        const int32_t* tb = s_tbl + (it & 1) * tbl_stride;
-        const int wn = w + gridDim.x;
-        if (has_table && wn < n_work) tbl_load(wn);
-        uint32_t rem = skip_bits(wi.mask, wi.kslot0);
-        int k = __ffs(rem) - 1, c = wi.chunk0;
-        for (int t = 0; t < wi.nsteps; ++t, ++g) {
-          if ((g & 1u) == (uint32_t)grp) {
-            const int ch0 = c * kChunk + q * 8;
-            GatherRegs gr;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int r = rl + h * 64;
-              int idx;
-              if (has_table) idx = tb[k * kTileM + r];
-              else idx = (wi.m0 + r < a.n_out) ? wi.m0 + r : -1;
-              gr.ok[h] = idx >= 0 && ch0 < a.c_in;
-              if (gr.ok[h]) {
-                const float* src = a.in + (size_t)idx * a.ld_in + ch0;
-                if (p.vec_ok) {
-                  gr.v[h][0] = __ldg((const float4*)src);
-                  gr.v[h][1] = __ldg((const float4*)src + 1);
-                } else {
-                  float e[8];
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj) e[jj] = (ch0 + jj < a.c_in) ? __ldg(src + jj) : 0.f;
-                  gr.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
-                  gr.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
-                }
-              }
-            }
-            const int s = (int)(g % STAGES);
-            const uint32_t use = g / STAGES;
-            if (use) {
-              if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-              __syncwarp();
-            }
-            uint8_t* As = sA + s * A_BYTES;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              float v[8];
-              if (gr.ok[h]) {
-                v[0] = gr.v[h][0].x; v[1] = gr.v[h][0].y; v[2] = gr.v[h][0].z; v[3] = gr.v[h][0].w;
-                v[4] = gr.v[h][1].x; v[5] = gr.v[h][1].y; v[6] = gr.v[h][1].z; v[7] = gr.v[h][1].w;
-                if (affine) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
-                }
-                if (relu) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-                }
-                if (!p.vec_ok) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e)
-                    if (ch0 + e >= a.c_in) v[e] = 0.f;
-                }
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.f;
-              }
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-              const int r = rl + h * 64;
-              uint8_t* arow = As + r * 128;
-              *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[s]);
-          }
-          if (++c == p.n_chunks) { c = 0; rem &= rem - 1; k = __ffs(rem) - 1; }
-        }
-        if (has_table && wn < n_work) tbl_store((it + 1) & 1);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-      }
-    }
-  } else if (warp == kPWarpB) {
-    // =========================================================== B producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t use = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const WorkItem wi = get_work(p, w, n_ntiles, splits);
-        const uint8_t* wp = w_all + (size_t)wi.nt * a.K * p.n_chunks * B_BYTES;
-        uint32_t rem = skip_bits(wi.mask, wi.kslot0);
-        int k = __ffs(rem) - 1, c = wi.chunk0;
-        for (int t = 0; t < wi.nsteps; ++t) {
-          if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&b_full[s], B_BYTES);
-          bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
-          if (++c == p.n_chunks) { c = 0; rem &= rem - 1; k = __ffs(rem) - 1; }
-          if (++s == STAGES) { s = 0; ++use; }
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      uint64_t adesc[STAGES], bdesc[STAGES];
-#pragma unroll
-      for (int i = 0; i < STAGES; ++i) {
-        adesc[i] = umma_desc_sw128(smem_u32(sA + i * A_BYTES));
-        bdesc[i] = umma_desc_sw128(smem_u32(sB + i * B_BYTES));
-      }
-      int s = 0, n_used = 0;
-      uint32_t use = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const WorkItem wi = get_work(p, w, n_ntiles, splits);
-        if (wi.nsteps == 0) continue;            // (the epilogue writes zeros for an empty item)
-        const int buf = n_used & 1;
-        const uint32_t ause = (uint32_t)(n_used >> 1);
-        ++n_used;
-        if (ause) mbar_wait(&acc_empty[buf], (ause & 1u) ^ 1u);
-        tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + buf * ACC_COLS;
-        for (int t = 0; t < wi.nsteps; ++t) {
-          mbar_wait(&a_full[s], use & 1u);
-          mbar_wait(&b_full[s], use & 1u);
-          tc_fence_after_sync();
-          uint64_t ad = adesc[0], bd = bdesc[0];
-#pragma unroll
-          for (int i = 1; i < STAGES; ++i)
-            if (s == i) { ad = adesc[i]; bd = bdesc[i]; }
-          umma_bf16(d_tmem, ad + 0, bd + 0, IDESC, t > 0);
-          umma_bf16(d_tmem, ad + 2, bd + 2, IDESC, 1);
-          umma_bf16(d_tmem, ad + 4, bd + 0, IDESC, 1);
-          umma_bf16(d_tmem, ad + 6, bd + 2, IDESC, 1);
-          umma_bf16(d_tmem, ad + 0, bd + 4, IDESC, 1);
-          umma_bf16(d_tmem, ad + 2, bd + 6, IDESC, 1);
-          umma_commit(&empty[s]);
-          if (++s == STAGES) { s = 0; ++use; }
-        }
-        umma_commit(&acc_full[buf]);
-      }
-    }
-    __syncwarp();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 2 * ACC_COLS);
-}
-
 // ---------------------------------------------------------------- fp32 -> operand form (one warp per 4 row-chunks)
 __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict__ raw, int ld_raw, int n, int c,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
@@ -1066,41 +667,7 @@ static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_
 }
 
 template <int N_TILE>
-static int launch_persistent(const GemmParams& p, int n_ntiles, int splits, cudaStream_t st) {
-  const bool has_table = p.a.table != nullptr;
-  size_t smem = 1024 + (size_t)PCfg<N_TILE>::kStages * (kTileM * 128 + N_TILE * 128) + 256 + (size_t)p.n_chunks * kChunk * 4 * 2 +
-                (has_table ? (size_t)2 * p.a.K * kTileM * 4 : 0);
-  if (smem > 227 * 1024) return 1;     // does not fit (very wide c_in): caller falls back to the per-tile kernel
-  static size_t configured = 0;
-  if (smem > configured) {
-    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_persistent_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  static int n_sms = 0;
-  if (!n_sms) {
-    int dev = 0;
-    UD3D_CUDA(cudaGetDevice(&dev));
-    UD3D_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  const int n_work = cdiv(p.a.n_out, kTileM) * n_ntiles * splits;
-  const int grid = n_work < n_sms ? n_work : n_sms;
-  gather_gemm_persistent_kernel<N_TILE><<<grid, kPThreads, smem, st>>>(p, n_work, n_ntiles, splits);
-  UD3D_LAUNCH_CHECK();
-  return UD3D_OK;
-}
-
-template <int N_TILE>
 static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
-  // UD3D_GEMM_KERNEL=tile selects the one-tile-per-CTA kernel (default: persistent)
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("UD3D_GEMM_KERNEL");
-    mode = (e && e[0] == 't') ? 0 : 1;
-  }
-  if (mode == 1) {
-    int rc = launch_persistent<N_TILE>(p, n_tiles, splits, st);
-    if (rc <= 0) return rc;
-  }
   return launch_tc_d<N_TILE, TcCfg<N_TILE>::kInFlight>(p, n_tiles, splits, st);
 }
 
