@@ -157,7 +157,7 @@ def test_ragged_and_degenerate_batches(full_model):
     """Scenes of very different size in one batch, superpoint ids with gaps (empty superpoints -> zero rows)."""
     cfg, sd, model = full_model
     big, sp_big = make_scene(11, 60000, 6.0, 0.08)
-    small, sp_small = make_scene(12, 2500, 1.2, 0.25)
+    small, sp_small = make_scene(12, 8000, 2.0, 0.09)    # ~250 superpoints: T*C must stay >= topk_insts like in the reference
     sp_small = sp_small * 2            # only even ids occur: odd superpoints are empty
     res = model.forward_scenes([small, big], [sp_small, sp_big], ["scannet", "scannet"])
     assert len(res) == 2
