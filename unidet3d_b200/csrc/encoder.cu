@@ -3,6 +3,8 @@
 // varlen multi-head self-attention (flash-style, bf16 hi/lo split on tensor cores), box decode.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ud3d {
 
 // ---------------------------------------------------------------- segmented mean
@@ -533,6 +535,233 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
   }
 }
 
+// ---------------------------------------------------------------- attention on tcgen05 (operand-form q|k|v)
+// CTA = 128 queries of one (scene, head); KV tiles of 64 keys.  Both GEMMs run on the tensor cores with TMEM
+// accumulators; the operand-form rows (128 B = bf16 hi|lo of one head) are used as they are:
+//   S[128 x 64]  = Q K^T : A = Q tile, B = K tile, both K-major SW128 (rows of 128 B), 6 MMAs (hi.hi, lo.hi, hi.lo)
+//   softmax      : 4 warps, one query row per thread: tcgen05.ld S, scale, online max / sum (exp2), P -> bf16 hi|lo
+//                  written to shared memory as the next A operand (two 32-key chunks of 128-byte rows)
+//   O'[128 x 64] = P V'  : B = V tile used MN-major (row = key, 128 B = [V_hi(32 dims) | V_lo(32 dims)] = N 64), so
+//                  O = O'[:, :32] + O'[:, 32:] = (P_hi + P_lo)(V_hi + V_lo); 8 MMAs; accumulated in registers with
+//                  the online-softmax rescale (head_dim 32 -> 32 floats per thread)
+//   warp 4 streams K/V tiles with cp.async through a 2-stage ring, warp 5 issues the MMAs; mbarrier hand-offs only.
+constexpr int kTcQ = 128, kTcKV = 64;
+constexpr int kTcThreads = 192;
+
+// UMMA descriptor for an MN-major operand tile with 128B swizzle: rows (K index) of 128 bytes, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_m128_bmn(uint32_t N) {   // B operand MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t* __restrict__ qkv, const int32_t* __restrict__ cu,
+                                                                  int num_heads, uint8_t* __restrict__ out) {
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int t0 = cu[b];
+  const int T = cu[b + 1] - t0;
+  const int q0 = blockIdx.x * kTcQ;
+  if (q0 >= T) return;
+  const int d_model = num_heads * kHeadDim;
+  const size_t ldb = (size_t)3 * d_model * 4;
+  const size_t ldo = (size_t)d_model * 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                         // 128 x 128 B
+  uint8_t* sK = sQ + 16384;                   // [2] 64 x 128 B
+  uint8_t* sV = sK + 2 * 8192;                // [2] 64 x 128 B
+  uint8_t* sP = sV + 2 * 8192;                // [2 chunks] 128 x 128 B (hi 32 keys | lo 32 keys)
+  uint64_t* bars = (uint64_t*)(sP + 2 * 16384);
+  uint64_t* kv_full = bars;                   // [2]
+  uint64_t* kv_empty = bars + 2;              // [2]
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_full = bars + 5;                // count 4 (softmax warps)
+  uint64_t* o_full = bars + 6;
+  uint64_t* o_free = bars + 7;                // count 4
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+  if (tid == 0) {
+    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_free, 4);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  // Q tile: 128 rows x 8 chunks, swizzled like every K-major operand tile
+  for (int id = tid; id < kTcQ * 8; id += kTcThreads) {
+    const int r = id >> 3, j = id & 7;
+    const int row = q0 + r;
+    const uint8_t* src = qkv + (size_t)(t0 + (row < T ? row : 0)) * ldb + (size_t)h * 128 + j * 16;
+    cp_async_16_zfill(smem_u32(sQ + r * 128 + ((j ^ (r & 7)) << 4)), src, row < T ? 16u : 0u);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
+  const int n_tiles = (T + kTcKV - 1) / kTcKV;
+
+  if (warp < 4) {
+    // =========================================================== softmax / output warps: thread = query row
+    const int row = warp * 32 + lane;
+    const float qscale = 1.44269504088896340736f * 0.17677669529663688110f;
+    float o[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int kv0 = j * kTcKV;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after_sync();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tmem_S + lane_off + 0, r0);
+      tmem_ld_32x32(tmem_S + lane_off + 32, r1);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float a = __uint_as_float(r0[i]) * qscale, c = __uint_as_float(r1[i]) * qscale;
+        if (kv0 + i >= T) a = -INFINITY;
+        if (kv0 + 32 + i >= T) c = -INFINITY;
+        r0[i] = __float_as_uint(a);
+        r1[i] = __float_as_uint(c);
+        mx = fmaxf(mx, fmaxf(a, c));
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = exp2f(m_run - m_new);
+      m_run = m_new;
+      float rs = 0.f;
+      // P chunks: chunk 0 = keys 0..31 (r0), chunk 1 = keys 32..63 (r1); row layout hi(64 B) | lo(64 B), swizzled
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = exp2f(__uint_as_float(ch ? r1[i] : r0[i]) - m_run);
+          const float p1 = exp2f(__uint_as_float(ch ? r1[i + 1] : r0[i + 1]) - m_run);
+          rs += p0 + p1;
+          split_bf16x2(p0, p1, hi[i >> 1], lo[i >> 1]);
+        }
+        uint8_t* prow = sP + ch * 16384 + row * 128;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          *(uint4*)(prow + ((c4 ^ (row & 7)) << 4)) = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
+          *(uint4*)(prow + (((4 + c4) ^ (row & 7)) << 4)) = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
+        }
+      }
+      l_run = l_run * alpha + rs;
+      fence_proxy_async_smem();           // P visible to the tensor core
+      tc_fence_before_sync();             // S reads are complete before the MMA warp may overwrite S
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- O' of this tile
+      mbar_wait(o_full, j & 1);
+      tc_fence_after_sync();
+      tmem_ld_32x32(tmem_O + lane_off + 0, r0);
+      tmem_ld_32x32(tmem_O + lane_off + 32, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + (__uint_as_float(r0[i]) + __uint_as_float(r1[i]));
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+    }
+    // ---- finalize: operand-form output row chunk of head h
+    const int grow = q0 + row;
+    if (grow < T) {
+      const float inv = 1.f / l_run;
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) split_bf16x2(o[i] * inv, o[i + 1] * inv, hi[i >> 1], lo[i >> 1]);
+      uint4* dst = (uint4*)(out + (size_t)(t0 + grow) * ldo + (size_t)h * 128);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        dst[c4] = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
+        dst[4 + c4] = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
+      }
+    }
+  } else if (warp == 4) {
+    // =========================================================== K/V loader: 2-stage cp.async ring
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      if (j >= 2) {
+        if (lane == 0) mbar_wait(&kv_empty[st], ((j >> 1) - 1) & 1);
+        __syncwarp();
+      }
+      const int kv0 = j * kTcKV;
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int id = lane + 32 * i;                 // 0..1023
+        const int which = id >> 9, rem = id & 511;
+        const int key = rem >> 3, jj = rem & 7;
+        const int kr = kv0 + key;
+        const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + jj * 16;
+        uint8_t* dst = (which ? sV : sK) + st * 8192 + key * 128 + ((jj ^ (key & 7)) << 4);
+        cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&kv_full[st]);
+    }
+  } else {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_S = umma_idesc_bf16_m128(64);
+      constexpr uint32_t IDESC_O = umma_idesc_bf16_m128_bmn(64);
+      const uint64_t qd = umma_desc_sw128(smem_u32(sQ));
+      const uint64_t pd0 = umma_desc_sw128(smem_u32(sP)), pd1 = umma_desc_sw128(smem_u32(sP + 16384));
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after_sync();
+        const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * 8192));
+        umma_bf16(tmem_S, qd + 0, kd + 0, IDESC_S, 0);
+        umma_bf16(tmem_S, qd + 2, kd + 2, IDESC_S, 1);
+        umma_bf16(tmem_S, qd + 4, kd + 0, IDESC_S, 1);
+        umma_bf16(tmem_S, qd + 6, kd + 2, IDESC_S, 1);
+        umma_bf16(tmem_S, qd + 0, kd + 4, IDESC_S, 1);
+        umma_bf16(tmem_S, qd + 2, kd + 6, IDESC_S, 1);
+        umma_commit(s_full);
+      };
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);                       // P(j) written, S(j) consumed
+        if (j > 0) mbar_wait(o_free, (j - 1) & 1);      // O'(j-1) consumed
+        tc_fence_after_sync();
+        const uint64_t vd = umma_desc_sw128_mn(smem_u32(sV + st * 8192));
+        // k-step i covers keys 16i..16i+15: P chunk i/2, hi at +(i%2)*32 B, lo at +64+(i%2)*32 B; V rows advance by 16*128 B
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint64_t pd = (i < 2 ? pd0 : pd1) + (uint64_t)((i & 1) * 2);
+          const uint64_t vdi = vd + (uint64_t)(i * 128);          // 2048 B >> 4
+          umma_bf16(tmem_O, pd, vdi, IDESC_O, i > 0);
+          umma_bf16(tmem_O, pd + 4, vdi, IDESC_O, 1);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+        if (j + 1 < n_tiles) issue_s(j + 1);            // overlaps the softmax warps' O' accumulation of tile j
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
 // ---------------------------------------------------------------- box decode / column gather
 __global__ void bbox_decode_kernel(const float* __restrict__ raw, int ld_raw, const float* __restrict__ centers, int T,
                                    int with_angle, float* __restrict__ out) {
@@ -668,8 +897,26 @@ int ud3d_attention_fwd_opform(const float* qkv_split, const int32_t* cu_seqlens,
   UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd_opform: bad sizes");
   UD3D_CHECK_ARG((((uintptr_t)qkv_split | (uintptr_t)out_split) & 15) == 0, "ud3d_attention_fwd_opform: pointers must be 16-byte aligned");
   if (max_T == 0) return UD3D_OK;
-  dim3 grid(cdiv(max_T, kAtt2Q), num_heads, B);
-  attention_opform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads, (uint8_t*)out_split);
+  // UD3D_ATTENTION=mma selects the mma.sync kernel; default: tcgen05 kernel (S and O' accumulators in TMEM)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("UD3D_ATTENTION");
+    mode = (e && e[0] == 'm') ? 0 : 1;
+  }
+  if (mode == 1) {
+    const size_t smem = 1024 + 16384 + 4 * 8192 + 2 * 16384 + 128;
+    static bool configured = false;
+    if (!configured) {
+      UD3D_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    dim3 grid(cdiv(max_T, kTcQ), num_heads, B);
+    attention_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads,
+                                                                           (uint8_t*)out_split);
+  } else {
+    dim3 grid(cdiv(max_T, kAtt2Q), num_heads, B);
+    attention_opform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads, (uint8_t*)out_split);
+  }
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }
