@@ -384,3 +384,6 @@ def test_attention_operand_form(lens):
     assert relerr(split_decode(out_s.cpu()), ref) < 1e-4, relerr(split_decode(out_s.cpu()), ref)
     out_s2 = ops.attention(qkv.to(DEV), cu.to(DEV), max(lens), H, split_out=True)
     assert relerr(split_decode(out_s2.cpu()), ref) < 1e-4
+    # tcgen05 variant (S / O' accumulators in TMEM, V as an MN-major operand)
+    out_s3 = ops.attention(split_encode(qkv).to(DEV), cu.to(DEV), max(lens), H, split_in=True, tcgen05=True)
+    assert relerr(split_decode(out_s3.cpu()), ref) < 1e-4, relerr(split_decode(out_s3.cpu()), ref)

@@ -3,8 +3,6 @@
 // varlen multi-head self-attention (flash-style, bf16 hi/lo split on tensor cores), box decode.
 #include "common.cuh"
 
-#include <stdlib.h>
-
 namespace ud3d {
 
 // ---------------------------------------------------------------- segmented mean
@@ -897,26 +895,27 @@ int ud3d_attention_fwd_opform(const float* qkv_split, const int32_t* cu_seqlens,
   UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd_opform: bad sizes");
   UD3D_CHECK_ARG((((uintptr_t)qkv_split | (uintptr_t)out_split) & 15) == 0, "ud3d_attention_fwd_opform: pointers must be 16-byte aligned");
   if (max_T == 0) return UD3D_OK;
-  // UD3D_ATTENTION=mma selects the mma.sync kernel; default: tcgen05 kernel (S and O' accumulators in TMEM)
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("UD3D_ATTENTION");
-    mode = (e && e[0] == 'm') ? 0 : 1;
+  dim3 grid(cdiv(max_T, kAtt2Q), num_heads, B);
+  attention_opform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads, (uint8_t*)out_split);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
+                          float* out_split, void* stream) {
+  UD3D_CHECK_ARG(qkv_split && cu_seqlens && out_split, "ud3d_attention_fwd_tc: NULL argument");
+  UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd_tc: bad sizes");
+  UD3D_CHECK_ARG((((uintptr_t)qkv_split | (uintptr_t)out_split) & 15) == 0, "ud3d_attention_fwd_tc: pointers must be 16-byte aligned");
+  if (max_T == 0) return UD3D_OK;
+  const size_t smem = 1024 + 16384 + 4 * 8192 + 2 * 16384 + 128;
+  static bool configured = false;
+  if (!configured) {
+    UD3D_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
   }
-  if (mode == 1) {
-    const size_t smem = 1024 + 16384 + 4 * 8192 + 2 * 16384 + 128;
-    static bool configured = false;
-    if (!configured) {
-      UD3D_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
-    dim3 grid(cdiv(max_T, kTcQ), num_heads, B);
-    attention_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads,
-                                                                           (uint8_t*)out_split);
-  } else {
-    dim3 grid(cdiv(max_T, kAtt2Q), num_heads, B);
-    attention_opform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads, (uint8_t*)out_split);
-  }
+  dim3 grid(cdiv(max_T, kTcQ), num_heads, B);
+  attention_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads,
+                                                                         (uint8_t*)out_split);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

@@ -262,7 +262,7 @@ def layernorm_split(x: torch.Tensor, gamma, beta, residual=None, eps: float = 1e
 
 
 def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_T: int, num_heads: int, split_out: bool = False,
-              split_in: bool = False) -> torch.Tensor:
+              split_in: bool = False, tcgen05: bool = False) -> torch.Tensor:
     """softmax(QK^T/sqrt(32))V per scene; ``split_out``: result in operand form for the out-projection GEMM;
     ``split_in``: qkv itself is in operand form (implies split_out)."""
     _req(qkv, torch.float32, "qkv"), _req(cu_seqlens, torch.int32, "cu_seqlens")
@@ -270,7 +270,10 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_T: int, num_heads
     if d != num_heads * 32:
         raise _lib.Ud3dError("attention: head_dim must be 32")
     out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
-    fn = _L().ud3d_attention_fwd_opform if split_in else (_L().ud3d_attention_fwd_split if split_out else _L().ud3d_attention_fwd)
+    if tcgen05 and not split_in:
+        raise _lib.Ud3dError("attention: the tcgen05 kernel takes operand-form q|k|v (split_in=True)")
+    fn = (_L().ud3d_attention_fwd_tc if tcgen05 else _L().ud3d_attention_fwd_opform) if split_in else (
+        _L().ud3d_attention_fwd_split if split_out else _L().ud3d_attention_fwd)
     check(fn(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, int(max_T), num_heads, _p(out), _stream()),
           "ud3d_attention_fwd")
     return out
