@@ -216,19 +216,38 @@ class UniDet3D(nn.Module):
         out = self.decoder.forward_packed(pooled, sp_centers, [int(v) for v in sp_off], datasets_names)
 
         per_scene = self.postprocess_batch(out, pts, sp_b, pt_off, sp_off, n_sps, ds_idx)
-        # one D2H round-trip for the whole batch
-        n_keeps = torch.cat([r["n_keep"] for r in per_scene]).cpu().tolist()
+        # one D2H round-trip for the whole batch: every scene's packed result buffer (scores | labels | keep | n_keep |
+        # candidate boxes | trimmed boxes, ~64 KB) is copied asynchronously into pinned memory, ONE stream sync, and the
+        # final row selection (a few hundred boxes) is done on the host copy
+        host = []
+        for i, r in enumerate(per_scene):
+            n = r["_buf"].numel()
+            cache = getattr(self, "_host_bufs", None)
+            if cache is None:
+                cache = self._host_bufs = {}
+            hb = cache.get((i, n))
+            if hb is None:
+                hb = cache[(i, n)] = torch.empty(n, dtype=torch.float32).pin_memory()
+            hb.copy_(r["_buf"], non_blocking=True)
+            host.append(hb)
+        torch.cuda.current_stream().synchronize()
         results = []
-        for r, nk in zip(per_scene, n_keeps):
-            keep = r["keep"][:nk].long()
-            scores, labels = r["scores"].index_select(0, keep), r["labels"].index_select(0, keep).long()
+        for r, hb in zip(per_scene, host):
+            k, bd = r["scores"].numel(), r["cand"].shape[1]
+            scores_h = hb[:k]
+            labels_h = hb[k:2 * k].view(torch.int32)
+            keep_h = hb[2 * k:3 * k].view(torch.int32)
+            nk = int(hb[3 * k:3 * k + 1].view(torch.int32)[0])
+            cand_h = hb[3 * k + 8:3 * k + 8 + k * bd].view(k, bd)
+            keep = keep_h[:nk].long()
+            scores, labels = scores_h.index_select(0, keep), labels_h.index_select(0, keep).long()
             if r["trimmed"] is not None:
-                boxes = r["trimmed"][:nk]
+                boxes = hb[3 * k + 8 + k * bd:].view(k, 6)[:nk].clone()
             else:
-                boxes = r["cand"].index_select(0, keep)
+                boxes = cand_h.index_select(0, keep)
                 if not r["with_yaw"] and self.fast_nms[r["ds"]]:
                     boxes = torch.cat((boxes, torch.zeros_like(boxes[:, :1])), dim=1)       # unidet3d.py:629-631
-            results.append((boxes.cpu(), labels.cpu(), scores.cpu()))
+            results.append((boxes, labels, scores))
         return results
 
     def predict(self, batch_inputs_dict, batch_data_samples, **kwargs):
