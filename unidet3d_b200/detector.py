@@ -191,7 +191,7 @@ class UniDet3D(nn.Module):
         if n_superpoints is not None:
             n_sps = [int(v) for v in n_superpoints]
         elif all(not s.is_cuda for s in S):
-            n_sps = [int(s.max()) + 1 for s in S]
+            n_sps = [int(s.numpy().max()) + 1 for s in S]      # numpy: no intra-op thread-pool wake-up per scene
         else:
             n_sps = [int(v) + 1 for v in torch.stack([s.max() for s in S]).cpu().tolist()]
         sp_off = np.concatenate([[0], np.cumsum(n_sps)]).astype(np.int64)
