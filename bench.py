@@ -272,11 +272,11 @@ def main():
         res = model.forward_scenes(h_pts, h_sps, names)
         e1.record()
         evs.append((e0, e1))
-        d2h = sum(b.numel() * 4 + l.numel() * 8 + s.numel() * 4 for b, l, s in res) + 4 * batch + 16 + 4 * 5
+        d2h = model.last_d2h_bytes       # packed per-scene result buffers + the small count / extent read-backs
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     t_e2e = sum(a.elapsed_time(b) for a, b in evs) / 1e3
-    h2d = sum(p.numel() * 4 for p in h_pts) + sum(s.numel() * 8 for s in h_sps) + 4 * (batch + 1)
+    h2d = model.last_h2d_bytes       # points fp32 [n,6] + superpoint ids int64 [n] + scene offsets
 
     # ---------------------------------------------------------------- dominant kernel: the 49 sparse convs
     offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device=dev)

@@ -208,6 +208,8 @@ class UniDet3D(nn.Module):
             if sp_off[i]:
                 sp_b[a:b] += int(sp_off[i])
         offs = torch.tensor(pt_off, dtype=torch.int32).to(dev, non_blocking=True)
+        self.last_h2d_bytes = int(sum(p.numel() * 4 for p in P if not p.is_cuda) + sum(s.numel() * 8 for s in S if not s.is_cuda)
+                                  + offs.numel() * 4)
 
         sp_centers = ops.segmented_mean(pts, sp_b, int(sp_off[-1]), channels=3)            # unidet3d.py:446-447
         x, inverse = self.collate(pts, offs, B)
@@ -231,6 +233,7 @@ class UniDet3D(nn.Module):
             hb.copy_(r["_buf"], non_blocking=True)
             host.append(hb)
         torch.cuda.current_stream().synchronize()
+        self.last_d2h_bytes = int(sum(hb.numel() * 4 for hb in host)) + 4 * 4 + 4 * (len(per_scene) + 4)   # + extents / counts read-backs
         results = []
         for r, hb in zip(per_scene, host):
             k, bd = r["scores"].numel(), r["cand"].shape[1]
