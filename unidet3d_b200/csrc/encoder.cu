@@ -537,14 +537,15 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
 // CTA = 128 queries of one (scene, head); KV tiles of 64 keys.  Both GEMMs run on the tensor cores with TMEM
 // accumulators; the operand-form rows (128 B = bf16 hi|lo of one head) are used as they are:
 //   S[128 x 64]  = Q K^T : A = Q tile, B = K tile, both K-major SW128 (rows of 128 B), 6 MMAs (hi.hi, lo.hi, hi.lo)
-//   softmax      : 4 warps, one query row per thread: tcgen05.ld S, scale, online max / sum (exp2), P -> bf16 hi|lo
+//   softmax      : 8 warps, thread = (query row, 32-key half): tcgen05.ld S, scale, online max / sum (ex2), P -> bf16 hi|lo
 //                  written to shared memory as the next A operand (two 32-key chunks of 128-byte rows)
 //   O'[128 x 64] = P V'  : B = V tile used MN-major (row = key, 128 B = [V_hi(32 dims) | V_lo(32 dims)] = N 64), so
 //                  O = O'[:, :32] + O'[:, 32:] = (P_hi + P_lo)(V_hi + V_lo); 8 MMAs; accumulated in registers with
 //                  the online-softmax rescale (head_dim 32 -> 32 floats per thread)
 //   warp 4 streams K/V tiles with cp.async through a 2-stage ring, warp 5 issues the MMAs; mbarrier hand-offs only.
 constexpr int kTcQ = 128, kTcKV = 64;
-constexpr int kTcThreads = 192;
+constexpr int kTcSoftmaxWarps = 8;                 // warps w and w+4 share query rows 32*(w&3).. and split the 64 keys
+constexpr int kTcThreads = 32 * (kTcSoftmaxWarps + 2);
 
 // UMMA descriptor for an MN-major operand tile with 128B swizzle: rows (K index) of 128 bytes, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
@@ -552,6 +553,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 }
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128_bmn(uint32_t N) {   // B operand MN-major
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((N >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t* __restrict__ qkv, const int32_t* __restrict__ cu,
@@ -571,20 +577,21 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
   uint8_t* sQ = smem;                         // 128 x 128 B
   uint8_t* sK = sQ + 16384;                   // [2] 64 x 128 B
   uint8_t* sV = sK + 2 * 8192;                // [2] 64 x 128 B
-  uint8_t* sP = sV + 2 * 8192;                // [2 chunks] 128 x 128 B (hi 32 keys | lo 32 keys)
-  uint64_t* bars = (uint64_t*)(sP + 2 * 16384);
+  uint8_t* sP = sV + 2 * 8192;                // [2 chunks] 128 x 128 B (hi 32 keys | lo 32 keys); reused for the final O exchange
+  float* s_rmax = (float*)(sP + 2 * 16384);   // [2 halves][128 rows] per-tile row maxima of each key half
+  uint64_t* bars = (uint64_t*)(s_rmax + 256);
   uint64_t* kv_full = bars;                   // [2]
   uint64_t* kv_empty = bars + 2;              // [2]
   uint64_t* s_full = bars + 4;
-  uint64_t* p_full = bars + 5;                // count 4 (softmax warps)
+  uint64_t* p_full = bars + 5;                // count 8 (softmax warps)
   uint64_t* o_full = bars + 6;
-  uint64_t* o_free = bars + 7;                // count 4
+  uint64_t* o_free = bars + 7;                // count 8
   uint32_t* tmem_slot = (uint32_t*)(bars + 8);
 
   if (tid == 0) {
     mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
     mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_free, 4);
+    mbar_init(s_full, 1); mbar_init(p_full, kTcSoftmaxWarps); mbar_init(o_full, 1); mbar_init(o_free, kTcSoftmaxWarps);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -608,49 +615,47 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
   const int n_tiles = (T + kTcKV - 1) / kTcKV;
 
-  if (warp < 4) {
-    // =========================================================== softmax / output warps: thread = query row
-    const int row = warp * 32 + lane;
+  if (warp < kTcSoftmaxWarps) {
+    // =========================================================== softmax / output warps: thread = (query row, key half)
+    const int quad = warp & 3, half = warp >> 2;
+    const int row = quad * 32 + lane;
     const float qscale = 1.44269504088896340736f * 0.17677669529663688110f;
-    float o[32];
+    float o[32];                               // half 0 accumulates P V_hi, half 1 accumulates P V_lo (summed at the end)
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;      // l_run: this half's share of the row sum (same rescaling in both halves)
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     for (int j = 0; j < n_tiles; ++j) {
-      const int kv0 = j * kTcKV;
+      const int kv0 = j * kTcKV + half * 32;
       mbar_wait(s_full, j & 1);
       tc_fence_after_sync();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(tmem_S + lane_off + 0, r0);
-      tmem_ld_32x32(tmem_S + lane_off + 32, r1);
+      uint32_t r0[32];
+      tmem_ld_32x32(tmem_S + lane_off + half * 32, r0);
       tmem_ld_wait();
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        float a = __uint_as_float(r0[i]) * qscale, c = __uint_as_float(r1[i]) * qscale;
+        float a = __uint_as_float(r0[i]) * qscale;
         if (kv0 + i >= T) a = -INFINITY;
-        if (kv0 + 32 + i >= T) c = -INFINITY;
         r0[i] = __float_as_uint(a);
-        r1[i] = __float_as_uint(c);
-        mx = fmaxf(mx, fmaxf(a, c));
+        mx = fmaxf(mx, a);
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f(m_run - m_new);
+      s_rmax[half * 128 + row] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");          // the two key halves of every row exchange their maxima
+      const float m_new = fmaxf(m_run, fmaxf(mx, s_rmax[(half ^ 1) * 128 + row]));
+      const float alpha = ex2_approx(m_run - m_new);
       m_run = m_new;
       float rs = 0.f;
-      // P chunks: chunk 0 = keys 0..31 (r0), chunk 1 = keys 32..63 (r1); row layout hi(64 B) | lo(64 B), swizzled
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = exp2f(__uint_as_float(ch ? r1[i] : r0[i]) - m_run);
-          const float p1 = exp2f(__uint_as_float(ch ? r1[i + 1] : r0[i + 1]) - m_run);
+          const float p0 = ex2_approx(__uint_as_float(r0[i]) - m_run);
+          const float p1 = ex2_approx(__uint_as_float(r0[i + 1]) - m_run);
           rs += p0 + p1;
           split_bf16x2(p0, p1, hi[i >> 1], lo[i >> 1]);
         }
-        uint8_t* prow = sP + ch * 16384 + row * 128;
+        uint8_t* prow = sP + half * 16384 + row * 128;        // chunk `half` = this thread's 32 keys
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           *(uint4*)(prow + ((c4 ^ (row & 7)) << 4)) = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
@@ -662,25 +667,33 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
       tc_fence_before_sync();             // S reads are complete before the MMA warp may overwrite S
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      // ---- O' of this tile
+      // ---- O' of this tile: this half's 32 columns
       mbar_wait(o_full, j & 1);
       tc_fence_after_sync();
-      tmem_ld_32x32(tmem_O + lane_off + 0, r0);
-      tmem_ld_32x32(tmem_O + lane_off + 32, r1);
+      tmem_ld_32x32(tmem_O + lane_off + half * 32, r0);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + (__uint_as_float(r0[i]) + __uint_as_float(r1[i]));
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r0[i]);
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_free);
     }
-    // ---- finalize: operand-form output row chunk of head h
+    // ---- combine the halves (O = P V_hi + P V_lo, l = l0 + l1) through shared memory, half 0 writes the output
+    float* xo = (float*)sP;                    // [128][33] floats (P is dead: the last o_full has been observed)
+    float* xl = xo + 128 * 33;
+    if (half == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) xo[row * 33 + i] = o[i];
+      xl[row] = l_run;
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");
     const int grow = q0 + row;
-    if (grow < T) {
-      const float inv = 1.f / l_run;
+    if (half == 0 && grow < T) {
+      const float inv = 1.f / (l_run + xl[row]);
       uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) split_bf16x2(o[i] * inv, o[i + 1] * inv, hi[i >> 1], lo[i >> 1]);
+      for (int i = 0; i < 32; i += 2)
+        split_bf16x2((o[i] + xo[row * 33 + i]) * inv, (o[i + 1] + xo[row * 33 + i + 1]) * inv, hi[i >> 1], lo[i >> 1]);
       uint4* dst = (uint4*)(out + (size_t)(t0 + grow) * ldo + (size_t)h * 128);
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
@@ -688,7 +701,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
         dst[4 + c4] = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kTcSoftmaxWarps) {
     // =========================================================== K/V loader: 2-stage cp.async ring
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j & 1;
@@ -907,7 +920,7 @@ int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_seqlens, int
   UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd_tc: bad sizes");
   UD3D_CHECK_ARG((((uintptr_t)qkv_split | (uintptr_t)out_split) & 15) == 0, "ud3d_attention_fwd_tc: pointers must be 16-byte aligned");
   if (max_T == 0) return UD3D_OK;
-  const size_t smem = 1024 + 16384 + 4 * 8192 + 2 * 16384 + 128;
+  const size_t smem = 1024 + 16384 + 4 * 8192 + 2 * 16384 + 1024 + 128;
   static bool configured = false;
   if (!configured) {
     UD3D_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
