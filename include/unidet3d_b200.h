@@ -97,6 +97,11 @@ int ud3d_rulebook_subm3(const int32_t* coords, int n, const int32_t dims_host[4]
  *   (ud3d_grid_build) and reads back n_coarse. */
 int ud3d_down2_parents(const int32_t* coords, int n, const int32_t in_shape_host[3], int32_t* parents,
                        void* stream);
+/* ancestors[i] = coordinates of voxel i after `levels` successive k=2,s=2 down-samplings (b = -1 when the voxel is
+ * dropped at any of them).  The coarse grids of every level can thus be built from the finest coordinates (or even the
+ * per-point coordinates) back to back, and all voxel counts read with a single host synchronisation. */
+int ud3d_down_ancestors(const int32_t* coords, int n, const int32_t in_shape_host[3], int levels, int32_t* ancestors,
+                        void* stream);
 /* phase 2: child[s][p] = fine row feeding coarse row p through slot s = (x&1)*4+(y&1)*2+(z&1);
  * up[s][i] = coarse row of fine row i (slot s), both -1-filled elsewhere.  The pair list is shared by
  * SparseInverseConv3d (spconv_unet.py:178-183).  coarse_ws = grid built on `parents`.

@@ -62,6 +62,7 @@ SIGNATURES = {
     "ud3d_voxel_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ud3d_rulebook_subm3": (_i, [_vp, _i, c_i32p, _vp, _vp, _vp, _vp, _vp]),
     "ud3d_down2_parents": (_i, [_vp, _i, c_i32p, _vp, _vp]),
+    "ud3d_down_ancestors": (_i, [_vp, _i, c_i32p, _i, _vp, _vp]),
     "ud3d_rulebook_down2": (_i, [_vp, _vp, _i, _i, c_i32p, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ud3d_gemm_packed_weight_bytes": (_sz, [_i, _i, _i]),
     "ud3d_gemm_pack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),

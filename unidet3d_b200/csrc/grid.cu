@@ -320,6 +320,26 @@ __global__ void down2_parents_kernel(const int4* __restrict__ coords, int n, int
   }
 }
 
+// ancestor of every input voxel after `levels` successive k2/s2 down-samplings, with the per-level drop rule
+// (coordinate/2 >= out_shape of that level -> the voxel and all its descendants contribute nothing deeper).
+// Lets the grids (and counts) of ALL coarse levels be built from the finest coordinates in one go, without
+// knowing the intermediate voxel counts on the host.
+__global__ void down_ancestors_kernel(const int4* __restrict__ coords, int n, int sx, int sy, int sz, int levels,
+                                      int4* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    int x = c.y, y = c.z, z = c.w, ax = sx, ay = sy, az = sz;
+    bool keep = c.x >= 0;
+    for (int l = 0; l < levels && keep; ++l) {
+      const int ox = (ax - 2) / 2 + 1, oy = (ay - 2) / 2 + 1, oz = (az - 2) / 2 + 1;
+      x >>= 1; y >>= 1; z >>= 1;
+      keep = x < ox && y < oy && z < oz;
+      ax = ox; ay = oy; az = oz;
+    }
+    out[i] = make_int4(keep ? c.x : -1, x, y, z);
+  }
+}
+
 __global__ void down2_fill_kernel(const int4* __restrict__ coords, const int4* __restrict__ parents, int n_fine, int n_coarse,
                                   GridDims g, const uint32_t* __restrict__ words, const uint32_t* __restrict__ prefix,
                                   int32_t* __restrict__ child, int32_t* __restrict__ up, uint32_t* child_mask,
@@ -495,6 +515,17 @@ int ud3d_down2_parents(const int32_t* coords, int n, const int32_t in_shape_host
   if (n == 0) return UD3D_OK;
   int ox = (in_shape_host[0] - 2) / 2 + 1, oy = (in_shape_host[1] - 2) / 2 + 1, oz = (in_shape_host[2] - 2) / 2 + 1;
   down2_parents_kernel<<<grid_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)coords, n, ox, oy, oz, (int4*)parents);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_down_ancestors(const int32_t* coords, int n, const int32_t in_shape_host[3], int levels, int32_t* ancestors,
+                        void* stream) {
+  UD3D_CHECK_ARG(in_shape_host && levels >= 1 && (n == 0 || (coords && ancestors)), "ud3d_down_ancestors: bad argument");
+  if (n == 0) return UD3D_OK;
+  down_ancestors_kernel<<<grid_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>((const int4*)coords, n, in_shape_host[0],
+                                                                              in_shape_host[1], in_shape_host[2], levels,
+                                                                              (int4*)ancestors);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

@@ -82,14 +82,16 @@ class UniDet3D(nn.Module):
         coords_pt, feats_pt, _, maxc = ops.point_coords(points, scene_offsets, self.voxel_size)
         ext = (maxc.cpu().numpy() + 1).tolist()                       # host sync #1 (spatial extents)
         spatial_shape = [max(int(e), int(self.min_spatial_shape)) for e in ext]
-        grid = ops.Grid([batch_size] + ext, points.device)
-        n_vox = int(grid.build(coords_pt).item())                     # host sync #2 (voxel count)
-        inverse = grid.rank(coords_pt)
-        coords = grid.coords(n_vox)
+        # occupancy grids of all five levels are built from the per-point coordinates back to back; the voxel counts of
+        # every level come back in ONE read-back (host sync #2), then the voxel list / inverse map / tables are emitted
+        pyr = build_pyramid(None, spatial_shape, batch_size, self.unet.n_levels(), canonical=True, extents=ext,
+                            seed_coords=coords_pt)
+        coords = pyr.levels[0].coords
+        n_vox = pyr.levels[0].n
+        inverse = pyr.grid0.rank(coords_pt)
         feats = ops.voxel_mean(feats_pt, inverse, n_vox)
         x = SparseConvTensor(feats, coords, spatial_shape, batch_size, canonical=True, extents=ext)
-        x.pyramid = build_pyramid(coords, spatial_shape, batch_size, self.unet.n_levels(), canonical=True,
-                                  extents=ext, grid=grid)
+        x.pyramid = pyr
         return x, inverse
 
     def extract_feat(self, x: SparseConvTensor, superpoints: torch.Tensor, inverse_mapping: torch.Tensor,

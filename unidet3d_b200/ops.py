@@ -119,6 +119,15 @@ def down2_parents(coords: torch.Tensor, in_shape: Sequence[int]) -> torch.Tensor
     return parents
 
 
+def down_ancestors(coords: torch.Tensor, in_shape: Sequence[int], levels: int) -> torch.Tensor:
+    """coords after ``levels`` k2/s2 down-samplings (b = -1 when dropped on the way); see ud3d_down_ancestors."""
+    _req(coords, torch.int32, "coords")
+    out = torch.empty_like(coords)
+    check(_L().ud3d_down_ancestors(_p(coords), coords.shape[0], _dims(in_shape), int(levels), _p(out), _stream()),
+          "ud3d_down_ancestors")
+    return out
+
+
 def rulebook_down2(coords: torch.Tensor, parents: torch.Tensor, n_coarse: int, coarse_grid: Grid, with_mask: bool = True):
     n_fine = coords.shape[0]
     dev = coords.device

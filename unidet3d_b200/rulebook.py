@@ -33,36 +33,55 @@ class Pyramid:
         return len(self.levels)
 
 
-def build_pyramid(coords: torch.Tensor, spatial_shape: Sequence[int], batch_size: int, n_levels: int,
+def build_pyramid(coords: Optional[torch.Tensor], spatial_shape: Sequence[int], batch_size: int, n_levels: int,
                   canonical: bool = False, extents: Optional[Sequence[int]] = None,
-                  grid: Optional[ops.Grid] = None) -> Pyramid:
+                  grid: Optional[ops.Grid] = None, seed_coords: Optional[torch.Tensor] = None) -> Pyramid:
     """coords int32 [N,4] on the GPU.  ``extents`` = max coord + 1 per axis (bounds the occupancy
     grid; computed here when not given).  ``grid``: an occupancy grid already built on ``coords``."""
-    if coords.dtype != torch.int32:
-        coords = coords.to(torch.int32)
-    coords = coords.contiguous()
-    dev = coords.device
+    if coords is not None:
+        if coords.dtype != torch.int32:
+            coords = coords.to(torch.int32)
+        coords = coords.contiguous()
+    else:
+        assert seed_coords is not None and extents is not None, "coords=None needs seed_coords and extents"
+    dev = (coords if coords is not None else seed_coords).device
     if extents is None:
         extents = (coords[:, 1:].amax(0) + 1).tolist() if coords.shape[0] else [1, 1, 1]
     dims = [int(batch_size)] + [max(1, int(e)) for e in extents]
     shape = [int(s) for s in spatial_shape]
+    count0 = None
     if grid is None:
         grid = ops.Grid(dims, dev)
-        grid.build(coords)
+        count0 = grid.build(coords if coords is not None else seed_coords)
+    # all coarse occupancy grids are built from the finest coordinates back to back (ancestor coordinates with the
+    # per-level drop rule), so the voxel counts of every level come back in ONE host synchronisation
+    shapes, dimss, grids, counts = [list(shape)], [list(dims)], [grid], []
+    src = coords if seed_coords is None else seed_coords            # any superset-free cover of the level-1 set works
+    for l in range(1, n_levels):
+        out_shape = [(s - 2) // 2 + 1 for s in shapes[-1]]
+        d = [dimss[-1][0]] + [max(1, min(o, (x + 1) // 2)) for o, x in zip(out_shape, dimss[-1][1:])]
+        g = ops.Grid(d, dev)
+        counts.append(g.build(ops.down_ancestors(src, shape, l)))
+        shapes.append(out_shape), dimss.append(d), grids.append(g)
+    if coords is None:
+        # level 1 itself comes from the seed (voxelisation): its count rides on the same read-back
+        ns = torch.cat([count0] + counts).cpu().tolist()                                # the only host sync here
+        coords = grid.coords(ns[0])
+        canonical = True
+    else:
+        ns = [coords.shape[0]] + (torch.cat(counts).cpu().tolist() if counts else [])  # the only host sync here
     levels: List[Level] = []
-    c, n = coords, coords.shape[0]
+    c = coords
     for l in range(n_levels):
-        table, mask = ops.rulebook_subm3(c, grid, canonical=(canonical or l > 0))
-        lv = Level(coords=c, shape=list(shape), n=n, subm=table, subm_mask=mask)
+        table, mask = ops.rulebook_subm3(c, grids[l], canonical=(canonical or l > 0))
+        lv = Level(coords=c, shape=list(shapes[l]), n=ns[l], subm=table, subm_mask=mask)
         levels.append(lv)
         if l + 1 == n_levels:
             break
-        parents = ops.down2_parents(c, shape)
-        out_shape = [(s - 2) // 2 + 1 for s in shape]
-        dims = [dims[0]] + [max(1, min(o, (d + 1) // 2)) for o, d in zip(out_shape, dims[1:])]
-        cgrid = ops.Grid(dims, dev)
-        n_next = int(cgrid.build(parents).item())            # one host sync per level
-        cc = cgrid.coords(n_next)
-        lv.child, lv.up, lv.child_mask, lv.up_mask = ops.rulebook_down2(c, parents, n_next, cgrid)
-        c, n, shape, grid = cc, n_next, out_shape, cgrid
-    return Pyramid(levels)
+        parents = ops.down2_parents(c, shapes[l])
+        cc = grids[l + 1].coords(ns[l + 1])
+        lv.child, lv.up, lv.child_mask, lv.up_mask = ops.rulebook_down2(c, parents, ns[l + 1], grids[l + 1])
+        c = cc
+    pyr = Pyramid(levels)
+    pyr.grid0 = grid              # occupancy grid of level 1 (rank() = inverse mapping of the voxelisation)
+    return pyr
