@@ -130,3 +130,19 @@ def test_encoder_logits_and_boxes_full_size():
     for i in range(2):
         assert relerr(out["cls_preds"][i], ref["cls_preds"][i]) < 1e-3
         assert relerr(out["bboxes"][i], ref["bboxes"][i]) < 1e-3
+
+
+def test_pinned_batch_stager_matches_direct_call():
+    """Double-buffered H2D staging (io.PinnedBatchStager) feeds the detector the same data as a direct call."""
+    from unidet3d_b200 import configs, io
+    cfg = configs.model_cfg(("scannet",), topk_insts=200)
+    model, det_sd, enc_sd = _build(cfg)
+    n, v, a, c = SCENE_PRESETS["tiny"]
+    cfg["voxel_size"] = model.voxel_size = v
+    batches = [([make_scene(10 * b + i, n, a, c)[0] for i in range(2)], [make_scene(10 * b + i, n, a, c)[1] for i in range(2)])
+               for b in range(3)]
+    got = [model.forward_scenes(p, s, ["scannet"] * 2, ns) for p, s, ns in io.PinnedBatchStager(batches, DEV)]
+    for (pts, sps), res in zip(batches, got):
+        ref = model.forward_scenes(pts, sps, ["scannet"] * 2)
+        for (b, l, s), (rb, rl, rs) in zip(res, ref):
+            assert torch.equal(l, rl) and torch.allclose(s, rs, rtol=1e-5, atol=1e-7)
