@@ -134,7 +134,10 @@ __global__ void grid_set_bits_kernel(const int4* __restrict__ coords, int n, Gri
     if ((unsigned)c.x >= (unsigned)g.B || (unsigned)c.y >= (unsigned)g.X || (unsigned)c.z >= (unsigned)g.Y ||
         (unsigned)c.w >= (unsigned)g.Z)
       continue;  // outside the declared box: ignored (caller sized the box from max_coord)
-    atomicOr(words + grid_word_index(g, c.x, c.y, c.z, c.w), 1u << (c.w & 31));
+    uint32_t* w = words + grid_word_index(g, c.x, c.y, c.z, c.w);
+    const uint32_t bit = 1u << (c.w & 31);
+    // many inputs map to the same cell (points -> voxels -> coarse ancestors): test before the atomic
+    if (!(*(volatile uint32_t*)w & bit)) atomicOr(w, bit);
   }
 }
 
