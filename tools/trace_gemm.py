@@ -29,11 +29,13 @@ act = torch.empty_like(xin)
 one = torch.ones(c, device="cuda"); zero = torch.zeros(c, device="cuda")
 lib = _lib.load()
 lib.ud3d_debug_set_trace.argtypes = [C.c_void_p, C.c_int]
+lib.ud3d_debug_set_flags.argtypes = [C.c_int]
+lib.ud3d_debug_set_flags(int(os.environ.get("FLAGS", 0)))
 for _ in range(3):
     ops.gemm(xs, w, table=lv.subm, tile_mask=lv.subm_mask, in_split=True, no_raw=True, acts=[(act, one, zero)])
 torch.cuda.synchronize()
 trace = torch.zeros(1024, dtype=torch.int64, device="cuda")
-blk = int(os.environ.get("BLOCK", 1000))
+blk = int(os.environ.get("BLOCK", 100))
 lib.ud3d_debug_set_trace(C.c_void_p(trace.data_ptr()), blk)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()

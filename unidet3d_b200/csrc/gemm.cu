@@ -35,10 +35,14 @@ struct GemmParams {
   int out_vec_ok;  // 16-byte vector epilogue allowed
   long long* trace;   // debug: clock64 timestamps of one CTA (ud3d_debug_set_trace), else nullptr
   int trace_block;
+  int trace_iter;     // which of the CTA's tiles is traced
+  int dbg;            // debug: feature-disable bits for timing breakdowns (ud3d_debug_set_flags), normally 0
 };
 
 static long long* g_trace = nullptr;
 static int g_trace_block = 0;
+static int g_dbg = 0;
+static int g_num_sms = 0;
 
 static inline int pick_ntile(int c_out) {
   if (c_out <= 32) return 32;
@@ -186,10 +190,18 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
   }
 }
 
+// position of tile row r inside an offset's 128-entry slice of the smem rulebook: lane group g = r & 3 owns the 32
+// consecutive entries of rows g, g + 4, g + 8, ... (a producer lane reads its 32 source rows with 8 x LDS.128)
+__device__ __forceinline__ int tbl_pos(int r) { return ((r & 3) << 5) + (r >> 2); }
+
 constexpr int kProducerWarps = 8;                 // warps 0..7 gather A (warps 0..3 also run the epilogue)
 constexpr int kWarpB = 8;                         // warp 8: weight-tile bulk copies
 // warp 9: tcgen05.mma issue
 constexpr int kThreadsTc = 32 * 10;
+// One CTA per row tile.  (A persistent variant of the same loop -- gridDim.x = 2 CTAs per SM striding over the tiles --
+// measured 10 % slower: the second resident CTA already overlaps prologue / epilogue, and the loop-carried state
+// costs registers.)
+constexpr bool kPersistent = false;
 
 // Ring depth S and copies-in-flight D per instantiation.  A stage cycles fill (L2 latency L) -> MMA round
 // trip (M: a_full arrive -> issue -> tcgen05.commit -> empty) -> refill, so steady-state step time per CTA is
@@ -207,7 +219,10 @@ struct GatherRegs {
   int ok[2];
 };
 
-template <int N_TILE, int D_INFLIGHT = TcCfg<N_TILE>::kInFlight>
+// Persistent: gridDim.x CTAs (2 per SM) walk the row tiles with stride gridDim.x; barriers, TMEM and the smem ring
+// are set up once per CTA and the ring state (stage, use count) runs on across tiles.  (One CTA per tile cost ~3 us of
+// launch / TMEM-allocation turnaround per tile: a third of the level-1 convolutions' time.)
+template <int N_TILE>
 __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p) {
   constexpr int STAGES = TcCfg<N_TILE>::kStages;
   constexpr int A_BYTES = kTileM * 128;
@@ -220,9 +235,8 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* tail = sB + STAGES * B_BYTES;
-  uint64_t* a_full = (uint64_t*)tail;            // [STAGES] count = producer warps
-  uint64_t* b_full = a_full + STAGES;            // [STAGES] count = 1 (+tx bytes)
-  uint64_t* empty = b_full + STAGES;             // [STAGES] count = 1 (tcgen05.commit)
+  uint64_t* a_full = (uint64_t*)tail;            // [STAGES] count = producer arrivals + 1 (weight copy, +tx bytes)
+  uint64_t* empty = a_full + 2 * STAGES;         // [STAGES] count = 1 (tcgen05.commit)
   uint64_t* acc_full = empty + STAGES;           // [1]
   uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
   uint32_t* s_mask = tmem_slot + 1;
@@ -231,19 +245,26 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   const ud3d_gemm_args& a = p.a;
   const int c_in_pad = p.n_chunks * kChunk;
   float* s_shift = s_scale + c_in_pad;
-  int32_t* s_tbl = (int32_t*)(s_shift + c_in_pad);   // [K][128] table slice of this tile
+  int32_t* s_tbl = (int32_t*)(s_shift + c_in_pad);   // [K][128] table slice of the current tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * kTileM;
   const int nt = blockIdx.y;
   const int n0 = nt * N_TILE;
   const bool has_table = a.table != nullptr;
-  if (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1019] = clock64();
+  const int n_row_tiles = (a.n_out + kTileM - 1) / kTileM;
 
+  // ------------------------------------------------------------ once per CTA
+  if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long gt; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[4 * blockIdx.x + 0] = (long long)gt;
+    p.trace[4 * blockIdx.x + 2] = smid;
+  }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&a_full[s], kProducerWarps);
-      mbar_init(&b_full[s], 1);
+      // operand-form input: every producer thread's async copies arrive by themselves (cp.async.mbarrier.arrive.noinc)
+      mbar_init(&a_full[s], (a.in_split ? 32 * (kProducerWarps / STAGES) : kProducerWarps) + 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_full, 1);
@@ -260,312 +281,329 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  // stage the tile's slice of the rulebook in shared memory (one coalesced pass, removes the
-  // dependent table -> row load chain from the mainloop)
-  uint32_t mybits = 0;
-  if (has_table) {
-    // all loads of a thread are issued back to back (one L2 round trip for the whole slice)
-    constexpr int kPer = (32 * kTileM + kThreadsTc - 1) / kThreadsTc;   // 13
-    int vals[kPer];
-    const int total = a.K * kTileM;
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) {
-      const int i = tid + j * kThreadsTc;
-      const int k = i >> 7, row = m0 + (i & 127);
-      vals[j] = (i < total && row < a.n_out) ? __ldg(a.table + (size_t)k * a.n_out + row) : -1;
-    }
-#pragma unroll
-    for (int j = 0; j < kPer; ++j) {
-      const int i = tid + j * kThreadsTc;
-      if (i < total) {
-        s_tbl[i] = vals[j];
-        if (vals[j] >= 0) mybits |= 1u << (i >> 7);
-      }
-    }
-  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  if (has_table && !a.tile_mask) {
-    mybits = __reduce_or_sync(0xffffffffu, mybits);
-    if (lane == 0 && mybits) atomicOr(s_mask, mybits);
-  }
-  __syncthreads();
   const uint32_t tmem_base = *tmem_slot;
-  uint32_t mask = has_table ? (a.tile_mask ? a.tile_mask[blockIdx.x] : *s_mask) : 1u;
-  if (tid == 0) {
-    int n = 0;
-    for (int k = 0; k < 32; ++k)
-      if ((mask >> k) & 1u) s_actk[n++] = (uint8_t)k;
-  }
-  __syncthreads();
-  const int nact = __popc(mask);
-  const int nsteps_all = nact * p.n_chunks;
-  // split-K: this CTA handles steps [t_begin, t_end) of the tile's active (offset, chunk) sequence
-  const int t_begin = (int)((long long)nsteps_all * blockIdx.z / gridDim.z);
-  const int t_end = (int)((long long)nsteps_all * (blockIdx.z + 1) / gridDim.z);
-  const int nsteps = t_end - t_begin;
   const uint8_t* wp = (const uint8_t*)a.w_packed + (size_t)nt * a.K * p.n_chunks * B_BYTES;
 
-  // (kslot, chunk) of this CTA's first step: the only integer division of the mainloop
-  const int kslot0 = t_begin / p.n_chunks;
-  const int chunk0 = t_begin - kslot0 * p.n_chunks;
+  // ring state: every role walks the same (stage, use) sequence, across tiles
+  int rs = 0;
+  uint32_t ruse = 0;
+  uint32_t acc_phase = 0;
 
-  if (warp < kProducerWarps) {
-    // =========================================================== A producers
-    if (a.in_split) {
-      // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
-      //      zero-fill for missing neighbours; D steps of copies in flight per thread, no ALU work
-      constexpr int D = D_INFLIGHT;
-      const size_t row_bytes = (size_t)a.ld_in * 4;
-      const int j = tid & 7;
-      const int rbase = tid >> 3;
-      const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
-      const uint32_t sA_addr = smem_u32(sA);
-      uint32_t dst_off[4];
-      int ident[4];
+  for (int tile = blockIdx.x, it = 0; tile < n_row_tiles; tile += gridDim.x, ++it) {
+    const int m0 = tile * kTileM;
+    const bool traced = p.trace && (int)blockIdx.x == p.trace_block && it == p.trace_iter;
+    if (traced && tid == 0) p.trace[1019] = clock64();
+    // ---------------------------------------------------------- per tile: rulebook slice -> smem, active offsets
+    // (one coalesced pass; removes the dependent table -> row load chain from the mainloop)
+    const uint32_t tmask = (has_table && a.tile_mask) ? __ldg(a.tile_mask + tile) : 0u;
+    uint32_t mybits = 0;
+    if (has_table) {
+      // all loads of a thread are issued back to back (one L2 round trip for the whole slice)
+      constexpr int kPer = (32 * kTileM + kThreadsTc - 1) / kThreadsTc;   // 13
+      int vals[kPer];
+      const int total = a.K * kTileM;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = rbase + 32 * i;
-        dst_off[i] = (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
-        ident[i] = (m0 + r < a.n_out) ? m0 + r : -1;
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kThreadsTc;
+        const int k = i >> 7, row = m0 + (i & 127);
+        vals[j] = (i < total && row < a.n_out) ? __ldg(a.table + (size_t)k * a.n_out + row) : -1;
       }
-      int kslot = kslot0, c = chunk0, s = 0, pub_s = 0;
-      uint32_t use = 0;
-      uint32_t dirty = 0xFFFFFFFFu;        // bit (stage*4 + i): this thread's chunk i of the stage may hold non-zero data
-      long long* tr = (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) ? p.trace : nullptr;
-      if (tr) { tr[1023] = nsteps; tr[1022] = clock64(); }
-      for (int t = 0; t < nsteps; ++t) {
-        if (use) {                         // one poller per warp (256 spinning threads starve the MMA / TMA warps)
-          if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-          __syncwarp();
-        }
-        if (tr && t < 64) tr[t * 8 + 0] = clock64();
-        const int32_t* trow = s_tbl + (int)s_actk[kslot] * kTileM + rbase;
-        const uint8_t* sb = src_base + c * 128;
-        const uint32_t as_addr = sA_addr + s * A_BYTES;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = has_table ? trow[32 * i] : ident[i];
-          const uint32_t bit = 1u << (s * 4 + i);
-          if (idx >= 0) {
-            cp_async_16(as_addr + dst_off[i], sb + (size_t)idx * row_bytes);
-            dirty |= bit;
-          } else if (dirty & bit) {
-            // missing neighbour: the chunk must read as zero.  It only needs a store when the previous use of this
-            // stage left data there (~60 % of all (row, offset) slots are missing: most of them cost nothing)
-            st_shared_zero16(as_addr + dst_off[i]);
-            dirty &= ~bit;
-          }
-        }
-        cp_async_commit();
-        if (tr && t < 64) tr[t * 8 + 1] = clock64();
-        if (++c == p.n_chunks) { c = 0; ++kslot; }
-        if (++s == STAGES) { s = 0; ++use; }
-        if (t >= D) {
-          cp_async_wait<D>();             // the copies of step t - D have landed
-          if (tr && t - D < 64) tr[(t - D) * 8 + 2] = clock64();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[pub_s]);
-          if (tr && t - D < 64) tr[(t - D) * 8 + 3] = clock64();
-          if (++pub_s == STAGES) pub_s = 0;
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kThreadsTc;
+        if (i < total) {
+          s_tbl[(i & ~127) + tbl_pos(i & 127)] = vals[j];
+          if (vals[j] >= 0) mybits |= 1u << (i >> 7);
         }
       }
-      // drain the last min(D, nsteps) steps
-#pragma unroll
-      for (int d = D - 1; d >= 0; --d) {
-        if (nsteps > d) {
-          if (d == 2) cp_async_wait<2>();
-          else if (d == 1) cp_async_wait<1>();
-          else cp_async_wait<0>();
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[pub_s]);
-          if (++pub_s == STAGES) pub_s = 0;
-        }
-      }
-    } else {
-      // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers (4 lanes per row, 8 channels each)
-      const int q = tid & 3;
-      const int rl = tid >> 2;
-      const bool affine = a.in_scale != nullptr;
-      const bool relu = a.in_relu != 0;
-      int ident[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) ident[h] = (m0 + rl + h * 64 < a.n_out) ? m0 + rl + h * 64 : -1;
-
-      auto issue_loads = [&](int kslot, int c, GatherRegs& g) {
-        const int32_t* trow = s_tbl + (int)s_actk[kslot] * kTileM + rl;
-        const int ch0 = c * kChunk + q * 8;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int idx = has_table ? trow[h * 64] : ident[h];
-          g.ok[h] = idx >= 0 && ch0 < a.c_in;
-          if (g.ok[h]) {
-            const float* src = a.in + (size_t)idx * a.ld_in + ch0;
-            if (p.vec_ok) {
-              g.v[h][0] = __ldg((const float4*)src);
-              g.v[h][1] = __ldg((const float4*)src + 1);
-            } else {
-              float e[8];
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) e[jj] = (ch0 + jj < a.c_in) ? __ldg(src + jj) : 0.f;
-              g.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
-              g.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
-            }
-          }
-        }
-      };
-      auto store_step = [&](int s, uint32_t use, int c, const GatherRegs& g) {
-        const int ch0 = c * kChunk + q * 8;
-        if (use) {
-          if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-          __syncwarp();
-        }
-        uint8_t* As = sA + s * A_BYTES;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float v[8];
-          if (g.ok[h]) {
-            v[0] = g.v[h][0].x; v[1] = g.v[h][0].y; v[2] = g.v[h][0].z; v[3] = g.v[h][0].w;
-            v[4] = g.v[h][1].x; v[5] = g.v[h][1].y; v[6] = g.v[h][1].z; v[7] = g.v[h][1].w;
-            if (affine) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
-            }
-            if (relu) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            if (!p.vec_ok) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if (ch0 + e >= a.c_in) v[e] = 0.f;     // padded channels stay exactly zero
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          }
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-          const int r = rl + h * 64;
-          uint8_t* arow = As + r * 128;
-          *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[s]);
-      };
-
-      // software pipeline: the global loads of step t+1 are in flight while step t is converted/stored
-      GatherRegs g0, g1;
-      int lk = kslot0, lc = chunk0;        // (kslot, chunk) of the next loads to issue
-      int sc = chunk0;                     // chunk of the next step to store
-      int s = 0;
-      uint32_t use = 0;
-      auto adv_load = [&]() { if (++lc == p.n_chunks) { lc = 0; ++lk; } };
-      auto adv_store = [&]() { if (++sc == p.n_chunks) sc = 0; if (++s == STAGES) { s = 0; ++use; } };
-      if (nsteps > 0) { issue_loads(lk, lc, g0); adv_load(); }
-      for (int t = 0; t < nsteps; t += 2) {
-        if (t + 1 < nsteps) { issue_loads(lk, lc, g1); adv_load(); }
-        store_step(s, use, sc, g0); adv_store();
-        if (t + 1 < nsteps) {
-          if (t + 2 < nsteps) { issue_loads(lk, lc, g0); adv_load(); }
-          store_step(s, use, sc, g1); adv_store();
-        }
-      }
+    } else if (a.in_split) {
+      if (tid < kTileM) s_tbl[tbl_pos(tid)] = (m0 + tid < a.n_out) ? m0 + tid : -1;   // identity gather as a one-offset table
     }
-  } else if (warp == kWarpB) {
-    // =========================================================== B producer: one bulk copy (TMA engine) per step
-    int kslot = kslot0, c = chunk0, s = 0;
-    uint32_t use = 0;
-    if (lane == 0) {
+    uint32_t mask;
+    if (!has_table) {
+      mask = 1u;
+    } else if (a.tile_mask) {
+      mask = tmask;
+    } else {
+      mybits = __reduce_or_sync(0xffffffffu, mybits);
+      if (lane == 0 && mybits) atomicOr(s_mask, mybits);
+      __syncthreads();
+      mask = *s_mask;
+    }
+    if (tid < 32 && ((mask >> tid) & 1u)) s_actk[__popc(mask & ((1u << tid) - 1u))] = (uint8_t)tid;
+    __syncthreads();
+    const int nact = __popc(mask);
+    const int nsteps_all = nact * p.n_chunks;
+    // split-K: this CTA handles steps [t_begin, t_end) of the tile's active (offset, chunk) sequence
+    const int t_begin = (int)((long long)nsteps_all * blockIdx.z / gridDim.z);
+    const int t_end = (int)((long long)nsteps_all * (blockIdx.z + 1) / gridDim.z);
+    const int nsteps = (p.dbg & 512) ? 0 : t_end - t_begin;
+    // (kslot, chunk) of this CTA's first step: the only integer division of the tile
+    const int kslot0 = t_begin / p.n_chunks;
+    const int chunk0 = t_begin - kslot0 * p.n_chunks;
+
+    if (warp < kProducerWarps) {
+      // ========================================================= A producers
+      if (a.in_split) {
+        // ---- operand-form input: pure async copies (LDGSTS), 16 B per lane, 8 lanes per 128-byte row-chunk,
+        //      zero-fill for missing neighbours, no ALU work.  The producers never wait for their own copies: each
+        //      thread's cp.async.mbarrier.arrive.noinc makes the stage's full barrier count its arrival when its copies
+        //      have landed, so the ring depth hides the L2 latency: wait empty -> 4 LDGSTS -> arrive.noinc.
+        const uint32_t row_bytes = (uint32_t)a.ld_in * 4u;
+        // The producer warps are bound to ring stages: stage s is filled, for every K-step that maps to it, by the same
+        // WPG = 8 / STAGES warps (each copies 128 / WPG rows: NI = 32 / WPG LDGSTS per lane).  One pass through the
+        // control code (empty wait, arrive) per NI copies instead of per 4 -- the loop is bound by the LSU (~8 cycles per
+        // LDGSTS instruction), not by each warp's serial instruction latency -- the stages fill concurrently, and
+        // every waiter sees all phases of its barrier in order (a parity wait cannot tell phases two apart).
+        // Lane (g = lane >> 3, j = lane & 7) copies chunk j of rows base + g, base + g + 4, ...: instruction i covers
+        // the 4 consecutive rows base + 4 i .. base + 4 i + 3.
+        constexpr int WPG = kProducerWarps / STAGES;
+        constexpr int NI = 32 / WPG;
+        const int grp = warp / WPG, half = warp - grp * WPG;
+        const int g = lane >> 3, j = lane & 7;
+        const uint32_t sw0 = (uint32_t)((j ^ g) << 4), sw1 = (uint32_t)(((j ^ g) ^ 4) << 4);   // (4 i + g) & 7 = 4 (i & 1) + g
+        const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
+        const uint32_t sA_lane = smem_u32(sA) + (uint32_t)((half * (kTileM / WPG) + g) * 128);
+        long long* tr = (traced && tid == 0) ? p.trace : nullptr;
+        if (tr) { tr[1023] = nsteps; tr[1022] = clock64(); }
+        if (grp < STAGES) {
+          for (int t = (grp - rs + STAGES) % STAGES; t < nsteps; t += STAGES) {     // the steps that land in stage grp
+            if (tr && t < 64) tr[t * 8 + 0] = clock64();
+            const int s = grp;
+            const uint32_t use = ruse + (uint32_t)((rs + t) / STAGES);
+            const int tt = t_begin + t;
+            const int kslot = tt / p.n_chunks;
+            const int c = tt - kslot * p.n_chunks;
+            const int k = has_table ? (int)s_actk[kslot] : 0;
+            int idx[NI];
+            {
+              const int4* tp = (const int4*)(s_tbl + k * kTileM + g * 32 + half * NI);
+#pragma unroll
+              for (int q = 0; q < NI / 4; ++q) {
+                const int4 v = tp[q];
+                idx[4 * q] = v.x; idx[4 * q + 1] = v.y; idx[4 * q + 2] = v.z; idx[4 * q + 3] = v.w;
+              }
+            }
+            if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+            if (tr && t < 64) tr[t * 8 + 1] = clock64();
+            const uint8_t* sb = src_base + c * 128;
+            const uint32_t as_addr = sA_lane + s * A_BYTES;
+            // branch-free: a missing neighbour is a zero-fill copy (src-size 0: no global read)
+            if (!(p.dbg & 4)) {
+#pragma unroll
+              for (int i = 0; i < NI; ++i) {
+                const int ix = (p.dbg & 32) ? -1 : idx[i];
+                cp_async_16_zfill(as_addr + i * 512 + ((i & 1) ? sw1 : sw0),
+                                  sb + (size_t)((uint32_t)(ix < 0 ? 0 : ix) * (uint64_t)row_bytes), ix < 0 ? 0u : 16u);
+              }
+            }
+            cp_async_mbar_arrive_noinc(&a_full[s]);
+            if (tr && t < 64) tr[t * 8 + 2] = tr[t * 8 + 3] = clock64();
+          }
+        }
+      } else {
+        // ---- fp32 input: gather + folded BN/ReLU + bf16 hi/lo split in registers (4 lanes per row, 8 channels each)
+        const int q = tid & 3;
+        const int rl = tid >> 2;
+        const bool affine = a.in_scale != nullptr;
+        const bool relu = a.in_relu != 0;
+        int ident[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) ident[h] = (m0 + rl + h * 64 < a.n_out) ? m0 + rl + h * 64 : -1;
+
+        auto issue_loads = [&](int kslot, int c, GatherRegs& g) {
+          const int32_t* trow = s_tbl + (int)s_actk[kslot] * kTileM;
+          const int ch0 = c * kChunk + q * 8;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int idx = has_table ? trow[tbl_pos(rl + h * 64)] : ident[h];
+            g.ok[h] = idx >= 0 && ch0 < a.c_in;
+            if (g.ok[h]) {
+              const float* src = a.in + (size_t)idx * a.ld_in + ch0;
+              if (p.vec_ok) {
+                g.v[h][0] = __ldg((const float4*)src);
+                g.v[h][1] = __ldg((const float4*)src + 1);
+              } else {
+                float e[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) e[jj] = (ch0 + jj < a.c_in) ? __ldg(src + jj) : 0.f;
+                g.v[h][0] = make_float4(e[0], e[1], e[2], e[3]);
+                g.v[h][1] = make_float4(e[4], e[5], e[6], e[7]);
+              }
+            }
+          }
+        };
+        auto store_step = [&](int s, uint32_t use, int c, const GatherRegs& g) {
+          const int ch0 = c * kChunk + q * 8;
+          if (use) {
+            if (lane == 0) mbar_wait(&empty[s], (use & 1u) ^ 1u);
+            __syncwarp();
+          }
+          uint8_t* As = sA + s * A_BYTES;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[8];
+            if (g.ok[h]) {
+              v[0] = g.v[h][0].x; v[1] = g.v[h][0].y; v[2] = g.v[h][0].z; v[3] = g.v[h][0].w;
+              v[4] = g.v[h][1].x; v[5] = g.v[h][1].y; v[6] = g.v[h][1].z; v[7] = g.v[h][1].w;
+              if (affine) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_scale[ch0 + e], s_shift[ch0 + e]);
+              }
+              if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              if (!p.vec_ok) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  if (ch0 + e >= a.c_in) v[e] = 0.f;     // padded channels stay exactly zero
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+            const int r = rl + h * 64;
+            uint8_t* arow = As + r * 128;
+            *(uint4*)(arow + ((q ^ (r & 7)) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *(uint4*)(arow + (((4 + q) ^ (r & 7)) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[s]);
+        };
+
+        // software pipeline: the global loads of step t+1 are in flight while step t is converted/stored
+        GatherRegs g0, g1;
+        int lk = kslot0, lc = chunk0;        // (kslot, chunk) of the next loads to issue
+        int sc = chunk0;                     // chunk of the next step to store
+        int s = rs;
+        uint32_t use = ruse;
+        auto adv_load = [&]() { if (++lc == p.n_chunks) { lc = 0; ++lk; } };
+        auto adv_store = [&]() { if (++sc == p.n_chunks) sc = 0; if (++s == STAGES) { s = 0; ++use; } };
+        if (nsteps > 0) { issue_loads(lk, lc, g0); adv_load(); }
+        for (int t = 0; t < nsteps; t += 2) {
+          if (t + 1 < nsteps) { issue_loads(lk, lc, g1); adv_load(); }
+          store_step(s, use, sc, g0); adv_store();
+          if (t + 1 < nsteps) {
+            if (t + 2 < nsteps) { issue_loads(lk, lc, g0); adv_load(); }
+            store_step(s, use, sc, g1); adv_store();
+          }
+        }
+      }
+    } else if (warp == kWarpB) {
+      // ========================================================= B producer: one bulk copy (TMA engine) per step; the
+      // warp stays converged and an elected lane issues (uniform-register operands)
+      int kslot = kslot0, c = chunk0, s = rs;
+      uint32_t use = ruse;
       for (int t = 0; t < nsteps; ++t) {
         if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
         const int k = s_actk[kslot];
-        mbar_arrive_expect_tx(&b_full[s], B_BYTES);
-        bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &b_full[s]);
+        if (elect_one_sync()) {
+          if (p.dbg & 2) {
+            mbar_arrive(&a_full[s]);
+          } else {
+            mbar_arrive_expect_tx(&a_full[s], B_BYTES);
+            bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &a_full[s]);
+          }
+        }
         if (++c == p.n_chunks) { c = 0; ++kslot; }
         if (++s == STAGES) { s = 0; ++use; }
       }
-    }
-    __syncwarp();
-  } else {
-    // =========================================================== MMA issuer (one lane; the other 31 idle at the
-    // final barrier).  A single thread's dependent instruction chain is the latency of this role, so the
-    // smem descriptors of every stage are built once and each K-step only adds the +32/+64/+96-byte offsets.
-    if (lane == 0) {
-      uint64_t adesc[STAGES], bdesc[STAGES];
-#pragma unroll
-      for (int i = 0; i < STAGES; ++i) {
-        adesc[i] = umma_desc_sw128(smem_u32(sA + i * A_BYTES));
-        bdesc[i] = umma_desc_sw128(smem_u32(sB + i * B_BYTES));
-      }
-      long long* tr = (p.trace && (int)blockIdx.x == p.trace_block) ? p.trace : nullptr;
-      uint32_t use = 0;
-      int t = 0;
-      while (t < nsteps) {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
-          if (t < nsteps) {
-            mbar_wait(&a_full[s], use & 1u);
-            if (tr && t < 64) tr[t * 8 + 4] = clock64();
-            mbar_wait(&b_full[s], use & 1u);
-            if (tr && t < 64) tr[t * 8 + 5] = clock64();
-            tc_fence_after_sync();
-            const uint64_t ad = adesc[s], bd = bdesc[s];
-            // start-address field is in 16-byte units: +2 = 32 B (second K=16 slice), +4 = lo half, +6 = lo second slice
-            umma_bf16(tmem_base, ad + 0, bd + 0, IDESC, t > 0);
-            umma_bf16(tmem_base, ad + 2, bd + 2, IDESC, 1);
-            umma_bf16(tmem_base, ad + 4, bd + 0, IDESC, 1);
-            umma_bf16(tmem_base, ad + 6, bd + 2, IDESC, 1);
-            umma_bf16(tmem_base, ad + 0, bd + 4, IDESC, 1);
-            umma_bf16(tmem_base, ad + 2, bd + 6, IDESC, 1);
-            umma_commit(&empty[s]);            // stage s reusable once these MMAs have read it
-            if (tr && t < 64) tr[t * 8 + 6] = clock64();
-            ++t;
-          }
+      __syncwarp();
+    } else {
+      // ========================================================= MMA issuer.  The whole warp runs the loop converged and
+      // one elected lane issues each tcgen05 instruction (elect.sync): operands stay in uniform registers.  Under a
+      // `lane == 0` branch the compiler wraps every UTCHMMA in an R2UR / vote loop (~80 cycles of issue per MMA).
+      const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
+      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
+      long long* tr = (traced && lane == 0) ? p.trace : nullptr;
+      int s = rs;
+      uint32_t use = ruse;
+      for (int t = 0; t < nsteps; ++t) {
+        mbar_wait(&a_full[s], use & 1u);   // A rows (producer threads) + weight tile (bulk copy tx bytes)
+        if (tr && t < 64) tr[t * 8 + 4] = tr[t * 8 + 5] = clock64();
+        tc_fence_after_sync();
+        if (p.dbg & 1) {
+          if (lane == 0) mbar_arrive(&empty[s]);
+        } else {
+          // the start-address field is in 16-byte units: stage s, then +2 = 32 B (second K=16 slice), +4 = lo half,
+          // +6 = lo second slice
+          const uint64_t ad = adesc0 + (uint64_t)(s * (A_BYTES >> 4)), bd = bdesc0 + (uint64_t)(s * (B_BYTES >> 4));
+          umma_bf16_elect(tmem_base, ad + 0, bd + 0, IDESC, t > 0);
+          umma_bf16_elect(tmem_base, ad + 2, bd + 2, IDESC, 1);
+          umma_bf16_elect(tmem_base, ad + 4, bd + 0, IDESC, 1);
+          umma_bf16_elect(tmem_base, ad + 6, bd + 2, IDESC, 1);
+          umma_bf16_elect(tmem_base, ad + 0, bd + 4, IDESC, 1);
+          umma_bf16_elect(tmem_base, ad + 2, bd + 6, IDESC, 1);
+          umma_commit_elect(&empty[s]);      // stage s reusable once these MMAs have read it
         }
-        ++use;
+        if (tr && t < 64) tr[t * 8 + 6] = clock64();
+        if (++s == STAGES) { s = 0; ++use; }
       }
-      umma_commit(acc_full);
-    }
-    __syncwarp();
-  }
-
-  // ------------------------------------------------------------ epilogue (warps 0..3, one row per thread)
-  if (warp < 4) {
-    if (nsteps > 0) {
-      mbar_wait(acc_full, 0);
-      tc_fence_after_sync();
-    }
-    if (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1021] = clock64();
-    const int row = warp * 32 + lane;
-    const int grow = m0 + row;
-    const bool row_ok = grow < a.n_out;
-    const bool split = gridDim.z > 1;
-    const bool lead = blockIdx.z == 0;       // the split that adds bias / residual
-#pragma unroll 1
-    for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-      uint32_t r[32];
       if (nsteps > 0) {
-        tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
+        if (p.dbg & 1) {
+          if (lane == 0) mbar_arrive(acc_full);
+        } else {
+          umma_commit_elect(acc_full);
+        }
       }
-      if (!row_ok) continue;
-      epilogue_store_chunk(p, r, grow, n0 + c0, split, lead);
+      __syncwarp();
     }
+    // every role advanced the ring by nsteps
+    {
+      const int adv = rs + nsteps;
+      ruse += (uint32_t)(adv / STAGES);
+      rs = adv % STAGES;
+    }
+
+    // ---------------------------------------------------------- epilogue (warps 0..3, one row per thread)
+    if (warp < 4) {
+      if (nsteps > 0) {
+        mbar_wait(acc_full, acc_phase);
+        tc_fence_after_sync();
+      }
+      if (traced && tid == 0) p.trace[1021] = clock64();
+      const int row = warp * 32 + lane;
+      const int grow = m0 + row;
+      const bool row_ok = grow < a.n_out;
+      const bool split = gridDim.z > 1;
+      const bool lead = blockIdx.z == 0;       // the split that adds bias / residual
+#pragma unroll 1
+      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        uint32_t r[32];
+        if (nsteps > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (!row_ok || (p.dbg & 16)) continue;
+        epilogue_store_chunk(p, r, grow, n0 + c0, split, lead);
+      }
+    }
+    if (nsteps > 0) acc_phase ^= 1u;
+    if (traced && tid == 0) p.trace[1020] = clock64();
+    // the next tile overwrites the rulebook slice, the active-offset list and the TMEM accumulator
+    if (tid == 0) *s_mask = 0u;
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (!kPersistent) break;
   }
-  if (p.trace && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1020] = clock64();
-  tc_fence_before_sync();
-  __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[4 * blockIdx.x + 1] = (long long)gt;
+  }
 }
 
 // ---------------------------------------------------------------- fp32 -> operand form (one warp per 4 row-chunks)
@@ -652,23 +690,50 @@ static size_t tc_smem_bytes(int n_chunks, int K, bool has_table) {
          (has_table ? (size_t)K * kTileM * 4 : 0);
 }
 
-template <int N_TILE, int D>
-static int launch_tc_d(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
-  size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr);
-  static size_t configured = 0;   // largest size this instantiation was configured for
-  if (smem > configured) {
-    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  dim3 grid(cdiv(p.a.n_out, kTileM), n_tiles, splits);
-  gather_gemm_tc_kernel<N_TILE, D><<<grid, kThreadsTc, smem, st>>>(p);
-  UD3D_LAUNCH_CHECK();
-  return UD3D_OK;
-}
-
 template <int N_TILE>
 static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
-  return launch_tc_d<N_TILE, TcCfg<N_TILE>::kInFlight>(p, n_tiles, splits, st);
+  size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr || p.a.in_split);
+  static size_t configured = 0;   // largest size this instantiation was configured for
+  static int ctas_per_sm = 1;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    UD3D_CUDA(cudaGetDevice(&dev));
+    UD3D_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if (smem > configured) {
+    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
+    UD3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gather_gemm_tc_kernel<N_TILE>, kThreadsTc, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    configured = smem;
+  }
+  // persistent over the row tiles: as many CTAs as are resident at once (the CTAs of the other grid dimensions
+  // share the same SMs)
+  const int row_tiles = cdiv(p.a.n_out, kTileM);
+  int gx = row_tiles;
+  if (kPersistent) {
+    const int want = N_TILE <= 128 ? 2 : 1;     // (the occupancy query under-reports the 2 resident CTAs)
+    gx = (g_num_sms * (ctas_per_sm > want ? ctas_per_sm : want)) / (n_tiles * splits);
+    if (gx < 1) gx = 1;
+    if (gx > row_tiles) gx = row_tiles;
+  }
+  dim3 grid(gx, n_tiles, splits);
+  if (p.dbg & 2048) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, gather_gemm_tc_kernel<N_TILE>);
+    int occ = -1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gather_gemm_tc_kernel<N_TILE>, kThreadsTc, smem);
+    int smem_sm = 0, regs_sm = 0;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, 0);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, 0);
+    printf("launch_tc<%d>: grid %d x %d x %d, ctas/SM %d (now %d, err %d), smem %zu, sms %d; regs %d static smem %zu maxdyn %d carveout %d; SM smem %d regs %d\n",
+           N_TILE, gx, n_tiles, splits, ctas_per_sm, occ, (int)e, smem, g_num_sms, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
+           fa.preferredShmemCarveout, smem_sm, regs_sm);
+  }
+  gather_gemm_tc_kernel<N_TILE><<<grid, kThreadsTc, smem, st>>>(p);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
 }
 
 static int check_args(const ud3d_gemm_args* a, const char* who) {
@@ -730,6 +795,8 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   p.n_chunks = cdiv(args->c_in, kChunk);
   p.trace = g_trace;
   p.trace_block = g_trace_block;
+  p.trace_iter = kPersistent ? 1 : 0;
+  p.dbg = g_dbg;
   p.vec_ok = (args->ld_in % 4 == 0) && (((uintptr_t)args->in & 15) == 0) && (args->c_in % 8 == 0);
   p.out_vec_ok = (args->ld_out % 4 == 0) && (((uintptr_t)args->out & 15) == 0) &&
                  (!args->bias || ((uintptr_t)args->bias & 15) == 0) &&
@@ -793,6 +860,11 @@ int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scal
 int ud3d_debug_set_trace(long long* buf, int block) {
   g_trace = buf;
   g_trace_block = block;
+  return UD3D_OK;
+}
+
+int ud3d_debug_set_flags(int flags) {
+  g_dbg = flags;
   return UD3D_OK;
 }
 
