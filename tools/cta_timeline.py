@@ -20,17 +20,21 @@ lib = _lib.load(); lib.ud3d_debug_set_trace.argtypes = [C.c_void_p, C.c_int]; li
 run = lambda: ops.gemm(xs, w, table=lv.subm, tile_mask=lv.subm_mask, in_split=True, no_raw=True, acts=[(act, one, zero)])
 for _ in range(3): run()
 torch.cuda.synchronize()
-trace = torch.zeros(4 * 4096, dtype=torch.int64, device="cuda")
+trace = torch.zeros(8 * 8192, dtype=torch.int64, device="cuda")
 lib.ud3d_debug_set_trace(C.c_void_p(trace.data_ptr()), -2)
 run(); torch.cuda.synchronize(); lib.ud3d_debug_set_trace(None, 0)
-t = trace.cpu().numpy().reshape(-1, 4); t = t[t[:, 0] > 0]
-t0 = t[:, 0].min(); st = (t[:, 0] - t0) / 1e3; en = (t[:, 1] - t0) / 1e3; sm = t[:, 2]
-print(f"{len(t)} CTAs; kernel span {en.max():.1f} us; CTA lifetime mean {np.mean(en - st):.1f} us (min {np.min(en - st):.1f}, max {np.max(en - st):.1f})")
+t = trace.cpu().numpy().reshape(-1, 8); t = t[t[:, 0] > 0]
+t0 = t[:, 0].min()
+rel = lambda col: (t[:, col] - t0) / 1e3
+st, en, sm = rel(0), rel(1), t[:, 2]
+print(f"level {level}: {len(t)} CTAs; kernel span {en.max():.1f} us; CTA lifetime mean {np.mean(en - st):.1f} us (min {np.min(en - st):.1f}, max {np.max(en - st):.1f})")
 print("start times (us) percentiles 0/25/50/75/100:", np.percentile(st, [0, 25, 50, 75, 100]).round(1))
-per_sm = {}
-for a, b, s_ in zip(st, en, sm): per_sm.setdefault(int(s_), []).append((a, b))
-occ = []
-for s_, iv in per_sm.items():
-    busy = sum(b - a for a, b in iv); occ.append(busy / en.max())
-print(f"SMs used {len(per_sm)}; mean concurrent CTAs per SM {np.mean(occ):.2f} (min {np.min(occ):.2f}, max {np.max(occ):.2f}); CTAs per SM min {min(len(v) for v in per_sm.values())} max {max(len(v) for v in per_sm.values())}")
-iv = sorted(per_sm[int(sm[0])]); print("SM", int(sm[0]), "intervals:", [(round(a, 1), round(b, 1)) for a, b in iv[:16]])
+names = {3: "prologue done", 4: "main loop done", 5: "partial parked", 6: "cluster barrier 1", 7: "reduced+stored", 1: "end"}
+prev = st
+for col in (3, 4, 5, 6, 7, 1):
+    if (t[:, col] > 0).all():
+        cur = rel(col)
+        d = cur - prev
+        print(f"  -> {names[col]:18s}: +{np.mean(d):6.2f} us mean (min {np.min(d):.2f}, max {np.max(d):.2f}); at {np.mean(cur):.1f} us mean")
+        prev = cur
+print("SMs used", len(set(sm.tolist())))

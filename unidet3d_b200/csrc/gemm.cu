@@ -4,21 +4,20 @@
 //   out[o,:] = act( sum_k pre(in[table[k][o],:]) @ W_k + bias ) + residual[o,:]
 //
 // Design (one CTA = 128 output rows x N_TILE output channels, 10 warps, warp-specialised):
-//   * the K-loop runs over (kernel offset k, 32-channel chunk c).  For each step the 8 warps gather
-//     the 128 input rows of that offset with coalesced 16-byte loads (4 lanes per row), apply the
-//     folded BatchNorm affine + ReLU in registers, split every fp32 value into bf16 hi + lo and
-//     write [hi(32ch) | lo(32ch)] = one 128-byte row into a 128B-swizzled K-major smem tile;
-//   * the matching weight tile (pre-packed on the host side of the ABI into the identical
-//     swizzled image, hi|lo per output channel) is fetched by ONE cp.async.bulk (TMA engine)
-//     onto an mbarrier;
-//   * one thread issues 6 tcgen05.mma (M=128, N=N_TILE, K=16): hi*hi, lo*hi, hi*lo -> fp32
-//     accumulation in TMEM (~2e-5 relative error end to end, vs 1.5e-3 for single-pass TF32);
-//   * roles: warps 0-7 gather/transform A (loads of step t+1 in flight while step t is stored),
-//     warp 8 issues the weight bulk copies, warp 9 issues the MMAs; a 3-4 stage smem ring linked only
-//     by mbarriers (a_full / b_full / empty via tcgen05.commit) -- no block barrier in the mainloop;
-//     the tile's rulebook slice is staged in smem first; offsets with no active input in the tile
-//     are skipped (rulebook tile mask); launches that cannot fill 148 SMs are split along K;
-//   * epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> global.
+//   * the K-loop runs over (kernel offset k, 32-channel chunk c).  Operand-form inputs (pre-activated bf16 hi|lo rows,
+//     128 bytes per row-chunk) are gathered with 16-byte cp.async copies (zero-fill for missing neighbours) straight
+//     into a 128B-swizzled K-major smem tile; the producer warps are bound to ring stages and never wait for their own
+//     copies (cp.async.mbarrier.arrive.noinc on the stage's full barrier).  fp32 inputs take a register path (coalesced
+//     16-byte loads, folded BatchNorm affine + ReLU, bf16 hi/lo split, st.shared);
+//   * the matching weight tile (pre-packed on the host side of the ABI into the identical swizzled image, hi|lo per
+//     output channel) is fetched by ONE cp.async.bulk (TMA engine) onto the same full barrier;
+//   * the MMA warp issues 6 tcgen05.mma (M=128, N=N_TILE, K=16; elect.sync): hi*hi, lo*hi, hi*lo -> fp32 accumulation
+//     in TMEM (~2e-5 relative error end to end, vs 1.5e-3 for single-pass TF32), then tcgen05.commit -> empty[stage];
+//   * a 3-5 stage smem ring linked only by mbarriers -- no block barrier in the mainloop; the tile's rulebook slice is
+//     staged in smem first; offsets with no active input in the tile are skipped (rulebook tile mask);
+//   * launches that cannot fill 148 SMs are split along K across the CTAs of a (1,1,z) thread-block cluster, which
+//     reduce their partial tiles through distributed shared memory (deterministic, no atomics, no second pass);
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> fp32 and/or operand-form stores.
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
 #include "common.cuh"
 
@@ -97,29 +96,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // One thread's 32 consecutive output columns [col0, col0+32) of row `grow`: bias / activation / residual, fp32 store
-// and/or operand-form stores (or the red.add of a split-K partial).  r = raw fp32 accumulator bits.
-__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], int grow, int col0,
-                                                     bool split, bool lead) {
+// and/or operand-form stores.  r = raw fp32 accumulator bits.
+__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], int grow, int col0) {
   const ud3d_gemm_args& a = p.a;
   if (col0 >= a.c_out) return;
   float* orow = a.out + (size_t)grow * a.ld_out;
-  const float* rrow = (a.residual && lead) ? a.residual + (size_t)grow * a.ld_res : nullptr;
-  const float* bias = lead ? a.bias : nullptr;
-  if (split) {
-    // partial sums of a split-K launch: fp32 red.add into the pre-zeroed output (act == 0 enforced;
-    // operand-form outputs are produced afterwards by act_split kernels on the host side of this call)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      int col = col0 + j;
-      if (col < a.c_out) {
-        float v = __uint_as_float(r[j]);
-        if (bias) v += __ldg(bias + col);
-        if (rrow) v += __ldg(rrow + col);
-        atomicAdd(orow + col, v);
-      }
-    }
-    return;
-  }
+  const float* rrow = a.residual ? a.residual + (size_t)grow * a.ld_res : nullptr;
+  const float* bias = a.bias;
   // final fp32 values of this thread's 32 columns
   float v[32];
   const bool full = col0 + 32 <= a.c_out;
@@ -210,7 +193,10 @@ constexpr bool kPersistent = false;
 // D = 3 (every step pays the full round trip).  S is the largest depth that keeps 2 CTAs/SM (1 for N_TILE >= 160).
 template <int N_TILE> struct TcCfg {
   static constexpr int kStages = N_TILE <= 64 ? 4 : N_TILE <= 128 ? 3 : N_TILE == 160 ? 5 : 4;
-  static constexpr int kInFlight = N_TILE == 160 ? 2 : 1;
+  // resident CTAs per SM the kernel is compiled for (register cap).  (3 CTAs x 3 stages for N_TILE = 32 and 3 CTAs x 2
+  // stages for N_TILE = 64 measured the same as 2 x 4: the main loop is bound by the gather latency x the stages in flight
+  // per SM, not by the number of CTAs; a 6-stage, 1 CTA/SM ring for the split-K launches lost more in waves than it won.)
+  static constexpr int kMinCtas = N_TILE <= 128 ? 2 : 1;
 };
 
 // Raw gathered operand of one K-step for this thread: 2 rows x 8 channels
@@ -222,8 +208,18 @@ struct GatherRegs {
 // Persistent: gridDim.x CTAs (2 per SM) walk the row tiles with stride gridDim.x; barriers, TMEM and the smem ring
 // are set up once per CTA and the ring state (stage, use count) runs on across tiles.  (One CTA per tile cost ~3 us of
 // launch / TMEM-allocation turnaround per tile: a third of the level-1 convolutions' time.)
+// debug timeline (ud3d_debug_set_trace(buf, -2)): globaltimer of phase `slot` of every CTA (thread 0), 8 slots per CTA
+#define UD3D_TL(slot)                                                                                        \
+  do {                                                                                                       \
+    if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0) {                                     \
+      unsigned long long gt__;                                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__));                                               \
+      p.trace[8 * (blockIdx.x * gridDim.z + blockIdx.z) + (slot)] = (long long)gt__;                         \
+    }                                                                                                        \
+  } while (0)
+
 template <int N_TILE>
-__global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_gemm_tc_kernel(const GemmParams p) {
   constexpr int STAGES = TcCfg<N_TILE>::kStages;
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = N_TILE * 128;
@@ -254,12 +250,11 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
   const int n_row_tiles = (a.n_out + kTileM - 1) / kTileM;
 
   // ------------------------------------------------------------ once per CTA
-  if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    unsigned long long gt; unsigned smid;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+  UD3D_TL(0);
+  if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0) {
+    unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    p.trace[4 * blockIdx.x + 0] = (long long)gt;
-    p.trace[4 * blockIdx.x + 2] = smid;
+    p.trace[8 * (blockIdx.x * gridDim.z + blockIdx.z) + 2] = smid;
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -335,6 +330,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     }
     if (tid < 32 && ((mask >> tid) & 1u)) s_actk[__popc(mask & ((1u << tid) - 1u))] = (uint8_t)tid;
     __syncthreads();
+    UD3D_TL(3);      // prologue done (rulebook slice staged)
     const int nact = __popc(mask);
     const int nsteps_all = nact * p.n_chunks;
     // split-K: this CTA handles steps [t_begin, t_end) of the tile's active (offset, chunk) sequence
@@ -564,30 +560,124 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     }
 
     // ---------------------------------------------------------- epilogue (warps 0..3, one row per thread)
-    if (warp < 4) {
-      if (nsteps > 0) {
-        mbar_wait(acc_full, acc_phase);
-        tc_fence_after_sync();
-      }
-      if (traced && tid == 0) p.trace[1021] = clock64();
-      const int row = warp * 32 + lane;
-      const int grow = m0 + row;
-      const bool row_ok = grow < a.n_out;
-      const bool split = gridDim.z > 1;
-      const bool lead = blockIdx.z == 0;       // the split that adds bias / residual
-#pragma unroll 1
-      for (int c0 = 0; c0 < N_TILE; c0 += 32) {
-        uint32_t r[32];
+    const bool split = gridDim.z > 1;
+    if (!split) {
+      if (warp < 4) {
         if (nsteps > 0) {
-          tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0u;
+          mbar_wait(acc_full, acc_phase);
+          tc_fence_after_sync();
         }
-        if (!row_ok || (p.dbg & 16)) continue;
-        epilogue_store_chunk(p, r, grow, n0 + c0, split, lead);
+        if (traced && tid == 0) p.trace[1021] = clock64();
+        UD3D_TL(4);  // main loop done
+        const int row = warp * 32 + lane;
+        const int grow = m0 + row;
+        const bool row_ok = grow < a.n_out;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t r[32];
+          if (nsteps > 0) {
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+          if (!row_ok || (p.dbg & 16)) continue;
+          epilogue_store_chunk(p, r, grow, n0 + c0);
+        }
       }
+    } else {
+      // ---- split-K: the gridDim.z CTAs of one (1, 1, z) thread-block cluster hold partial sums of the same output tile.
+      //      Each parks its fp32 partial in its own (now idle) operand ring, then CTA `rank` sums rows
+      //      [rank * rp, (rank + 1) * rp) over all peers through distributed shared memory, in rank order (deterministic),
+      //      and runs the normal epilogue on them: no atomics, no pre-zeroed output, no second pass.
+      //      Partial tile: [128 rows][N_TILE] fp32, 16-byte chunks XOR-swizzled with (row & 7) (conflict-free stores).
+      const uint32_t sP = smem_u32(sA);
+      if (warp < 4) {
+        if (nsteps > 0) {
+          mbar_wait(acc_full, acc_phase);
+          tc_fence_after_sync();
+        }
+        UD3D_TL(4);  // main loop done
+        const int row = warp * 32 + lane;
+        const uint32_t prow = sP + (uint32_t)(row * N_TILE * 4);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t r[32];
+          if (nsteps > 0) {
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow + (uint32_t)(c0 * 4) + (uint32_t)((j ^ (row & 7)) << 4)),
+                         "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                         : "memory");
+        }
+      }
+      UD3D_TL(5);    // partial parked
+      cluster_arrive_release();
+      cluster_wait_acquire();
+      UD3D_TL(6);    // all partials visible
+      constexpr int NC16 = N_TILE / 4;
+      constexpr int NCH = N_TILE / 32;
+      const int z = (int)gridDim.z;
+      uint32_t rank;
+      asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+      const int rp = (kTileM + z - 1) / z;
+      const int r_begin = (int)rank * rp;
+      const int r_end = r_begin + rp < kTileM ? r_begin + rp : kTileM;
+      const int n_rows = r_end > r_begin ? r_end - r_begin : 0;
+      {
+        // phase 1 (all warps): thread = (row, 16-byte chunk): one float4 per peer, all loads independent (the peers are
+        // visited starting at this CTA's own rank, so the cluster's CTAs do not all hit the same SM at once); the sum is
+        // written back in place -- rows [r_begin, r_end) of this CTA's own partial tile are read by nobody else
+        for (int item = tid; item < n_rows * NC16; item += kThreadsTc) {
+          const int row = r_begin + item / NC16;
+          const uint32_t off = (uint32_t)(row * N_TILE * 4) + (uint32_t)((item - (item / NC16) * NC16) << 4);   // (swizzled slot: same in every CTA)
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          int q = (int)rank;
+          for (int q0 = 0; q0 < z; q0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (q0 + u < z) v[u] = ld_shared_cluster_f4(cluster_map_shared(sP, (uint32_t)q) + off);
+              if (++q == z) q = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if (q0 + u < z) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
+          }
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "f"(acc.x), "f"(acc.y), "f"(acc.z), "f"(acc.w) : "memory");
+        }
+      }
+      __syncthreads();
+      if (warp < 4) {
+        // phase 2: thread = (row, 32-column chunk) of the reduced rows: the normal epilogue
+        for (int item = tid; item < n_rows * NCH; item += 128) {
+          const int row = r_begin + item / NCH;
+          const int cc = item - (item / NCH) * NCH;
+          const int grow = m0 + row;
+          if (grow >= a.n_out) continue;
+          const uint32_t base = sP + (uint32_t)(row * N_TILE * 4 + cc * 128);
+          uint32_t r[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[4 * j]), "=r"(r[4 * j + 1]), "=r"(r[4 * j + 2]), "=r"(r[4 * j + 3])
+                         : "r"(base + (uint32_t)((j ^ (row & 7)) << 4))
+                         : "memory");
+          epilogue_store_chunk(p, r, grow, n0 + cc * 32);
+        }
+      }
+      UD3D_TL(7);    // reduced + stored
+      // no CTA may exit (or reuse its ring) while a peer still reads its partial tile
+      cluster_arrive_release();
+      cluster_wait_acquire();
     }
     if (nsteps > 0) acc_phase ^= 1u;
     if (traced && tid == 0) p.trace[1020] = clock64();
@@ -599,11 +689,7 @@ __global__ void __launch_bounds__(kThreadsTc) gather_gemm_tc_kernel(const GemmPa
     if (!kPersistent) break;
   }
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
-  if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.trace[4 * blockIdx.x + 1] = (long long)gt;
-  }
+  UD3D_TL(1);
 }
 
 // ---------------------------------------------------------------- fp32 -> operand form (one warp per 4 row-chunks)
@@ -731,7 +817,23 @@ static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t 
            N_TILE, gx, n_tiles, splits, ctas_per_sm, occ, (int)e, smem, g_num_sms, fa.numRegs, fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes,
            fa.preferredShmemCarveout, smem_sm, regs_sm);
   }
-  gather_gemm_tc_kernel<N_TILE><<<grid, kThreadsTc, smem, st>>>(p);
+  if (splits > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreadsTc);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UD3D_CUDA(cudaLaunchKernelEx(&cfg, gather_gemm_tc_kernel<N_TILE>, p));
+  } else {
+    gather_gemm_tc_kernel<N_TILE><<<grid, kThreadsTc, smem, st>>>(p);
+  }
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }
@@ -804,23 +906,20 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   int nts = pick_ntile(args->c_out);
   int n_tiles = cdiv(args->c_out, nts);
   cudaStream_t st = (cudaStream_t)stream;
-  // split-K for launches that cannot fill the 148 SMs (deep U-Net levels: 5..91 row tiles x 100+ K-steps):
-  // the (offset, chunk) sequence is cut across gridDim.z CTAs that red.add fp32 partials into the output
+  // split-K for launches that cannot fill the 148 SMs (deep U-Net levels: 5..91 row tiles x 100+ K-steps): the
+  // (offset, chunk) sequence is cut across the gridDim.z CTAs of a (1, 1, z) thread-block cluster, which reduce their
+  // partial tiles through distributed shared memory (see the kernel's epilogue)
   int splits = 1;
   {
     long long ctas = (long long)cdiv(args->n_out, kTileM) * n_tiles;
     int max_steps = args->K * p.n_chunks;
-    if (args->act == 0 && ctas < 120 && max_steps >= 16 && (const float*)args->out != args->in &&
-        (const float*)args->out != args->residual) {
+    if (ctas < 120 && max_steps >= 16) {
       splits = (int)(296 / ctas);
       if (splits > max_steps / 6) splits = max_steps / 6;
-      if (splits > 16) splits = 16;
+      if (splits > 8) splits = 8;      // portable cluster size (14..16-CTA clusters scheduled in two waves: slower)
       if (splits < 1) splits = 1;
     }
-    if (splits > 1)
-      UD3D_CUDA(cudaMemset2DAsync(args->out, (size_t)args->ld_out * 4, 0, (size_t)args->c_out * 4, (size_t)args->n_out, st));
   }
-  if (splits > 1) p.a.no_raw = 0;
   int rc2;
   switch (nts) {
     case 32: rc2 = launch_tc<32>(p, n_tiles, splits, st); break;
@@ -830,19 +929,7 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
     case 160: rc2 = launch_tc<160>(p, n_tiles, splits, st); break;
     default: rc2 = launch_tc<256>(p, n_tiles, splits, st); break;
   }
-  if (rc2) return rc2;
-  if (splits > 1) {
-    // the complete sums exist only now: derive the operand-form outputs from the fp32 result
-    for (int i = 0; i < 2; ++i) {
-      if (!args->out_act[i]) continue;
-      UD3D_CHECK_ARG(args->ld_out % 4 == 0 && ((uintptr_t)args->out & 15) == 0, "ud3d_gemm_fwd: split-K + out_act needs an aligned `out`");
-      int rc3 = launch_act_split(args->out, args->ld_out, args->n_out, args->c_out, args->act_scale[i], args->act_shift[i],
-                                 !((args->act_norelu >> i) & 1),
-                                 args->out_act[i], args->ld_act[i], st);
-      if (rc3) return rc3;
-    }
-  }
-  return UD3D_OK;
+  return rc2;
 }
 
 int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scale, const float* shift, int relu,
