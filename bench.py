@@ -290,7 +290,8 @@ def main():
         bn0 = model.unet.first_bn()
         f_act = torch.empty((lv0.n, plan["w_in"].c_out), dtype=torch.float32, device=dev)
         vox_s = ops.act_split(x.features, relu=False)
-        f = ops.gemm(vox_s, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask, in_split=True, acts=[(f_act, bn0[0], bn0[1])])
+        tb, tm, pm = lv0.subm_conv
+        f = ops.gemm(vox_s, plan["w_in"], table=tb, tile_mask=tm, in_split=True, acts=[(f_act, bn0[0], bn0[1])], row_perm=pm)
         y = x.replace_feature(f)
         y.features_act = f_act
         return model.unet(y)

@@ -90,6 +90,19 @@ int ud3d_voxel_mean(const float* feats_pts, const int32_t* rank, int n, int C, i
  * an input for offset k. */
 int ud3d_rulebook_subm3(const int32_t* coords, int n, const int32_t dims_host[4], const void* ws,
                         int32_t* row_of_rank, int32_t* table, uint32_t* tile_mask, void* stream);
+/* Tile order for the SubM3 convolutions of one level (no reference counterpart: spconv's implicit-GEMM kernels carry
+ * their own per-tile masks, `pair_mask_fwd_splits`, produced inside get_indice_pairs_implicit_gemm).  ud3d_gemm_fwd skips
+ * kernel offset k for a 128-row tile only when no row of the tile has that neighbour; rows are regrouped by a 16-bit
+ * key of their rarest neighbours so that tiles hold rows with similar neighbourhoods (26 -> 17..20 active offsets per
+ * tile on indoor scans):
+ *   perm [n]              a permutation of 0..n-1 (position -> row); order inside a key bucket is unspecified
+ *   table_p [27, n]       table_p[k][i] = table[k][perm[i]]
+ *   tile_mask_p [tiles]   tile mask of table_p
+ * Pass table_p / tile_mask_p / perm as table / tile_mask / row_perm of ud3d_gemm_args: results are bit-identical to the
+ * unpermuted call.  ws: ud3d_subm3_tile_order_workspace_bytes(n), 16-byte aligned. */
+size_t ud3d_subm3_tile_order_workspace_bytes(int n);
+int ud3d_subm3_tile_order(const int32_t* table, int n, int32_t* perm, int32_t* table_p, uint32_t* tile_mask_p,
+                          void* ws, size_t ws_bytes, void* stream);
 
 /* SparseConv3d(k=2,s=2) (spconv_unet.py:148-154 `spconv{l}`), phase 1:
  *   parents[i] = (b, x/2, y/2, z/2), or b=-1 when x/2 >= out_shape (odd extent, last index dropped),
@@ -147,6 +160,9 @@ typedef struct {
   float* out_act[2]; int32_t ld_act[2]; const float* act_scale[2]; const float* act_shift[2];
   int32_t act_norelu;          /* bit i set: out_act[i] = split(result * scale + shift) without the ReLU;
                                   act_scale[i] == NULL means identity (scale 1, shift 0) */
+  const int32_t* row_perm;     /* optional [n_out] (requires table): position i of the table / tile_mask describes output
+                                  row row_perm[i], i.e. out / out_act / residual are addressed at row_perm[i]
+                                  (see ud3d_subm3_tile_order); NULL = identity */
 } ud3d_gemm_args;
 size_t ud3d_gemm_packed_weight_bytes(int K, int c_in, int c_out);
 int ud3d_gemm_pack_weight(const float* w, int K, int c_in, int c_out, void* packed, void* stream);

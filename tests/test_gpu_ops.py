@@ -387,3 +387,53 @@ def test_attention_operand_form(lens):
     # tcgen05 variant (S / O' accumulators in TMEM, V as an MN-major operand)
     out_s3 = ops.attention(split_encode(qkv).to(DEV), cu.to(DEV), max(lens), H, split_in=True, tcgen05=True)
     assert relerr(split_decode(out_s3.cpu()), ref) < 1e-4, relerr(split_decode(out_s3.cpu()), ref)
+
+
+@pytest.mark.gpu
+def test_subm3_tile_order_is_a_pure_regrouping():
+    """ud3d_subm3_tile_order: perm is a permutation, table_p / tile_mask_p describe the same rulebook in the regrouped
+    order, tiles see fewer active offsets, and a convolution through (table_p, tile_mask_p, row_perm) is bit-identical
+    to the canonical-order call (fp32 and operand-form paths, with residual and operand-form outputs)."""
+    from unidet3d_b200 import ops
+    from unidet3d_b200.rulebook import build_pyramid
+    scenes, _ = _scenes("small20k", 2, seed0=5)
+    pts = torch.as_tensor(np.concatenate([s[0] for s in scenes])).cuda()
+    offs = torch.tensor(np.cumsum([0] + [len(s[0]) for s in scenes]), dtype=torch.int32, device="cuda")
+    coords_pt, _, _, maxc = ops.point_coords(pts, offs, 0.02)          # 2 cm voxels: ~20k voxels, 150+ tiles
+    ext = (maxc.cpu().numpy() + 1).tolist()
+    pyr = build_pyramid(None, [max(e, 128) for e in ext], 2, 1, extents=ext, seed_coords=coords_pt)
+    lv = pyr.levels[0]
+    perm, table_p, mask_p = ops.subm3_tile_order(lv.subm)
+    torch.cuda.synchronize()
+    n = lv.n
+    perm_h, tab_h = perm.cpu().numpy(), lv.subm.cpu().numpy()
+    assert np.array_equal(np.sort(perm_h), np.arange(n))
+    assert np.array_equal(table_p.cpu().numpy(), tab_h[:, perm_h])
+
+    def tile_masks(t):
+        v = t >= 0
+        pad = (-n) % 128
+        v = np.concatenate([v, np.zeros((27, pad), bool)], 1).reshape(27, -1, 128).any(2)
+        return (v * (1 << np.arange(27))[:, None]).sum(0).astype(np.uint32)
+    ref_mask_p = tile_masks(tab_h[:, perm_h])
+    assert np.array_equal(mask_p.cpu().numpy().view(np.uint32), ref_mask_p)
+    pop = lambda m: np.array([bin(int(x)).count("1") for x in m]).mean()
+    assert pop(ref_mask_p) < 0.85 * pop(tile_masks(tab_h)), (pop(ref_mask_p), pop(tile_masks(tab_h)))
+    # bit-identical convolutions
+    g = torch.Generator(device="cuda").manual_seed(0)
+    c = 32
+    x = torch.randn(n, c, device="cuda", generator=g)
+    w = ops.PackedWeight(torch.randn(c, 27, c, device="cuda", generator=g) * 0.1)
+    res = torch.randn(n, c, device="cuda", generator=g)
+    sc = torch.rand(c, device="cuda", generator=g) + 0.5
+    sh = torch.randn(c, device="cuda", generator=g) * 0.1
+    y0 = ops.gemm(x, w, table=lv.subm, tile_mask=lv.subm_mask, in_scale=sc, in_shift=sh, in_relu=True, residual=res)
+    y1 = ops.gemm(x, w, table=table_p, tile_mask=mask_p, in_scale=sc, in_shift=sh, in_relu=True, residual=res, row_perm=perm)
+    assert torch.equal(y0, y1)
+    xs = ops.act_split(x, sc, sh, relu=True)
+    a0, a1 = torch.empty_like(x), torch.empty_like(x)
+    z0 = ops.gemm(xs, w, table=lv.subm, tile_mask=lv.subm_mask, in_split=True, residual=res, acts=[(a0, sc, sh)])
+    z1 = ops.gemm(xs, w, table=table_p, tile_mask=mask_p, in_split=True, residual=res, acts=[(a1, sc, sh)], row_perm=perm)
+    assert torch.equal(z0, z1) and torch.equal(a0, a1)
+    rel = float((z0 - y0).abs().max() / y0.abs().max())
+    assert rel < 1e-3, rel

@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("out_act", C.c_void_p * 2), ("ld_act", C.c_int32 * 2),
         ("act_scale", C.c_void_p * 2), ("act_shift", C.c_void_p * 2),
         ("act_norelu", C.c_int32),
+        ("row_perm", C.c_void_p),
     ]
 
 
@@ -57,6 +58,8 @@ SIGNATURES = {
     "ud3d_point_coords": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ud3d_grid_workspace_bytes": (_sz, [c_i32p]),
     "ud3d_grid_build": (_i, [_vp, _i, c_i32p, _vp, _sz, _vp, _vp]),
+    "ud3d_subm3_tile_order_workspace_bytes": (_sz, [_i]),
+    "ud3d_subm3_tile_order": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ud3d_grid_rank": (_i, [_vp, _i, c_i32p, _vp, _vp, _vp]),
     "ud3d_grid_coords": (_i, [c_i32p, _vp, _vp, _i, _vp]),
     "ud3d_voxel_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),

@@ -570,8 +570,9 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         if (traced && tid == 0) p.trace[1021] = clock64();
         UD3D_TL(4);  // main loop done
         const int row = warp * 32 + lane;
-        const int grow = m0 + row;
-        const bool row_ok = grow < a.n_out;
+        const bool row_ok = m0 + row < a.n_out;
+        // regrouped rows (ud3d_subm3_tile_order): position m0 + row of the table stands for output row row_perm[m0 + row]
+        const int grow = (row_ok && a.row_perm) ? __ldg(a.row_perm + m0 + row) : m0 + row;
 #pragma unroll 1
         for (int c0 = 0; c0 < N_TILE; c0 += 32) {
           uint32_t r[32];
@@ -661,8 +662,8 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         for (int item = tid; item < n_rows * NCH; item += 128) {
           const int row = r_begin + item / NCH;
           const int cc = item - (item / NCH) * NCH;
-          const int grow = m0 + row;
-          if (grow >= a.n_out) continue;
+          if (m0 + row >= a.n_out) continue;
+          const int grow = a.row_perm ? __ldg(a.row_perm + m0 + row) : m0 + row;
           const uint32_t base = sP + (uint32_t)(row * N_TILE * 4 + cc * 128);
           uint32_t r[32];
 #pragma unroll
@@ -766,8 +767,9 @@ __global__ void gather_gemm_simt_kernel(const ud3d_gemm_args a, const float* __r
   }
   if (a.bias) acc += a.bias[col];
   acc = apply_act(acc, a.act);
-  if (a.residual) acc += a.residual[(size_t)row * a.ld_res + col];
-  a.out[(size_t)row * a.ld_out + col] = acc;
+  const int orow = a.row_perm ? a.row_perm[row] : row;
+  if (a.residual) acc += a.residual[(size_t)orow * a.ld_res + col];
+  a.out[(size_t)orow * a.ld_out + col] = acc;
 }
 
 template <int N_TILE>
@@ -846,6 +848,7 @@ static int check_args(const ud3d_gemm_args* a, const char* who) {
   UD3D_CHECK_ARG(!a->residual || a->ld_res >= a->c_out, "%s: bad ld_res", who);
   UD3D_CHECK_ARG((a->in_scale == nullptr) == (a->in_shift == nullptr), "%s: in_scale/in_shift must both be set", who);
   UD3D_CHECK_ARG(!a->table || a->K <= 32, "%s: a gather table supports at most 32 kernel offsets", who);
+  UD3D_CHECK_ARG(!a->row_perm || a->table, "%s: row_perm requires a gather table", who);
   if (a->in_split) {
     UD3D_CHECK_ARG(!a->in_scale && !a->in_relu, "%s: in_split input is already activated (no in_scale / in_relu)", who);
     UD3D_CHECK_ARG(a->c_in % 32 == 0 && a->ld_in % 32 == 0 && ((uintptr_t)a->in & 15) == 0,

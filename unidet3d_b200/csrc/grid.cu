@@ -361,6 +361,135 @@ __global__ void down2_fill_kernel(const int4* __restrict__ coords, const int4* _
   }
 }
 
+
+// ---------------------------------------------------------------- SubM3 tile order
+// The gather-GEMM skips a kernel offset for a whole 128-row tile only when NO row of the tile has that neighbour.  In
+// canonical (b,x,y,z) order nearly every tile sees all 27 offsets although a voxel has ~11-14 neighbours.  Rows are
+// therefore regrouped by their neighbourhood pattern: a 16-bit key of the rarest offsets (8 corners, then the 8 edges
+// with dx = 0 or dy = 0), counting-sorted (histogram -> scan -> scatter).  The order inside a bucket is whatever the
+// atomics produce: it only changes which rows share a tile, never a result (every output row accumulates its own
+// offsets in ascending k).  Measured on ScanNet-like scenes: 26.2 -> 19.6 active offsets per tile at 2 cm, 25.4 -> 16.5
+// at 4 cm.
+constexpr int kOrderKeyBits = 16;
+__device__ __constant__ int8_t kOrderKeyOffsets[kOrderKeyBits] = {0, 2, 6, 8, 18, 20, 24, 26, 9, 11, 15, 17, 3, 5, 21, 23};
+
+__device__ __forceinline__ uint32_t order_key(const int32_t* __restrict__ table, int n, int i) {
+  uint32_t key = 0;
+#pragma unroll
+  for (int b = 0; b < kOrderKeyBits; ++b) key = (key << 1) | (table[(size_t)kOrderKeyOffsets[b] * n + i] >= 0 ? 1u : 0u);
+  return key;
+}
+
+// warp-aggregated atomicAdd on counters[key]: returns this lane's slot
+__device__ __forceinline__ uint32_t bucket_take(uint32_t* counters, uint32_t key, bool active) {
+  const uint32_t act = __ballot_sync(0xffffffffu, active);
+  uint32_t slot = 0;
+  if (active) {
+    const uint32_t peers = __match_any_sync(act, key);
+    const int leader = __ffs(peers) - 1;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    slot = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  }
+  return slot;
+}
+
+__global__ void __launch_bounds__(256) order_hist_kernel(const int32_t* __restrict__ table, int n, uint16_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ hist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  uint32_t key = 0;
+  if (active) {
+    key = order_key(table, n, i);
+    keys[i] = (uint16_t)key;
+  }
+  bucket_take(hist, key, active);
+}
+
+// exclusive scan of the 65536 bucket counts (one CTA, 1024 threads x 64 consecutive buckets)
+__global__ void __launch_bounds__(1024) order_scan_kernel(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t warp_sums[32];
+  constexpr int kPer = (1 << kOrderKeyBits) / 1024;
+  const int t = threadIdx.x;
+  uint32_t v[kPer];
+  uint32_t sum = 0;
+  const uint4* src = (const uint4*)(hist + (size_t)t * kPer);
+#pragma unroll
+  for (int j = 0; j < kPer / 4; ++j) {
+    uint4 q = src[j];
+    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    sum += q.x + q.y + q.z + q.w;
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += u;
+  }
+  if ((t & 31) == 31) warp_sums[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t w = warp_sums[t], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+      if (t >= o) wi += u;
+    }
+    warp_sums[t] = wi - w;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[t >> 5] + incl - sum;
+  uint4* dst = (uint4*)(hist + (size_t)t * kPer);
+#pragma unroll
+  for (int j = 0; j < kPer / 4; ++j) {
+    uint4 q;
+    q.x = run; run += v[4 * j];
+    q.y = run; run += v[4 * j + 1];
+    q.z = run; run += v[4 * j + 2];
+    q.w = run; run += v[4 * j + 3];
+    dst[j] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) order_scatter_kernel(const uint16_t* __restrict__ keys, int n, uint32_t* __restrict__ cursor,
+                                                            int32_t* __restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  const uint32_t key = active ? keys[i] : 0u;
+  const uint32_t slot = bucket_take(cursor, key, active);
+  if (active) perm[slot] = i;
+}
+
+// table_p[k][i] = table[k][perm[i]] and the tile mask of the regrouped rows (one CTA per 128-row tile)
+__global__ void __launch_bounds__(UD3D_TILE_M) order_permute_kernel(const int32_t* __restrict__ table, const int32_t* __restrict__ perm,
+                                                                    int n, int32_t* __restrict__ table_p, uint32_t* __restrict__ tile_mask_p) {
+  __shared__ uint32_t s_mask[UD3D_TILE_M / 32];
+  const int i = blockIdx.x * UD3D_TILE_M + threadIdx.x;
+  uint32_t mask = 0;
+  if (i < n) {
+    const int r = perm[i];
+    int32_t v[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) v[k] = __ldg(table + (size_t)k * n + r);
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      table_p[(size_t)k * n + i] = v[k];
+      if (v[k] >= 0) mask |= 1u << k;
+    }
+  }
+  mask = __reduce_or_sync(0xffffffffu, mask);
+  if ((threadIdx.x & 31) == 0) s_mask[threadIdx.x >> 5] = mask;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < UD3D_TILE_M / 32; ++w) m |= s_mask[w];
+    tile_mask_p[blockIdx.x] = m;
+  }
+}
+
 static int grid_blocks(long long n, int threads) {
   long long b = (n + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -509,6 +638,32 @@ int ud3d_rulebook_subm3(const int32_t* coords, int n, const int32_t dims_host[4]
   int tiles = cdiv(n, UD3D_TILE_M);
   if (tile_mask) UD3D_CUDA(cudaMemsetAsync(tile_mask, 0, (size_t)tiles * 4, st));
   subm3_table_kernel<<<tiles, UD3D_TILE_M, 0, st>>>((const int4*)coords, n, g, v.words, v.prefix, row_of_rank, table, tile_mask);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+size_t ud3d_subm3_tile_order_workspace_bytes(int n) {
+  return align_up((size_t)(1 << kOrderKeyBits) * 4, 256) + align_up((size_t)(n > 0 ? n : 1) * 2, 256);
+}
+
+int ud3d_subm3_tile_order(const int32_t* table, int n, int32_t* perm, int32_t* table_p, uint32_t* tile_mask_p, void* ws,
+                          size_t ws_bytes, void* stream) {
+  UD3D_CHECK_ARG(n >= 0 && (n == 0 || (table && perm && table_p && tile_mask_p && ws)), "ud3d_subm3_tile_order: NULL argument");
+  UD3D_CHECK_ARG(ws_bytes >= ud3d_subm3_tile_order_workspace_bytes(n), "ud3d_subm3_tile_order: workspace too small");
+  UD3D_CHECK_ARG(((uintptr_t)ws & 15) == 0, "ud3d_subm3_tile_order: workspace must be 16-byte aligned");
+  if (n == 0) return UD3D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  uint32_t* hist = (uint32_t*)ws;
+  uint16_t* keys = (uint16_t*)((uint8_t*)ws + align_up((size_t)(1 << kOrderKeyBits) * 4, 256));
+  UD3D_CUDA(cudaMemsetAsync(hist, 0, (size_t)(1 << kOrderKeyBits) * 4, st));
+  const int blocks = cdiv(n, 256);
+  order_hist_kernel<<<blocks, 256, 0, st>>>(table, n, keys, hist);
+  UD3D_LAUNCH_CHECK();
+  order_scan_kernel<<<1, 1024, 0, st>>>(hist);
+  UD3D_LAUNCH_CHECK();
+  order_scatter_kernel<<<blocks, 256, 0, st>>>(keys, n, hist, perm);
+  UD3D_LAUNCH_CHECK();
+  order_permute_kernel<<<cdiv(n, UD3D_TILE_M), UD3D_TILE_M, 0, st>>>(table, perm, n, table_p, tile_mask_p);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

@@ -106,8 +106,9 @@ class UniDet3D(nn.Module):
             # the 6-channel voxel features go through the operand form too (one zero-padded 32-channel chunk): the
             # 27-offset gather then is the cp.async path instead of 24-byte scalar row loads
             vox_s = ops.act_split(x.features, relu=False)
-            f = ops.gemm(vox_s, plan["w_in"], table=lv0.subm, tile_mask=lv0.subm_mask, in_split=True,
-                         acts=[(f_act, bn0[0], bn0[1])])
+            tb, tm, pm = lv0.subm_conv
+            f = ops.gemm(vox_s, plan["w_in"], table=tb, tile_mask=tm, in_split=True, acts=[(f_act, bn0[0], bn0[1])],
+                         row_perm=pm)
             x = x.replace_feature(f)
             x.features_act = f_act      # operand form for the U-Net's first conv, emitted by the input conv epilogue
         else:
@@ -168,6 +169,14 @@ class UniDet3D(nn.Module):
                 cur.wait_stream(st)
         return per_scene
 
+    def _mark_stage(self, name):
+        ev = getattr(self, "stage_events", None)
+        if ev is not None:
+            import time
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e, time.perf_counter()))
+
     # ------------------------------------------------------------------ public API
     @torch.no_grad()
     def forward_scenes(self, points: List, superpoints: List, datasets_names: List[str],
@@ -213,13 +222,19 @@ class UniDet3D(nn.Module):
         self.last_h2d_bytes = int(sum(p.numel() * 4 for p in P if not p.is_cuda) + sum(s.numel() * 8 for s in S if not s.is_cuda)
                                   + offs.numel() * 4)
 
+        mark = self._mark_stage                     # optional CUDA-event timeline (tools/stage_timeline.py)
+        mark("start")
         sp_centers = ops.segmented_mean(pts, sp_b, int(sp_off[-1]), channels=3)            # unidet3d.py:446-447
         x, inverse = self.collate(pts, offs, B)
+        mark("collate")
         pooled = self.extract_feat(x, sp_b, inverse, sp_off)
+        mark("backbone")
         ds_idx = [self.decoder.datasets.index(n) for n in datasets_names]
         out = self.decoder.forward_packed(pooled, sp_centers, [int(v) for v in sp_off], datasets_names)
+        mark("encoder")
 
         per_scene = self.postprocess_batch(out, pts, sp_b, pt_off, sp_off, n_sps, ds_idx)
+        mark("post")
         # one D2H round-trip for the whole batch: every scene's packed result buffer (scores | labels | keep | n_keep |
         # candidate boxes | trimmed boxes, ~64 KB) is copied asynchronously into pinned memory, ONE stream sync, and the
         # final row selection (a few hundred boxes) is done on the host copy

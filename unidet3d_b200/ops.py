@@ -17,8 +17,14 @@ def _L():
     return _lib.load()
 
 
+_raw_stream = torch._C._cuda_getCurrentRawStream
+_cur_device = torch._C._cuda_getDevice
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw cudaStream_t of torch's current stream: the two C calls cost ~0.3 us; torch.cuda.current_stream() builds a
+    # Stream object through several Python layers (~4 us, 170 calls per forward step)
+    return C.c_void_p(_raw_stream(_cur_device()))
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -112,6 +118,21 @@ def rulebook_subm3(coords: torch.Tensor, grid: Grid, canonical: bool, with_mask:
     return table, mask
 
 
+def subm3_tile_order(table: torch.Tensor):
+    """-> (perm int32 [n], table_p int32 [27,n], tile_mask_p [ceil(n/128)]): rows regrouped by neighbourhood pattern
+    (see ud3d_subm3_tile_order)."""
+    _req(table, torch.int32, "table")
+    n = table.shape[1]
+    dev = table.device
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    table_p = torch.empty_like(table)
+    mask_p = torch.empty((n + TILE_M - 1) // TILE_M, dtype=torch.int32, device=dev)
+    ws = torch.empty(int(_L().ud3d_subm3_tile_order_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    check(_L().ud3d_subm3_tile_order(_p(table), n, _p(perm), _p(table_p), _p(mask_p), _p(ws), ws.numel(), _stream()),
+          "ud3d_subm3_tile_order")
+    return perm, table_p, mask_p
+
+
 def down2_parents(coords: torch.Tensor, in_shape: Sequence[int]) -> torch.Tensor:
     _req(coords, torch.int32, "coords")
     parents = torch.empty_like(coords)
@@ -158,7 +179,7 @@ class PackedWeight:
 
 
 def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act, residual,
-               w_packed_ptr, in_split=False, no_raw=False, acts=None):
+               w_packed_ptr, in_split=False, no_raw=False, acts=None, row_perm=None):
     a = GemmArgs()
     a.in_ = x.data_ptr(); a.ld_in = x.stride(0); a.c_in = c_in
     a.table = table.data_ptr() if table is not None else None
@@ -184,19 +205,22 @@ def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_
         if len(spec) > 3 and not spec[3]:
             norelu |= 1 << i
     a.act_norelu = norelu
+    a.row_perm = row_perm.data_ptr() if row_perm is not None else None
     return a
 
 
 def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = None, tile_mask=None,
          n_out: Optional[int] = None, out: Optional[torch.Tensor] = None, in_scale=None, in_shift=None,
          in_relu: bool = False, bias=None, act=None, residual=None, in_split: bool = False, no_raw: bool = False,
-         acts=None) -> torch.Tensor:
+         acts=None, row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = act(sum_k pre(x[table[k]]) @ W_k + bias) + residual   (see ud3d_gemm_fwd).
     ``x``/``out``/``residual`` may be column slices of wider row-major buffers (stride(1) == 1).
     ``in_split``: x is an operand-form (pre-activated, bf16 hi|lo) feature map, see ``act_split``.
     ``acts``: up to two (buffer, scale, shift[, relu=True]): also store relu?(out*scale+shift) in operand
     form (scale/shift None = identity).
-    ``no_raw``: the fp32 result itself is not needed (``out`` is then scratch)."""
+    ``no_raw``: the fp32 result itself is not needed (``out`` is then scratch).
+    ``row_perm``: int32 [n_out]; ``table`` / ``tile_mask`` are in the regrouped row order of ``subm3_tile_order`` and
+    position i produces output row row_perm[i] (same results, fewer active offsets per tile)."""
     if not x.is_cuda or x.dtype != torch.float32 or x.stride(1) != 1:
         raise _lib.Ud3dError("gemm: x must be a CUDA fp32 matrix with unit column stride")
     if n_out is None:
@@ -206,7 +230,7 @@ def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = No
     c_in = w.c_in if not in_split else (w.c_in + 31) // 32 * 32     # operand form pads the last chunk with zeros
     assert out.stride(1) == 1 and out.shape[1] == w.c_out and x.shape[1] == c_in
     a = _gemm_args(x, w.K, c_in, w.c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act,
-                   residual, w.data.data_ptr(), in_split, no_raw, acts)
+                   residual, w.data.data_ptr(), in_split, no_raw, acts, row_perm)
     check(_L().ud3d_gemm_fwd(C.byref(a), _stream()), "ud3d_gemm_fwd")
     return out
 

@@ -23,6 +23,37 @@ class Level:
     child_mask: Optional[torch.Tensor] = None
     up: Optional[torch.Tensor] = None          # int32 [8,N]        (inverse conv gather table)
     up_mask: Optional[torch.Tensor] = None
+    # rows regrouped by neighbourhood pattern (ops.subm3_tile_order): fewer active offsets per 128-row tile
+    perm: Optional[torch.Tensor] = None        # int32 [N]   position -> row
+    subm_p: Optional[torch.Tensor] = None      # int32 [27,N] = subm[:, perm]
+    subm_mask_p: Optional[torch.Tensor] = None
+
+    order_ready: Optional[torch.cuda.Event] = None   # the regrouping runs on a side stream
+
+    @property
+    def subm_conv(self):
+        """(table, tile_mask, row_perm) to run a SubM3 convolution of this level with."""
+        if self.perm is not None:
+            if self.order_ready is not None:
+                torch.cuda.current_stream().wait_event(self.order_ready)
+                self.order_ready = None
+            return self.subm_p, self.subm_mask_p, self.perm
+        return self.subm, self.subm_mask, None
+
+
+# levels with at least this many voxels get the regrouped SubM3 tile order (smaller levels are split-K launches whose
+# time is not in the main loop; the regrouping pass would cost more than it saves)
+TILE_ORDER_MIN_ROWS = 16384
+
+
+_SIDE = {}
+
+
+def _side_stream(dev) -> torch.cuda.Stream:
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
 
 
 class Pyramid:
@@ -75,6 +106,19 @@ def build_pyramid(coords: Optional[torch.Tensor], spatial_shape: Sequence[int], 
     for l in range(n_levels):
         table, mask = ops.rulebook_subm3(c, grids[l], canonical=(canonical or l > 0))
         lv = Level(coords=c, shape=list(shapes[l]), n=ns[l], subm=table, subm_mask=mask)
+        if ns[l] >= TILE_ORDER_MIN_ROWS:
+            # regroup on a side stream: it overlaps the rulebooks of the deeper levels (and, for level 2+, the
+            # convolutions of the levels above); the first SubM3 conv of the level waits for `order_ready`
+            cur = torch.cuda.current_stream()
+            side = _side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                lv.perm, lv.subm_p, lv.subm_mask_p = ops.subm3_tile_order(table)
+                lv.order_ready = torch.cuda.Event()
+                lv.order_ready.record(side)
+            for t in (table, lv.perm, lv.subm_p, lv.subm_mask_p):
+                t.record_stream(cur)
+            table.record_stream(side)
         levels.append(lv)
         if l + 1 == n_levels:
             break

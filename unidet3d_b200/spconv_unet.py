@@ -137,7 +137,7 @@ class SpConvUNet(nn.Module):
     # cp.async with no per-use conversion.  A conv epilogue emits one operand-form copy per consumer
     # BatchNorm (at most two) plus the raw fp32 map only where it is needed as a residual / output.
     @staticmethod
-    def _conv(x_act, w, table, mask, n_out, *, residual=None, raw=None, want_raw=True, acts=()):
+    def _conv(x_act, w, table, mask, n_out, *, residual=None, raw=None, want_raw=True, acts=(), perm=None):
         """x_act: operand-form input.  acts: sequence of (buffer|None, (scale, shift)).  Returns (raw, [act bufs])."""
         dev = x_act.device
         bufs = []
@@ -146,15 +146,16 @@ class SpConvUNet(nn.Module):
                 buf = torch.empty((n_out, w.c_out), dtype=torch.float32, device=dev)
             bufs.append((buf, bn[0], bn[1]))
         out = ops.gemm(x_act, w, table=table, tile_mask=mask, n_out=n_out, in_split=True, residual=residual, out=raw,
-                       no_raw=not want_raw, acts=bufs)
+                       no_raw=not want_raw, acts=bufs, row_perm=perm)
         return (out if want_raw else None), [b[0] for b in bufs]
 
     def _run_block(self, bp, x_raw, x_act, lv, *, out_raw=None, want_raw=True, out_acts=()):
         """ResidualBlock (spconv_unet.py:74-91) with equal channel counts: x + SubM3(BN.SubM3(BN.x)).
         x_act = operand form of relu(bn0(x))."""
-        _, (y_act,) = self._conv(x_act, bp["w0"], lv.subm, lv.subm_mask, lv.n, want_raw=False, acts=[(None, bp["bn1"])])
-        return self._conv(y_act, bp["w1"], lv.subm, lv.subm_mask, lv.n, residual=x_raw, raw=out_raw, want_raw=want_raw,
-                          acts=out_acts)
+        tb, tm, pm = lv.subm_conv
+        _, (y_act,) = self._conv(x_act, bp["w0"], tb, tm, lv.n, want_raw=False, acts=[(None, bp["bn1"])], perm=pm)
+        return self._conv(y_act, bp["w1"], tb, tm, lv.n, residual=x_raw, raw=out_raw, want_raw=want_raw,
+                          acts=out_acts, perm=pm)
 
     def _forward_level(self, x_raw, x_act, pyr: Pyramid, l: int, outputs: list, out_bn=None):
         """x_raw: fp32 [N_l, c]; x_act: operand form of relu(blocks.block0.bn0(x)).
@@ -197,9 +198,10 @@ class SpConvUNet(nn.Module):
                    acts=[(cat_act[:, c:], (t_sc[c:], t_sh[c:]))])
         # tail block 0: SubM1(cat) + SubM3(BN.SubM3(BN.cat))   (in 2c -> c, spconv_unet.py:36-38)
         r = ops.gemm(cat_raw, tail[0]["wi"])
-        _, (y_act,) = self._conv(cat_act, tail[0]["w0"], lv.subm, lv.subm_mask, lv.n, want_raw=False, acts=[(None, tail[0]["bn1"])])
-        raw, (act,) = self._conv(y_act, tail[0]["w1"], lv.subm, lv.subm_mask, lv.n, residual=r,
-                                 acts=[(None, tail[1]["bn0"])] if len(tail) > 1 else out_acts_final)
+        tb, tm, pm = lv.subm_conv
+        _, (y_act,) = self._conv(cat_act, tail[0]["w0"], tb, tm, lv.n, want_raw=False, acts=[(None, tail[0]["bn1"])], perm=pm)
+        raw, (act,) = self._conv(y_act, tail[0]["w1"], tb, tm, lv.n, residual=r,
+                                 acts=[(None, tail[1]["bn0"])] if len(tail) > 1 else out_acts_final, perm=pm)
         for i in range(1, len(tail)):
             last = i == len(tail) - 1
             acts = out_acts_final if last else [(None, tail[i + 1]["bn0"])]
