@@ -35,16 +35,18 @@ def _corners(box):
     return rx.astype(F), ry.astype(F)
 
 
-def _in_box(box, px, py):
+def _in_box(box, px, py, margin=MARGIN):
     cx, cy = box[..., 0], box[..., 1]
     c, s = np.cos(-box[..., 6]).astype(F), np.sin(-box[..., 6]).astype(F)
     rx = (px - cx) * c + (py - cy) * (-s)
     ry = (px - cx) * s + (py - cy) * c
-    return (np.abs(rx) < box[..., 3] / F(2) + MARGIN) & (np.abs(ry) < box[..., 4] / F(2) + MARGIN)
+    return (np.abs(rx) < box[..., 3] / F(2) + F(margin)) & (np.abs(ry) < box[..., 4] / F(2) + F(margin))
 
 
-def box_overlap_rotated(a, b):
-    """a, b float32 [P,7] -> intersection area [P] (mmcv iou3d ``box_overlap``)."""
+def box_overlap_rotated(a, b, margin=MARGIN):
+    """a, b float32 [P,7] -> intersection area [P] (mmcv iou3d ``box_overlap``; ``margin`` = its corner-in-box
+    tolerance MARGIN = 1e-2, which over-estimates the area by up to ~1 %.  oracle/criterion.py passes 1e-6, the
+    tolerance of mmcv's exact ``diff_iou_rotated`` intersection that the reference's rotated DIoU loss is built on)."""
     a, b = a.astype(F), b.astype(F)
     P = len(a)
     ax, ay = _corners(a)
@@ -73,8 +75,8 @@ def box_overlap_rotated(a, b):
                 y2 = (a1 * c0 - a0 * c1) / D
                 px.append(np.where(gen, x1, x2)), py.append(np.where(gen, y1, y2)), valid.append(ok)
         for k in range(4):
-            px.append(bx[:, k]), py.append(by[:, k]), valid.append(_in_box(a, bx[:, k], by[:, k]))
-            px.append(ax[:, k]), py.append(ay[:, k]), valid.append(_in_box(b, ax[:, k], ay[:, k]))
+            px.append(bx[:, k]), py.append(by[:, k]), valid.append(_in_box(a, bx[:, k], by[:, k], margin))
+            px.append(ax[:, k]), py.append(ay[:, k]), valid.append(_in_box(b, ax[:, k], ay[:, k], margin))
         px, py, valid = np.stack(px, 1).astype(F), np.stack(py, 1).astype(F), np.stack(valid, 1)
         cnt = valid.sum(1)
         cxs, cys = np.zeros(P, F), np.zeros(P, F)

@@ -4,7 +4,7 @@ Run (build container only -- /root/reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{encoder_ref,unet_ref,post_ref}.npz.  The reference modules are
+Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref}.npz (all, or the ones named on the command line).  The reference modules are
 imported unmodified from /root/reference; their absent third-party imports
 (mmengine, mmdet3d, spconv, MinkowskiEngine, torch_scatter, mmcv) are replaced by
 minimal stand-ins defined here:
@@ -34,11 +34,18 @@ sys.path.insert(0, ROOT)
 
 # ----------------------------------------------------------------------------- stubs
 class _Registry:
+    """``@X.register_module()`` records the class, ``X.build(dict(type=..., **kw))`` instantiates it."""
+    classes = {}
+
     def register_module(self, *a, **k):
-        return lambda cls: cls
+        def deco(cls):
+            _Registry.classes[cls.__name__] = cls
+            return cls
+        return deco
 
     def build(self, cfg):
-        raise RuntimeError("not used")
+        cfg = dict(cfg)
+        return _Registry.classes[cfg.pop("type")](**cfg)
 
 
 def _mod(name, **attrs):
@@ -143,12 +150,27 @@ def install_stubs():
     class InstanceData:
         def __init__(self, **kw):
             self.__dict__.update(kw)
+
+        def __len__(self):                                   # mmengine: length of the data fields
+            return len(next(iter(self.__dict__.values()))) if self.__dict__ else 0
     _mod("mmengine.structures", InstanceData=InstanceData)
     _mod("mmdet3d"); _mod("mmdet3d.registry", MODELS=reg, TASK_UTILS=reg)
 
     class DepthInstance3DBoxes:
+        """stand-in: built with origin (0.5, 0.5, 0.5) everywhere in the reference, so ``tensor[:, :3]`` is kept as
+        the gravity centre (mmdet3d stores the bottom centre and converts back in ``gravity_center``)."""
         def __init__(self, tensor, box_dim=7, with_yaw=True, origin=(0.5, 0.5, 0)):
             self.tensor, self.box_dim, self.with_yaw = tensor, box_dim, with_yaw
+
+        @property
+        def gravity_center(self):
+            return self.tensor[:, :3]
+
+        def __len__(self):
+            return len(self.tensor)
+
+        def __getitem__(self, idx):
+            return DepthInstance3DBoxes(self.tensor[idx], self.box_dim, self.with_yaw)
 
     def rotation_3d_in_axis(points, angles, axis=0):
         assert axis in (2, -1)
@@ -159,8 +181,73 @@ def install_stubs():
 
     class Base3DDetector(nn.Module):
         pass
-    _mod("mmdet3d.structures", DepthInstance3DBoxes=DepthInstance3DBoxes, rotation_3d_in_axis=rotation_3d_in_axis)
-    _mod("mmdet3d.models", Base3DDetector=Base3DDetector)
+    class AxisAlignedBboxOverlaps3D:
+        """mmdet3d.structures.ops.iou3d_calculator (1.4.0), the is_aligned branch the reference uses."""
+        def __call__(self, b1, b2, mode="iou", is_aligned=False):
+            assert is_aligned and mode == "iou"
+            a1 = (b1[..., 3] - b1[..., 0]) * (b1[..., 4] - b1[..., 1]) * (b1[..., 5] - b1[..., 2])
+            a2 = (b2[..., 3] - b2[..., 0]) * (b2[..., 4] - b2[..., 1]) * (b2[..., 5] - b2[..., 2])
+            lt, rb = torch.max(b1[..., :3], b2[..., :3]), torch.min(b1[..., 3:], b2[..., 3:])
+            wh = (rb - lt).clamp(min=0)
+            overlap = wh[..., 0] * wh[..., 1] * wh[..., 2]
+            union = torch.max(a1 + a2 - overlap, a1.new_tensor([1e-6]))
+            return overlap / union
+    _mod("mmdet3d.structures", DepthInstance3DBoxes=DepthInstance3DBoxes, rotation_3d_in_axis=rotation_3d_in_axis,
+         AxisAlignedBboxOverlaps3D=AxisAlignedBboxOverlaps3D)
+    _mod("mmdet3d.models", Base3DDetector=Base3DDetector, axis_aligned_iou_loss=None, rotated_iou_3d_loss=None)
+
+    def weighted_loss(fn):                                    # mmdet: reduction 'none', weight None -> identity
+        def wrapper(pred, target, weight=None, reduction="mean", avg_factor=None, **kw):
+            assert weight is None and reduction == "none" and avg_factor is None
+            return fn(pred, target, **kw)
+        return wrapper
+    _mod("mmdet"); _mod("mmdet.models"); _mod("mmdet.models.losses")
+    _mod("mmdet.models.losses.utils", weighted_loss=weighted_loss)
+
+    def box2corners(box):                                     # mmcv.ops.diff_iou_rotated.box2corners
+        B = box.size()[0]
+        x, y, w, h, alpha = box.split([1, 1, 1, 1, 1], dim=-1)
+        x4 = box.new_tensor([0.5, -0.5, -0.5, 0.5]) * w
+        y4 = box.new_tensor([0.5, 0.5, -0.5, -0.5]) * h
+        corners = torch.stack([x4, y4], dim=-1)
+        sin, cos = torch.sin(alpha), torch.cos(alpha)
+        rot_T = torch.stack([torch.cat([cos, sin], dim=-1), torch.cat([-sin, cos], dim=-1)], dim=-2)
+        rotated = torch.bmm(corners.view([-1, 4, 2]), rot_T.view([-1, 2, 2])).view([B, -1, 4, 2])
+        rotated[..., 0] += x
+        rotated[..., 1] += y
+        return rotated
+
+    def oriented_box_intersection_2d(c1, c2):
+        """intersection area of two convex quadrilaterals: float64 Sutherland-Hodgman clipping, independent of the
+        oracle's restatement of mmcv's vertex-sorting algorithm."""
+        def clip(poly, a, b):
+            out = []
+            for i in range(len(poly)):
+                p, q = poly[i], poly[(i + 1) % len(poly)]
+                sp = (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+                sq = (b[0] - a[0]) * (q[1] - a[1]) - (b[1] - a[1]) * (q[0] - a[0])
+                if sp >= 0:
+                    out.append(p)
+                if sp * sq < 0:
+                    t = sp / (sp - sq)
+                    out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+            return out
+        a1, a2 = c1.double().reshape(-1, 4, 2).numpy(), c2.double().reshape(-1, 4, 2).numpy()
+        area = np.zeros(len(a1))
+        for n in range(len(a1)):
+            poly = [tuple(v) for v in a1[n]]
+            q = a2[n]
+            if (q[1, 0] - q[0, 0]) * (q[2, 1] - q[0, 1]) - (q[1, 1] - q[0, 1]) * (q[2, 0] - q[0, 0]) < 0:
+                q = q[::-1]
+            for i in range(4):
+                poly = clip(poly, q[i], q[(i + 1) % 4])
+                if not poly:
+                    break
+            if len(poly) >= 3:
+                xs, ys = np.array([v[0] for v in poly]), np.array([v[1] for v in poly])
+                area[n] = 0.5 * abs(np.dot(xs, np.roll(ys, -1)) - np.dot(ys, np.roll(xs, -1)))
+        return torch.as_tensor(area, dtype=torch.float32).reshape(c1.shape[:-2]), None
+    _mod("mmcv.ops.diff_iou_rotated", box2corners=box2corners, oriented_box_intersection_2d=oriented_box_intersection_2d)
     _mod("mmdet3d.models.layers")
 
     def aligned_3d_nms(boxes, scores, classes, thr):
@@ -262,6 +349,90 @@ def gen_unet():
     print("unet_ref.npz", coords.shape, y.features.shape, float(y.features.abs().mean()))
 
 
+def gen_criterion():
+    """The reference's own criterion.py / axis_aligned_iou_loss.py / rotated_iou_loss.py and the GT-target helpers of
+    unidet3d.py on a 3-scene batch (axis-aligned x2 incl. a scene without GT, rotated x1), final layer + 2 aux."""
+    import unidet3d.axis_aligned_iou_loss  # noqa: F401  (registers UniDet3DAxisAlignedIoULoss)
+    import unidet3d.rotated_iou_loss  # noqa: F401
+    from unidet3d.criterion import UniDet3DCriterion
+    from unidet3d.unidet3d import UniDet3D
+    InstanceData = sys.modules["mmengine.structures"].InstanceData
+    Boxes = sys.modules["mmdet3d.structures"].DepthInstance3DBoxes
+    torch.manual_seed(21)
+    rng = np.random.default_rng(21)
+    datasets = ["scannet", "s3dis", "arkitscenes"]
+    diou = lambda t: dict(type=t, mode="diou", reduction="none")
+    simple, rotated = diou("UniDet3DAxisAlignedIoULoss"), diou("UniDet3DRotatedIoU3DLoss")
+    crit = UniDet3DCriterion(
+        matcher=dict(type="UniMatcher", costs=[dict(type="QueryClassificationCost", weight=0.5),
+                                               dict(type="BboxCostJointTraining", weight=2.0, loss_simple=simple,
+                                                    loss_rotated=rotated)]),
+        loss_weight=[0.5, 1.0], non_object_weight=0.1, iter_matcher=True, bbox_loss_simple=simple,
+        bbox_loss_rotated=rotated, datasets=datasets, datasets_weights=[1.0, 0.7, 1.3], topk=[6, 4, 5])
+    names = ["scannet", "arkitscenes", "s3dis", "scannet"]
+    T = [90, 80, 70, 40]
+    G = [7, 5, 6, 0]
+    C = {"scannet": 5, "s3dis": 4, "arkitscenes": 6}
+    save = {"names": np.array(names)}
+
+    def rand_boxes(n, dim):
+        c = rng.uniform(0.5, 3.5, (n, 3))
+        sz = rng.uniform(0.3, 1.6, (n, 3))
+        b = np.concatenate([c, sz] + ([rng.uniform(-3, 3, (n, 1))] if dim == 7 else []), 1)
+        return torch.as_tensor(b.astype(np.float32))
+    insts = []
+    for i, nm in enumerate(names):
+        dim = 7 if nm == "arkitscenes" else 6
+        gt = rand_boxes(G[i], dim)
+        labels = torch.as_tensor(rng.integers(0, C[nm], G[i]))
+        qm = torch.as_tensor(rng.random((G[i], T[i])) < 0.35)
+        if G[i]:
+            qm[0, :] = False
+            qm[0, :3] = True                                  # a GT with fewer than topk+1 candidate queries
+        insts.append(InstanceData(labels_3d=labels, bboxes_3d=Boxes(gt, box_dim=dim, with_yaw=dim == 7,
+                                                                    origin=(0.5, 0.5, 0.5)), query_masks=qm))
+        save.update({f"gt_boxes{i}": gt.numpy(), f"gt_labels{i}": labels.numpy(), f"qmask{i}": qm.numpy()})
+
+    def layer():
+        cls, box = [], []
+        for i, nm in enumerate(names):
+            dim = 7 if nm == "arkitscenes" else 6
+            cls.append(torch.randn(T[i], C[nm] + 1) * 1.5)
+            b = rand_boxes(T[i], dim)
+            k = min(G[i], T[i])
+            if k:                                             # some predictions close to a GT
+                b[:k] = insts[i].bboxes_3d.tensor + 0.05 * torch.randn(k, dim)
+            box.append(b)
+        return dict(cls_preds=cls, bboxes=box)
+    pred = layer()
+    pred["aux_outputs"] = [layer(), layer()]
+    out = crit(pred, insts, names)
+    save["det_loss"] = out["det_loss"].numpy()
+    for l, lay in enumerate([pred] + pred["aux_outputs"]):
+        save[f"layer_loss{l}"] = crit.get_layer_loss(lay, insts, names).numpy()
+        for i in range(len(names)):
+            save[f"l{l}_cls{i}"], save[f"l{l}_box{i}"] = lay["cls_preds"][i].numpy(), lay["bboxes"][i].numpy()
+            if G[i]:
+                pi = InstanceData(scores=lay["cls_preds"][i], bboxes=lay["bboxes"][i])
+                gi = InstanceData(labels=insts[i].labels_3d, query_masks=insts[i].query_masks, bboxes=insts[i].bboxes_3d.tensor)
+                iq, ig = crit.matcher(pi, gi, crit.topk[datasets.index(names[i])])
+                save[f"l{l}_iq{i}"], save[f"l{l}_ig{i}"] = iq.numpy(), ig.numpy()
+    # GT-target helpers of the detector (unidet3d.py:220-275, 371-409)
+    det = object.__new__(UniDet3D)
+    pts = torch.as_tensor(rng.uniform(0, 4, (3000, 3)).astype(np.float32))
+    inst = torch.as_tensor(rng.integers(-1, 9, 3000))
+    masks = UniDet3D.get_gt_inst_masks(det, inst)
+    bb = UniDet3D.get_bboxes_by_masks(det, masks.T, pts)
+    save.update(bm_points=pts.numpy(), bm_inst=inst.numpy(), bm_boxes=bb.tensor.numpy())
+    spc = torch.as_tensor(rng.uniform(0, 4, (400, 3)).astype(np.float32))
+    gtb = Boxes(rand_boxes(9, 7), box_dim=7, with_yaw=True, origin=(0.5, 0.5, 0.5))
+    tg = UniDet3D.get_targets(det, spc, gtb, 6)
+    save.update(tg_centers=spc.numpy(), tg_boxes=gtb.tensor.numpy(), tg_masks=tg.numpy())
+    np.savez_compressed(os.path.join(HERE, "criterion_ref.npz"), **save)
+    print("criterion_ref.npz det_loss", float(out["det_loss"]), "matches per layer/scene",
+          [[len(save.get(f"l{l}_iq{i}", [])) for i in range(len(names))] for l in range(3)])
+
+
 def gen_post():
     from unidet3d.unidet3d import UniDet3D, get_face_distances
     from unidet3d.encoder import _bbox_pred_to_bbox
@@ -309,6 +480,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    gen_encoder()
-    gen_unet()
-    gen_post()
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion"]
+    for name in which:
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion}[name]()

@@ -123,3 +123,46 @@ def test_voxelize_and_scatter_mean_semantics():
     src = torch.arange(12.0).view(6, 2)
     out = scatter_mean(src, torch.tensor([0, 0, 3, 3, 3, 1]))
     assert out.shape == (4, 2) and torch.equal(out[2], torch.zeros(2)) and torch.equal(out[0], torch.tensor([1.0, 2.0]))
+
+
+def _criterion_case(golden_dir):
+    g = np.load(os.path.join(golden_dir, "criterion_ref.npz"))
+    names = [str(n) for n in g["names"]]
+    cfg = dict(datasets=["scannet", "s3dis", "arkitscenes"], datasets_weights=[1.0, 0.7, 1.3], topk=[6, 4, 5],
+               loss_weight=[0.5, 1.0], non_object_weight=0.1, w_cls=0.5, w_box=2.0, iter_matcher=True)
+    gts = [dict(labels=torch.as_tensor(g[f"gt_labels{i}"]), boxes=torch.as_tensor(g[f"gt_boxes{i}"]),
+                query_masks=torch.as_tensor(g[f"qmask{i}"])) for i in range(len(names))]
+    layers = [dict(cls_preds=[torch.as_tensor(g[f"l{l}_cls{i}"]) for i in range(len(names))],
+                   bboxes=[torch.as_tensor(g[f"l{l}_box{i}"]) for i in range(len(names))]) for l in range(3)]
+    return g, names, cfg, gts, layers
+
+
+def test_criterion_matches_reference_criterion(golden_dir):
+    """oracle/criterion.py vs the reference's own criterion.py + IoU losses (tests/golden/criterion_ref.npz):
+    matched (query, gt) pairs bit-exact, per-layer losses and det_loss within 1e-5."""
+    from oracle import criterion as oc
+    g, names, cfg, gts, layers = _criterion_case(golden_dir)
+    total = 0.0
+    for l, lay in enumerate(layers):
+        for i in range(len(names)):
+            if len(gts[i]["labels"]) == 0:
+                continue
+            iq, ig = oc.uni_matcher(lay["cls_preds"][i], lay["bboxes"][i], gts[i]["labels"], gts[i]["boxes"],
+                                    gts[i]["query_masks"], cfg["topk"][cfg["datasets"].index(names[i])])
+            assert np.array_equal(iq.numpy(), g[f"l{l}_iq{i}"]) and np.array_equal(ig.numpy(), g[f"l{l}_ig{i}"]), (l, i)
+        loss, _ = oc.layer_loss(lay["cls_preds"], lay["bboxes"], gts, names, cfg)
+        assert abs(float(loss) - float(g[f"layer_loss{l}"])) < 1e-5 * max(1.0, abs(float(g[f"layer_loss{l}"])))
+        total += float(loss)
+    pred = dict(layers[0], aux_outputs=layers[1:])
+    det = float(oc.criterion(pred, gts, names, cfg))
+    assert abs(det - float(g["det_loss"])) < 1e-5 * abs(float(g["det_loss"])) and abs(det - total) < 1e-4
+
+
+def test_gt_target_helpers_match_reference(golden_dir):
+    """get_bboxes_by_masks / get_targets (unidet3d.py:220-275, 371-409) restatements vs the reference functions."""
+    from oracle import criterion as oc
+    g = np.load(os.path.join(golden_dir, "criterion_ref.npz"))
+    bb = oc.bboxes_by_masks(g["bm_inst"], g["bm_points"])
+    assert np.array_equal(bb.numpy(), g["bm_boxes"])
+    tg = oc.targets_by_distance(g["tg_centers"], g["tg_boxes"], 6)
+    assert np.array_equal(tg.numpy(), g["tg_masks"])
