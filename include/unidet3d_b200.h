@@ -263,6 +263,41 @@ typedef struct {
 size_t ud3d_postprocess_workspace_bytes(const ud3d_post_args* args);
 int ud3d_postprocess_scene(const ud3d_post_args* args, void* ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------ training-side targets, matcher, loss values
+ * (forward values only -- no gradients yet)
+ *
+ * get_bboxes_by_masks (unidet3d.py:220-275): inst int64 [n] (-1 = no instance), points [n, >=3] ->
+ * out [n_inst, 6] = (centre, size) of the tight AABB of every instance's points.  ws >= n_inst*6*4 bytes. */
+int ud3d_boxes_by_instance(const float* points, int ld_pts, const int64_t* inst, int n, int n_inst, float* out,
+                           void* ws, size_t ws_bytes, void* stream);
+/* get_targets (unidet3d.py:371-409): superpoint centres [S,3], gt_boxes [G, box_dim] (gravity centre first) ->
+ * masks uint8 [G, S]: every box keeps the centres strictly nearer than its (topk+1)-th nearest, every centre goes to
+ * the nearest box that kept it.  ws >= G*4 bytes. */
+int ud3d_targets_by_distance(const float* centers, int S, const float* gt_boxes, int box_dim, int G, int topk,
+                             uint8_t* masks, void* ws, size_t ws_bytes, void* stream);
+/* One (decoder layer, scene) of UniDet3DCriterion.get_layer_loss (criterion.py:44-142) with its UniMatcher
+ * (criterion.py:286-320; costs QueryClassificationCost * w_cls + BboxCostJointTraining * w_box, criterion.py:200-284):
+ *   cost[q,g] = -w_cls * softmax(logits[q])[labels[g]] + w_box * DIoU_loss(boxes[q], gt_boxes[g]),  1e8 where
+ *               !query_masks[g,q];   thr[g] = (topk+1)-th smallest cost of column g;   match[q,g] = cost < thr[g]
+ *   target[q] = labels[largest matched g] or C (no object);  class weights 1 (objects) / non_object_weight
+ *   sums[0] = sum_q w[target] * -log_softmax(logits[q])[target],  sums[1] = sum_q w[target]   (weighted CE = s0/s1)
+ *   sums[2] = sum over matched pairs of DIoU_loss(boxes[q], gt_boxes[g]),  sums[3] = number of matched pairs
+ * box_dim 6: (centre, size), axis-aligned DIoU (axis_aligned_iou_loss.py:14-53; as a matching cost the reference adds
+ * the centre-distance penalty of GT 0 to every column, line 51 -- kept); box_dim 7: (x,y,z,w,h,l,alpha), rotated DIoU
+ * (rotated_iou_loss.py:14-82, exact BEV intersection).  G == 0: no match, every query is "no object".
+ * Requires T >= topk+1 (torch.topk raises otherwise).  Deterministic (fixed-order reductions). */
+typedef struct {
+  const float* logits; int32_t ld_logits; int32_t T; int32_t C1;     /* [T, C+1] */
+  const float* boxes; int32_t box_dim;                               /* [T, box_dim] predicted boxes */
+  const float* gt_boxes; const int64_t* gt_labels; int32_t G;        /* [G, box_dim], [G] */
+  const uint8_t* query_masks;                                        /* bool [G, T] */
+  int32_t topk; float w_cls; float w_box; float non_object_weight;
+  uint8_t* match;                                                    /* out [T, G] */
+  float* sums;                                                       /* out [4] */
+} ud3d_criterion_args;
+size_t ud3d_criterion_workspace_bytes(int T, int G);
+int ud3d_criterion_layer(const ud3d_criterion_args* args, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

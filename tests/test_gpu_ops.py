@@ -437,3 +437,104 @@ def test_subm3_tile_order_is_a_pure_regrouping():
     assert torch.equal(z0, z1) and torch.equal(a0, a1)
     rel = float((z0 - y0).abs().max() / y0.abs().max())
     assert rel < 1e-3, rel
+
+
+# ------------------------------------------------------------------ training-side targets / matcher / loss values (R14)
+def _criterion_case(golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "criterion_ref.npz"))
+    names = [str(n) for n in g["names"]]
+    cfg = dict(datasets=["scannet", "s3dis", "arkitscenes"], datasets_weights=[1.0, 0.7, 1.3], topk=[6, 4, 5],
+               loss_weight=[0.5, 1.0], non_object_weight=0.1, w_cls=0.5, w_box=2.0, iter_matcher=True)
+    return g, names, cfg
+
+
+def test_criterion_layer_vs_reference_fixture(golden_dir):
+    """ud3d_criterion_layer against the reference's own criterion.py (tests/golden/criterion_ref.npz): matched
+    (query, gt) pairs bit-exact, per-layer loss and det_loss within 1e-4 relative; axis-aligned and rotated boxes,
+    a GT with fewer than topk+1 candidate queries, a scene without GT."""
+    import unidet3d_b200 as u
+    from unidet3d_b200.structures import DepthInstance3DBoxes, InstanceData
+    g, names, cfg = _criterion_case(golden_dir)
+    diou = lambda t: dict(type=t, mode="diou", reduction="none")
+    crit = u.MODELS.build(dict(
+        type="UniDet3DCriterion",
+        matcher=dict(type="UniMatcher", costs=[dict(type="QueryClassificationCost", weight=0.5),
+                                               dict(type="BboxCostJointTraining", weight=2.0)]),
+        loss_weight=cfg["loss_weight"], non_object_weight=0.1, iter_matcher=True,
+        bbox_loss_simple=diou("UniDet3DAxisAlignedIoULoss"), bbox_loss_rotated=diou("UniDet3DRotatedIoU3DLoss"),
+        datasets=cfg["datasets"], datasets_weights=cfg["datasets_weights"], topk=cfg["topk"]))
+    insts = []
+    for i in range(len(names)):
+        gb = torch.as_tensor(g[f"gt_boxes{i}"]).to(DEV)
+        dim = gb.shape[1] if gb.numel() else (7 if names[i] == "arkitscenes" else 6)
+        insts.append(InstanceData(labels_3d=torch.as_tensor(g[f"gt_labels{i}"]).to(DEV),
+                                  bboxes_3d=DepthInstance3DBoxes(gb, box_dim=dim, with_yaw=dim == 7, origin=(0.5, 0.5, 0.5)),
+                                  query_masks=torch.as_tensor(g[f"qmask{i}"]).to(DEV)))
+    layers = [dict(cls_preds=[torch.as_tensor(g[f"l{l}_cls{i}"]).to(DEV) for i in range(len(names))],
+                   bboxes=[torch.as_tensor(g[f"l{l}_box{i}"]).to(DEV) for i in range(len(names))]) for l in range(3)]
+    for l, lay in enumerate(layers):
+        terms = crit.layer_terms(lay, insts, names)
+        for i, (match, sums) in enumerate(terms):
+            if f"l{l}_iq{i}" in g.files:
+                ids = torch.argwhere(match).cpu().numpy()
+                assert np.array_equal(ids[:, 0], g[f"l{l}_iq{i}"]) and np.array_equal(ids[:, 1], g[f"l{l}_ig{i}"]), (l, i)
+            else:
+                assert match.numel() == 0 and float(sums[3]) == 0
+        loss = float(crit.get_layer_loss(lay, insts, names))
+        ref = float(g[f"layer_loss{l}"])
+        assert abs(loss - ref) < 1e-4 * abs(ref), (l, loss, ref)
+    det = float(crit(dict(layers[0], aux_outputs=layers[1:]), insts, names)["det_loss"])
+    assert abs(det - float(g["det_loss"])) < 1e-4 * abs(float(g["det_loss"]))
+
+
+def test_criterion_layer_vs_oracle_large():
+    """full-size (T = 3000 queries = query_thr, G = 40) scene against the CPU oracle: same matches (up to costs within
+    1e-4 of a column threshold), same loss sums."""
+    from unidet3d_b200 import ops
+    from oracle import criterion as oc
+    rng = np.random.default_rng(3)
+    for dim, C, topk in [(6, 18, 6), (7, 17, 6)]:
+        T, G = 3000, 40
+        gt = np.concatenate([rng.uniform(0.5, 7.5, (G, 3)), rng.uniform(0.3, 2.0, (G, 3))] +
+                            ([rng.uniform(-3, 3, (G, 1))] if dim == 7 else []), 1).astype(np.float32)
+        pb = np.concatenate([rng.uniform(0.5, 7.5, (T, 3)), rng.uniform(0.3, 2.0, (T, 3))] +
+                            ([rng.uniform(-3, 3, (T, 1))] if dim == 7 else []), 1).astype(np.float32)
+        pb[:G * 8] = np.repeat(gt, 8, 0) + 0.08 * rng.standard_normal((G * 8, dim)).astype(np.float32)
+        pb[:, 3:6] = np.abs(pb[:, 3:6]) + 0.05
+        cls = (rng.standard_normal((T, C + 1)) * 2).astype(np.float32)
+        labels = rng.integers(0, C, G)
+        qm = rng.random((G, T)) < 0.3
+        match, sums = ops.criterion_layer(torch.as_tensor(cls).to(DEV), torch.as_tensor(pb).to(DEV), torch.as_tensor(gt).to(DEV),
+                                          torch.as_tensor(labels).to(DEV), torch.as_tensor(qm).to(DEV), topk, 0.5, 2.0, 0.1)
+        # matched set: identical to the oracle's except where a cost lies within fp noise of its column's threshold
+        # (the rotated BEV intersection is evaluated with different float operations on the two sides)
+        cost = oc.match_cost(torch.as_tensor(cls), torch.as_tensor(pb), torch.as_tensor(labels), torch.as_tensor(gt))
+        cost = torch.where(torch.as_tensor(qm).T, cost, torch.tensor(1e8))
+        kth = torch.topk(cost, topk + 1, dim=0, largest=False).values[-1:]
+        ref = cost < kth
+        m = match.cpu()
+        borderline = (cost - kth).abs() < 1e-4 * kth.abs().clamp(min=1.0)
+        assert bool(((m == ref) | borderline).all()), torch.argwhere((m != ref) & ~borderline)[:8]
+        assert int((m != ref).sum()) <= 2
+        # loss terms: recomputed by the oracle for the matched set the kernel produced
+        ids = torch.argwhere(m)
+        iq, ig = ids[:, 0], ids[:, 1]
+        tgt = torch.full((T,), C, dtype=torch.long)
+        tgt[iq] = torch.as_tensor(labels)[ig]
+        w = torch.tensor([1.0] * C + [0.1])
+        ce_num = float((w[tgt] * torch.nn.functional.cross_entropy(torch.as_tensor(cls), tgt, reduction="none")).sum())
+        box = float(oc.box_loss(torch.as_tensor(pb)[iq], torch.as_tensor(gt)[ig]).sum())
+        s = sums.cpu().numpy()
+        assert abs(s[0] - ce_num) < 1e-4 * ce_num and abs(s[1] - float(w[tgt].sum())) < 1e-3
+        assert abs(s[2] - box) < 1e-4 * abs(box) + 1e-4 and int(s[3]) == len(iq)
+
+
+def test_gt_target_helpers_vs_reference_fixture(golden_dir):
+    """ud3d_boxes_by_instance / ud3d_targets_by_distance against the reference's get_bboxes_by_masks / get_targets."""
+    from unidet3d_b200 import ops
+    g, _, _ = _criterion_case(golden_dir)
+    bb = ops.boxes_by_instance(torch.as_tensor(g["bm_points"]).to(DEV), torch.as_tensor(g["bm_inst"]).to(DEV), len(g["bm_boxes"]))
+    assert np.array_equal(bb.cpu().numpy(), g["bm_boxes"])
+    tg = ops.targets_by_distance(torch.as_tensor(g["tg_centers"]).to(DEV), torch.as_tensor(g["tg_boxes"]).to(DEV), 6)
+    assert np.array_equal(tg.cpu().numpy(), g["tg_masks"])

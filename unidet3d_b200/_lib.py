@@ -48,6 +48,18 @@ class PostArgs(C.Structure):
     ]
 
 
+class CriterionArgs(C.Structure):
+    """Mirror of ``ud3d_criterion_args``."""
+    _fields_ = [
+        ("logits", C.c_void_p), ("ld_logits", C.c_int32), ("T", C.c_int32), ("C1", C.c_int32),
+        ("boxes", C.c_void_p), ("box_dim", C.c_int32),
+        ("gt_boxes", C.c_void_p), ("gt_labels", C.c_void_p), ("G", C.c_int32),
+        ("query_masks", C.c_void_p),
+        ("topk", C.c_int32), ("w_cls", C.c_float), ("w_box", C.c_float), ("non_object_weight", C.c_float),
+        ("match", C.c_void_p), ("sums", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list EVERY symbol declared in include/unidet3d_b200.h
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -87,6 +99,10 @@ SIGNATURES = {
     "ud3d_trim_workspace_bytes": (_sz, [_i, _i, _i]),
     "ud3d_postprocess_workspace_bytes": (_sz, [C.POINTER(PostArgs)]),
     "ud3d_postprocess_scene": (_i, [C.POINTER(PostArgs), _vp, _sz, _vp]),
+    "ud3d_boxes_by_instance": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "ud3d_targets_by_distance": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "ud3d_criterion_workspace_bytes": (_sz, [_i, _i]),
+    "ud3d_criterion_layer": (_i, [C.POINTER(CriterionArgs), _vp, _sz, _vp]),
     "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _f, _f, _vp, _vp, _sz, _vp]),
 }
 

@@ -41,7 +41,8 @@ class UniDet3D(nn.Module):
         if backbone is not None:
             self.unet = MODELS.build(backbone)
         self.decoder = MODELS.build(decoder)
-        self.criterion_cfg = criterion          # training-side component: not built in round 1
+        self.criterion_cfg = criterion
+        self.criterion = MODELS.build(criterion) if criterion is not None else None     # loss values
         self.voxel_size = voxel_size
         self.min_spatial_shape = min_spatial_shape
         self.query_thr = query_thr

@@ -8,7 +8,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, check
+from ._lib import CriterionArgs, GemmArgs, check
 
 TILE_M = 128
 
@@ -412,3 +412,57 @@ def postprocess_scene(logits: torch.Tensor, boxes: torch.Tensor, k: int, nms_mod
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     check(_L().ud3d_postprocess_scene(C.byref(a), _p(ws), wsb, _stream()), "ud3d_postprocess_scene")
     return dict(scores=scores, labels=labels, cand=cand, keep=keep, n_keep=n_keep, trimmed=trimmed, _buf=buf)
+
+
+# ------------------------------------------------------------------ training-side targets / matcher / loss values
+def boxes_by_instance(points: torch.Tensor, inst: torch.Tensor, n_inst: int) -> torch.Tensor:
+    """get_bboxes_by_masks (unidet3d.py:220-275): points fp32 [n, >=3], inst int64 [n] (-1 = none) -> [n_inst, 6]."""
+    _req(inst, torch.int64, "inst")
+    if not points.is_cuda or points.dtype != torch.float32 or points.stride(1) != 1:
+        raise _lib.Ud3dError("boxes_by_instance: points must be a CUDA fp32 matrix with unit column stride")
+    out = torch.empty((n_inst, 6), dtype=torch.float32, device=points.device)
+    ws = torch.empty(max(n_inst, 1) * 24, dtype=torch.uint8, device=points.device)
+    check(_L().ud3d_boxes_by_instance(_p(points), points.stride(0), _p(inst), inst.numel(), int(n_inst), _p(out), _p(ws),
+                                      ws.numel(), _stream()), "ud3d_boxes_by_instance")
+    return out
+
+
+def targets_by_distance(centers: torch.Tensor, gt_boxes: torch.Tensor, topk: int) -> torch.Tensor:
+    """get_targets (unidet3d.py:371-409): centres [S,3], boxes [G, 6|7] -> bool [G, S]."""
+    _req(centers, torch.float32, "centers"), _req(gt_boxes, torch.float32, "gt_boxes")
+    S, G = centers.shape[0], gt_boxes.shape[0]
+    masks = torch.zeros((G, S), dtype=torch.uint8, device=centers.device)
+    ws = torch.empty(max(G, 1) * 4, dtype=torch.uint8, device=centers.device)
+    check(_L().ud3d_targets_by_distance(_p(centers), S, _p(gt_boxes), gt_boxes.shape[1] if G else 6, G, int(topk),
+                                        _p(masks), _p(ws), ws.numel(), _stream()), "ud3d_targets_by_distance")
+    return masks.bool()
+
+
+def criterion_layer(logits: torch.Tensor, boxes: torch.Tensor, gt_boxes: torch.Tensor, gt_labels: torch.Tensor,
+                    query_masks: torch.Tensor, topk: int, w_cls: float, w_box: float, non_object_weight: float):
+    """UniMatcher + the loss terms of one (layer, scene) (ud3d_criterion_layer).
+    -> (match bool [T, G], sums fp32 [4] = CE numerator, CE denominator, box-loss sum, number of matched pairs)."""
+    if not logits.is_cuda or logits.dtype != torch.float32 or logits.stride(1) != 1:
+        raise _lib.Ud3dError("criterion_layer: logits must be a CUDA fp32 matrix with unit column stride")
+    _req(boxes, torch.float32, "boxes")
+    T, G = logits.shape[0], gt_labels.shape[0]
+    dev = logits.device
+    match = torch.empty((T, G), dtype=torch.uint8, device=dev)
+    sums = torch.empty(4, dtype=torch.float32, device=dev)
+    a = CriterionArgs()
+    a.logits = logits.data_ptr(); a.ld_logits = logits.stride(0); a.T = T; a.C1 = logits.shape[1]
+    a.boxes = boxes.data_ptr(); a.box_dim = boxes.shape[1]
+    if G:
+        _req(gt_boxes, torch.float32, "gt_boxes"), _req(gt_labels, torch.int64, "gt_labels")
+        qm = query_masks if query_masks.dtype == torch.uint8 else query_masks.to(torch.uint8)
+        qm = _req(qm.contiguous(), torch.uint8, "query_masks")
+        if tuple(qm.shape) != (G, T) or gt_boxes.shape[1] != boxes.shape[1]:
+            raise _lib.Ud3dError("criterion_layer: query_masks must be [G, T] and gt_boxes match the predicted box_dim")
+        a.gt_boxes = gt_boxes.data_ptr(); a.gt_labels = gt_labels.data_ptr(); a.query_masks = qm.data_ptr()
+    a.G = G
+    a.topk = int(topk); a.w_cls = float(w_cls); a.w_box = float(w_box); a.non_object_weight = float(non_object_weight)
+    a.match = match.data_ptr() if G else None
+    a.sums = sums.data_ptr()
+    ws = torch.empty(int(_L().ud3d_criterion_workspace_bytes(T, G)), dtype=torch.uint8, device=dev)
+    check(_L().ud3d_criterion_layer(C.byref(a), _p(ws), ws.numel(), _stream()), "ud3d_criterion_layer")
+    return match.bool(), sums
