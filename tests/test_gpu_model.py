@@ -146,3 +146,76 @@ def test_pinned_batch_stager_matches_direct_call():
         ref = model.forward_scenes(pts, sps, ["scannet"] * 2)
         for (b, l, s), (rb, rl, rs) in zip(res, ref):
             assert torch.equal(l, rl) and torch.allclose(s, rs, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_loss_value_vs_oracle():
+    """UniDet3D.loss (unidet3d.py:277-364, forward value): GT boxes by instance masks (scannet) / shifted GT boxes with
+    distance targets (arkitscenes, rotated), all seven heads, matcher + criterion -- against the CPU oracle end to end."""
+    import unidet3d_b200 as u
+    from unidet3d_b200 import configs
+    from unidet3d_b200.structures import DepthInstance3DBoxes, Det3DDataSample, InstanceData, PointData
+    from unidet3d_b200.synthetic import make_scene, make_model_state_dict, SCENE_PRESETS
+    from oracle import criterion as oc, encoder as oenc, unet as ounet, voxelize as ovox
+    from oracle.pool import scatter_mean, superpoint_pool
+    datasets = ("scannet", "arkitscenes")
+    cfg = configs.model_cfg(datasets, topk_insts=100)
+    n, v, a, c = SCENE_PRESETS["tiny"]
+    cfg["voxel_size"] = v
+    model = u.MODELS.build(cfg).eval()
+    sd = make_model_state_dict(cfg, 0)
+    model.load_state_dict(sd, strict=False)
+    model.cuda()
+    rng = np.random.default_rng(4)
+    scenes = [make_scene(20 + i, n, a, c) for i in range(2)]
+    names = ["scannet", "arkitscenes"]
+    samples, gts_ref = [], []
+    for i, (pts, sp) in enumerate(scenes):
+        xyz = pts[:, :3] - pts[:, :3].min(0)
+        n_sp = int(sp.max()) + 1
+        if names[i] == "scannet":
+            # instances = unions of superpoints; GT boxes come from the instance masks, sp_masks from the loader
+            sp_inst = rng.integers(-1, 6, n_sp)
+            sp_inst[:6] = np.arange(6)
+            inst = sp_inst[sp]
+            labels = rng.integers(0, 18, 6)
+            sp_masks = np.stack([sp_inst == k for k in range(6)])
+            gi = InstanceData(labels_3d=torch.as_tensor(labels), sp_masks=torch.as_tensor(sp_masks))
+            seg = PointData(sp_pts_mask=torch.as_tensor(sp), pts_instance_mask=torch.as_tensor(inst))
+            boxes = oc.bboxes_by_masks(inst, xyz)
+            qm = torch.as_tensor(sp_masks)
+        else:
+            G = 5
+            ctr = rng.uniform(xyz.min(0), xyz.max(0), (G, 3))
+            t = np.concatenate([ctr + pts[:, :3].min(0), rng.uniform(0.3, 1.2, (G, 3)), rng.uniform(-3, 3, (G, 1))], 1).astype(np.float32)
+            labels = rng.integers(0, 17, G)
+            gi = InstanceData(labels_3d=torch.as_tensor(labels),
+                              bboxes_3d=DepthInstance3DBoxes(torch.as_tensor(t), box_dim=7, with_yaw=True, origin=(0.5, 0.5, 0.5)))
+            seg = PointData(sp_pts_mask=torch.as_tensor(sp))
+            boxes = torch.as_tensor(t.copy())
+            boxes[:, :3] -= torch.as_tensor(pts[:, :3].min(0))
+            centers = scatter_mean(torch.as_tensor(xyz), torch.as_tensor(sp))
+            qm = oc.targets_by_distance(centers, boxes, 6)
+        samples.append(Det3DDataSample(lidar_path=f"data/{names[i]}/points/x.bin", gt_pts_seg=seg, gt_instances_3d=gi))
+        gts_ref.append(dict(labels=torch.as_tensor(labels), boxes=boxes, query_masks=qm))
+    out = model.loss(dict(points=[torch.as_tensor(s[0]) for s in scenes]), samples)
+    loss = float(out["det_loss"])
+    # oracle pipeline
+    det_sd = {k: t for k, t in sd.items() if not k.startswith("decoder.")}
+    enc_sd = {k[len("decoder."):]: t for k, t in sd.items() if k.startswith("decoder.")}
+    ocfg = configs.oracle_cfg(cfg)
+    pts = [s[0] for s in scenes]
+    sps = [s[1] for s in scenes]
+    n_sps = [int(s.max()) + 1 for s in sps]
+    sp_off = np.concatenate([[0], np.cumsum(n_sps)])
+    coords, feats, inverse, shape = ovox.voxelize(pts, ocfg["voxel_size"], ocfg["min_spatial_shape"])
+    x, _ = ounet.backbone_forward(det_sd, coords, torch.as_tensor(feats), shape)
+    pooled = superpoint_pool(x, inverse, np.concatenate([s + o for s, o in zip(sps, sp_off[:-1])]), int(sp_off[-1]))
+    xs = [pooled[sp_off[i]:sp_off[i + 1]] for i in range(2)]
+    ctrs = [scatter_mean(torch.as_tensor(p[:, :3] - p[:, :3].min(0)), torch.as_tensor(s)) for p, s in zip(pts, sps)]
+    pred = oenc.encoder_forward(enc_sd, ocfg["encoder"], xs, ctrs, names, all_heads=True)
+    cc = cfg["criterion"]
+    ref = float(oc.criterion(pred, gts_ref, names, dict(datasets=list(datasets), datasets_weights=cc["datasets_weights"],
+                                                         topk=cc["topk"], loss_weight=cc["loss_weight"],
+                                                         non_object_weight=cc["non_object_weight"], iter_matcher=True)))
+    assert abs(loss - ref) < 2e-3 * abs(ref), (loss, ref)

@@ -44,9 +44,22 @@ def model_cfg(datasets=('scannet',), num_channels=32, voxel_size=0.02, num_plane
         decoder=dict(type='UniDet3DEncoder', num_layers=num_layers, datasets_classes=[CLASSES[d] for d in ds],
                      in_channels=planes[0], d_model=d_model, num_heads=num_heads, hidden_dim=hidden_dim, dropout=0.0,
                      activation_fn='gelu', datasets=ds, angles=[per[d][4] for d in ds]),
-        criterion=None, train_cfg=dict(topk=6),
+        criterion=criterion_cfg(ds), train_cfg=dict(topk=6),
         test_cfg=dict(low_sp_thr=0.18, up_sp_thr=0.81, topk_insts=topk_insts, score_thr=0,
                       iou_thr=[per[d][5] for d in ds]))
+
+
+def criterion_cfg(datasets):
+    """configs/unidet3d_1xb8_scannet.py:60-89 / the joint config's :60-92."""
+    diou = lambda t: dict(type=t, mode='diou', reduction='none')
+    simple, rotated = diou('UniDet3DAxisAlignedIoULoss'), diou('UniDet3DRotatedIoU3DLoss')
+    topk = dict(scannet=6, s3dis=6, multiscan=3, scannetpp=3, arkitscenes=3, **{'3rscan': 3})
+    return dict(type='UniDet3DCriterion', datasets=list(datasets), datasets_weights=[1] * len(datasets),
+                bbox_loss_simple=simple, bbox_loss_rotated=rotated,
+                matcher=dict(type='UniMatcher', costs=[dict(type='QueryClassificationCost', weight=0.5),
+                                                       dict(type='BboxCostJointTraining', weight=2.0, loss_simple=simple,
+                                                            loss_rotated=rotated)]),
+                loss_weight=[0.5, 1.0], non_object_weight=0.1, topk=[topk[d] for d in datasets], iter_matcher=True)
 
 
 JOINT = ('scannet', 's3dis', 'multiscan', '3rscan', 'scannetpp', 'arkitscenes')

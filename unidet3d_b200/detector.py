@@ -8,7 +8,8 @@ Same registry name and constructor arguments as the reference; ``input_conv.0.we
 Differences from the reference, all documented in DESIGN.md:
   * ``predict`` post-processes EVERY scene of the batch (the reference reads scene 0 only,
     unidet3d.py:498-502; scene 0 is identical);
-  * the training path (``loss``) is not part of round 1.
+  * ``loss`` returns the VALUE of the training loss (matcher + criterion on the GPU); gradients and train-mode
+    BatchNorm statistics are not implemented yet.
 """
 from __future__ import annotations
 
@@ -283,9 +284,78 @@ class UniDet3D(nn.Module):
                                                     points=batch_inputs_dict["points"][0])
         return batch_data_samples
 
+    def _select_queries(self, x, sp_centers, sp_masks):
+        """unidet3d.py:182-218: scenes with more than ``query_thr`` superpoints keep a random subset
+        (``torch.randperm`` on the host RNG, like the reference)."""
+        queries, centers, qmasks = [], [], []
+        for xi, ci, mi in zip(x, sp_centers, sp_masks):
+            if len(xi) > self.query_thr:
+                ids = torch.randperm(len(xi))[:self.query_thr].to(xi.device)
+                xi, ci, mi = xi[ids], ci[ids], mi[:, ids]
+            queries.append(xi), centers.append(ci), qmasks.append(mi)
+        return queries, centers, qmasks
+
+    @torch.no_grad()
     def loss(self, batch_inputs_dict, batch_data_samples, **kwargs):
-        raise NotImplementedError("training path (unidet3d.py:277-364) is scheduled after the forward hot path "
-                                  "(SURVEY.md section 8f rank 2)")
+        """unidet3d.py:277-364 -- the VALUE of the training loss, ``{'det_loss': tensor}``.
+
+        GT boxes from instance masks (``get_bboxes_by_masks``) or shifted GT boxes, superpoint centres, distance
+        targets (``get_targets``), backbone + pooling, query selection, the encoder with all seven heads, and the
+        criterion, every stage on our kernels.  Not implemented yet: gradients, and the
+        batch statistics of train-mode (Sync)BatchNorm -- the backbone runs with the running statistics, so this is
+        the validation-style loss of the current weights.  ``elastic_coords`` (the ElasticTransfrom augmentation's
+        side input) is not supported."""
+        if self.criterion is None:
+            raise RuntimeError("UniDet3D was built without a criterion config")
+        if batch_inputs_dict.get("elastic_coords") is not None:
+            raise NotImplementedError("loss() with elastic_coords")
+        dev = next(self.parameters()).device
+        B = len(batch_data_samples)
+        names = [self.get_dataset(s.lidar_path) for s in batch_data_samples]
+        P = [torch.as_tensor(p).to(dev, torch.float32) for p in batch_inputs_dict["points"]]
+        S = [torch.as_tensor(s.gt_pts_seg.sp_pts_mask).to(dev, torch.int64) for s in batch_data_samples]
+        n_sps = [int(v) + 1 for v in torch.stack([s.max() for s in S]).cpu().tolist()]
+        sp_off = np.concatenate([[0], np.cumsum(n_sps)]).astype(np.int64)
+        pt_off = np.concatenate([[0], np.cumsum([len(p) for p in P])]).astype(np.int64)
+        gt_insts, sp_centers, sp_masks = [], [], []
+        for i, sample in enumerate(batch_data_samples):
+            ds = self.decoder.datasets.index(names[i])
+            gi = sample.gt_instances_3d
+            shift = P[i][:, :3].min(0)[0]
+            xyz = (P[i][:, :3] - shift).contiguous()
+            if self.bbox_by_mask[ds]:
+                inst = torch.as_tensor(sample.gt_pts_seg.pts_instance_mask).to(dev, torch.int64).contiguous()
+                n_inst = int(inst.max()) + 1 if inst.numel() else 0
+                boxes = DepthInstance3DBoxes(ops.boxes_by_instance(xyz, inst, max(n_inst, 0)), with_yaw=False, box_dim=6,
+                                             origin=(0.5, 0.5, 0.5))
+            else:
+                b = gi.bboxes_3d
+                t = torch.cat((b.gravity_center.to(dev) - shift, b.tensor[:, 3:].to(dev)), dim=1)
+                boxes = DepthInstance3DBoxes(t, with_yaw=b.with_yaw, box_dim=t.shape[1], origin=(0.5, 0.5, 0.5))
+            c = ops.segmented_mean(xyz, S[i].contiguous(), n_sps[i], channels=3)
+            if self.target_by_distance[ds]:
+                gb = torch.cat((boxes.gravity_center, boxes.tensor[:, 3:]), dim=1).contiguous()
+                m = ops.targets_by_distance(c, gb, int(self.train_cfg["topk"]))
+            else:
+                m = torch.as_tensor(gi.sp_masks).to(dev)
+            gt_insts.append(InstanceData(labels_3d=torch.as_tensor(gi.labels_3d).to(dev), bboxes_3d=boxes))
+            sp_centers.append(c), sp_masks.append(m)
+        pts = torch.cat(P) if B > 1 else P[0].contiguous()
+        sp_b = torch.cat([s + int(o) for s, o in zip(S, sp_off[:-1])])
+        offs = torch.tensor(pt_off, dtype=torch.int32, device=dev)
+        x, inverse = self.collate(pts, offs, B)
+        pooled = self.extract_feat(x, sp_b, inverse, sp_off)
+        xs = [pooled[int(sp_off[i]):int(sp_off[i + 1])] for i in range(B)]
+        queries, centers, qmasks = self._select_queries(xs, sp_centers, sp_masks)
+        for g, m in zip(gt_insts, qmasks):
+            g.query_masks = m
+        prev = self.decoder.eval_aux_outputs
+        self.decoder.eval_aux_outputs = True             # the criterion reads all seven heads (criterion.py:166-176)
+        try:
+            out = self.decoder(queries, centers, names)
+        finally:
+            self.decoder.eval_aux_outputs = prev
+        return self.criterion(out, gt_insts, names)
 
     def forward(self, inputs, data_samples=None, mode="predict", **kwargs):
         if mode == "predict":
