@@ -325,7 +325,8 @@ def main():
     achieved = (abytes / n_conv) / (t_conv / n_conv) / 1e9
     traffic = None
     try:   # DRAM bytes per launch of the same kernel from the committed ncu capture (profiles/)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1h_gemm_traffic.json")))["dram_bytes_per_launch"]
+        tfile = [f for f in ("r2_gemm_traffic.json", "r1h_gemm_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", f))][0]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tfile)))["dram_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
     roof = {"bound": "hbm", "kernel": "gather_gemm_tc_kernel (the 49 sparse convs of the backbone)",

@@ -69,6 +69,12 @@ size_t ud3d_grid_workspace_bytes(const int32_t dims_host[4]);
  * *n_unique (device int32) = number of distinct cells. */
 int ud3d_grid_build(const int32_t* coords, int n, const int32_t dims_host[4], void* ws, size_t ws_bytes,
                     int32_t* n_unique, void* stream);
+/* Occupancy grid of the NEXT (k=2, s=2 down-sampled) level straight from the finer level's bitmap: cell c -> c / 2,
+ * cells whose coarse coordinate falls outside `dims_host` are dropped (spconv's odd-extent rule, see
+ * ud3d_down2_parents).  Same result as ud3d_grid_build on ud3d_down_ancestors(coords, 1), without touching the points
+ * or voxels again (a pass over the fine bitmap words). */
+int ud3d_grid_build_coarser(const int32_t fine_dims_host[4], const void* fine_ws, const int32_t dims_host[4], void* ws,
+                            size_t ws_bytes, int32_t* n_unique, void* stream);
 /* rank_out[i] = canonical row of coords[i] or -1 (absent / outside the grid / coords[i][0] < 0) */
 int ud3d_grid_rank(const int32_t* coords, int n, const int32_t dims_host[4], const void* ws,
                    int32_t* rank_out, void* stream);

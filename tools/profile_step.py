@@ -28,11 +28,12 @@ def main():
     model.cuda()
     pts = [torch.as_tensor(s[0]).cuda() for s in scenes]
     sps = [torch.as_tensor(s[1]).cuda() for s in scenes]
+    n_sps = [int(s[1].max()) + 1 for s in scenes]
     for _ in range(a.warmup):
-        model.forward_scenes(pts, sps, names)
+        model.forward_scenes(pts, sps, names, n_sps)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    model.forward_scenes(pts, sps, names)
+    model.forward_scenes(pts, sps, names, n_sps)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "ud3d_grid_build": (_i, [_vp, _i, c_i32p, _vp, _sz, _vp, _vp]),
     "ud3d_subm3_tile_order_workspace_bytes": (_sz, [_i]),
     "ud3d_subm3_tile_order": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ud3d_grid_build_coarser": (_i, [c_i32p, _vp, c_i32p, _vp, _sz, _vp, _vp]),
     "ud3d_grid_rank": (_i, [_vp, _i, c_i32p, _vp, _vp, _vp]),
     "ud3d_grid_coords": (_i, [c_i32p, _vp, _vp, _i, _vp]),
     "ud3d_voxel_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),

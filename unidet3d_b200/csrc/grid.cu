@@ -141,6 +141,36 @@ __global__ void grid_set_bits_kernel(const int4* __restrict__ coords, int n, Gri
   }
 }
 
+// coarse occupancy bitmap of a k=2,s=2 down-sampling straight from the finer bitmap: cell (b,x,y,z) -> (b,x/2,y/2,z/2);
+// coordinates outside the coarse box are dropped (spconv's odd-extent rule: out_shape = (in_shape-2)/2+1, the coarse
+// box is min(out_shape, (extent+1)/2)).  One thread per fine word: the 32 z-cells of the word fold into 16 coarse
+// z-cells = one half of a coarse word -> at most one atomicOr per non-empty fine word.
+__global__ void grid_downsample_kernel(const uint32_t* __restrict__ fine, GridDims gf, uint32_t* coarse, GridDims gc) {
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < gf.nwords; w += (long long)gridDim.x * blockDim.x) {
+    uint32_t bits = fine[w];
+    if (!bits) continue;
+    long long t = w;
+    const int zw = (int)(t % gf.Zw); t /= gf.Zw;
+    const int y = (int)(t % gf.Y); t /= gf.Y;
+    const int x = (int)(t % gf.X);
+    const int b = (int)(t / gf.X);
+    const int cx = x >> 1, cy = y >> 1;
+    if (cx >= gc.X || cy >= gc.Y) continue;
+    uint32_t m = (bits | (bits >> 1)) & 0x55555555u;       // coarse cell i <- fine cells 2i, 2i+1 (at bit 2i)
+    m = (m | (m >> 1)) & 0x33333333u;
+    m = (m | (m >> 2)) & 0x0f0f0f0fu;
+    m = (m | (m >> 4)) & 0x00ff00ffu;
+    m = (m | (m >> 8)) & 0x0000ffffu;                       // 16 coarse cells, z = zw * 16 + i
+    const int cz0 = zw * 16;
+    if (cz0 >= gc.Z) continue;
+    if (cz0 + 16 > gc.Z) m &= (1u << (gc.Z - cz0)) - 1u;    // coarse z >= extent: dropped
+    if (!m) continue;
+    uint32_t* dst = coarse + grid_word_index(gc, b, cx, cy, cz0);
+    const uint32_t val = m << (cz0 & 31);
+    if ((*(volatile uint32_t*)dst & val) != val) atomicOr(dst, val);
+  }
+}
+
 // exclusive scan of popc(words): phase 1 block sums
 __global__ void __launch_bounds__(256) grid_scan_phase1(const uint32_t* __restrict__ words, long long nwords, uint32_t* bsum) {
   long long base = (long long)blockIdx.x * kScanBlockWords;
@@ -568,6 +598,33 @@ int ud3d_grid_build(const int32_t* coords, int n, const int32_t dims_host[4], vo
     grid_set_bits_kernel<<<grid_blocks(n, 256), 256, 0, st>>>((const int4*)coords, n, g, v.words);
     UD3D_LAUNCH_CHECK();
   }
+  grid_scan_phase1<<<v.nblocks, 256, 0, st>>>(v.words, g.nwords, v.bsum);
+  UD3D_LAUNCH_CHECK();
+  grid_scan_phase2<<<1, 1024, 0, st>>>(v.bsum, v.nblocks, n_unique);
+  UD3D_LAUNCH_CHECK();
+  grid_scan_phase3<<<v.nblocks, 256, 0, st>>>(v.words, g.nwords, v.bsum, v.prefix);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_grid_build_coarser(const int32_t fine_dims_host[4], const void* fine_ws, const int32_t dims_host[4], void* ws,
+                            size_t ws_bytes, int32_t* n_unique, void* stream) {
+  int rc = check_dims(dims_host, "ud3d_grid_build_coarser");
+  if (rc) return rc;
+  rc = check_dims(fine_dims_host, "ud3d_grid_build_coarser");
+  if (rc) return rc;
+  UD3D_CHECK_ARG(ws && fine_ws, "ud3d_grid_build_coarser: NULL argument");
+  UD3D_CHECK_ARG(dims_host[0] == fine_dims_host[0], "ud3d_grid_build_coarser: batch sizes differ");
+  GridDims gf = make_grid_dims(fine_dims_host), g = make_grid_dims(dims_host);
+  if (ws_bytes < grid_ws_bytes(g)) {
+    set_error("ud3d_grid_build_coarser: workspace too small (%zu < %zu)", ws_bytes, grid_ws_bytes(g));
+    return UD3D_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  GridView vf = grid_view(gf, fine_ws), v = grid_view(g, ws);
+  UD3D_CUDA(cudaMemsetAsync(v.words, 0, (size_t)g.nwords * 4, st));
+  grid_downsample_kernel<<<grid_blocks(gf.nwords, 256), 256, 0, st>>>(vf.words, gf, v.words, g);
+  UD3D_LAUNCH_CHECK();
   grid_scan_phase1<<<v.nblocks, 256, 0, st>>>(v.words, g.nwords, v.bsum);
   UD3D_LAUNCH_CHECK();
   grid_scan_phase2<<<1, 1024, 0, st>>>(v.bsum, v.nblocks, n_unique);

@@ -84,6 +84,12 @@ class Grid:
                                    _p(self.n_unique), _stream()), "ud3d_grid_build")
         return self.n_unique
 
+    def build_from_finer(self, fine: "Grid"):
+        """Occupancy of the k=2,s=2 down-sampled level from the finer grid's bitmap (ud3d_grid_build_coarser)."""
+        check(_L().ud3d_grid_build_coarser(fine._cd, _p(fine.ws), self._cd, _p(self.ws), self.ws_bytes, _p(self.n_unique),
+                                           _stream()), "ud3d_grid_build_coarser")
+        return self.n_unique
+
     def rank(self, coords: torch.Tensor) -> torch.Tensor:
         _req(coords, torch.int32, "coords")
         out = torch.empty(coords.shape[0], dtype=torch.int32, device=coords.device)

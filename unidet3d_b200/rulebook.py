@@ -84,15 +84,14 @@ def build_pyramid(coords: Optional[torch.Tensor], spatial_shape: Sequence[int], 
     if grid is None:
         grid = ops.Grid(dims, dev)
         count0 = grid.build(coords if coords is not None else seed_coords)
-    # all coarse occupancy grids are built from the finest coordinates back to back (ancestor coordinates with the
+    # the occupancy grid of every coarser level is folded out of the finer level's bitmap back to back (k=2,s=2 with the
     # per-level drop rule), so the voxel counts of every level come back in ONE host synchronisation
     shapes, dimss, grids, counts = [list(shape)], [list(dims)], [grid], []
-    src = coords if seed_coords is None else seed_coords            # any superset-free cover of the level-1 set works
     for l in range(1, n_levels):
         out_shape = [(s - 2) // 2 + 1 for s in shapes[-1]]
         d = [dimss[-1][0]] + [max(1, min(o, (x + 1) // 2)) for o, x in zip(out_shape, dimss[-1][1:])]
         g = ops.Grid(d, dev)
-        counts.append(g.build(ops.down_ancestors(src, shape, l)))
+        counts.append(g.build_from_finer(grids[-1]))     # a pass over the finer bitmap; the points are not touched again
         shapes.append(out_shape), dimss.append(d), grids.append(g)
     if coords is None:
         # level 1 itself comes from the seed (voxelisation): its count rides on the same read-back
