@@ -9,9 +9,12 @@ Default workload = BASELINE.json configs[1]: unidet3d_1xb8_scannet, 8 synthetic 
 ScanNet-shaped scenes per batch (voxel 0.02 m, ~33k voxels/scene, 19-way head), random-init
 weights of the reference architecture (no datasets / checkpoints offline).
 
-* ``value``    : scenes/s with the batch already resident in HBM (device-timed, CUDA events);
-* ``e2e``      : scenes/s through the public API ``UniDet3D.forward_scenes`` with HOST buffers --
-                 pinned H2D of points+superpoints and D2H of the detections inside the timed region;
+* ``value``    : scenes/s with the batch already resident in HBM (device-timed, CUDA events): EXACTLY K batches through
+                 ``UniDet3D.forward_pipelined`` (``--pipeline-depth`` batches in flight, default 2: the host-bound
+                 voxelisation / launch work of batch i+1 overlaps the kernels of batch i);
+* ``e2e``      : the same loop through the same public API with HOST buffers -- pinned H2D of points+superpoints
+                 and D2H of the detections of every step inside the timed region;
+                 ``config.latency_ms_per_batch`` = one batch at a time (``forward_scenes``), both input kinds;
 * ``roofline`` : the dominant kernel (tcgen05 gather-GEMM, the 49 sparse convs): algorithmic bytes
                  (BASELINE.md section 3 model) / measured launch time vs measured HBM peak;
 * ``cpu_baseline`` / ``--impl reference``: the CPU oracle (oracle/detector.py) on the host cores.
@@ -50,6 +53,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="scannet_b8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-depth", type=int, default=2,
+                    help="batches in flight in the timed loops (UniDet3D.forward_pipelined); 1 = one batch at a time")
     return ap.parse_args()
 
 
@@ -234,28 +239,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    depth = max(1, args.pipeline_depth)
+
+    def run_latency(P, S, n_sps_arg, reps):
+        """one batch at a time (submit -> wait -> next): ms per batch"""
+        evs = []
+        for _ in range(reps):
+            flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.forward_scenes(P, S, names, n_sps_arg)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / reps
+
+    def run_throughput(P, S, n_sps_arg):
+        """EXACTLY K batches through the public pipelined API (`depth` batches in flight, each on its own stream; the L2
+        flush of every step is issued on the step's stream inside the timed region); device time from the first
+        submit to the last result, seconds"""
+        cur = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        n_done = 0
+        for res in model.forward_pipelined(((P, S, names, n_sps_arg) for _ in range(K)), depth=depth, pre_submit=flush_l2):
+            n_done += 1
+        for st in model._pipe_streams:
+            cur.wait_stream(st)
+        e1.record()
+        barrier()
+        assert n_done == K
+        return e0.elapsed_time(e1) / 1e3
+
     # ---------------------------------------------------------------- device-resident arm (value)
     d_pts = [torch.as_tensor(p).to(dev) for p in pts]
     d_sps = [torch.as_tensor(s).to(dev) for s in sps]
     n_sps = [int(s.max()) + 1 for s in sps]
     for _ in range(W):
         model.forward_scenes(d_pts, d_sps, names, n_sps)
+    for _ in model.forward_pipelined(((d_pts, d_sps, names, n_sps) for _ in range(2 * depth)), depth=depth):
+        pass
     barrier()
+    lat_dev = run_latency(d_pts, d_sps, n_sps, max(3, min(K, 5)))
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
     if rank == 0:
         sampler.start()
     ops.launch_count(reset=True)
-    evs = []
-    for _ in range(K):
-        flush_l2()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        model.forward_scenes(d_pts, d_sps, names, n_sps)
-        e1.record()
-        evs.append((e0, e1))
-    barrier()
+    t_dev = run_throughput(d_pts, d_sps, n_sps)
     launches = ops.launch_count()
-    t_dev = sum(a.elapsed_time(b) for a, b in evs) / 1e3
 
     # ---------------------------------------------------------------- end-to-end arm (host buffers)
     h_pts = [torch.as_tensor(p).pin_memory() for p in pts]
@@ -263,19 +295,10 @@ def main():
     for _ in range(2):
         model.forward_scenes(h_pts, h_sps, names)
     barrier()
-    evs = []
-    d2h = 0
-    for _ in range(K):
-        flush_l2()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        res = model.forward_scenes(h_pts, h_sps, names)
-        e1.record()
-        evs.append((e0, e1))
-        d2h = model.last_d2h_bytes       # packed per-scene result buffers + the small count / extent read-backs
-    barrier()
+    t_e2e = run_throughput(h_pts, h_sps, None)
+    d2h = model.last_d2h_bytes       # packed per-scene result buffers + the small count / extent read-backs
     clocks = sampler.stop() if rank == 0 else None
-    t_e2e = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    lat_e2e = run_latency(h_pts, h_sps, None, max(3, min(K, 5)))
     h2d = model.last_h2d_bytes       # points fp32 [n,6] + superpoint ids int64 [n] + scene offsets
 
     # ---------------------------------------------------------------- dominant kernel: the 49 sparse convs
@@ -357,7 +380,9 @@ def main():
                        "points_per_scene": int(pts[0].shape[0]), "voxels_per_level": [lv.n for lv in x.pyramid.levels],
                        "superpoints": int(sum(int(s.max()) + 1 for s in sps)), "datasets": list(cfg["decoder"]["datasets"]),
                        "precision": "fp32 storage; bf16 hi/lo 3-term split on tcgen05, fp32 accumulate",
-                       "l2": "flushed between timed iterations (256 MiB memset)", "parallelism": f"scene-sharded dp{world}"},
+                       "l2": "flushed before every step (256 MiB memset on the step's stream, inside the timed region)",
+                       "parallelism": f"scene-sharded dp{world}", "pipeline_depth": depth,
+                       "latency_ms_per_batch": {"device_resident": lat_dev, "host_buffers": lat_e2e}},
             "e2e": {"value": e2e, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * t_e2e / K},
             "gpu_launches": launches, "roofline": roof, "clocks": clocks}

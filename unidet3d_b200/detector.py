@@ -183,7 +183,7 @@ class UniDet3D(nn.Module):
     @torch.no_grad()
     def forward_scenes(self, points: List, superpoints: List, datasets_names: List[str],
                        n_superpoints: Optional[Sequence[int]] = None):
-        """End-to-end forward for a batch of scenes.
+        """End-to-end forward for a batch of scenes (= ``collect(submit_scenes(...))``).
 
         points: list of fp32 [N_i, 6] (numpy / CPU / CUDA tensors), superpoints: list of int64 [N_i];
         n_superpoints: optional per-scene max(id)+1 (saves a reduction + host sync for device-resident ids).
@@ -191,6 +191,14 @@ class UniDet3D(nn.Module):
         when the dataset trims by superpoints, else [n,7] (fast NMS pads yaw=0, unidet3d.py:629-631)
         or [n,6|7] as predicted.
         """
+        return self.collect(self.submit_scenes(points, superpoints, datasets_names, n_superpoints))
+
+    @torch.no_grad()
+    def submit_scenes(self, points: List, superpoints: List, datasets_names: List[str],
+                      n_superpoints: Optional[Sequence[int]] = None, slot: int = 0):
+        """Issue the whole forward of one batch on the current stream, including the asynchronous D2H of the packed
+        per-scene results, WITHOUT waiting for it.  Returns a handle for ``collect``.  ``slot`` selects the set of
+        pinned result buffers (batches in flight at the same time need different slots, see ``forward_pipelined``)."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("unidet3d_b200.UniDet3D runs on CUDA only (no CPU fallback)")
@@ -246,13 +254,21 @@ class UniDet3D(nn.Module):
             cache = getattr(self, "_host_bufs", None)
             if cache is None:
                 cache = self._host_bufs = {}
-            hb = cache.get((i, n))
+            hb = cache.get((slot, i, n))
             if hb is None:
-                hb = cache[(i, n)] = torch.empty(n, dtype=torch.float32).pin_memory()
+                hb = cache[(slot, i, n)] = torch.empty(n, dtype=torch.float32).pin_memory()
             hb.copy_(r["_buf"], non_blocking=True)
             host.append(hb)
-        torch.cuda.current_stream().synchronize()
+        done = torch.cuda.Event()
+        done.record()
         self.last_d2h_bytes = int(sum(hb.numel() * 4 for hb in host)) + 4 * 4 + 4 * (len(per_scene) + 4)   # + extents / counts read-backs
+        # (the handle keeps the device tensors of the step alive until its results have been read)
+        return dict(per_scene=per_scene, host=host, done=done, keep=(pts, sp_b, out))
+
+    def collect(self, handle):
+        """Wait for a submitted batch and build the per-scene (boxes, labels, scores) CPU tensors."""
+        handle["done"].synchronize()
+        per_scene, host = handle["per_scene"], handle["host"]
         results = []
         for r, hb in zip(per_scene, host):
             k, bd = r["scores"].numel(), r["cand"].shape[1]
@@ -271,6 +287,30 @@ class UniDet3D(nn.Module):
                     boxes = torch.cat((boxes, torch.zeros_like(boxes[:, :1])), dim=1)       # unidet3d.py:629-631
             results.append((boxes, labels, scores))
         return results
+
+    def forward_pipelined(self, batches, depth: int = 2, pre_submit=None):
+        """Throughput mode: yields the results of every batch of ``batches`` (an iterable of
+        (points, superpoints, datasets_names[, n_superpoints]) tuples) in order, with up to ``depth`` batches in
+        flight on their own CUDA streams.  The host-bound stages of batch i+1 (staging copies, voxelisation with its
+        two small read-backs, ~300 kernel launches) run while the GPU still works on batch i, and the H2D copies of
+        pinned inputs overlap its kernels.  ``pre_submit`` (optional callable) runs on the batch's stream right
+        before its work is issued (bench.py flushes the L2 there)."""
+        dev = next(self.parameters()).device
+        if getattr(self, "_pipe_streams", None) is None or len(self._pipe_streams) < depth:
+            self._pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        cur = torch.cuda.current_stream()
+        pending = []
+        for j, b in enumerate(batches):
+            st = self._pipe_streams[j % depth]
+            if len(pending) == depth:
+                yield self.collect(pending.pop(0))
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                if pre_submit is not None:
+                    pre_submit()
+                pending.append(self.submit_scenes(*b, slot=j % depth))
+        while pending:
+            yield self.collect(pending.pop(0))
 
     def predict(self, batch_inputs_dict, batch_data_samples, **kwargs):
         """unidet3d.py:411-473: fills ``pred_instances_3d`` (bboxes_3d, scores_3d, labels_3d) of every sample."""
