@@ -219,3 +219,36 @@ def test_loss_value_vs_oracle():
                                                          topk=cc["topk"], loss_weight=cc["loss_weight"],
                                                          non_object_weight=cc["non_object_weight"], iter_matcher=True)))
     assert abs(loss - ref) < 2e-3 * abs(ref), (loss, ref)
+
+
+@pytest.mark.gpu
+def test_pipelined_batches_match_one_at_a_time():
+    """forward_pipelined (several batches in flight on their own streams, pinned host inputs) returns, in order, what
+    forward_scenes returns for each batch on its own."""
+    import unidet3d_b200 as u
+    from unidet3d_b200 import configs
+    from unidet3d_b200.synthetic import make_scene, make_model_state_dict, SCENE_PRESETS
+    cfg = configs.model_cfg(("scannet", "arkitscenes"), topk_insts=100)
+    n, v, a, c = SCENE_PRESETS["tiny"]
+    cfg["voxel_size"] = v
+    model = u.MODELS.build(cfg).eval()
+    model.load_state_dict(make_model_state_dict(cfg, 0), strict=False)
+    model.cuda()
+    batches = []
+    for j in range(5):
+        scenes = [make_scene(100 + 3 * j + i, n + 100 * i, a, c) for i in range(2 + j % 2)]
+        names = [("scannet", "arkitscenes")[(i + j) % 2] for i in range(len(scenes))]
+        batches.append(([torch.as_tensor(s[0]).pin_memory() for s in scenes], [torch.as_tensor(s[1]).pin_memory() for s in scenes], names))
+    ref = [model.forward_scenes(*b) for b in batches]
+    for depth in (1, 2, 3):
+        got = list(model.forward_pipelined(iter(batches), depth=depth))
+        assert len(got) == len(ref)
+        for rb, gb in zip(ref, got):
+            assert len(rb) == len(gb)
+            for (b0, l0, s0), (b1, l1, s1) in zip(rb, gb):
+                assert b0.shape == b1.shape and torch.equal(l0, l1)
+                assert torch.allclose(s0, s1, atol=1e-5)
+                # boxes: the superpoint pooling sums with float atomics (1e-7 run-to-run noise), and a trimmed box is the
+                # AABB of a voted point set -- a point on a box face can flip in or out, moving one face by a point spacing
+                d = (b0 - b1).abs()
+                assert float(d.max()) < 0.05 and float((d <= 1e-4).float().mean()) > 0.9, d.max()
