@@ -301,12 +301,17 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t N) {
 }
 
 // fp32 -> bf16 hi + bf16 lo (x ~= hi + lo, |err| <~ 2^-17 |x|)
+// Packed conversions (one F2FP.BF16.PACK_AB per pair, FMA-pipe) instead of scalar __float2bfloat16_rn (F2F, quarter-rate
+// XU pipe: it co-limited the attention kernel, 96 F2F next to 96 HMMA per K/V tile); same round-to-nearest-even results.
+__device__ __forceinline__ uint32_t cvt_bf16x2_rn(float lo16, float hi16) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi16), "f"(lo16));
+  return d;
+}
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  __nv_bfloat16 al = __float2bfloat16_rn(a - __bfloat162float(ah));
-  __nv_bfloat16 bl = __float2bfloat16_rn(b - __bfloat162float(bh));
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  lo = (uint32_t)__bfloat16_as_ushort(al) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+  hi = cvt_bf16x2_rn(a, b);
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  lo = cvt_bf16x2_rn(a - ah, b - bh);
 }
 #endif  // __CUDACC__
 
