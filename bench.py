@@ -359,9 +359,9 @@ def main():
             "algorithmic_tflops": flops / t_conv / 1e12,
             "tensor_frac_bf16x3": 3 * flops / t_conv / 1e12 / tf_peak,
             "backbone_ms_per_batch": 1e3 * t_conv,
-            "note": "DRAM traffic ~= algorithmic bytes (no re-reads); the kernel is bound by the L2 gather: each input row is "
-                    "read ~10.6x (once per active kernel offset) plus the weight tiles, ~0.9 GB of L2 traffic per level-1 conv "
-                    "at ~5 TB/s (profiles/r1h_*)"}
+            "note": "DRAM traffic == algorithmic bytes (ratio 1.00, profiles/r2_gemm_traffic.json: every feature map crosses DRAM "
+                    "once each way, the ~10x gather re-reads are L2 hits); the kernel is bound by the loaded gather latency "
+                    "(~2400 cycles) x the 8 ring stages in flight per SM, not by a bandwidth (profiles/r2_summary.md)"}
 
     # ---------------------------------------------------------------- aggregate over ranks
     from unidet3d_b200 import sharding
