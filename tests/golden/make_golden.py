@@ -428,6 +428,31 @@ def gen_criterion():
     gtb = Boxes(rand_boxes(9, 7), box_dim=7, with_yaw=True, origin=(0.5, 0.5, 0.5))
     tg = UniDet3D.get_targets(det, spc, gtb, 6)
     save.update(tg_centers=spc.numpy(), tg_boxes=gtb.tensor.numpy(), tg_masks=tg.numpy())
+    # edge cases on one axis-aligned scene each: a single GT; T == topk + 1; duplicated predictions (exactly tied costs:
+    # `cost < kth` then matches fewer than topk queries); all queries masked out for one GT
+    edge = []
+    for tag, T_e, G_e, dup, mask_all in [("one_gt", 30, 1, False, False), ("t_eq_k1", 7, 3, False, False),
+                                         ("ties", 24, 3, True, False), ("masked", 20, 2, False, True)]:
+        gt = rand_boxes(G_e, 6)
+        labels = torch.as_tensor(rng.integers(0, 5, G_e))
+        cls = torch.randn(T_e, 6) * 1.5
+        box = rand_boxes(T_e, 6)
+        box[:G_e] = gt + 0.03 * torch.randn(G_e, 6)
+        if dup:
+            cls[8:16] = cls[0:8]
+            box[8:16] = box[0:8]
+        qm = torch.ones(G_e, T_e, dtype=torch.bool)
+        if mask_all:
+            qm[1] = False
+        inst = InstanceData(labels_3d=labels, bboxes_3d=Boxes(gt, box_dim=6, with_yaw=False, origin=(0.5, 0.5, 0.5)), query_masks=qm)
+        lay = dict(cls_preds=[cls], bboxes=[box])
+        loss = crit.get_layer_loss(lay, [inst], ["scannet"])
+        iq, ig = crit.matcher(InstanceData(scores=cls, bboxes=box), InstanceData(labels=labels, query_masks=qm, bboxes=gt), 6)
+        save.update({f"e_{tag}_cls": cls.numpy(), f"e_{tag}_box": box.numpy(), f"e_{tag}_gt": gt.numpy(),
+                     f"e_{tag}_labels": labels.numpy(), f"e_{tag}_qm": qm.numpy(), f"e_{tag}_loss": loss.numpy(),
+                     f"e_{tag}_iq": iq.numpy(), f"e_{tag}_ig": ig.numpy()})
+        edge.append((tag, len(iq), float(loss)))
+    print("criterion edge cases", edge)
     np.savez_compressed(os.path.join(HERE, "criterion_ref.npz"), **save)
     print("criterion_ref.npz det_loss", float(out["det_loss"]), "matches per layer/scene",
           [[len(save.get(f"l{l}_iq{i}", [])) for i in range(len(names))] for l in range(3)])

@@ -166,3 +166,20 @@ def test_gt_target_helpers_match_reference(golden_dir):
     assert np.array_equal(bb.numpy(), g["bm_boxes"])
     tg = oc.targets_by_distance(g["tg_centers"], g["tg_boxes"], 6)
     assert np.array_equal(tg.numpy(), g["tg_masks"])
+
+
+@pytest.mark.parametrize("tag", ["one_gt", "t_eq_k1", "ties", "masked"])
+def test_criterion_edge_cases_match_reference(golden_dir, tag):
+    """single GT / T == topk + 1 / duplicated predictions (tied costs) / a GT whose queries are all masked out:
+    matched pairs bit-exact and layer loss within 1e-5 of the reference's own criterion.py."""
+    from oracle import criterion as oc
+    g = np.load(os.path.join(golden_dir, "criterion_ref.npz"))
+    cfg = dict(datasets=["scannet", "s3dis", "arkitscenes"], datasets_weights=[1.0, 0.7, 1.3], topk=[6, 4, 5],
+               loss_weight=[0.5, 1.0], non_object_weight=0.1, w_cls=0.5, w_box=2.0, iter_matcher=True)
+    cls, box = torch.as_tensor(g[f"e_{tag}_cls"]), torch.as_tensor(g[f"e_{tag}_box"])
+    gt = dict(labels=torch.as_tensor(g[f"e_{tag}_labels"]), boxes=torch.as_tensor(g[f"e_{tag}_gt"]),
+              query_masks=torch.as_tensor(g[f"e_{tag}_qm"]))
+    iq, ig = oc.uni_matcher(cls, box, gt["labels"], gt["boxes"], gt["query_masks"], 6)
+    assert np.array_equal(iq.numpy(), g[f"e_{tag}_iq"]) and np.array_equal(ig.numpy(), g[f"e_{tag}_ig"])
+    loss, _ = oc.layer_loss([cls], [box], [gt], ["scannet"], cfg)
+    assert abs(float(loss) - float(g[f"e_{tag}_loss"])) < 1e-5 * max(1.0, abs(float(g[f"e_{tag}_loss"])))
