@@ -4,7 +4,7 @@ Run (build container only -- /root/reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref}.npz (all, or the ones named on the command line).  The reference modules are
+Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,gt_prep_ref}.npz (all, or the ones named on the command line).  The reference modules are
 imported unmodified from /root/reference; their absent third-party imports
 (mmengine, mmdet3d, spconv, MinkowskiEngine, torch_scatter, mmcv) are replaced by
 minimal stand-ins defined here:
@@ -263,6 +263,17 @@ def install_stubs():
             return o_scatter_mean(src.t().contiguous(), index).t()
         return o_scatter_mean(src, index)
     _mod("torch_scatter", scatter_mean=scatter_mean)
+
+    class BaseTransform:
+        def __call__(self, results):
+            return self.transform(results)
+
+    class PointSample(BaseTransform):                          # mmdet3d.datasets.transforms.PointSample (ctor only)
+        def __init__(self, num_points, sample_range=None, replace=False):
+            self.num_points, self.sample_range, self.replace = num_points, sample_range, replace
+    _mod("mmcv.transforms", BaseTransform=BaseTransform)
+    _mod("mmdet3d.datasets"); _mod("mmdet3d.datasets.transforms", PointSample=PointSample)
+    sys.modules["mmdet3d.registry"].TRANSFORMS = reg
     _mod("MinkowskiEngine")
     sp = _mod("spconv")
     spp = _mod("spconv.pytorch", SparseConvTensor=SparseConvTensor, SubMConv3d=SubMConv3d, SparseConv3d=SparseConv3d,
@@ -458,6 +469,46 @@ def gen_criterion():
           [[len(save.get(f"l{l}_iq{i}", [])) for i in range(len(names))] for l in range(3)])
 
 
+def gen_gt_prep():
+    """The reference's GT-preparation transforms (unidet3d/transforms_3d.py) on synthetic masks."""
+    from unidet3d.transforms_3d import PointDetClassMappingScanNet, PointDetClassMappingS3DIS, PointSample_
+    rng = np.random.default_rng(33)
+    n = 5000
+    save = {}
+    # superpoints: 120 ids; instances: unions of superpoints with 8 % label noise (so the > 0.5 majority matters)
+    sp = rng.integers(0, 120, n)
+    sp_inst = rng.integers(0, 14, 120)
+    inst = sp_inst[sp].copy()
+    noise = rng.random(n) < 0.08
+    inst[noise] = rng.integers(0, 14, int(noise.sum()))
+    inst_sem = rng.integers(0, 21, 14)                        # 0,1 = stuff, 20 = unlabelled
+    inst_sem[:3] = [0, 1, 20]
+    sem = inst_sem[inst]
+    d = dict(pts_instance_mask=inst.astype(np.int64), pts_semantic_mask=sem.astype(np.int64), sp_pts_mask=sp.astype(np.int64))
+    out = PointDetClassMappingScanNet(num_classes=20, stuff_classes=[0, 1]).transform({k: v.copy() for k, v in d.items()})
+    save.update({"sn_" + k: v for k, v in d.items()})
+    save.update(sn_out_inst=out["pts_instance_mask"], sn_out_labels=out["gt_labels_3d"], sn_out_sp_masks=out["gt_sp_masks"].numpy())
+    # S3DIS: instance ids 0..11, classes subset
+    inst2 = rng.integers(0, 12, 60)[rng.integers(0, 60, n)]
+    inst2[:12] = np.arange(12)
+    sem2 = rng.integers(0, 13, 12)[inst2]
+    d2 = dict(pts_instance_mask=inst2.astype(np.int64), pts_semantic_mask=sem2.astype(np.int64), sp_pts_mask=sp.astype(np.int64))
+    out2 = PointDetClassMappingS3DIS(classes=[7, 8, 9, 10, 11]).transform({k: v.copy() for k, v in d2.items()})
+    save.update({"s3_" + k: v for k, v in d2.items()})
+    save.update(s3_out_inst=out2["pts_instance_mask"], s3_out_labels=out2["gt_labels_3d"].numpy(), s3_out_sp_masks=out2["gt_sp_masks"].numpy())
+    # PointSample_: fixed choices through a patched sampler
+    choices = rng.choice(n, 1800, replace=False)
+    ps = PointSample_(num_points=1800)
+    ps._points_random_sampling = lambda points, num: (points[choices], choices)
+    d3 = dict(points=np.zeros((n, 6), np.float32), pts_instance_mask=out["pts_instance_mask"].copy(), pts_semantic_mask=sem.copy(),
+              sp_pts_mask=sp.copy())
+    out3 = ps.transform(d3)
+    save.update(ps_choices=choices, ps_in_inst=out["pts_instance_mask"], ps_out_inst=out3["pts_instance_mask"],
+                ps_out_sem=out3["pts_semantic_mask"], ps_out_sp=out3["sp_pts_mask"])
+    np.savez_compressed(os.path.join(HERE, "gt_prep_ref.npz"), **save)
+    print("gt_prep_ref.npz", out["gt_sp_masks"].shape, out2["gt_sp_masks"].shape, len(np.unique(out3["sp_pts_mask"])))
+
+
 def gen_post():
     from unidet3d.unidet3d import UniDet3D, get_face_distances
     from unidet3d.encoder import _bbox_pred_to_bbox
@@ -505,6 +556,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "gt_prep"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "gt_prep": gen_gt_prep}[name]()
