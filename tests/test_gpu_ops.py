@@ -307,19 +307,7 @@ def test_trim_boxes():
 
 
 # ------------------------------------------------------------------ operand-form (pre-split) feature maps
-def split_encode(x):
-    """fp32 [N,C] -> operand form [N,C] (bytes: per 32-ch chunk 32 bf16 hi then 32 bf16 lo)."""
-    N, C = x.shape
-    hi = x.bfloat16()
-    lo = (x - hi.float()).bfloat16()
-    packed = torch.cat([hi.view(N, C // 32, 32), lo.view(N, C // 32, 32)], dim=2).contiguous()
-    return packed.view(torch.float32).view(N, C)
-
-
-def split_decode(s):
-    N, C = s.shape
-    b = s.contiguous().view(torch.bfloat16).view(N, C // 32, 64).float()
-    return (b[:, :, :32] + b[:, :, 32:]).reshape(N, C)
+from opform import split_encode, split_decode  # noqa: E402
 
 
 def test_act_split_roundtrip():

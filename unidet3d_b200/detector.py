@@ -27,7 +27,14 @@ from .structures import DepthInstance3DBoxes, InstanceData, SparseConvTensor
 
 
 class TestCfg(dict):
-    __getattr__ = dict.__getitem__
+    """dict with attribute access (mmengine ConfigDict style): a missing key is an AttributeError, so that
+    ``getattr(cfg, name, default)``, ``hasattr`` and ``copy.deepcopy`` work."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
 
 
 @register_model
@@ -71,6 +78,17 @@ class UniDet3D(nn.Module):
         if self._plan is None:
             self._plan = dict(w_in=ops.PackedWeight(self.input_conv[0].weight), out_bn=fold_bn(self.output_layer[0]))
         return self._plan
+
+    def prepare(self):
+        """Build every lazily created plan (packed weights, folded BatchNorm) NOW, on the current stream.  Work issued
+        later on other streams must be ordered after this point (``forward_pipelined`` does ``wait_stream``): the pack
+        kernels of a cold model otherwise race with the first GEMMs of a second stream."""
+        self._get_plan()
+        unet = getattr(self, "unet", None)
+        while unet is not None:
+            unet._get_plan()
+            unet = getattr(unet, "u", None)
+        self.decoder._get_plan()
 
     def get_dataset(self, lidar_path):
         for dataset in self.decoder.datasets:
@@ -299,6 +317,7 @@ class UniDet3D(nn.Module):
         if getattr(self, "_pipe_streams", None) is None or len(self._pipe_streams) < depth:
             self._pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
         cur = torch.cuda.current_stream()
+        self.prepare()          # plans are built on `cur`; every pipe stream waits on `cur` before its first batch
         pending = []
         for j, b in enumerate(batches):
             st = self._pipe_streams[j % depth]

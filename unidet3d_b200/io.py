@@ -54,6 +54,7 @@ class PinnedBatchStager:
         self.stream = torch.cuda.Stream(device=self.device)
         self.depth = depth
         self._pinned = {}
+        self._slot_events = {}     # slot -> event of the last H2D copies issued from the slot's pinned buffers
 
     def _pin(self, key, shape, dtype):
         buf = self._pinned.get(key)
@@ -64,6 +65,11 @@ class PinnedBatchStager:
     def _stage(self, slot: int, batch):
         pts, sps = batch
         d_pts, d_sps, n_sps = [], [], []
+        # the pinned buffers of this slot may still be the source of an asynchronous H2D copy issued earlier: wait for
+        # it ON THE HOST before overwriting them (a device-side wait_event does not order the host writes)
+        prev = self._slot_events.get(slot)
+        if prev is not None:
+            prev.synchronize()
         with torch.cuda.stream(self.stream):
             for i, (p, s) in enumerate(zip(pts, sps)):
                 p = np.asarray(p, np.float32)
@@ -77,6 +83,7 @@ class PinnedBatchStager:
                 d_sps.append(hs.to(self.device, non_blocking=True))
             ev = torch.cuda.Event()
             ev.record(self.stream)
+        self._slot_events[slot] = ev
         return d_pts, d_sps, n_sps, ev
 
     def __iter__(self) -> Iterator[Tuple[List[torch.Tensor], List[torch.Tensor], List[int]]]:
