@@ -169,9 +169,14 @@ typedef struct {
   const int32_t* row_perm;     /* optional [n_out] (requires table): position i of the table / tile_mask describes output
                                   row row_perm[i], i.e. out / out_act / residual are addressed at row_perm[i]
                                   (see ud3d_subm3_tile_order); NULL = identity */
+  const void* w_packed_ts;     /* optional, from ud3d_gemm_pack_weight_ts: the same weight in the K order of the kernel
+                                  variant that gathers the A operand through registers into TMEM (operand-form inputs
+                                  of launches that fill the GPU); NULL => the shared-memory-operand kernel is used */
 } ud3d_gemm_args;
 size_t ud3d_gemm_packed_weight_bytes(int K, int c_in, int c_out);
 int ud3d_gemm_pack_weight(const float* w, int K, int c_in, int c_out, void* packed, void* stream);
+/* second packing of the same weight (same size), see ud3d_gemm_args.w_packed_ts */
+int ud3d_gemm_pack_weight_ts(const float* w, int K, int c_in, int c_out, void* packed, void* stream);
 int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream);
 /* operand form of a feature map: per row, per 32-channel chunk, 64 bytes of bf16 "hi" followed by 64 bytes of
  * bf16 "lo" (x ~= hi + lo), i.e. the same 4 bytes per element as fp32 and exactly the 128-byte row of the

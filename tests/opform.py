@@ -5,7 +5,7 @@ hi of channels 0..31, pieces 4..7 = bf16 lo.  Layout 2 (INTERLEAVED = True): pie
 piece 2q+1 = bf16 lo of the same channels (x ~= hi + lo): one 32-byte load = one thread's share of a tcgen05.st."""
 import torch
 
-INTERLEAVED = False
+INTERLEAVED = True
 
 
 def split_encode(x):

@@ -91,7 +91,7 @@ def _stagewise(model, cfg, sd, pts, sps, names, *, box_tol=1e-5):
     #      logits / boxes (the discrete decisions then see identical inputs on both sides)
     res = model.forward_scenes(pts, sps, names)
     tc = ocfg["test_cfg"]
-    n_exact = 0
+    n_exact = n_box = n_box_bad = 0
     for i, name in enumerate(names):
         ds = ocfg["encoder"]["datasets"].index(name)
         rb, rl, rs = opost.predict_by_feat(out["cls_preds"][i].cpu(), out["bboxes"][i].cpu(), torch.as_tensor(sps[i]),
@@ -118,8 +118,10 @@ def _stagewise(model, cfg, sd, pts, sps, names, *, box_tol=1e-5):
                 # threshold may flip, moving one face by a point spacing -- bounded, and rare
                 fin = np.isfinite(rbb)
                 assert np.array_equal(np.isfinite(bb), fin)
-                close = np.isclose(bb[fin], rbb[fin], rtol=1e-5, atol=1e-5)
-                assert close.mean() > 0.98, close.mean()
+                close = np.isclose(np.where(fin, bb, 0), np.where(fin, rbb, 0), rtol=1e-5, atol=1e-5).all(1)
+                n_box_bad += int((~close).sum())
+                n_box += len(close)
+                assert int((~close).sum()) <= max(1, len(close) // 50), (int((~close).sum()), len(close))
             else:
                 _check_boxes(bb, rbb, box_tol)
         else:
@@ -128,6 +130,7 @@ def _stagewise(model, cfg, sd, pts, sps, names, *, box_tol=1e-5):
             m = min(len(l), len(rl))
             assert float((l[:m] == rl[:m].long()).float().mean()) > 0.98
     assert n_exact >= B - 1, n_exact     # at most one scene of a batch may hit such a tie
+    assert n_box_bad <= max(1, n_box // 50), (n_box_bad, n_box)
     return res
 
 

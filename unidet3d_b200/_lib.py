@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("act_scale", C.c_void_p * 2), ("act_shift", C.c_void_p * 2),
         ("act_norelu", C.c_int32),
         ("row_perm", C.c_void_p),
+        ("w_packed_ts", C.c_void_p),
     ]
 
 
@@ -82,6 +83,7 @@ SIGNATURES = {
     "ud3d_rulebook_down2": (_i, [_vp, _vp, _i, _i, c_i32p, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ud3d_gemm_packed_weight_bytes": (_sz, [_i, _i, _i]),
     "ud3d_gemm_pack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ud3d_gemm_pack_weight_ts": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ud3d_gemm_fwd": (_i, [C.POINTER(GemmArgs), _vp]),
     "ud3d_act_split": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "ud3d_gemm_fwd_simt": (_i, [C.POINTER(GemmArgs), _vp, _vp]),

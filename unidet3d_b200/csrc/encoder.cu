@@ -109,13 +109,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.w = (v[j * 4 + 3] - mean) * rstd * g.w + b.w;
     if (out) *(float4*)(out + (size_t)row * C + c) = o;
     if (out_split) {
-      // operand form: chunk = c / 32, 4 channels at (c % 32): hi 8 bytes, lo 8 bytes (+64)
+      // operand form: chunk = c / 32, 4 channels at (c % 32): hi 8 bytes, lo 8 bytes (+16)
       uint32_t h0, l0, h1, l1;
       split_bf16x2(o.x, o.y, h0, l0);
       split_bf16x2(o.z, o.w, h1, l1);
-      uint8_t* d = (uint8_t*)(out_split + (size_t)row * C) + (c >> 5) * 128 + (c & 31) * 2;
+      uint8_t* d = (uint8_t*)(out_split + (size_t)row * C) + (c >> 5) * 128 + opf_hi_off(c & 31);
       *(uint2*)d = make_uint2(h0, h1);
-      *(uint2*)(d + 64) = make_uint2(l0, l1);
+      *(uint2*)(d + kOpfLo) = make_uint2(l0, l1);
     }
   }
 }
@@ -318,19 +318,19 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   for (int dn = 0; dn < 4; ++dn) {
     const int col = h * kHeadDim + dn * 8 + 2 * t;
     if constexpr (SPLIT_OUT) {
-      // operand form: head h == 32-channel chunk h; hi pair at (dn*8+2t)*2 bytes, lo pair +64
+      // operand form: head h == 32-channel chunk h
       uint32_t hi, lo;
       if (r0 < T) {
         split_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0, hi, lo);
-        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r0) * d_model) + h * 128 + (dn * 8 + 2 * t) * 2;
+        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r0) * d_model) + h * 128 + opf_hi_off(dn * 8 + 2 * t);
         *(uint32_t*)d = hi;
-        *(uint32_t*)(d + 64) = lo;
+        *(uint32_t*)(d + kOpfLo) = lo;
       }
       if (r1 < T) {
         split_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1, hi, lo);
-        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r1) * d_model) + h * 128 + (dn * 8 + 2 * t) * 2;
+        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r1) * d_model) + h * 128 + opf_hi_off(dn * 8 + 2 * t);
         *(uint32_t*)d = hi;
-        *(uint32_t*)(d + 64) = lo;
+        *(uint32_t*)(d + kOpfLo) = lo;
       }
     } else {
       if (r0 < T) *(float2*)(out + (size_t)(t0 + r0) * d_model + col) = make_float2(o[dn][0] * inv0, o[dn][1] * inv0);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
       const int key = rem >> 3, j = rem & 7;
       const int kr = kv0 + key;
       const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + j * 16;
-      uint8_t* dst = (which ? sV[stage] : sK[stage]) + key * 128 + ((j ^ (key & 7)) << 4);
+      uint8_t* dst = (which ? sV[stage] : sK[stage]) + key * 128 + ((opf_logical_piece(j) ^ (key & 7)) << 4);
       cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
     }
     cp_async_commit();
@@ -401,9 +401,9 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
         const int col = ks * 16 + 2 * t + ((part >> 1) ? 8 : 0);
         uint32_t vh = 0, vl = 0;
         if (row < T) {
-          const uint8_t* qp = qkv + (size_t)(t0 + row) * ldb + (size_t)h * 128 + col * 2;
+          const uint8_t* qp = qkv + (size_t)(t0 + row) * ldb + (size_t)h * 128 + opf_hi_off(col);
           vh = *(const uint32_t*)qp;
-          vl = *(const uint32_t*)(qp + 64);
+          vl = *(const uint32_t*)(qp + kOpfLo);
         }
         qh[ks][part] = vh;
         ql[ks][part] = vl;
@@ -526,15 +526,15 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
     uint32_t hi, lo;
     if (r0 < T) {
       split_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0, hi, lo);
-      uint8_t* d = out + (size_t)(t0 + r0) * ldo + h * 128 + (dn * 8 + 2 * t) * 2;
+      uint8_t* d = out + (size_t)(t0 + r0) * ldo + h * 128 + opf_hi_off(dn * 8 + 2 * t);
       *(uint32_t*)d = hi;
-      *(uint32_t*)(d + 64) = lo;
+      *(uint32_t*)(d + kOpfLo) = lo;
     }
     if (r1 < T) {
       split_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1, hi, lo);
-      uint8_t* d = out + (size_t)(t0 + r1) * ldo + h * 128 + (dn * 8 + 2 * t) * 2;
+      uint8_t* d = out + (size_t)(t0 + r1) * ldo + h * 128 + opf_hi_off(dn * 8 + 2 * t);
       *(uint32_t*)d = hi;
-      *(uint32_t*)(d + 64) = lo;
+      *(uint32_t*)(d + kOpfLo) = lo;
     }
   }
 }
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
     const int r = id >> 3, j = id & 7;
     const int row = q0 + r;
     const uint8_t* src = qkv + (size_t)(t0 + (row < T ? row : 0)) * ldb + (size_t)h * 128 + j * 16;
-    cp_async_16_zfill(smem_u32(sQ + r * 128 + ((j ^ (r & 7)) << 4)), src, row < T ? 16u : 0u);
+    cp_async_16_zfill(smem_u32(sQ + r * 128 + ((opf_logical_piece(j) ^ (r & 7)) << 4)), src, row < T ? 16u : 0u);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -698,8 +698,8 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
       uint4* dst = (uint4*)(out + (size_t)(t0 + grow) * ldo + (size_t)h * 128);
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
-        dst[c4] = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
-        dst[4 + c4] = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
+        dst[2 * c4] = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
+        dst[2 * c4 + 1] = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
       }
     }
   } else if (warp == kTcSoftmaxWarps) {
@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
         const int key = rem >> 3, jj = rem & 7;
         const int kr = kv0 + key;
         const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + jj * 16;
-        uint8_t* dst = (which ? sV : sK) + st * 8192 + key * 128 + ((jj ^ (key & 7)) << 4);
+        uint8_t* dst = (which ? sV : sK) + st * 8192 + key * 128 + ((opf_logical_piece(jj) ^ (key & 7)) << 4);
         cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
       }
       cp_async_commit();

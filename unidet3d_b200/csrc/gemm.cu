@@ -19,29 +19,33 @@
 //     reduce their partial tiles through distributed shared memory (deterministic, no atomics, no second pass);
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> fp32 and/or operand-form stores.
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 
 namespace ud3d {
 
-constexpr int kTileM = UD3D_TILE_M;   // 128
-constexpr int kChunk = 32;            // input channels per K-step
-
-struct GemmParams {
-  ud3d_gemm_args a;
-  int n_chunks;
-  int vec_ok;      // 16-byte vector gather allowed
-  int out_vec_ok;  // 16-byte vector epilogue allowed
-  long long* trace;   // debug: clock64 timestamps of one CTA (ud3d_debug_set_trace), else nullptr
-  int trace_block;
-  int trace_iter;     // which of the CTA's tiles is traced
-  int dbg;            // debug: feature-disable bits for timing breakdowns (ud3d_debug_set_flags), normally 0
-};
-
 static long long* g_trace = nullptr;
 static int g_trace_block = 0;
 static int g_dbg = 0;
-static int g_num_sms = 0;
+
+// gemm_ts.cu
+int launch_gemm_ts(const GemmParams& p, int nts, int num_sms, cudaStream_t st);
+int launch_pack_weight_ts(const float* w, int K, int c_in, int c_out, int nts, void* packed, cudaStream_t st);
+
+// per-device facts, cached (cudaFuncSetAttribute / the SM count belong to a device, not to the process)
+constexpr int kMaxDevices = 64;
+static int device_sms(int* dev_out) {
+  static int sms[kMaxDevices] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    sms[dev] = n;
+  }
+  if (dev_out) *dev_out = dev;
+  return sms[dev];
+}
 
 static inline int pick_ntile(int c_out) {
   if (c_out <= 32) return 32;
@@ -85,179 +89,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int c_in,
     }
     size_t tile = ((size_t)nt * K + k) * n_chunks + c;
     out[tile * n_tile_sz * 8 + (size_t)n * 8 + (j ^ (n & 7))] = make_uint4(v[0], v[1], v[2], v[3]);
-  }
-}
-
-// ---------------------------------------------------------------- the tensor-core kernel
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == 1) return fmaxf(v, 0.f);
-  // (an Abramowitz-Stegun 7.1.26 erf -- rcp + ex2 + 5 FMA -- measured slower than libdevice's erff here)
-  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-  return v;
-}
-
-// ---- warp-collective row-segment transposition through shared memory.
-// In the epilogue every lane owns one output row and produces 128-byte row segments (32 fp32 columns, or one operand-form
-// row-chunk).  Stored directly, one st.global.v4 instruction touches 32 different rows (32 partial-line writes of 16 B,
-// 8 instructions per segment).  Staged through 4 KB of shared memory per warp (16-byte pieces XOR-swizzled with the
-// row: conflict-free both ways), lanes 8r..8r+7 write the 8 pieces of one row: every instruction stores 4 complete
-// 128-byte lines.  `dst` / `src` == nullptr: this lane's row is skipped.  All 32 lanes must call.
-__device__ __forceinline__ void warp_store_rows(uint32_t stage, const uint4 (&pc)[8], uint8_t* dst, int lane) {
-  const uint32_t mine = stage + (uint32_t)lane * 128u;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(mine + (uint32_t)((j ^ (lane & 7)) << 4)), "r"(pc[j].x),
-                 "r"(pc[j].y), "r"(pc[j].z), "r"(pc[j].w)
-                 : "memory");
-  __syncwarp();
-  const int jj = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = (lane >> 3) + 4 * i;
-    uint4 v;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"(stage + (uint32_t)(rr * 128) + (uint32_t)((jj ^ (rr & 7)) << 4))
-                 : "memory");
-    uint8_t* ptr = (uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)dst, rr);
-    if (ptr) *(uint4*)(ptr + jj * 16) = v;
-  }
-  __syncwarp();
-}
-__device__ __forceinline__ void warp_load_rows(uint32_t stage, const uint8_t* src, uint4 (&pc)[8], int lane) {
-  const int jj = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = (lane >> 3) + 4 * i;
-    const uint8_t* ptr = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)src, rr);
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (ptr) v = __ldg((const uint4*)(ptr + jj * 16));
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(rr * 128) + (uint32_t)((jj ^ (rr & 7)) << 4)),
-                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-                 : "memory");
-  }
-  __syncwarp();
-  const uint32_t mine = stage + (uint32_t)lane * 128u;
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(pc[j].x), "=r"(pc[j].y), "=r"(pc[j].z), "=r"(pc[j].w)
-                 : "r"(mine + (uint32_t)((j ^ (lane & 7)) << 4))
-                 : "memory");
-  __syncwarp();
-}
-
-// One thread's 32 consecutive output columns [col0, col0+32) of row `grow`: bias / activation / residual, fp32 store
-// and/or operand-form stores.  r = raw fp32 accumulator bits.  WARP-COLLECTIVE: all 32 lanes call it (`valid` = this
-// lane has a row to write); `stage` = 4 KB of shared memory owned by the warp.
-__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], int grow, int col0, bool valid,
-                                                     uint32_t stage, int lane) {
-  const ud3d_gemm_args& a = p.a;
-  valid = valid && col0 < a.c_out;
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  // (launch-uniform) vector path: every 32-column chunk is complete and all row pointers are 16-byte aligned
-  if (p.out_vec_ok && (a.c_out & 31) == 0) {
-    if (a.bias) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = __ldg((const float4*)(a.bias + (valid ? col0 : 0) + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    }
-    if (a.act) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], a.act);
-    }
-    if (a.residual) {
-      uint4 t[8];
-      warp_load_rows(stage, valid ? (const uint8_t*)(a.residual + (size_t)grow * a.ld_res + col0) : nullptr, t, lane);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[4 * j] += __uint_as_float(t[j].x); v[4 * j + 1] += __uint_as_float(t[j].y);
-        v[4 * j + 2] += __uint_as_float(t[j].z); v[4 * j + 3] += __uint_as_float(t[j].w);
-      }
-    }
-    if (!a.no_raw) {
-      uint4 t[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        t[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                          __float_as_uint(v[4 * j + 3]));
-      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out + (size_t)grow * a.ld_out + col0) : nullptr, lane);
-    }
-#pragma unroll
-    for (int oi = 0; oi < 2; ++oi) {
-      if (!a.out_act[oi]) continue;
-      const float* sc = a.act_scale[oi] ? a.act_scale[oi] + (valid ? col0 : 0) : nullptr;
-      const float* sh = a.act_scale[oi] ? a.act_shift[oi] + (valid ? col0 : 0) : nullptr;
-      const bool do_relu = !((a.act_norelu >> oi) & 1);
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float x0 = v[j], x1 = v[j + 1];
-        if (sc) {
-          x0 = fmaf(x0, __ldg(sc + j), __ldg(sh + j));
-          x1 = fmaf(x1, __ldg(sc + j + 1), __ldg(sh + j + 1));
-        }
-        if (do_relu) {
-          x0 = fmaxf(x0, 0.f);
-          x1 = fmaxf(x1, 0.f);
-        }
-        split_bf16x2(x0, x1, hi[j >> 1], lo[j >> 1]);
-      }
-      uint4 t[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        t[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        t[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-      }
-      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4 : nullptr, lane);
-    }
-    return;
-  }
-  // generic path (ragged channel counts / unaligned views): per-thread scalar stores
-  if (!valid) return;
-  float* orow = a.out + (size_t)grow * a.ld_out;
-  const float* rrow = a.residual ? a.residual + (size_t)grow * a.ld_res : nullptr;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    int col = col0 + j;
-    if (col < a.c_out) {
-      if (a.bias) v[j] += __ldg(a.bias + col);
-      v[j] = apply_act(v[j], a.act);
-      if (rrow) v[j] += __ldg(rrow + col);
-      if (!a.no_raw) orow[col] = v[j];
-    }
-  }
-  // operand-form outputs (c_out % 32 == 0 and 16-byte aligned rows are enforced on the host): direct 16-byte stores
-#pragma unroll
-  for (int oi = 0; oi < 2; ++oi) {
-    if (!a.out_act[oi]) continue;
-    const float* sc = a.act_scale[oi] ? a.act_scale[oi] + col0 : nullptr;
-    const float* sh = a.act_scale[oi] ? a.act_shift[oi] + col0 : nullptr;
-    const bool do_relu = !((a.act_norelu >> oi) & 1);
-    uint4* dst = (uint4*)((uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4);
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      float x0 = v[j], x1 = v[j + 1];
-      if (sc) {
-        x0 = fmaf(x0, __ldg(sc + j), __ldg(sh + j));
-        x1 = fmaf(x1, __ldg(sc + j + 1), __ldg(sh + j + 1));
-      }
-      if (do_relu) {
-        x0 = fmaxf(x0, 0.f);
-        x1 = fmaxf(x1, 0.f);
-      }
-      split_bf16x2(x0, x1, hi[j >> 1], lo[j >> 1]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      dst[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-      dst[4 + j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-    }
   }
 }
 
@@ -448,7 +279,8 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         constexpr int NI = 32 / WPG;
         const int grp = warp / WPG, half = warp - grp * WPG;
         const int g = lane >> 3, j = lane & 7;
-        const uint32_t sw0 = (uint32_t)((j ^ g) << 4), sw1 = (uint32_t)(((j ^ g) ^ 4) << 4);   // (4 i + g) & 7 = 4 (i & 1) + g
+        const int jl = opf_logical_piece(j);      // memory piece j holds logical piece jl of the K-major tile
+        const uint32_t sw0 = (uint32_t)((jl ^ g) << 4), sw1 = (uint32_t)(((jl ^ g) ^ 4) << 4);   // (4 i + g) & 7 = 4 (i & 1) + g
         const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
         const uint32_t sA_lane = smem_u32(sA) + (uint32_t)((half * (kTileM / WPG) + g) * 128);
         long long* tr = (traced && tid == 0) ? p.trace : nullptr;
@@ -826,8 +658,8 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
 #pragma unroll
     for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
     uint4* dst = (uint4*)((uint8_t*)(out + (size_t)row * ld_out) + (size_t)ch * 128);
-    dst[q] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    dst[4 + q] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    dst[2 * q] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[2 * q + 1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -878,19 +710,16 @@ static size_t tc_smem_bytes(int n_chunks, int K, bool has_table) {
 template <int N_TILE>
 static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
   size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr || p.a.in_split);
-  static size_t configured = 0;   // largest size this instantiation was configured for
-  static int ctas_per_sm = 1;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    UD3D_CUDA(cudaGetDevice(&dev));
-    UD3D_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static size_t configured_dev[kMaxDevices] = {0};   // per device: largest size this instantiation was configured for
+  int dev = 0;
+  const int g_num_sms = device_sms(&dev);
+  if (g_num_sms <= 0) { set_error("ud3d_gemm_fwd: cannot query the current device"); return UD3D_ECUDA; }
+  size_t& configured = configured_dev[dev];
+  int ctas_per_sm = N_TILE <= 128 ? 2 : 1;
   if (smem > configured) {
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    (int)cudaSharedmemCarveoutMaxShared));
-    UD3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gather_gemm_tc_kernel<N_TILE>, kThreadsTc, smem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
     configured = smem;
   }
   // persistent over the row tiles: as many CTAs as are resident at once (the CTAs of the other grid dimensions
@@ -987,6 +816,12 @@ int ud3d_gemm_pack_weight(const float* w, int K, int c_in, int c_out, void* pack
   return UD3D_OK;
 }
 
+int ud3d_gemm_pack_weight_ts(const float* w, int K, int c_in, int c_out, void* packed, void* stream) {
+  UD3D_CHECK_ARG(w && packed && K > 0 && c_in > 0 && c_out > 0, "ud3d_gemm_pack_weight_ts: bad argument");
+  UD3D_CHECK_ARG(((uintptr_t)packed & 127) == 0, "ud3d_gemm_pack_weight_ts: packed buffer must be 128-byte aligned");
+  return launch_pack_weight_ts(w, K, c_in, c_out, pick_ntile(c_out), packed, (cudaStream_t)stream);
+}
+
 int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   int rc = check_args(args, "ud3d_gemm_fwd");
   if (rc) return rc;
@@ -1019,6 +854,14 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
       if (splits > 8) splits = 8;      // portable cluster size (14..16-CTA clusters scheduled in two waves: slower)
       if (splits < 1) splits = 1;
     }
+  }
+  // operand-form inputs of launches that fill the GPU: the A operand goes global -> registers -> TMEM (gemm_ts.cu)
+  if (args->in_split && args->w_packed_ts && splits == 1 && nts <= 160 && !(g_dbg & 4096)) {
+    UD3D_CHECK_ARG(((uintptr_t)args->w_packed_ts & 127) == 0, "ud3d_gemm_fwd: w_packed_ts misaligned");
+    UD3D_CHECK_ARG(((uintptr_t)args->in & 31) == 0 && args->ld_in % 8 == 0, "ud3d_gemm_fwd: operand-form input must be 32-byte aligned");
+    const int sms = device_sms(nullptr);
+    if (sms <= 0) { set_error("ud3d_gemm_fwd: cannot query the current device"); return UD3D_ECUDA; }
+    return launch_gemm_ts(p, nts, sms, st);
   }
   int rc2;
   switch (nts) {

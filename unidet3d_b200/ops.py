@@ -182,10 +182,14 @@ class PackedWeight:
         nbytes = int(_L().ud3d_gemm_packed_weight_bytes(self.K, self.c_in, self.c_out))
         self.data = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         check(_L().ud3d_gemm_pack_weight(_p(w), self.K, self.c_in, self.c_out, _p(self.data), _stream()), "ud3d_gemm_pack_weight")
+        # second image in the K order of the kernel variant whose A operand goes through registers into TMEM
+        self.data_ts = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        check(_L().ud3d_gemm_pack_weight_ts(_p(w), self.K, self.c_in, self.c_out, _p(self.data_ts), _stream()),
+              "ud3d_gemm_pack_weight_ts")
 
 
 def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act, residual,
-               w_packed_ptr, in_split=False, no_raw=False, acts=None, row_perm=None):
+               w_packed_ptr, in_split=False, no_raw=False, acts=None, row_perm=None, w_packed_ts_ptr=None):
     a = GemmArgs()
     a.in_ = x.data_ptr(); a.ld_in = x.stride(0); a.c_in = c_in
     a.table = table.data_ptr() if table is not None else None
@@ -212,6 +216,7 @@ def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_
             norelu |= 1 << i
     a.act_norelu = norelu
     a.row_perm = row_perm.data_ptr() if row_perm is not None else None
+    a.w_packed_ts = w_packed_ts_ptr
     return a
 
 
@@ -236,7 +241,7 @@ def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = No
     c_in = w.c_in if not in_split else (w.c_in + 31) // 32 * 32     # operand form pads the last chunk with zeros
     assert out.stride(1) == 1 and out.shape[1] == w.c_out and x.shape[1] == c_in
     a = _gemm_args(x, w.K, c_in, w.c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act,
-                   residual, w.data.data_ptr(), in_split, no_raw, acts, row_perm)
+                   residual, w.data.data_ptr(), in_split, no_raw, acts, row_perm, w.data_ts.data_ptr())
     check(_L().ud3d_gemm_fwd(C.byref(a), _stream()), "ud3d_gemm_fwd")
     return out
 
