@@ -33,61 +33,66 @@ def timed(run, reps=10):
     return float(np.median(ts[2:]))
 
 
-cfg, scenes, names, preset = bench.make_workload(os.environ.get("WORKLOAD", "scannet_b8"), 0)
-model = u.MODELS.build(cfg).eval()
-model.load_state_dict(make_model_state_dict(cfg, 0), strict=False)
-model.cuda()
-pts = [torch.as_tensor(s[0]).cuda() for s in scenes]
-offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device="cuda")
-x, inv = model.collate(torch.cat(pts), offs, len(pts))
-for level in [int(v) for v in os.environ.get("LEVELS", "0,1,2").split(",")]:
-    lv = x.pyramid.levels[level]
-    c = cfg["backbone"]["num_planes"][level]
-    xin = torch.relu(torch.randn(lv.n, c, device="cuda"))
-    xs = ops.act_split(xin, relu=False)
-    w = ops.PackedWeight(torch.randn(c, 27, c, device="cuda") * 0.05)
-    res = torch.randn(lv.n, c, device="cuda")
-    one = torch.ones(c, device="cuda"); zero = torch.zeros(c, device="cuda")
-    tb, tm, pm = lv.subm_conv
-    outs = {}
-    for order, (t_, m_, p_) in (("canonical", (lv.subm, lv.subm_mask, None)), ("regrouped", (tb, tm, pm))):
+def main():
+    cfg, scenes, names, preset = bench.make_workload(os.environ.get("WORKLOAD", "scannet_b8"), 0)
+    model = u.MODELS.build(cfg).eval()
+    model.load_state_dict(make_model_state_dict(cfg, 0), strict=False)
+    model.cuda()
+    pts = [torch.as_tensor(s[0]).cuda() for s in scenes]
+    offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device="cuda")
+    x, inv = model.collate(torch.cat(pts), offs, len(pts))
+    for level in [int(v) for v in os.environ.get("LEVELS", "0,1,2").split(",")]:
+        lv = x.pyramid.levels[level]
+        c = cfg["backbone"]["num_planes"][level]
+        xin = torch.relu(torch.randn(lv.n, c, device="cuda"))
+        xs = ops.act_split(xin, relu=False)
+        w = ops.PackedWeight(torch.randn(c, 27, c, device="cuda") * 0.05)
+        res = torch.randn(lv.n, c, device="cuda")
+        one = torch.ones(c, device="cuda"); zero = torch.zeros(c, device="cuda")
+        tb, tm, pm = lv.subm_conv
+        outs = {}
+        for order, (t_, m_, p_) in (("canonical", (lv.subm, lv.subm_mask, None)), ("regrouped", (tb, tm, pm))):
+            for path, fl in (("smem", 4096), ("tmem", 0)):
+                lib.ud3d_debug_set_flags(fl)
+                act = torch.zeros_like(xin); raw = torch.zeros_like(xin)
+                run = lambda: ops.gemm(xs, w, table=t_, tile_mask=m_, in_split=True, residual=res, out=raw, acts=[(act, one, zero)], row_perm=p_)
+                try:
+                    us = timed(run)
+                except Exception as e:  # noqa: BLE001
+                    print(f"level {level} {order} {path}: FAILED {e}")
+                    continue
+                outs[(order, path)] = (raw.clone(), act.clone())
+                print(f"level {level} n={lv.n} c={c} {order:9s} {path}: {us:8.1f} us/launch", flush=True)
+        lib.ud3d_debug_set_flags(0)
+        ref = outs.get(("canonical", "smem"))
+        for k, v in outs.items():
+            if ref is not None and k != ("canonical", "smem"):
+                e0 = float((v[0] - ref[0]).abs().max() / ref[0].abs().max())
+                e1 = float((v[1].view(torch.int32) != ref[1].view(torch.int32)).float().mean())
+                print(f"   {k}: raw rel err vs canonical/smem {e0:.2e}, operand-form words differing {e1:.2e}")
+    # encoder-shaped dense GEMMs
+    T = 13447
+    for (ci, co, actf) in ((256, 768, None), (256, 256, None), (256, 1024, "gelu"), (1024, 256, None)):
+        xin = torch.randn(T, ci, device="cuda")
+        xs = ops.act_split(xin, relu=False)
+        w = ops.PackedWeight(torch.randn(co, ci, device="cuda") * 0.05)
+        b = torch.randn(co, device="cuda")
+        outs = {}
         for path, fl in (("smem", 4096), ("tmem", 0)):
             lib.ud3d_debug_set_flags(fl)
-            act = torch.zeros_like(xin); raw = torch.zeros_like(xin)
-            run = lambda: ops.gemm(xs, w, table=t_, tile_mask=m_, in_split=True, residual=res, out=raw, acts=[(act, one, zero)], row_perm=p_)
+            act = torch.zeros(T, co, device="cuda")
+            run = lambda: ops.gemm(xs, w, in_split=True, bias=b, act=actf, no_raw=True, acts=[(act, None, None, False)])
             try:
                 us = timed(run)
             except Exception as e:  # noqa: BLE001
-                print(f"level {level} {order} {path}: FAILED {e}")
+                print(f"dense {ci}->{co} {path}: FAILED {e}")
                 continue
-            outs[(order, path)] = (raw.clone(), act.clone())
-            print(f"level {level} n={lv.n} c={c} {order:9s} {path}: {us:8.1f} us/launch", flush=True)
-    lib.ud3d_debug_set_flags(0)
-    ref = outs.get(("canonical", "smem"))
-    for k, v in outs.items():
-        if ref is not None and k != ("canonical", "smem"):
-            e0 = float((v[0] - ref[0]).abs().max() / ref[0].abs().max())
-            e1 = float((v[1].view(torch.int32) != ref[1].view(torch.int32)).float().mean())
-            print(f"   {k}: raw rel err vs canonical/smem {e0:.2e}, operand-form words differing {e1:.2e}")
-# encoder-shaped dense GEMMs
-T = 13447
-for (ci, co, actf) in ((256, 768, None), (256, 256, None), (256, 1024, "gelu"), (1024, 256, None)):
-    xin = torch.randn(T, ci, device="cuda")
-    xs = ops.act_split(xin, relu=False)
-    w = ops.PackedWeight(torch.randn(co, ci, device="cuda") * 0.05)
-    b = torch.randn(co, device="cuda")
-    outs = {}
-    for path, fl in (("smem", 4096), ("tmem", 0)):
-        lib.ud3d_debug_set_flags(fl)
-        act = torch.zeros(T, co, device="cuda")
-        run = lambda: ops.gemm(xs, w, in_split=True, bias=b, act=actf, no_raw=True, acts=[(act, None, None, False)])
-        try:
-            us = timed(run)
-        except Exception as e:  # noqa: BLE001
-            print(f"dense {ci}->{co} {path}: FAILED {e}")
-            continue
-        outs[path] = act.clone()
-        print(f"dense {ci}->{co} {actf} {path}: {us:8.1f} us/launch", flush=True)
-    lib.ud3d_debug_set_flags(0)
-    if len(outs) == 2:
-        print("   operand-form words differing:", float((outs["smem"].view(torch.int32) != outs["tmem"].view(torch.int32)).float().mean()))
+            outs[path] = act.clone()
+            print(f"dense {ci}->{co} {actf} {path}: {us:8.1f} us/launch", flush=True)
+        lib.ud3d_debug_set_flags(0)
+        if len(outs) == 2:
+            print("   operand-form words differing:", float((outs["smem"].view(torch.int32) != outs["tmem"].view(torch.int32)).float().mean()))
+
+
+if __name__ == "__main__":
+    main()

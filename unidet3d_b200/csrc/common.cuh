@@ -150,6 +150,20 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
+// try_wait without a suspend-time hint (the default, short, system-dependent time limit), in a bounded loop
+__device__ __forceinline__ void mbar_wait_nohint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (++spins > (1u << 24)) __trap();
+  }
+}
 // spin on test_wait (no hardware suspend): lowest wake-up latency, for single-thread roles
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0, spins = 0;

@@ -471,14 +471,21 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
       alpha[r] = ex2_approx(m_run[r] - m_new);
       m_run[r] = m_new;
     }
+    // P is used as ONE bf16 term (P_hi) in P V: the row sum is accumulated from the SAME rounded values, so numerator
+    // and denominator of softmax(S) V agree exactly (the result is an exact convex combination of V rows with weights
+    // perturbed by 2^-9 relative -- a second-order effect, measured 5e-5 on the encoder's final logits / boxes; with the
+    // fp32 row sum a single dominant key would carry the full 2^-9 rounding error of its weight).  V keeps hi + lo.
+    uint32_t pb[8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = ex2_approx(fmaf(s[nt][0], qscale, -m_run[0]));     // scale folded into the exponent's FMA
-      s[nt][1] = ex2_approx(fmaf(s[nt][1], qscale, -m_run[0]));
-      s[nt][2] = ex2_approx(fmaf(s[nt][2], qscale, -m_run[1]));
-      s[nt][3] = ex2_approx(fmaf(s[nt][3], qscale, -m_run[1]));
-      rs[0] += s[nt][0] + s[nt][1];
-      rs[1] += s[nt][2] + s[nt][3];
+      const float p0 = ex2_approx(fmaf(s[nt][0], qscale, -m_run[0]));     // scale folded into the exponent's FMA
+      const float p1 = ex2_approx(fmaf(s[nt][1], qscale, -m_run[0]));
+      const float p2 = ex2_approx(fmaf(s[nt][2], qscale, -m_run[1]));
+      const float p3 = ex2_approx(fmaf(s[nt][3], qscale, -m_run[1]));
+      pb[nt][0] = cvt_bf16x2_rn(p0, p1);
+      pb[nt][1] = cvt_bf16x2_rn(p2, p3);
+      rs[0] += __uint_as_float(pb[nt][0] << 16) + __uint_as_float(pb[nt][0] & 0xffff0000u);
+      rs[1] += __uint_as_float(pb[nt][1] << 16) + __uint_as_float(pb[nt][1] & 0xffff0000u);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -494,11 +501,7 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
     // ---- O += P V : V fragments by ldmatrix.trans from the row-major (key, dim) tile
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t ph[4], pl[4];
-      split_bf16x2(s[2 * j][0], s[2 * j][1], ph[0], pl[0]);
-      split_bf16x2(s[2 * j][2], s[2 * j][3], ph[1], pl[1]);
-      split_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
-      split_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
+      const uint32_t ph[4] = {pb[2 * j][0], pb[2 * j][1], pb[2 * j + 1][0], pb[2 * j + 1][1]};
       // lane -> (matrix = lane >> 3, row = lane & 7): matrices {keys 0-7, keys 8-15} x {dim tile dn, dn + 1}
       const int key = 16 * j + (lane & 7) + ((lane >> 3) & 1) * 8;
       const uint32_t vrow = Vs + key * 128;
@@ -509,10 +512,8 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
         ldmatrix_x4_trans(vh, vrow + (((2 * dp + csel) ^ (key & 7)) << 4));
         ldmatrix_x4_trans(vl, vrow + (((4 + 2 * dp + csel) ^ (key & 7)) << 4));
         mma_bf16_16816(o[2 * dp], ph, vh[0], vh[1]);
-        mma_bf16_16816(o[2 * dp], pl, vh[0], vh[1]);
         mma_bf16_16816(o[2 * dp], ph, vl[0], vl[1]);
         mma_bf16_16816(o[2 * dp + 1], ph, vh[2], vh[3]);
-        mma_bf16_16816(o[2 * dp + 1], pl, vh[2], vh[3]);
         mma_bf16_16816(o[2 * dp + 1], ph, vl[2], vl[3]);
       }
     }

@@ -856,7 +856,8 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
     }
   }
   // operand-form inputs of launches that fill the GPU: the A operand goes global -> registers -> TMEM (gemm_ts.cu)
-  if (args->in_split && args->w_packed_ts && splits == 1 && nts <= 160 && !(g_dbg & 4096)) {
+  if (args->in_split && args->w_packed_ts && splits == 1 && nts <= 160 && !(g_dbg & 4096) &&
+      (!args->table || args->tile_mask)) {
     UD3D_CHECK_ARG(((uintptr_t)args->w_packed_ts & 127) == 0, "ud3d_gemm_fwd: w_packed_ts misaligned");
     UD3D_CHECK_ARG(((uintptr_t)args->in & 31) == 0 && args->ld_in % 8 == 0, "ud3d_gemm_fwd: operand-form input must be 32-byte aligned");
     const int sms = device_sms(nullptr);

@@ -33,7 +33,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // 8 instructions per segment).  Staged through 4 KB of shared memory per warp (16-byte pieces XOR-swizzled with the
 // row: conflict-free both ways), lanes 8r..8r+7 write the 8 pieces of one row: every instruction stores 4 complete
 // 128-byte lines.  `dst` / `src` == nullptr: this lane's row is skipped.  All 32 lanes must call.
-__device__ __forceinline__ void warp_store_rows(uint32_t stage, const uint4 (&pc)[8], uint8_t* dst, int lane) {
+__device__ __forceinline__ void st_global_v4_na(void* p, const uint4& v) {     // streaming store: do not allocate in L1
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void warp_store_rows(uint32_t stage, const uint4 (&pc)[8], uint8_t* dst, int lane, bool na = false) {
   const uint32_t mine = stage + (uint32_t)lane * 128u;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -51,7 +54,10 @@ __device__ __forceinline__ void warp_store_rows(uint32_t stage, const uint4 (&pc
                  : "r"(stage + (uint32_t)(rr * 128) + (uint32_t)((jj ^ (rr & 7)) << 4))
                  : "memory");
     uint8_t* ptr = (uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)dst, rr);
-    if (ptr) *(uint4*)(ptr + jj * 16) = v;
+    if (ptr) {
+      if (na) st_global_v4_na(ptr + jj * 16, v);
+      else *(uint4*)(ptr + jj * 16) = v;
+    }
   }
   __syncwarp();
 }
@@ -116,7 +122,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
       for (int j = 0; j < 8; ++j)
         t[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                           __float_as_uint(v[4 * j + 3]));
-      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out + (size_t)grow * a.ld_out + col0) : nullptr, lane);
+      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out + (size_t)grow * a.ld_out + col0) : nullptr, lane, (p.dbg & 64) != 0);
     }
 #pragma unroll
     for (int oi = 0; oi < 2; ++oi) {
@@ -144,7 +150,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
         t[2 * j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
         t[2 * j + 1] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
       }
-      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4 : nullptr, lane);
+      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4 : nullptr, lane,
+                      (p.dbg & 64) != 0);
     }
     return;
   }

@@ -25,10 +25,24 @@ template <int N_TILE> struct TsCfg {
   // ring depth: TMEM A stages (32 columns each, next to the two N_TILE-column accumulators) == weight stages in smem
   static constexpr int kStages = N_TILE <= 64 ? 8 : N_TILE <= 96 ? 6 : N_TILE <= 128 ? 5 : 4;
 };
-constexpr int kTsThreads = 32 * 15;
+// Warp roles (28 warps = 7 warpgroups): 0-3 epilogue; 4-23 A producers, five per TMEM lane quadrant (quadrant = warp & 3,
+// turn = (warp - 4) >> 2: the warp fills K-steps g == turn (mod 5)); 24, 25 weight tiles; 26 MMA issue; 27 idle.
+// Memory-level parallelism comes from the NUMBER of producer warps, each with a single K-step (32 rows x 32 B per lane)
+// in flight: one warp cannot keep several independent load batches in flight without waiting for the newest (loads
+// that share a hardware scoreboard complete "in order" as far as a dependent instruction is concerned).
+constexpr int kTsThreads = 32 * 28;
 constexpr int kTsEpiWarps = 4;
-constexpr int kTsProdWarps = 8;
-constexpr int kTsWarpTbl = 12, kTsWarpB = 13, kTsWarpMma = 14;
+constexpr int kTsTurns = 5;           // producer warps per quadrant
+constexpr int kTsProdWarps = 4 * kTsTurns;
+constexpr int kTsWarpB = kTsEpiWarps + kTsProdWarps;    // 24, 25: weight tiles (alternate K-steps)
+constexpr int kTsWarpMma = kTsWarpB + 2;
+// registers per thread after the role split (setmaxnreg, per warpgroup): the launch allocates 65536 / 896 = 72
+constexpr int kTsRegsEpi = 120, kTsRegsProd = 64, kTsRegsCtl = 64;   // 120: the pool is what the others release (6144 registers)
+#ifndef UD3D_TS_NO_SETMAXNREG
+#define UD3D_TS_SETMAXNREG(dir, n) asm volatile("setmaxnreg." dir ".sync.aligned.u32 %0;" ::"n"(n))
+#else
+#define UD3D_TS_SETMAXNREG(dir, n) do { } while (0)
+#endif
 
 // 16 TMEM lanes x 32 columns (one A stage of a half quadrant); register layout of .16x256b.x4: registers 4g, 4g+1 =
 // columns 8g + 2q, 8g + 2q + 1 of lane base + t/4; registers 4g+2, 4g+3 = the same columns of lane base + 8 + t/4
@@ -103,60 +117,93 @@ int launch_pack_weight_ts(const float* w, int K, int c_in, int c_out, int nts, v
 }
 
 // ---------------------------------------------------------------- the kernel
-// A rulebook slot in shared memory (two slots, filled two tiles ahead by the table warp):
-//   int32 tbl[K + 1][128]   the tile's slice of the gather table; row K is all -1 (the "null" offset)
-//   int32 nsteps, pad[3]
-//   uint16 steps[kTsMaxSteps]   (k << 8) | chunk of every K-step of the tile, k == K for a null step
-// nsteps = max(active offsets x chunks, kTsMinSteps): a tile of at least kTsMinSteps steps keeps a producer's load cursor
-// at most one tile ahead of its store cursor, which is what makes two slots enough (no deadlock).
-constexpr int kTsMaxSteps = 256;
-constexpr int kTsMinSteps = 4;
+// Every role derives the K-step sequence of a tile from ONE word, the tile's mask of active kernel offsets
+// (ud3d_gemm_args.tile_mask; 1 for a dense GEMM): steps = (active offset in ascending order) x (32-channel chunk).
+// Nothing about the rulebook is staged in shared memory: a producer thread reads the four row indices of its next
+// step straight from the gather table (one 32-byte sector per 8 rows), two of its steps ahead of the row loads, which
+// are two steps ahead of the TMEM store -- the dependent index -> row chain is software-pipelined in registers.
 constexpr int kTsInFlight = 2;        // K-steps in flight per producer warp (32 registers each); the two warps of a TMEM lane
                                       // quadrant take alternate steps -> 4 steps (64 KB) in flight per SM
 
 __device__ uint4 g_ts_zero_row[8];    // 128 bytes of zeros: the source row of a missing neighbour (always an L1 hit)
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
-}
 __device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p));
 }
+// idx = ok ? *p : -1, as a predicated load (no select on the loaded value: the result is not needed before its use two
+// iterations later, so the warp must not wait for it here)
+__device__ __forceinline__ int ldg_s32_or_m1(const int32_t* p, bool ok) {
+  int v;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "mov.b32 %0, -1;\n\t"
+      "@p ld.global.nc.s32 %0, [%1];\n\t}"
+      : "=r"(v)
+      : "l"(p), "r"((int)ok));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32_raw(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// The 6 MMAs of one K-step + the commit that frees the stage, issued by ONE elected lane from one asm block (one
+// elect / predicate region instead of seven).  A slices (8 TMEM columns each): hi(P0), hi(P1), lo(P0), lo(P1); B slices
+// (+32 B = +2 in the descriptor's address field): hi(P0), hi(P1), lo(P0), lo(P1); products hi.hi, lo.hi, hi.lo.
+__device__ __forceinline__ void umma_ts_step(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate, uint32_t empty_bar) {
+  if (elect_one_sync()) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 a1, a2, a3;\n\t.reg .b64 b2, b4, b6;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "add.u64 b2, %2, 2;\n\tadd.u64 b4, %2, 4;\n\tadd.u64 b6, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b2, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], %2, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b2, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], b4, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b6, %3, q;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(empty_bar)
+        : "memory");
+  }
+}
+
+// debug trace (ud3d_debug_set_trace(buf >= 4096 int64, block)): clock64 of CTA `block`; per K-step g < 256: [8g + 0]
+// MMA warp saw the stage full, +1 MMAs issued, +2 producer (quadrant 0) starts waiting for the stage, +3 has it, +4 stage
+// published, +5 next loads issued, +6 weight copy issued; per tile it < 64: [2048 + 4 it + 0] epilogue sees the
+// accumulator, +1 epilogue done, +2 MMA warp starts the tile
+#define UD3D_TS_TR(idx)                                                              \
+  do {                                                                               \
+    if (traced && lane == 0 && (idx) < 4096) p.trace[(idx)] = clock64();             \
+  } while (0)
 
 // one K-step of the MMA warp at ring stage S (compile-time): wait, 6 MMAs, commit.  All tensor-memory / descriptor
-// operands are compile-time offsets from two loop-invariant values, so the elected lane issues from uniform registers.
+// operands are compile-time offsets from loop-invariant values.
 #define UD3D_TS_MMA_STEP(S)                                                                                   \
   if (t < nsteps) {                                                                                           \
     mbar_wait(&full[S], use & 1u);                                                                            \
     tc_fence_after_sync();                                                                                    \
-    {                                                                                                         \
-      const uint32_t at = tmem_base + COL_A + (uint32_t)((S) * 32);                                           \
-      const uint64_t bd = bdesc0 + (uint64_t)((S) * (B_BYTES >> 4));                                          \
-      umma_bf16_ts_elect(d_tmem, at + 0, bd + 0, IDESC, t > 0);                                               \
-      umma_bf16_ts_elect(d_tmem, at + 8, bd + 2, IDESC, 1);                                                   \
-      umma_bf16_ts_elect(d_tmem, at + 16, bd + 0, IDESC, 1);                                                  \
-      umma_bf16_ts_elect(d_tmem, at + 24, bd + 2, IDESC, 1);                                                  \
-      umma_bf16_ts_elect(d_tmem, at + 0, bd + 4, IDESC, 1);                                                   \
-      umma_bf16_ts_elect(d_tmem, at + 8, bd + 6, IDESC, 1);                                                   \
-      umma_commit_elect(&empty[S]);                                                                           \
+    if (traced && gbase + t < 256) UD3D_TS_TR(8 * (gbase + t) + 0);                                           \
+    if (!(p.dbg & 1)) {                                                                                       \
+      umma_ts_step(d_tmem, tmem_base + COL_A + (uint32_t)((S) * 32), bdesc0 + (uint64_t)((S) * (B_BYTES >> 4)), IDESC, \
+                   t > 0, empty_u32 + 8u * (S));                                                              \
+    } else if (lane == 0) {                                                                                   \
+      mbar_arrive(&empty[S]);                                                                                 \
     }                                                                                                         \
+    if (traced && gbase + t < 256) UD3D_TS_TR(8 * (gbase + t) + 1);                                           \
     ++t;                                                                                                      \
     if ((S) == STAGES - 1) ++use;                                                                             \
   }
 
+// A tile's mask of active kernel offsets as every role sees it: the tile_mask word, or 1 when it is 0 (a tile without
+// any input still runs one all-zero K-step per chunk so that its accumulator is defined) or when there is no table.
 template <int N_TILE>
 __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const GemmParams p) {
   constexpr int STAGES = TsCfg<N_TILE>::kStages;
@@ -165,22 +212,22 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
   constexpr uint32_t COL_A = 2 * N_TILE;            // TMEM: [acc 0 | acc 1 | A stage 0 | A stage 1 | ...]
   static_assert(COL_A + STAGES * 32 <= 512, "TMEM budget");
   static_assert(STAGES <= 8, "the MMA warp's stage dispatch covers 8 stages");
+  // weight tiles: one bulk copy (TMA engine) per step for the wide tiles -- its issue costs ~300 cycles, hidden behind >= 192
+  // cycles of MMAs per step and two alternating warps -- and 16-byte cp.async for the 4 KB tiles of N = 32, where a step is
+  // too short for that
+  constexpr bool kBulkB = N_TILE >= 64;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const ud3d_gemm_args& a = p.a;
   const bool has_table = a.table != nullptr;
-  const int tbl_bytes = has_table ? (a.K + 1) * kTileM * 4 : 0;
-  const int slot_bytes = tbl_bytes + 16 + kTsMaxSteps * 2;
   uint8_t* sB = smem;                                        // [STAGES][N_TILE x 128 B]
   uint8_t* sEpi = sB + STAGES * B_BYTES;                     // [4 warps][4 KB] row-segment transposition
-  uint8_t* sTbl = sEpi + kTsEpiWarps * 4096;                 // [2 slots]
-  uint64_t* bars = (uint64_t*)(sTbl + 2 * slot_bytes);
-  uint64_t* full = bars;                   // [STAGES] 4 producer warps + 1 weight copy (+ tx bytes)
+  uint8_t* sIdx = sEpi + kTsEpiWarps * 4096;                 // [producer warp][2][32 lanes x 16 B] row indices of the next step
+  uint64_t* bars = (uint64_t*)(sIdx + kTsProdWarps * 1024);
+  uint64_t* full = bars;                   // [STAGES] 4 producer warps (one per quadrant) + 32 lanes of a weight warp (cp.async arrivals)
   uint64_t* empty = full + 8;              // [STAGES] tcgen05.commit
-  uint64_t* tbl_full = empty + 8;          // [2] table warp
-  uint64_t* tbl_empty = tbl_full + 2;      // [2] 8 producer warps + weight warp + MMA warp
-  uint64_t* acc_full = tbl_empty + 2;      // [2] tcgen05.commit
+  uint64_t* acc_full = empty + 8;          // [2] tcgen05.commit
   uint64_t* acc_empty = acc_full + 2;      // [2] 4 epilogue warps
   uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
@@ -188,23 +235,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
   const int n_row_tiles = (a.n_out + kTileM - 1) / kTileM;
   const int n_ntiles = (a.c_out + N_TILE - 1) / N_TILE;
   const int n_items = n_row_tiles * n_ntiles;
-  const uint32_t sTbl_u32 = smem_u32(sTbl);
+  const bool traced = p.trace != nullptr && (int)blockIdx.x == p.trace_block;
+  // trace_block == -3: globaltimer at start / end + SM id of every CTA: p.trace[4 * blockIdx.x + {0, 1, 2}]
+  if (p.trace != nullptr && p.trace_block == -3 && tid == 0) {
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[4 * blockIdx.x + 0] = (long long)gt;
+    p.trace[4 * blockIdx.x + 2] = smid;
+  }
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], kTsProdWarps / 2 + 1);
+      mbar_init(&full[s], 4 + (kBulkB ? 1 : 32));
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tbl_full[s], 1);
-      mbar_init(&tbl_empty[s], kTsProdWarps + 2);
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], kTsEpiWarps);
     }
     fence_mbar_init();
   }
-  if (has_table && tid < 2 * kTileM)      // the null offset: row K of both slots
-    sts_u32(sTbl_u32 + (uint32_t)((tid >> 7) * slot_bytes + (a.K * kTileM + (tid & 127)) * 4), 0xffffffffu);
   if (warp == 0) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
@@ -216,6 +268,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
 
   if (warp < kTsEpiWarps) {
     // ================================================================= epilogue: TMEM -> registers -> global
+    UD3D_TS_SETMAXNREG("inc", kTsRegsEpi);
     const int quad = warp;
     const uint32_t stage = smem_u32(sEpi) + (uint32_t)warp * 4096u;
     int it = 0;
@@ -228,6 +281,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
       const int buf = it & 1;
       mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
       tc_fence_after_sync();
+      if (warp == 0 && it < 64) UD3D_TS_TR(2048 + 4 * it + 0);
 #pragma unroll 1
       for (int c0 = 0; c0 < N_TILE; c0 += 32) {
         uint32_t r[32];
@@ -239,200 +293,175 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        epilogue_store_chunk(p, r, grow, n0 + c0, row_ok, stage, lane);
+        epilogue_store_chunk(p, r, grow, n0 + c0, row_ok && !(p.dbg & 16), stage, lane);
       }
+      if (warp == 0 && it < 64) UD3D_TS_TR(2048 + 4 * it + 1);
     }
   } else if (warp < kTsEpiWarps + kTsProdWarps) {
     // ================================================================= A producers: global -> registers -> TMEM
+    UD3D_TS_SETMAXNREG("dec", kTsRegsProd);
     const int pw = warp - kTsEpiWarps;
-    const int quad = pw & 3, par = pw >> 2;             // this warp fills the quadrant's 32 lanes for steps g == par (mod 2)
+    const int quad = pw & 3, turn = pw >> 2;            // this warp fills the quadrant's 32 lanes for steps g == turn (mod 5)
     const int rsub = lane >> 2, q = lane & 3;
     const int r0 = quad * 32 + rsub;                    // this thread's four tile rows: r0, r0 + 8, r0 + 16, r0 + 24
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + COL_A;
-    const size_t row_bytes = (size_t)a.ld_in * 4u;
+    const uint32_t row_bytes = (uint32_t)a.ld_in * 4u;
     const uint8_t* in_q = (const uint8_t*)a.in + q * 32;
     const uint8_t* zero_q = (const uint8_t*)g_ts_zero_row + q * 32;
+    const uint32_t full_u32 = smem_u32(full);
+    constexpr uint32_t kInvalid = 0xffffffffu;
 
-    // two cursors over the CTA's flattened K-step sequence: `is` issues the loads kTsInFlight of this warp's steps
-    // ahead of `cs`, which stores them to TMEM
-    struct Cur {
-      int it, w, t, nsteps, m0;
-      uint32_t tbl, steps;         // shared-memory addresses of the tile's rulebook slice / step list
+    // ---- the step generator.  Cursor = (tile, remaining active offsets, chunk); gen() emits this warp's next step --
+    //      meta = chunk byte offset (or kInvalid past the end) and the four row indices, loaded from the gather table
+    //      (not waited for here) -- and moves kTsTurns steps ahead.
+    int g_w = blockIdx.x;                 // work item
+    uint32_t g_m = 0u;                    // active offsets of the tile not yet passed (lowest set bit = current offset)
+    int g_c = 0, g_m0 = 0;
+    uint32_t g_mnext = 0u;                // raw mask of the CTA's next tile (loaded one tile ahead)
+    auto g_open = [&]() {                 // g_w is a valid item whose (raw) mask is in g_mnext
+      g_m = (has_table && g_mnext) ? g_mnext : 1u;
+      g_c = 0;
+      g_m0 = (g_w / n_ntiles) * kTileM;
+      const int wn = g_w + (int)gridDim.x;
+      if (has_table && wn < n_items) g_mnext = ldg_u32_raw(a.tile_mask + wn / n_ntiles);    // used one tile later
     };
-    auto open_tile = [&](Cur& cu, bool wait) {
-      if (cu.w >= n_items) return;
-      if (wait) mbar_wait(&tbl_full[cu.it & 1], (uint32_t)(cu.it >> 1) & 1u);
-      cu.tbl = sTbl_u32 + (uint32_t)((cu.it & 1) * slot_bytes);
-      cu.steps = cu.tbl + (uint32_t)tbl_bytes + 16u;
-      cu.nsteps = (int)lds_u32(cu.tbl + (uint32_t)tbl_bytes);
-      cu.m0 = (cu.w / n_ntiles) * kTileM;
-    };
-    auto advance = [&](Cur& cu, bool is_issue) {
-      cu.t += 2;
-      if (cu.t >= cu.nsteps) {
-        cu.t -= cu.nsteps;            // (< 2 <= kTsMinSteps <= the next tile's step count)
-        if (!is_issue) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tbl_empty[cu.it & 1]);       // this warp is done with the tile's slot
+    auto g_step1 = [&]() {                // advance the cursor by one K-step
+      if (++g_c == p.n_chunks) {
+        g_c = 0;
+        g_m &= g_m - 1u;
+        if (g_m == 0u) {
+          g_w += (int)gridDim.x;
+          if (g_w < n_items) g_open();
         }
-        ++cu.it;
-        cu.w += gridDim.x;
-        open_tile(cu, is_issue);
       }
     };
-    Cur is, cs;
-    is.it = cs.it = 0;
-    is.w = cs.w = blockIdx.x;
-    is.t = cs.t = par;
-    is.nsteps = cs.nsteps = 0; is.m0 = cs.m0 = 0; is.tbl = cs.tbl = is.steps = cs.steps = 0;
-    open_tile(is, true);
-    open_tile(cs, false);
-
-    uint32_t buf[kTsInFlight][4][8];
-    auto issue = [&](uint32_t (&v)[4][8]) {
-      if (is.w >= n_items) return;
-      const uint32_t st = lds_u16(is.steps + 2u * (uint32_t)is.t);
-      const int k = (int)(st >> 8), c = (int)(st & 255u);
-      int idx[4];
+    // The four row indices of a step travel global -> shared memory by cp.async (4 bytes each, this lane's own 16-byte
+    // slot) and are read back with one LDS.128 an iteration later: an asynchronous copy is tracked by the cp.async group
+    // counter, not by a register scoreboard, so having it in flight does not stall the instructions that touch the
+    // previously loaded indices or the row registers.  Rows beyond n_out (last tile) read a clamped, valid table entry:
+    // whatever they gather lands in accumulator rows the epilogue never stores.
+    const uint32_t idx_slot = smem_u32(sIdx) + (uint32_t)(pw * 1024 + lane * 16);
+    auto gen = [&](uint32_t& meta, uint32_t slot) {
+      if (g_w >= n_items) { meta = kInvalid; return; }
+      meta = (uint32_t)g_c * 128u;
       if (has_table) {
-        const uint32_t trow = is.tbl + (uint32_t)((k * kTileM + r0) * 4);
+        const int k = __ffs(g_m) - 1;
+        const int32_t* trow = a.table + (size_t)k * a.n_out;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = (int)lds_u32(trow + 32u * j);
+        for (int j = 0; j < 4; ++j) {
+          int r = g_m0 + r0 + 8 * j;
+          r = r < a.n_out ? r : a.n_out - 1;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(idx_slot + slot * 512u + 4u * j), "l"(trow + r) : "memory");
+        }
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = (k == 0 && is.m0 + r0 + 8 * j < a.n_out) ? is.m0 + r0 + 8 * j : -1;
+        for (int j = 0; j < 4; ++j) {
+          const int r = g_m0 + r0 + 8 * j;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(idx_slot + slot * 512u + 4u * j), "r"(r < a.n_out ? r : -1) : "memory");
+        }
       }
-      const uint8_t* src = in_q + c * 128;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ldg256(idx[j] >= 0 ? src + (size_t)idx[j] * row_bytes : zero_q, v[j]);
-      advance(is, true);
+      cp_async_commit();
+#pragma unroll 1
+      for (int j = 0; j < kTsTurns && g_w < n_items; ++j) g_step1();
     };
-    int gs = par;              // ring stage / use count of this warp's next step (global step g == par mod 2)
-    uint32_t guse = 0;
-    if (gs >= STAGES) { gs -= STAGES; ++guse; }
-    auto consume = [&](const uint32_t (&v)[4][8]) {
-      if (cs.w >= n_items) return;
-      if (guse) mbar_wait(&empty[gs], (guse & 1u) ^ 1u);
+    if (g_w < n_items) {
+      if (has_table) g_mnext = ldg_u32_raw(a.tile_mask + g_w / n_ntiles);
+      g_open();
+#pragma unroll 1
+      for (int j = 0; j < turn && g_w < n_items; ++j) g_step1();
+    }
+    uint32_t g = (uint32_t)turn;      // global K-step index of this warp's next step
+    uint32_t meta_n, it = 0;
+    gen(meta_n, 0u);
+    while (meta_n != kInvalid) {
+      if (traced && quad == 0 && g < 256) UD3D_TS_TR(8 * g + 6);
+      const uint32_t meta = meta_n;
+      cp_async_wait<0>();
+      int4 iv;
+      asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(iv.x), "=r"(iv.y), "=r"(iv.z), "=r"(iv.w) : "r"(idx_slot + (it & 1u) * 512u));
+      const int idx[4] = {iv.x, iv.y, iv.z, iv.w};
+      uint32_t rows[4][8];
+      const uint8_t* src = in_q + meta;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        ldg256((idx[r] >= 0 && !(p.dbg & 32)) ? src + (size_t)((uint32_t)idx[r]) * row_bytes : zero_q, rows[r]);
+      if (traced && quad == 0 && g < 256) UD3D_TS_TR(8 * g + 7);
+      ++it;
+      gen(meta_n, it & 1u);        // indices of this warp's next step: in flight while the rows arrive and are stored
+      const uint32_t gs = g % STAGES, gph = ((g / STAGES) & 1u) ^ 1u;
+      if (traced && quad == 0 && g < 256) UD3D_TS_TR(8 * g + 2);
+      mbar_wait(&empty[gs], gph);
       tc_fence_after_sync();
-      const uint32_t ta = t_lane + (uint32_t)(gs * 32);
-      tmem_st_16x256b_x4(ta, v[0], v[1]);                        // lanes +0..15  (rows r0, r0 + 8)
-      tmem_st_16x256b_x4(ta + (16u << 16), v[2], v[3]);          // lanes +16..31 (rows r0 + 16, r0 + 24)
+      if (traced && quad == 0 && g < 256) UD3D_TS_TR(8 * g + 3);
+      const uint32_t ta = t_lane + gs * 32u;
+      tmem_st_16x256b_x4(ta, rows[0], rows[1]);                    // lanes +0..15  (rows r0, r0 + 8)
+      tmem_st_16x256b_x4(ta + (16u << 16), rows[2], rows[3]);      // lanes +16..31 (rows r0 + 16, r0 + 24)
+      if (traced && quad == 0 && g < 256) UD3D_TS_TR(8 * g + 5);
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full[gs]);
-      gs += 2;
-      if (gs >= STAGES) { gs -= STAGES; ++guse; }
-      advance(cs, false);
-    };
-#pragma unroll
-    for (int j = 0; j < kTsInFlight; ++j) issue(buf[j]);
-    while (cs.w < n_items) {
-#pragma unroll
-      for (int j = 0; j < kTsInFlight; ++j) {
-        consume(buf[j]);
-        issue(buf[j]);
-      }
-    }
-  } else if (warp == kTsWarpTbl) {
-    // ================================================================= rulebook slices + step lists, two tiles ahead
-    int it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const int rt = w / n_ntiles;
-      const int m0 = rt * kTileM;
-      if (it >= 2) mbar_wait(&tbl_empty[it & 1], (uint32_t)((it >> 1) - 1) & 1u);
-      const uint32_t slot = sTbl_u32 + (uint32_t)((it & 1) * slot_bytes);
-      uint32_t mask = 1u;
-      if (has_table) {
-        const bool full_tile = m0 + kTileM <= a.n_out && (a.n_out & 3) == 0 && ((uintptr_t)a.table & 15) == 0;
-        if (full_tile) {
-          for (int i = lane; i < a.K * (kTileM / 4); i += 32) {
-            const int k = i >> 5, r4 = (i & 31) * 4;
-            cp_async_16(slot + (uint32_t)((k * kTileM + r4) * 4), a.table + (size_t)k * a.n_out + m0 + r4);
-          }
-          cp_async_commit();
-          cp_async_wait<0>();
-        } else {
-          for (int i = lane; i < a.K * kTileM; i += 32) {
-            const int k = i >> 7, r = i & 127;
-            sts_u32(slot + (uint32_t)(i * 4), (m0 + r < a.n_out) ? (uint32_t)__ldg(a.table + (size_t)k * a.n_out + m0 + r) : 0xffffffffu);
-          }
-        }
-        __syncwarp();
-        if (a.tile_mask) {
-          mask = __ldg(a.tile_mask + rt);
-        } else {
-          mask = 0u;
-          for (int k = 0; k < a.K; ++k) {
-            int4 v;
-            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                         : "r"(slot + (uint32_t)((k * kTileM + lane * 4) * 4)));
-            const bool any = (v.x >= 0) | (v.y >= 0) | (v.z >= 0) | (v.w >= 0);
-            if (__any_sync(0xffffffffu, any)) mask |= 1u << k;
-          }
-        }
-      }
-      // step list: (active offset, chunk) pairs, padded with null steps up to kTsMinSteps
-      const int nact = __popc(mask);
-      const int nreal = nact * p.n_chunks;
-      const int nsteps = nreal < kTsMinSteps ? kTsMinSteps : nreal;
-      const uint32_t steps = slot + (uint32_t)tbl_bytes + 16u;
-      for (int i = lane; i < nsteps; i += 32) {
-        uint32_t e = (uint32_t)(has_table ? a.K : 1) << 8;         // null step
-        if (i < nreal) {
-          const int ks = i / p.n_chunks, c = i - ks * p.n_chunks;
-          // ks-th set bit of the mask
-          uint32_t m = mask;
-          for (int j = 0; j < ks; ++j) m &= m - 1u;
-          e = ((uint32_t)(__ffs(m) - 1) << 8) | (uint32_t)c;
-        }
-        sts_u16(steps + 2u * (uint32_t)i, e);
-      }
-      if (lane == 0) sts_u32(slot + (uint32_t)tbl_bytes, (uint32_t)nsteps);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tbl_full[it & 1]);
-    }
-  } else if (warp == kTsWarpB) {
-    // ================================================================= weight tiles: one bulk copy per step
-    int it = 0, s = 0;
-    uint32_t use = 0;
-    const int knull = has_table ? a.K : 1;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      const int rt = w / n_ntiles, nt = w - rt * n_ntiles;
-      mbar_wait(&tbl_full[it & 1], (uint32_t)(it >> 1) & 1u);
-      const uint32_t slot = sTbl_u32 + (uint32_t)((it & 1) * slot_bytes);
-      const int nsteps = (int)lds_u32(slot + (uint32_t)tbl_bytes);
-      const uint32_t steps = slot + (uint32_t)tbl_bytes + 16u;
-      const uint8_t* wp = (const uint8_t*)a.w_packed_ts + (size_t)nt * a.K * p.n_chunks * B_BYTES;
-      for (int t = 0; t < nsteps; ++t) {
-        const uint32_t st = lds_u16(steps + 2u * (uint32_t)t);
-        int k = (int)(st >> 8);
-        const int c = (int)(st & 255u);
-        if (k == knull) k = 0;                 // a null step multiplies all-zero A rows: any weight tile will do
-        if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
-        if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full[s], B_BYTES);
-          bulk_copy_g2s(sB + s * B_BYTES, wp + ((size_t)k * p.n_chunks + c) * B_BYTES, B_BYTES, &full[s]);
-        }
-        if (++s == STAGES) { s = 0; ++use; }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tbl_empty[it & 1]);
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full_u32 + 8u * gs) : "memory");
+      if (traced && quad == 0 && g < 256) UD3D_TS_TR(8 * g + 4);
+      g += kTsTurns;
     }
   } else {
+   // (one setmaxnreg for the whole control warpgroup, before its warps part ways)
+   UD3D_TS_SETMAXNREG("dec", kTsRegsCtl);
+   if (warp < kTsWarpMma) {
+    // ================================================================= weight tiles: 16-byte async copies (LDGSTS), the two
+    //                                                                   warps take alternate K-steps
+    const int bw = warp - kTsWarpB;
+    constexpr int kPer = N_TILE * 8 / 32;                // 16-byte pieces per lane and step
+    uint32_t s = (uint32_t)bw, ph = 1u;
+    if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
+    uint32_t g = 0;                                      // global step index
+    int gtr = bw;
+    const uint32_t sB_u32 = smem_u32(sB) + (uint32_t)lane * 16u;
+    uint32_t mnext = (has_table && (int)blockIdx.x < n_items) ? ldg_u32_raw(a.tile_mask + blockIdx.x / n_ntiles) : 1u;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const int rt = w / n_ntiles, nt = w - rt * n_ntiles;
+      uint32_t m = (has_table && mnext) ? mnext : 1u;
+      if (has_table && w + (int)gridDim.x < n_items) mnext = ldg_u32_raw(a.tile_mask + (w + (int)gridDim.x) / n_ntiles);
+      const uint8_t* wp = (const uint8_t*)a.w_packed_ts + (size_t)nt * a.K * p.n_chunks * B_BYTES + lane * 16;
+      while (m) {
+        const int k = __ffs(m) - 1;
+        m &= m - 1u;
+        for (int c = 0; c < p.n_chunks; ++c, ++g) {
+          if ((g & 1u) != (uint32_t)bw) continue;
+          mbar_wait(&empty[s], ph);
+          const uint8_t* src = wp + ((size_t)k * p.n_chunks + c) * B_BYTES;
+          if (kBulkB) {
+            if (elect_one_sync()) {
+              mbar_arrive_expect_tx(&full[s], B_BYTES);
+              bulk_copy_g2s(sB + s * B_BYTES, src - lane * 16, B_BYTES, &full[s]);
+            }
+          } else {
+            const uint32_t dst = sB_u32 + s * (uint32_t)B_BYTES;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) cp_async_16(dst + (uint32_t)i * 512u, src + i * 512);
+            cp_async_mbar_arrive_noinc(&full[s]);
+          }
+          gtr += 2;
+          s += 2u;
+          if (s >= STAGES) { s -= STAGES; ph ^= 1u; }
+        }
+      }
+    }
+   } else if (warp == kTsWarpMma) {
     // ================================================================= MMA issue (whole warp converged, elect.sync)
     const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
+    const uint32_t empty_u32 = smem_u32(empty);
     int it = 0;
     uint32_t gbase = 0;             // K-steps issued so far by this CTA: ring stage = gbase % STAGES, use = gbase / STAGES
+    uint32_t mnext = (has_table && (int)blockIdx.x < n_items) ? ldg_u32_raw(a.tile_mask + blockIdx.x / n_ntiles) : 1u;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      mbar_wait(&tbl_full[it & 1], (uint32_t)(it >> 1) & 1u);
-      const int nsteps = (int)lds_u32(sTbl_u32 + (uint32_t)((it & 1) * slot_bytes + tbl_bytes));
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tbl_empty[it & 1]);         // (only the step count is needed)
+      const int nsteps = __popc((has_table && mnext) ? mnext : 1u) * p.n_chunks;
+      if (has_table && w + (int)gridDim.x < n_items) mnext = ldg_u32_raw(a.tile_mask + (w + (int)gridDim.x) / n_ntiles);
       const int buf = it & 1;
       if (it >= 2) mbar_wait(&acc_empty[buf], (uint32_t)((it >> 1) - 1) & 1u);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N_TILE);
+      if (it < 64) UD3D_TS_TR(2048 + 4 * it + 2);
       int t = 0;
       uint32_t s = gbase % STAGES, use = gbase / STAGES;
       while (t < nsteps) {
@@ -452,37 +481,46 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
         s = 0;
       }
       gbase += (uint32_t)nsteps;
-      umma_commit_elect(&acc_full[buf]);
+      if (!(p.dbg & 1)) {
+        umma_commit_elect(&acc_full[buf]);
+      } else if (lane == 0) {
+        mbar_arrive(&acc_full[buf]);
+      }
     }
     __syncwarp();
+   }
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (p.trace != nullptr && p.trace_block == -3 && tid == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[4 * blockIdx.x + 1] = (long long)gt;
+  }
 }
 
 template <int N_TILE>
-static size_t ts_smem_bytes(int K, bool has_table) {
-  const size_t slot = (has_table ? (size_t)(K + 1) * kTileM * 4 : 0) + 16 + kTsMaxSteps * 2;
-  return 1024 + (size_t)TsCfg<N_TILE>::kStages * N_TILE * 128 + kTsEpiWarps * 4096 + 2 * slot + (16 + 8) * 8 + 16;
+static size_t ts_smem_bytes() {
+  return 1024 + (size_t)TsCfg<N_TILE>::kStages * N_TILE * 128 + kTsEpiWarps * 4096 + kTsProdWarps * 1024 + (16 + 4) * 8 + 16;
 }
 
 template <int N_TILE>
 static int launch_ts(const GemmParams& p, int num_sms, cudaStream_t st) {
-  const size_t smem = ts_smem_bytes<N_TILE>(p.a.K, p.a.table != nullptr);
+  const size_t smem = ts_smem_bytes<N_TILE>();
   // per-device configuration (cudaFuncSetAttribute applies to the current device)
-  static size_t configured[64] = {0};
+  static bool configured[64] = {false};
   int dev = 0;
   UD3D_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) { set_error("ud3d_gemm_fwd: device index %d out of range", dev); return UD3D_EINVAL; }
-  if (smem > configured[dev]) {
+  if (!configured[dev]) {
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_ts_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // leave the rest of the 256 KB to L1: gathered rows are re-used across the kernel offsets of a tile
     int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
     if (pct > 100) pct = 100;
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_ts_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-    configured[dev] = smem;
+    configured[dev] = true;
   }
   const int n_items = cdiv(p.a.n_out, kTileM) * cdiv(p.a.c_out, N_TILE);
   const int grid = n_items < num_sms ? n_items : num_sms;
