@@ -52,8 +52,8 @@ def main():
         tb, tm, pm = lv.subm_conv
         outs = {}
         for order, (t_, m_, p_) in (("canonical", (lv.subm, lv.subm_mask, None)), ("regrouped", (tb, tm, pm))):
-            for path, fl in (("smem", 4096), ("tmem", 0)):
-                lib.ud3d_debug_set_flags(fl)
+            for path, fl in (("smem", 4096), ("tmem", 8192)):
+                lib.ud3d_debug_set_flags(fl | 8192 if not (fl & 4096) else fl)
                 act = torch.zeros_like(xin); raw = torch.zeros_like(xin)
                 run = lambda: ops.gemm(xs, w, table=t_, tile_mask=m_, in_split=True, residual=res, out=raw, acts=[(act, one, zero)], row_perm=p_)
                 try:
@@ -78,8 +78,8 @@ def main():
         w = ops.PackedWeight(torch.randn(co, ci, device="cuda") * 0.05)
         b = torch.randn(co, device="cuda")
         outs = {}
-        for path, fl in (("smem", 4096), ("tmem", 0)):
-            lib.ud3d_debug_set_flags(fl)
+        for path, fl in (("smem", 4096), ("tmem", 8192)):
+            lib.ud3d_debug_set_flags(fl | 8192 if not (fl & 4096) else fl)
             act = torch.zeros(T, co, device="cuda")
             run = lambda: ops.gemm(xs, w, in_split=True, bias=b, act=actf, no_raw=True, acts=[(act, None, None, False)])
             try:

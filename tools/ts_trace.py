@@ -37,9 +37,9 @@ for level in [int(v) for v in os.environ.get("LEVELS", "0,1").split(",")]:
     tb, tm, pm = lv.subm_conv
     run = lambda: ops.gemm(xs, w, table=tb, tile_mask=tm, in_split=True, no_raw=True, acts=[(act, one, zero)], row_perm=pm)
     for fl in (0,):
-        lib.ud3d_debug_set_flags(fl)
+        lib.ud3d_debug_set_flags(fl | 8192 if not (fl & 4096) else fl)
         print(f"level {level} c={c} flags {fl:3d}: {timed(run):8.1f} us", flush=True)
-    lib.ud3d_debug_set_flags(int(os.environ.get("TRACE_FLAGS", "0")))
+    lib.ud3d_debug_set_flags(int(os.environ.get("TRACE_FLAGS", "0")) | 8192)
     trace = torch.zeros(4096, dtype=torch.int64, device="cuda")
     lib.ud3d_debug_set_trace(C.c_void_p(trace.data_ptr()), -3)
     run(); torch.cuda.synchronize()

@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
       const int which = id >> 9, rem = id & 511;
       const int key = rem >> 3, j = rem & 7;
       const int kr = kv0 + key;
-      const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + j * 16;
-      uint8_t* dst = (which ? sV[stage] : sK[stage]) + key * 128 + ((opf_logical_piece(j) ^ (key & 7)) << 4);
+      const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + opf_mem_piece(j) * 16;
+      uint8_t* dst = (which ? sV[stage] : sK[stage]) + key * 128 + ((j ^ (key & 7)) << 4);      // lane j = logical piece j
       cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
     }
     cp_async_commit();
@@ -604,8 +604,8 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
   for (int id = tid; id < kTcQ * 8; id += kTcThreads) {
     const int r = id >> 3, j = id & 7;
     const int row = q0 + r;
-    const uint8_t* src = qkv + (size_t)(t0 + (row < T ? row : 0)) * ldb + (size_t)h * 128 + j * 16;
-    cp_async_16_zfill(smem_u32(sQ + r * 128 + ((opf_logical_piece(j) ^ (r & 7)) << 4)), src, row < T ? 16u : 0u);
+    const uint8_t* src = qkv + (size_t)(t0 + (row < T ? row : 0)) * ldb + (size_t)h * 128 + opf_mem_piece(j) * 16;
+    cp_async_16_zfill(smem_u32(sQ + r * 128 + ((j ^ (r & 7)) << 4)), src, row < T ? 16u : 0u);
   }
   cp_async_commit();
   cp_async_wait<0>();
@@ -718,8 +718,8 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
         const int which = id >> 9, rem = id & 511;
         const int key = rem >> 3, jj = rem & 7;
         const int kr = kv0 + key;
-        const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + jj * 16;
-        uint8_t* dst = (which ? sV : sK) + st * 8192 + key * 128 + ((opf_logical_piece(jj) ^ (key & 7)) << 4);
+        const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + opf_mem_piece(jj) * 16;
+        uint8_t* dst = (which ? sV : sK) + st * 8192 + key * 128 + ((jj ^ (key & 7)) << 4);
         cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
       }
       cp_async_commit();

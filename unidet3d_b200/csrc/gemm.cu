@@ -20,6 +20,7 @@
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / activation / residual -> fp32 and/or operand-form stores.
 // HBM/L2 roofline: see DESIGN.md section 4 (algorithmic bytes per layer).
 #include "gemm_common.cuh"
+#include <stdlib.h>
 
 
 namespace ud3d {
@@ -279,9 +280,12 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         constexpr int NI = 32 / WPG;
         const int grp = warp / WPG, half = warp - grp * WPG;
         const int g = lane >> 3, j = lane & 7;
-        const int jl = opf_logical_piece(j);      // memory piece j holds logical piece jl of the K-major tile
-        const uint32_t sw0 = (uint32_t)((jl ^ g) << 4), sw1 = (uint32_t)(((jl ^ g) ^ 4) << 4);   // (4 i + g) & 7 = 4 (i & 1) + g
-        const uint8_t* src_base = (const uint8_t*)a.in + j * 16;
+        // lane j fills LOGICAL piece j of the K-major tile, i.e. it reads memory piece opf_mem_piece(j) of the row: the 8
+        // lanes of a row still read one 128-byte line, and consecutive lanes keep writing consecutive 16-byte chunks of
+        // shared memory (permuting the DESTINATION instead cost 35 % on the level-1 convolutions: the kernel runs at the
+        // shared-memory port, and LDGSTS writes of adjacent lanes to adjacent chunks are cheaper)
+        const uint32_t sw0 = (uint32_t)((j ^ g) << 4), sw1 = (uint32_t)(((j ^ g) ^ 4) << 4);   // (4 i + g) & 7 = 4 (i & 1) + g
+        const uint8_t* src_base = (const uint8_t*)a.in + opf_mem_piece(j) * 16;
         const uint32_t sA_lane = smem_u32(sA) + (uint32_t)((half * (kTileM / WPG) + g) * 128);
         long long* tr = (traced && tid == 0) ? p.trace : nullptr;
         if (tr) { tr[1023] = nsteps; tr[1022] = clock64(); }
@@ -856,7 +860,11 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
     }
   }
   // operand-form inputs of launches that fill the GPU: the A operand goes global -> registers -> TMEM (gemm_ts.cu)
-  if (args->in_split && args->w_packed_ts && splits == 1 && nts <= 160 && !(g_dbg & 4096) &&
+  // Opt-in (environment UD3D_GEMM_TS=1, or ud3d_debug_set_flags bit 8192): measured on B200 it wins with warm caches
+  // (graph-replayed level-1 SubM3 32->32: 127 vs 182 us, 64->64: 61 vs 92 us) but not inside the real step, where every
+  // launch starts on cold inputs (ncu launch list: 112 vs 103 us, 65 vs 53 us) -- see DESIGN.md section 4.
+  static const bool ts_env = [] { const char* e = getenv("UD3D_GEMM_TS"); return e && e[0] == '1'; }();
+  if ((ts_env || (g_dbg & 8192)) && args->in_split && args->w_packed_ts && splits == 1 && nts <= 160 && !(g_dbg & 4096) &&
       (!args->table || args->tile_mask)) {
     UD3D_CHECK_ARG(((uintptr_t)args->w_packed_ts & 127) == 0, "ud3d_gemm_fwd: w_packed_ts misaligned");
     UD3D_CHECK_ARG(((uintptr_t)args->in & 31) == 0 && args->ld_in % 8 == 0, "ud3d_gemm_fwd: operand-form input must be 32-byte aligned");
