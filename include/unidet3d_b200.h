@@ -159,6 +159,9 @@ typedef struct {
    * in_split != 0: `in` holds the split-bf16 operand form of the ALREADY ACTIVATED input (ld_in, c_in in
    * channels = 4-byte units as for fp32; c_in % 32 == 0); it is gathered with cp.async straight into the
    * swizzled tile, no per-use conversion.  in_scale must be NULL.
+   * in_split == 2: the same data in the INTERLEAVED operand form (per 32-channel chunk the 16-byte pieces in the order
+   * hi(ch 0-7), lo(ch 0-7), hi(ch 8-15), lo(ch 8-15), ...): the input form of the experimental kernel that gathers
+   * the A operand through registers into TMEM (needs w_packed_ts; not used by the product path).
    * out_act[i] != NULL: additionally store relu(result * act_scale[i] + act_shift[i]) in operand form
    * (the consumer conv's folded BatchNorm+ReLU, applied ONCE per element instead of once per use);
    * c_out % 32 == 0.  no_raw != 0: skip the fp32 store to `out` (still used as scratch by split-K). */

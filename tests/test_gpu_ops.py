@@ -533,13 +533,10 @@ def test_gt_target_helpers_vs_reference_fixture(golden_dir):
 @pytest.mark.parametrize("c_in,c_out,K,n", [(32, 32, 27, 40000), (64, 64, 27, 24000), (64, 32, 27, 24000), (128, 64, 8, 30000),
                                             (256, 768, 1, 20000), (1024, 256, 1, 20000), (32, 32, 27, 19000 + 77)])
 def test_gemm_tmem_operand_kernel(c_in, c_out, K, n):
-    """The opt-in kernel variant whose A operand goes global -> registers -> TMEM (gemm_ts.cu, ud3d_debug_set_flags bit
-    8192 / UD3D_GEMM_TS=1): same contract and tolerances as the shared-memory-operand kernel, with a rulebook + tile mask,
-    a row permutation, a ragged last tile, and as a dense GEMM."""
-    import ctypes as C
-    from unidet3d_b200 import ops, _lib
-    lib = _lib.load()
-    lib.ud3d_debug_set_flags.argtypes = [C.c_int]
+    """The experimental kernel variant whose A operand goes global -> registers -> TMEM (gemm_ts.cu; input in the
+    interleaved operand form, in_split=2): same contract and tolerances as the shared-memory-operand kernel, with a
+    rulebook + tile mask, a ragged last tile, and as a dense GEMM."""
+    from unidet3d_b200 import ops
     rng = np.random.default_rng(n + c_in)
     g = torch.Generator().manual_seed(n + c_out)
     x = torch.relu(torch.randn(n, c_in, generator=g))
@@ -547,6 +544,8 @@ def test_gemm_tmem_operand_kernel(c_in, c_out, K, n):
     res = torch.randn(n, c_out, generator=g)
     s1, h1 = torch.rand(c_out, generator=g) + 0.5, torch.randn(c_out, generator=g) * 0.3
     xs = split_encode(x).to(DEV)
+    xs_il = split_encode(x, interleaved=True).to(DEV)
+    assert torch.equal(ops.operand_form_interleave(xs).view(torch.int32), xs_il.view(torch.int32))
     if K > 1:
         table = _rand_table(rng, K, n, n, 0.35)
         # make some (tile, offset) pairs empty so that the tile masks differ between tiles
@@ -562,15 +561,11 @@ def test_gemm_tmem_operand_kernel(c_in, c_out, K, n):
         tb, mask = None, None
         ref = x @ w[:, 0].t() + res
     outs = []
-    for fl in (4096, 8192):
-        lib.ud3d_debug_set_flags(fl)
-        try:
-            a1 = torch.zeros(n, c_out, device=DEV)
-            out = ops.gemm(xs, ops.PackedWeight(w.to(DEV)), table=tb, tile_mask=mask, in_split=True, residual=res.to(DEV),
-                           acts=[(a1, s1.to(DEV), h1.to(DEV))])
-            torch.cuda.synchronize()
-        finally:
-            lib.ud3d_debug_set_flags(0)
+    for fl, xin in ((1, xs), (2, xs_il)):
+        a1 = torch.zeros(n, c_out, device=DEV)
+        out = ops.gemm(xin, ops.PackedWeight(w.to(DEV)), table=tb, tile_mask=mask, in_split=fl, residual=res.to(DEV),
+                       acts=[(a1, s1.to(DEV), h1.to(DEV))])
+        torch.cuda.synchronize()
         assert relerr(out, ref) < 2e-4, (fl, relerr(out, ref))
         assert relerr(split_decode(a1.cpu()), torch.relu(ref * s1 + h1)) < 2e-4
         outs.append(out)

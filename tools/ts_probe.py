@@ -52,10 +52,11 @@ def main():
         tb, tm, pm = lv.subm_conv
         outs = {}
         for order, (t_, m_, p_) in (("canonical", (lv.subm, lv.subm_mask, None)), ("regrouped", (tb, tm, pm))):
-            for path, fl in (("smem", 4096), ("tmem", 8192)):
-                lib.ud3d_debug_set_flags(fl | 8192 if not (fl & 4096) else fl)
+            for path, fl in (("smem", 1), ("tmem", 2)):
+                lib.ud3d_debug_set_flags(fl if fl > 2 else 0)
                 act = torch.zeros_like(xin); raw = torch.zeros_like(xin)
-                run = lambda: ops.gemm(xs, w, table=t_, tile_mask=m_, in_split=True, residual=res, out=raw, acts=[(act, one, zero)], row_perm=p_)
+                xin_ = xs if fl == 1 else ops.operand_form_interleave(xs)
+                run = lambda: ops.gemm(xin_, w, table=t_, tile_mask=m_, in_split=fl, residual=res, out=raw, acts=[(act, one, zero)], row_perm=p_)
                 try:
                     us = timed(run)
                 except Exception as e:  # noqa: BLE001
@@ -78,10 +79,11 @@ def main():
         w = ops.PackedWeight(torch.randn(co, ci, device="cuda") * 0.05)
         b = torch.randn(co, device="cuda")
         outs = {}
-        for path, fl in (("smem", 4096), ("tmem", 8192)):
-            lib.ud3d_debug_set_flags(fl | 8192 if not (fl & 4096) else fl)
+        for path, fl in (("smem", 1), ("tmem", 2)):
+            lib.ud3d_debug_set_flags(fl if fl > 2 else 0)
             act = torch.zeros(T, co, device="cuda")
-            run = lambda: ops.gemm(xs, w, in_split=True, bias=b, act=actf, no_raw=True, acts=[(act, None, None, False)])
+            xin_ = xs if fl == 1 else ops.operand_form_interleave(xs)
+        run = lambda: ops.gemm(xin_, w, in_split=fl, bias=b, act=actf, no_raw=True, acts=[(act, None, None, False)])
             try:
                 us = timed(run)
             except Exception as e:  # noqa: BLE001

@@ -35,11 +35,12 @@ for level in [int(v) for v in os.environ.get("LEVELS", "0,1").split(",")]:
     act = torch.empty_like(xin)
     one = torch.ones(c, device="cuda"); zero = torch.zeros(c, device="cuda")
     tb, tm, pm = lv.subm_conv
-    run = lambda: ops.gemm(xs, w, table=tb, tile_mask=tm, in_split=True, no_raw=True, acts=[(act, one, zero)], row_perm=pm)
+    xs_il = ops.operand_form_interleave(xs)
+    run = lambda: ops.gemm(xs_il, w, table=tb, tile_mask=tm, in_split=2, no_raw=True, acts=[(act, one, zero)], row_perm=pm)
     for fl in (0,):
-        lib.ud3d_debug_set_flags(fl | 8192 if not (fl & 4096) else fl)
+        lib.ud3d_debug_set_flags(fl if fl > 2 else 0)
         print(f"level {level} c={c} flags {fl:3d}: {timed(run):8.1f} us", flush=True)
-    lib.ud3d_debug_set_flags(int(os.environ.get("TRACE_FLAGS", "0")) | 8192)
+    lib.ud3d_debug_set_flags(int(os.environ.get("TRACE_FLAGS", "0")))
     trace = torch.zeros(4096, dtype=torch.int64, device="cuda")
     lib.ud3d_debug_set_trace(C.c_void_p(trace.data_ptr()), -3)
     run(); torch.cuda.synchronize()

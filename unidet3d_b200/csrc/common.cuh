@@ -315,14 +315,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t N) {
 }
 
 // ---- operand form of a feature map: per row, per 32-channel chunk, 128 bytes = 8 pieces of
-// 16 bytes; memory piece 2q = bf16 hi of channels 8q..8q+7, piece 2q+1 = bf16 lo of the same channels.  One 32-byte
-// load (LDG.256) is thus one thread's share of a tcgen05.st.16x256b into a TMEM A operand.  "Logical" piece L of the
-// K-major shared-memory tiles: L = 0..3 hi of channel quarter L, L = 4..7 lo of quarter L - 4.
-__host__ __device__ __forceinline__ constexpr int opf_mem_piece(int L) { return ((L & 3) << 1) | (L >> 2); }
-__host__ __device__ __forceinline__ constexpr int opf_logical_piece(int m) { return (m >> 1) | ((m & 1) << 2); }
+// 16 bytes: pieces 0..3 = bf16 hi of channels 0..31, pieces 4..7 = bf16 lo -- byte for byte the 128-byte row of the
+// K-major shared-memory tile, so that lane j of a gather copies piece j to chunk j (^ swizzle).  (An interleaved layout
+// -- hi / lo of 8 channels next to each other, one 32-byte load = one thread's share of a tcgen05.st into a TMEM A
+// operand, the input form of the experimental kernel in gemm_ts.cu -- was measured 35 % slower for the cp.async gather:
+// any non-XOR permutation between lane order and address order inside the 128-byte row costs LDGSTS efficiency.)
+// Every producer / consumer addresses the layout through these helpers.
+__host__ __device__ __forceinline__ constexpr int opf_mem_piece(int L) { return L; }        // logical piece -> memory piece
 // byte offset of the bf16 hi of channel ch (0..31) inside a 128-byte row-chunk; its lo part is kOpfLo bytes further
-__host__ __device__ __forceinline__ constexpr int opf_hi_off(int ch) { return ((ch >> 3) << 5) | ((ch & 7) << 1); }
-constexpr int kOpfLo = 16;
+__host__ __device__ __forceinline__ constexpr int opf_hi_off(int ch) { return ch << 1; }
+constexpr int kOpfLo = 64;
 
 // fp32 -> bf16 hi + bf16 lo (x ~= hi + lo, |err| <~ 2^-17 |x|)
 // Packed conversions (one F2FP.BF16.PACK_AB per pair, FMA-pipe) instead of scalar __float2bfloat16_rn (F2F, quarter-rate

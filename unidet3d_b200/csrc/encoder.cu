@@ -699,8 +699,8 @@ __global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t*
       uint4* dst = (uint4*)(out + (size_t)(t0 + grow) * ldo + (size_t)h * 128);
 #pragma unroll
       for (int c4 = 0; c4 < 4; ++c4) {
-        dst[2 * c4] = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
-        dst[2 * c4 + 1] = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
+        dst[opf_mem_piece(c4)] = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
+        dst[opf_mem_piece(4 + c4)] = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
       }
     }
   } else if (warp == kTcSoftmaxWarps) {

@@ -280,10 +280,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         constexpr int NI = 32 / WPG;
         const int grp = warp / WPG, half = warp - grp * WPG;
         const int g = lane >> 3, j = lane & 7;
-        // lane j fills LOGICAL piece j of the K-major tile, i.e. it reads memory piece opf_mem_piece(j) of the row: the 8
-        // lanes of a row still read one 128-byte line, and consecutive lanes keep writing consecutive 16-byte chunks of
-        // shared memory (permuting the DESTINATION instead cost 35 % on the level-1 convolutions: the kernel runs at the
-        // shared-memory port, and LDGSTS writes of adjacent lanes to adjacent chunks are cheaper)
+        // lane j copies piece j of the row-chunk to chunk j of the K-major tile row (opf_mem_piece is the identity)
         const uint32_t sw0 = (uint32_t)((j ^ g) << 4), sw1 = (uint32_t)(((j ^ g) ^ 4) << 4);   // (4 i + g) & 7 = 4 (i & 1) + g
         const uint8_t* src_base = (const uint8_t*)a.in + opf_mem_piece(j) * 16;
         const uint32_t sA_lane = smem_u32(sA) + (uint32_t)((half * (kTileM / WPG) + g) * 128);
@@ -662,8 +659,8 @@ __global__ void __launch_bounds__(256) act_split_kernel(const float* __restrict_
 #pragma unroll
     for (int e = 0; e < 4; ++e) split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
     uint4* dst = (uint4*)((uint8_t*)(out + (size_t)row * ld_out) + (size_t)ch * 128);
-    dst[2 * q] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    dst[2 * q + 1] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    dst[opf_mem_piece(q)] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    dst[opf_mem_piece(4 + q)] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
 }
 
@@ -860,12 +857,14 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
     }
   }
   // operand-form inputs of launches that fill the GPU: the A operand goes global -> registers -> TMEM (gemm_ts.cu)
-  // Opt-in (environment UD3D_GEMM_TS=1, or ud3d_debug_set_flags bit 8192): measured on B200 it wins with warm caches
+  // The experimental TMEM-operand kernel (gemm_ts.cu) takes its input in the INTERLEAVED operand form (in_split == 2,
+  // ops.operand_form_interleave); the product path does not use it: measured on B200 it wins with warm caches
   // (graph-replayed level-1 SubM3 32->32: 127 vs 182 us, 64->64: 61 vs 92 us) but not inside the real step, where every
   // launch starts on cold inputs (ncu launch list: 112 vs 103 us, 65 vs 53 us) -- see DESIGN.md section 4.
-  static const bool ts_env = [] { const char* e = getenv("UD3D_GEMM_TS"); return e && e[0] == '1'; }();
-  if ((ts_env || (g_dbg & 8192)) && args->in_split && args->w_packed_ts && splits == 1 && nts <= 160 && !(g_dbg & 4096) &&
-      (!args->table || args->tile_mask)) {
+  if (args->in_split == 2) {
+    UD3D_CHECK_ARG(args->w_packed_ts && splits == 1 && nts <= 160 && (!args->table || args->tile_mask),
+                   "ud3d_gemm_fwd: the interleaved operand form (in_split == 2) is the input of the TMEM-operand kernel only: it needs "
+                   "w_packed_ts, a tile mask with a table, c_out <= 160 per tile and a launch that fills the GPU");
     UD3D_CHECK_ARG(((uintptr_t)args->w_packed_ts & 127) == 0, "ud3d_gemm_fwd: w_packed_ts misaligned");
     UD3D_CHECK_ARG(((uintptr_t)args->in & 31) == 0 && args->ld_in % 8 == 0, "ud3d_gemm_fwd: operand-form input must be 32-byte aligned");
     const int sms = device_sms(nullptr);

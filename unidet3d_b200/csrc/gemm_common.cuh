@@ -147,8 +147,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
       uint4 t[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        t[2 * j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-        t[2 * j + 1] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        t[opf_mem_piece(j)] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        t[opf_mem_piece(4 + j)] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
       }
       warp_store_rows(stage, t, valid ? (uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4 : nullptr, lane,
                       (p.dbg & 64) != 0);
@@ -193,8 +193,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      dst[2 * j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-      dst[2 * j + 1] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      dst[opf_mem_piece(j)] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      dst[opf_mem_piece(4 + j)] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
     }
   }
 }

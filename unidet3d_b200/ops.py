@@ -204,7 +204,7 @@ def _gemm_args(x, pw_K, c_in, c_out, n_out, table, tile_mask, out, in_scale, in_
     a.act = {None: 0, "none": 0, "relu": 1, "gelu": 2}[act]
     a.residual = residual.data_ptr() if residual is not None else None
     a.ld_res = residual.stride(0) if residual is not None else 0
-    a.in_split = 1 if in_split else 0
+    a.in_split = int(in_split)
     a.no_raw = 1 if no_raw else 0
     norelu = 0
     for i, spec in enumerate(acts or ()):
@@ -244,6 +244,14 @@ def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = No
                    residual, w.data.data_ptr(), in_split, no_raw, acts, row_perm, w.data_ts.data_ptr())
     check(_L().ud3d_gemm_fwd(C.byref(a), _stream()), "ud3d_gemm_fwd")
     return out
+
+
+def operand_form_interleave(x_split: torch.Tensor) -> torch.Tensor:
+    """operand form -> interleaved operand form (``gemm(..., in_split=2)``, the experimental TMEM-operand kernel): per
+    32-channel chunk the eight 16-byte pieces [h0 h1 h2 h3 l0 l1 l2 l3] become [h0 l0 h1 l1 h2 l2 h3 l3]."""
+    n, c = x_split.shape
+    v = x_split.contiguous().view(n, c // 32, 2, 4, 4)             # [row, chunk, hi|lo, quarter, 4 words]
+    return v.permute(0, 1, 3, 2, 4).contiguous().view(n, c)
 
 
 def act_split(raw: torch.Tensor, scale=None, shift=None, relu: bool = True, out: Optional[torch.Tensor] = None):
