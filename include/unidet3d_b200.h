@@ -192,6 +192,28 @@ int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scal
  * (diagnostic cross-check of the tensor-core path; not used by the product path) */
 int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream);
 
+/* ------------------------------------------------------------------ training side of the backbone
+ * Train-mode (Sync)BatchNorm of the reference (spconv_unet.py:119-124, unidet3d.py:104-107; torch.nn.SyncBatchNorm,
+ * eps 1e-4, momentum 0.1): statistics over ALL active voxels of the (global) batch.
+ *   ud3d_bn_batch_sums : sums[0..C) = sum_r x[r,c], sums[C..2C) = sum_r x[r,c]^2 (fp64, deterministic order).
+ *     For SyncBatchNorm the caller all-reduces `sums` (and the row count) across ranks before the fold.
+ *   ud3d_bn_train_fold : mean / biased variance -> scale = gamma / sqrt(var + eps), shift = beta - mean * scale (the
+ *     form ud3d_gemm_args.in_scale / in_shift and ud3d_act_split consume), running_mean / running_var updated in place
+ *     (unbiased variance, like torch); save_mean / save_invstd optional (for the backward pass). */
+size_t ud3d_bn_batch_sums_workspace_bytes(int n, int C);
+int ud3d_bn_batch_sums(const float* x, int ld, int n, int C, double* sums, void* ws, size_t ws_bytes, void* stream);
+int ud3d_bn_train_fold(const double* sums, double count, int C, const float* gamma, const float* beta, float eps,
+                       float momentum, float* running_mean, float* running_var, float* scale, float* shift,
+                       float* save_mean, float* save_invstd, void* stream);
+/* Weight gradient of a sparse convolution / linear layer (autograd of spconv's conv forward, spconv_unet.py:37-72):
+ *   dw[co][k][ci] (+)= sum_o dy[o][co] * x[table[k][o]][ci]      (layout of the reference parameter [C_out, K, C_in])
+ * x = the conv's input as it entered the contraction (after its BatchNorm + ReLU), fp32; deterministic.  The input
+ * gradient needs no kernel of its own: it is ud3d_gemm_fwd on dy with the transposed weight and the transposed
+ * rulebook (SubM3: the same table with the kernel offsets reversed; k2s2 <-> its inverse conv's table). */
+size_t ud3d_conv_wgrad_workspace_bytes(int n_out, int K, int c_in, int c_out);
+int ud3d_conv_wgrad(const float* x, int ld_x, int c_in, const float* dy, int ld_dy, int c_out, const int32_t* table,
+                    int n_out, int K, float* dw, int accumulate, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ superpoint pooling
  * reference: torch_scatter.scatter_mean at unidet3d.py:130 (features, with the output
  * BatchNorm+ReLU of unidet3d.py:104-111,129 and the x.features[inverse_mapping] gather fused)

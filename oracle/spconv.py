@@ -30,8 +30,12 @@ def sparse_conv(feats, table, w_koc, n_out=None):
     return out
 
 
+TRAIN_MODE = False      # True: batch statistics (momentum 0.1, running statistics updated in place), like module.train()
+
+
 def bn_relu(x, bn, eps=1e-4, relu=True):
-    """Eval-mode BatchNorm1d(eps=1e-4) + ReLU (spconv_unet.py:119-124, unidet3d.py:104-111)."""
+    """BatchNorm1d(eps=1e-4, momentum=0.1) + ReLU (spconv_unet.py:119-124, unidet3d.py:104-111): eval mode by default,
+    train mode (statistics over all rows = all active voxels of the batch) when ``TRAIN_MODE`` is set."""
     w, b, mean, var = bn
-    y = torch.nn.functional.batch_norm(x, mean, var, w, b, False, 0.0, eps)
+    y = torch.nn.functional.batch_norm(x, mean, var, w, b, TRAIN_MODE, 0.1 if TRAIN_MODE else 0.0, eps)
     return torch.relu(y) if relu else y

@@ -18,15 +18,20 @@ in the CUDA path) is ascending lexicographic (b, x, y, z).
 import numpy as np
 
 
-def point_coords(points_list, voxel_size):
-    """Per-point int32 (b,x,y,z) and fp32 6-ch features (before dedup)."""
+def point_coords(points_list, voxel_size, elastic_list=None):
+    """Per-point int32 (b,x,y,z) and fp32 6-ch features (before dedup).  ``elastic_list`` (unidet3d.py:162-166): per
+    scene fp32 [n,3] coordinates already in voxel units; coords = floor(el - el.min(0)), features unchanged."""
     coords, feats = [], []
     vs = np.float32(voxel_size)
     for b, p in enumerate(points_list):
         p = np.asarray(p, dtype=np.float32)
         xyz = p[:, :3]
         mn = xyz.min(0)
-        c = np.floor((xyz - mn) / vs).astype(np.int32)
+        if elastic_list is not None:
+            el = np.asarray(elastic_list[b], dtype=np.float32)
+            c = np.floor(el - el.min(0)).astype(np.int32)
+        else:
+            c = np.floor((xyz - mn) / vs).astype(np.int32)
         mean = (xyz.astype(np.float64).sum(0) / len(xyz)).astype(np.float32)
         f = np.concatenate([p[:, 3:], xyz - mean], 1).astype(np.float32)
         coords.append(np.concatenate([np.full((len(c), 1), b, np.int32), c], 1))
@@ -40,9 +45,9 @@ def linear_key(coords, dims=None):
     return ((c[:, 0] * (1 << 16) + c[:, 1]) * (1 << 16) + c[:, 2]) * (1 << 16) + c[:, 3]
 
 
-def voxelize(points_list, voxel_size, min_spatial_shape=128):
+def voxelize(points_list, voxel_size, min_spatial_shape=128, elastic_list=None):
     """-> coords int32 [M,4], feats fp32 [M,6], inverse int64 [N], spatial_shape int[3]."""
-    bcoords, feats = point_coords(points_list, voxel_size)
+    bcoords, feats = point_coords(points_list, voxel_size, elastic_list)
     spatial_shape = np.clip(bcoords[:, 1:].max(0) + 1, min_spatial_shape, None).astype(np.int64)
     key = linear_key(bcoords)
     uniq, first, inverse, counts = np.unique(key, return_index=True, return_inverse=True,

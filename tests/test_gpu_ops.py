@@ -570,3 +570,30 @@ def test_gemm_tmem_operand_kernel(c_in, c_out, K, n):
         assert relerr(split_decode(a1.cpu()), torch.relu(ref * s1 + h1)) < 2e-4
         outs.append(out)
     assert relerr(outs[1], outs[0]) < 1e-5
+
+
+def test_collate_with_elastic_coords():
+    """UniDet3D.collate with the ElasticTransfrom side input (unidet3d.py:162-166): voxel coordinates from the distorted
+    coordinates (already in voxel units), features from the original points -- bit-exact vs the oracle."""
+    import unidet3d_b200 as u
+    from unidet3d_b200 import configs
+    cfg = configs.model_cfg(("scannet",), topk_insts=100)
+    n, v, a, c = SCENE_PRESETS["tiny"]
+    cfg["voxel_size"] = v
+    model = u.MODELS.build(cfg).eval().to(DEV)
+    rng = np.random.default_rng(5)
+    pts = [make_scene(40 + i, n + 50 * i, a, c)[0] for i in range(3)]
+    # smooth distortion of the voxel-unit coordinates, like transforms_3d.py:39-43
+    els = [(p[:, :3] / v + 3.0 * np.sin(p[:, :3] * 2.0 + rng.uniform(0, 6, 3))).astype(np.float32) for p in pts]
+    coords, feats, inverse, shape = ovox.voxelize(pts, v, 128, elastic_list=els)
+    P = torch.as_tensor(np.concatenate(pts)).to(DEV)
+    E = torch.as_tensor(np.concatenate(els)).to(DEV)
+    offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device=DEV)
+    x, inv = model.collate(P, offs, 3, E)
+    assert np.array_equal(x.indices.cpu().numpy(), coords)
+    assert np.array_equal(inv.cpu().numpy().astype(np.int64), inverse)
+    assert x.spatial_shape == list(shape)
+    assert relerr(x.features, feats) < 1e-5
+    # and it differs from the plain voxelisation
+    x0, _ = model.collate(P, offs, 3)
+    assert x0.indices.shape != x.indices.shape or not torch.equal(x0.indices, x.indices)

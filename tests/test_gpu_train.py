@@ -1,0 +1,151 @@
+"""Training-side kernels of the backbone (SURVEY.md 8a R6 second half, 8f rank 2) against torch (CPU) autograd / the
+oracle: train-mode (Sync)BatchNorm statistics + running-stat update, sparse-conv weight gradient, sparse-conv input
+gradient (= the forward gather-GEMM over the transposed rulebook), train-mode backbone forward."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import spconv as ospconv, unet as ounet, rulebook as orb
+from oracle.spconv import sparse_conv
+from unidet3d_b200.synthetic import make_scene, SCENE_PRESETS
+
+DEV = "cuda"
+
+
+def relerr(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("n,c", [(1, 32), (777, 32), (20000, 96), (5001, 320)])
+def test_bn_train_statistics(n, c):
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn(n, c, generator=g) * 2 + torch.randn(c, generator=g)
+    bn = torch.nn.BatchNorm1d(c, eps=1e-4, momentum=0.1)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5); bn.bias.copy_(torch.randn(c, generator=g))
+        bn.running_mean.copy_(torch.randn(c, generator=g)); bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    import copy
+    ref_bn = copy.deepcopy(bn).train()
+    if n > 1:
+        ref = ref_bn(x)
+    bn_d = copy.deepcopy(bn).to(DEV)
+    sc, sh, mean, invstd = ops.bn_train(x.to(DEV), bn_d)
+    y = x.to(DEV) * sc + sh
+    if n > 1:
+        assert relerr(y, ref) < 1e-5
+        assert relerr(bn_d.running_mean, ref_bn.running_mean) < 1e-5
+        assert relerr(bn_d.running_var, ref_bn.running_var) < 1e-5
+        assert int(bn_d.num_batches_tracked) == 1
+    assert relerr(mean, x.double().mean(0)) < 1e-5
+
+
+@pytest.mark.parametrize("c_in,c_out,K,n", [(32, 32, 27, 3000), (64, 32, 27, 900), (6, 32, 27, 5000), (96, 64, 8, 2000),
+                                            (256, 100, 1, 1500)])
+def test_conv_weight_and_input_gradients_vs_autograd(c_in, c_out, K, n):
+    """dW and dX of  y = sum_k x[table[k]] @ W_k  against torch autograd on the oracle's gather -> mm -> index_add_."""
+    from unidet3d_b200 import ops
+    rng = np.random.default_rng(n + c_in)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, c_in, generator=g, requires_grad=True)
+    w = (torch.randn(c_out, K, c_in, generator=g) / (c_in * 3) ** 0.5).requires_grad_(True)
+    if K > 1:
+        table = np.where(rng.random((K, n)) < 0.4, rng.integers(0, n, (K, n)), -1).astype(np.int32)
+        # a proper rulebook has at most one output per (offset, input): make every offset's map injective
+        for k in range(K):
+            idx = table[k]
+            seen = {}
+            for o in np.nonzero(idx >= 0)[0]:
+                if idx[o] in seen:
+                    idx[o] = -1
+                else:
+                    seen[idx[o]] = o
+        y = sparse_conv(x, table, w.permute(1, 2, 0))
+    else:
+        table = None
+        y = x @ w[:, 0].t()
+    dy = torch.randn(n, c_out, generator=g)
+    y.backward(dy)
+    tb = torch.as_tensor(table).to(DEV) if table is not None else None
+    dw = ops.conv_wgrad(x.detach().to(DEV), dy.to(DEV), K, tb)
+    assert relerr(dw, w.grad) < 1e-4, relerr(dw, w.grad)
+    # accumulate flag
+    dw2 = ops.conv_wgrad(x.detach().to(DEV), dy.to(DEV), K, tb, out=dw.clone(), accumulate=True)
+    assert relerr(dw2, 2 * w.grad) < 1e-4
+    # input gradient through the transposed rulebook: table_t[k][i] = o  <=>  table[k][o] = i
+    if table is not None:
+        tt = np.full((K, n), -1, np.int32)
+        for k in range(K):
+            o = np.nonzero(table[k] >= 0)[0]
+            tt[k, table[k, o]] = o
+        dx = ops.conv_dgrad(dy.to(DEV), w.detach().to(DEV), torch.as_tensor(tt).to(DEV), n, reverse_offsets=False)
+    else:
+        dx = ops.conv_dgrad(dy.to(DEV), w.detach().to(DEV), None, n, reverse_offsets=False)
+    assert relerr(dx, x.grad) < 1e-4, relerr(dx, x.grad)
+
+
+def test_subm3_input_gradient_uses_the_same_table_reversed():
+    """For a submanifold conv the transposed rulebook is the SAME table with the 27 kernel offsets reversed
+    (table[k][o] = i  <=>  table[26 - k][i] = o): dX = conv(dY, W^T with offsets flipped) on the level's own table."""
+    from unidet3d_b200 import ops
+    rng = np.random.default_rng(0)
+    coords = np.unique(rng.integers(0, 12, (1500, 3)), axis=0).astype(np.int32)
+    coords = np.concatenate([np.zeros((len(coords), 1), np.int32), coords], 1)
+    table = orb.subm3_table(coords, np.array([12, 12, 12]))
+    n = len(coords)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, 32, generator=g, requires_grad=True)
+    w = (torch.randn(32, 27, 32, generator=g) * 0.1).requires_grad_(True)
+    y = sparse_conv(x, table, w.permute(1, 2, 0))
+    dy = torch.randn(n, 32, generator=g)
+    y.backward(dy)
+    dx = ops.conv_dgrad(dy.to(DEV), w.detach().to(DEV), torch.as_tensor(table).to(DEV), n, reverse_offsets=True)
+    assert relerr(dx, x.grad) < 1e-4, relerr(dx, x.grad)
+
+
+def test_backbone_train_mode_forward_vs_oracle():
+    """module.train(): batch-statistics BatchNorm through the whole U-Net and the output layer, running statistics
+    updated like torch -- against the oracle with F.batch_norm(training=True)."""
+    import copy
+    import unidet3d_b200 as u
+    from unidet3d_b200 import configs
+    from unidet3d_b200.synthetic import make_model_state_dict
+    cfg = configs.model_cfg(("scannet",), topk_insts=100)
+    n, v, a, c = SCENE_PRESETS["tiny"]
+    cfg["voxel_size"] = v
+    model = u.MODELS.build(cfg)
+    sd = make_model_state_dict(cfg, 0)
+    model.load_state_dict(sd, strict=False)
+    model.to(DEV).train()
+    scenes = [make_scene(60 + i, n, a, c) for i in range(2)]
+    pts, sps = [s[0] for s in scenes], [s[1] for s in scenes]
+    P = torch.as_tensor(np.concatenate(pts)).to(DEV)
+    offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device=DEV)
+    with torch.no_grad():
+        x, inv = model.collate(P, offs, 2)
+        n_sps = [int(s.max()) + 1 for s in sps]
+        sp_off = np.concatenate([[0], np.cumsum(n_sps)])
+        sp_b = torch.as_tensor(np.concatenate([s + o for s, o in zip(sps, sp_off[:-1])])).to(DEV)
+        pooled = model.extract_feat(x, sp_b, inv, sp_off)
+    # oracle, train mode (its BatchNorm updates the running statistics of det_sd in place)
+    from oracle import voxelize as ovox
+    from oracle.pool import superpoint_pool
+    det_sd = {k: t.clone() for k, t in sd.items() if not k.startswith("decoder.")}
+    coords, feats, inverse, shape = ovox.voxelize(pts, v, 128)
+    ospconv.TRAIN_MODE = True
+    try:
+        xo, _ = ounet.backbone_forward(det_sd, coords, torch.as_tensor(feats), shape)
+    finally:
+        ospconv.TRAIN_MODE = False
+    ref = superpoint_pool(xo, inverse, np.concatenate([s + o for s, o in zip(sps, sp_off[:-1])]), int(sp_off[-1]))
+    assert relerr(pooled, ref) < 1e-3, relerr(pooled, ref)
+    msd = model.state_dict()
+    for k in ("unet.blocks.block0.conv_branch.0.running_mean", "unet.u.u.blocks.block1.conv_branch.3.running_var",
+              "unet.blocks_tail.block0.conv_branch.0.running_var", "output_layer.0.running_mean"):
+        assert relerr(msd[k], det_sd[k]) < 1e-3, (k, relerr(msd[k], det_sd[k]))
+    # eval mode is unaffected by the mode switch itself (but sees the updated running statistics)
+    model.eval()

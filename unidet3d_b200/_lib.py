@@ -84,6 +84,11 @@ SIGNATURES = {
     "ud3d_gemm_packed_weight_bytes": (_sz, [_i, _i, _i]),
     "ud3d_gemm_pack_weight": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ud3d_gemm_pack_weight_ts": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "ud3d_bn_batch_sums_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "ud3d_bn_batch_sums": (_i, [_vp, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_bn_train_fold": (_i, [_vp, C.c_double, _i, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ud3d_conv_wgrad_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "ud3d_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, C.c_size_t, _vp]),
     "ud3d_gemm_fwd": (_i, [C.POINTER(GemmArgs), _vp]),
     "ud3d_act_split": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "ud3d_gemm_fwd_simt": (_i, [C.POINTER(GemmArgs), _vp, _vp]),

@@ -96,10 +96,18 @@ class UniDet3D(nn.Module):
                 return dataset
 
     # ------------------------------------------------------------------ stages
-    def collate(self, points: torch.Tensor, scene_offsets: torch.Tensor, batch_size: int):
+    def collate(self, points: torch.Tensor, scene_offsets: torch.Tensor, batch_size: int,
+                elastic_points: Optional[torch.Tensor] = None):
         """unidet3d.py:136-176 on a packed [n,6] point tensor.
-        -> SparseConvTensor (canonical voxel order, rulebook-ready), inverse_mapping int32 [n]."""
+        -> SparseConvTensor (canonical voxel order, rulebook-ready), inverse_mapping int32 [n].
+
+        ``elastic_points`` (packed fp32 [n,3], the ``elastic_coords`` of the ElasticTransfrom augmentation, already in
+        voxel units): voxel coordinates are ``floor(el - el.min(0))`` per scene (unidet3d.py:162-166) while the features
+        still are (colour, xyz - mean) of the un-distorted points."""
         coords_pt, feats_pt, _, maxc = ops.point_coords(points, scene_offsets, self.voxel_size)
+        if elastic_points is not None:
+            el = torch.cat((elastic_points.to(points.dtype), points[:, 3:]), dim=1).contiguous()
+            coords_pt, _, _, maxc = ops.point_coords(el, scene_offsets, 1.0)       # x / 1.0 is exact: floor(el - min)
         ext = (maxc.cpu().numpy() + 1).tolist()                       # host sync #1 (spatial extents)
         spatial_shape = [max(int(e), int(self.min_spatial_shape)) for e in ext]
         # occupancy grids of all five levels are built from the per-point coordinates back to back; the voxel counts of
@@ -120,6 +128,14 @@ class UniDet3D(nn.Module):
         batch_offsets[i]:batch_offsets[i+1] belong to scene i)."""
         plan = self._get_plan()
         lv0 = x.pyramid.levels[0]
+        if self.training:
+            # train mode: batch-statistics BatchNorm everywhere (SpConvUNet._forward_level_train) incl. the output layer
+            # (unidet3d.py:104-107, 129); forward values only
+            f = ops.gemm(x.features, ops.PackedWeight(self.input_conv[0].weight), table=lv0.subm, tile_mask=lv0.subm_mask)
+            y, _ = self.unet(x.replace_feature(f)) if self.unet.return_blocks else (self.unet(x.replace_feature(f)), None)
+            sc, sh, _, _ = ops.bn_train(y.features, self.output_layer[0])
+            return ops.segmented_mean(y.features, superpoints, int(batch_offsets[-1]), gather=inverse_mapping, scale=sc,
+                                      shift=sh, relu=True)
         if self.unet.operand_form_ok():
             bn0 = self.unet.first_bn()
             f_act = torch.empty((lv0.n, plan["w_in"].c_out), dtype=torch.float32, device=x.features.device)
@@ -363,11 +379,9 @@ class UniDet3D(nn.Module):
         criterion, every stage on our kernels.  Not implemented yet: gradients, and the
         batch statistics of train-mode (Sync)BatchNorm -- the backbone runs with the running statistics, so this is
         the validation-style loss of the current weights.  ``elastic_coords`` (the ElasticTransfrom augmentation's
-        side input) is not supported."""
+        side input, unidet3d.py:349) replaces the voxel coordinates like in the reference."""
         if self.criterion is None:
             raise RuntimeError("UniDet3D was built without a criterion config")
-        if batch_inputs_dict.get("elastic_coords") is not None:
-            raise NotImplementedError("loss() with elastic_coords")
         dev = next(self.parameters()).device
         B = len(batch_data_samples)
         names = [self.get_dataset(s.lidar_path) for s in batch_data_samples]
@@ -402,7 +416,10 @@ class UniDet3D(nn.Module):
         pts = torch.cat(P) if B > 1 else P[0].contiguous()
         sp_b = torch.cat([s + int(o) for s, o in zip(S, sp_off[:-1])])
         offs = torch.tensor(pt_off, dtype=torch.int32, device=dev)
-        x, inverse = self.collate(pts, offs, B)
+        el = batch_inputs_dict.get("elastic_coords")
+        if el is not None:
+            el = torch.cat([torch.as_tensor(e).to(dev, torch.float32) for e in el]).contiguous()
+        x, inverse = self.collate(pts, offs, B, el)
         pooled = self.extract_feat(x, sp_b, inverse, sp_off)
         xs = [pooled[int(sp_off[i]):int(sp_off[i + 1])] for i in range(B)]
         queries, centers, qmasks = self._select_queries(xs, sp_centers, sp_masks)
@@ -410,6 +427,8 @@ class UniDet3D(nn.Module):
             g.query_masks = m
         prev = self.decoder.eval_aux_outputs
         self.decoder.eval_aux_outputs = True             # the criterion reads all seven heads (criterion.py:166-176)
+        # (self.training decides the BatchNorm mode of the backbone: module.train() -> batch statistics + running-stat
+        #  updates, SyncBatchNorm-style all-reduce under torch.distributed; module.eval() -> running statistics)
         try:
             out = self.decoder(queries, centers, names)
         finally:

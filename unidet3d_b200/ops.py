@@ -485,3 +485,83 @@ def criterion_layer(logits: torch.Tensor, boxes: torch.Tensor, gt_boxes: torch.T
     ws = torch.empty(int(_L().ud3d_criterion_workspace_bytes(T, G)), dtype=torch.uint8, device=dev)
     check(_L().ud3d_criterion_layer(C.byref(a), _p(ws), ws.numel(), _stream()), "ud3d_criterion_layer")
     return match.bool(), sums
+
+
+# ------------------------------------------------------------------ training side of the backbone
+def bn_batch_sums(x: torch.Tensor) -> torch.Tensor:
+    """-> fp64 [2, C]: per-channel sum and sum of squares over the rows of ``x`` (deterministic)."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.stride(1) != 1:
+        raise _lib.Ud3dError("bn_batch_sums: x must be a CUDA fp32 matrix with unit column stride")
+    n, c = x.shape
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    wsb = int(_L().ud3d_bn_batch_sums_workspace_bytes(n, c))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
+    check(_L().ud3d_bn_batch_sums(_p(x), x.stride(0), n, c, _p(sums), _p(ws), ws.numel(), _stream()), "ud3d_bn_batch_sums")
+    return sums
+
+
+def bn_train_fold(sums: torch.Tensor, count: float, bn, update_running: bool = True):
+    """Train-mode BatchNorm as (scale, shift) [+ (mean, invstd) for the backward pass]: ``bn`` is the nn.BatchNorm1d /
+    SyncBatchNorm holding gamma, beta, eps, momentum and the running statistics (updated in place like torch)."""
+    c = sums.shape[1]
+    dev = sums.device
+    scale = torch.empty(c, dtype=torch.float32, device=dev)
+    shift = torch.empty(c, dtype=torch.float32, device=dev)
+    mean = torch.empty(c, dtype=torch.float32, device=dev)
+    invstd = torch.empty(c, dtype=torch.float32, device=dev)
+    rm = bn.running_mean if update_running else None
+    rv = bn.running_var if update_running else None
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    check(_L().ud3d_bn_train_fold(_p(sums), float(count), c, _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps), mom,
+                                  _p(rm), _p(rv), _p(scale), _p(shift), _p(mean), _p(invstd), _stream()), "ud3d_bn_train_fold")
+    if update_running and getattr(bn, "num_batches_tracked", None) is not None:
+        bn.num_batches_tracked += 1
+    return scale, shift, mean, invstd
+
+
+def bn_train(x: torch.Tensor, bn, group=None, update_running: bool = True):
+    """Batch statistics of ``x`` [N, C] (all active voxels of the batch) -> (scale, shift, mean, invstd).  With an
+    initialised torch.distributed process group of more than one rank the sums and the row count are all-reduced first
+    (SyncBatchNorm, spconv_unet.py:119-121): ONE collective of 2C + 1 doubles per BatchNorm."""
+    sums = bn_batch_sums(x)
+    count = float(x.shape[0])
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        buf = torch.cat((sums.flatten(), sums.new_tensor([count])))
+        dist.all_reduce(buf, group=group)
+        sums = buf[:-1].view(2, -1).contiguous()
+        count = float(buf[-1].item())
+    return bn_train_fold(sums, count, bn, update_running)
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, K: int, table: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """dW [C_out, K, C_in] (+)= sum_o dy[o]^T x[table[k][o]]   (``x`` = the conv's input after its BatchNorm + ReLU)."""
+    for t, nme in ((x, "x"), (dy, "dy")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.stride(1) != 1:
+            raise _lib.Ud3dError(f"conv_wgrad: {nme} must be a CUDA fp32 matrix with unit column stride")
+    n_out, c_out = dy.shape
+    c_in = x.shape[1]
+    if table is not None:
+        _req(table, torch.int32, "table")
+    if out is None:
+        out = torch.empty((c_out, K, c_in), dtype=torch.float32, device=x.device)
+        accumulate = False
+    wsb = int(_L().ud3d_conv_wgrad_workspace_bytes(n_out, K, c_in, c_out))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
+    check(_L().ud3d_conv_wgrad(_p(x), x.stride(0), c_in, _p(dy), dy.stride(0), c_out, _p(table), n_out, K, _p(out),
+                               1 if accumulate else 0, _p(ws), ws.numel(), _stream()), "ud3d_conv_wgrad")
+    return out
+
+
+def conv_dgrad(dy: torch.Tensor, weight: torch.Tensor, table_t: Optional[torch.Tensor], n_in: int, *, reverse_offsets: bool,
+               tile_mask_t=None) -> torch.Tensor:
+    """dX [n_in, C_in] = sum_k dy[table_t[k][i]] @ W_k^T: the input gradient of a sparse conv IS a sparse conv of dy with
+    the transposed weight over the transposed rulebook -- for SubM3 the same table with the kernel offsets reversed
+    (``reverse_offsets``), for the k2/s2 conv the table of its inverse conv and vice versa -- on the same tcgen05 kernel.
+    ``weight``: the reference parameter [C_out, K, C_in] (flattened)."""
+    w = weight.reshape(weight.shape[0], -1, weight.shape[-1])
+    wt = w.permute(2, 1, 0)                                   # [C_in, K, C_out]
+    if reverse_offsets:
+        wt = wt.flip(1)
+    return gemm(dy, PackedWeight(wt.contiguous()), table=table_t, tile_mask=tile_mask_t, n_out=n_in)

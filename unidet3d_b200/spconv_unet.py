@@ -243,6 +243,45 @@ class SpConvUNet(nn.Module):
         outputs.append((l, x))
         return x
 
+    # ---- train-mode executor: BatchNorm with BATCH statistics (spconv_unet.py:119-124: SyncBatchNorm over all active
+    #      voxels of the global batch; running statistics updated with momentum 0.1).  A BatchNorm's statistics need the
+    #      producer's complete output, so the producer-epilogue fusion of the eval executor does not apply: each conv
+    #      writes its fp32 map, ud3d_bn_batch_sums reduces it (+ one all-reduce under torch.distributed), and the
+    #      normalisation + ReLU is folded into the CONSUMER's operand load.  Forward values only -- the backward kernels
+    #      available so far are the weight / input gradients of the convolutions (ops.conv_wgrad / ops.conv_dgrad).
+    @staticmethod
+    def _block_train(blk: ResidualBlock, x, lv):
+        cb = blk.conv_branch
+        identity = ops.gemm(x, ops.PackedWeight(blk.i_branch[0].weight)) if isinstance(blk.i_branch[0], SparseConvWeight) else x
+        s0, h0, _, _ = ops.bn_train(x, cb[0])
+        y = ops.gemm(x, ops.PackedWeight(cb[2].weight), table=lv.subm, tile_mask=lv.subm_mask, in_scale=s0, in_shift=h0, in_relu=True)
+        s1, h1, _, _ = ops.bn_train(y, cb[3])
+        return ops.gemm(y, ops.PackedWeight(cb[5].weight), table=lv.subm, tile_mask=lv.subm_mask, in_scale=s1, in_shift=h1,
+                        in_relu=True, residual=identity)
+
+    def _forward_level_train(self, x: torch.Tensor, pyr: Pyramid, l: int, outputs: list) -> torch.Tensor:
+        lv = pyr.levels[l]
+        c = self.num_planes[0]
+        has_sub = len(self.num_planes) > 1
+        for blk in self.blocks:
+            x = self._block_train(blk, x, lv)
+        if has_sub:
+            nxt = pyr.levels[l + 1]
+            cat = torch.empty((lv.n, 2 * c), dtype=torch.float32, device=x.device)
+            cat[:, :c] = x
+            s, h, _, _ = ops.bn_train(x, self.conv[0])
+            d = ops.gemm(x, ops.PackedWeight(self.conv[2].weight), table=lv.child, tile_mask=lv.child_mask, n_out=nxt.n,
+                         in_scale=s, in_shift=h, in_relu=True)
+            d = self.u._forward_level_train(d, pyr, l + 1, outputs)
+            s, h, _, _ = ops.bn_train(d, self.deconv[0])
+            ops.gemm(d, ops.PackedWeight(self.deconv[2].weight), table=lv.up, tile_mask=lv.up_mask, n_out=lv.n, in_scale=s,
+                     in_shift=h, in_relu=True, out=cat[:, c:])
+            x = cat
+            for blk in self.blocks_tail:
+                x = self._block_train(blk, x, lv)
+        outputs.append((l, x))
+        return x
+
     def operand_form_ok(self):
         return all(c % 32 == 0 for c in self.num_planes)
 
@@ -250,8 +289,6 @@ class SpConvUNet(nn.Module):
         return len(self.num_planes)
 
     def forward(self, input: SparseConvTensor, previous_outputs: Optional[List] = None):
-        if self.training:
-            raise NotImplementedError("unidet3d_b200.SpConvUNet implements the forward/eval path only (round 1)")
         if input.pyramid is None or len(input.pyramid) < self.n_levels():
             input.pyramid = build_pyramid(input.indices, input.spatial_shape, input.batch_size, self.n_levels(),
                                           canonical=input.canonical, extents=input.extents)
@@ -261,7 +298,9 @@ class SpConvUNet(nn.Module):
             raise RuntimeError("SpConvUNet needs CUDA fp32 features (no CPU fallback)")
         outs: list = []
         x = x.contiguous() if x.stride(1) != 1 else x
-        if self.operand_form_ok():
+        if self.training:
+            y = self._forward_level_train(x, pyr, 0, outs)
+        elif self.operand_form_ok():
             x_act = getattr(input, "features_act", None)   # operand form under blocks.block0.bn0, if the caller has it
             if x_act is None:
                 bn0 = self._get_plan()["blocks"][0]["bn0"]
