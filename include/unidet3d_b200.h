@@ -244,10 +244,10 @@ int ud3d_attention_fwd_split(const float* qkv, const int32_t* cu_seqlens, int B,
  * K/V tiles stream through cp.async as raw 128-byte rows, no per-tile conversion */
 int ud3d_attention_fwd_opform(const float* qkv_split, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
                               float* out_split, void* stream);
-/* same contract, tcgen05 variant: S = QK^T and O' = PV' accumulate in TMEM (V tile used as an MN-major operand).
- * Parity-tested; currently ~20 % slower than the mma.sync kernel above at T ~ 1700 (its softmax runs on 4 warps
- * per CTA), so the encoder uses ud3d_attention_fwd_opform. */
-int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
+/* same contract on the 5th-gen tensor cores (csrc/attention_tc.cu): S = Q K^T and O' = P V' accumulate in TMEM, P goes
+ * softmax -> TMEM -> second GEMM without touching shared memory, row sums on the tensor core, Q / K / V tiles by TMA
+ * tensor-map copies.  total_T = number of token rows of qkv_split (= cu_seqlens[B]), needed for the tensor map. */
+int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_seqlens, int B, int max_T, int total_T, int num_heads,
                           float* out_split, void* stream);
 /* PredBBox exp + _bbox_pred_to_bbox (encoder.py:109-111,241-283): raw [T,ld_raw>=8], centres [T,3]
  * -> out [T, with_angle ? 7 : 6] */

@@ -369,12 +369,10 @@ def test_attention_operand_form(lens):
         ref.append(a.transpose(0, 1).reshape(T, d))
     ref = torch.cat(ref)
     out_s = ops.attention(split_encode(qkv).to(DEV), cu.to(DEV), max(lens), H, split_in=True)
-    # (the product-path kernel uses P as a single bf16 term with a consistent row sum: 2^-9 perturbed softmax weights;
-    #  gate = north_star's 1e-3, measured ~2e-4 here and 5e-5 on the encoder's final logits)
-    assert relerr(split_decode(out_s.cpu()), ref) < 1e-3, relerr(split_decode(out_s.cpu()), ref)
+    assert relerr(split_decode(out_s.cpu()), ref) < 1e-4, relerr(split_decode(out_s.cpu()), ref)
     out_s2 = ops.attention(qkv.to(DEV), cu.to(DEV), max(lens), H, split_out=True)
     assert relerr(split_decode(out_s2.cpu()), ref) < 1e-4
-    # tcgen05 variant (S / O' accumulators in TMEM, V as an MN-major operand)
+    # tcgen05 kernel (the product path: S / O' / row sums in TMEM, P TMEM-resident, TMA tensor-map loads)
     out_s3 = ops.attention(split_encode(qkv).to(DEV), cu.to(DEV), max(lens), H, split_in=True, tcgen05=True)
     assert relerr(split_decode(out_s3.cpu()), ref) < 1e-4, relerr(split_decode(out_s3.cpu()), ref)
 

@@ -32,11 +32,17 @@ def prod(a, b, terms):
     return out
 
 
-def run(mode_qk, mode_pv, T=(1700, 1500), seed=0):
+def run(mode_qk, mode_pv, T=(1700, 1500), seed=0, sharpen=1.0):
     cfg = configs.model_cfg(("scannet",))
     ocfg = configs.oracle_cfg(cfg)["encoder"]
     n_union = len(set(sum(cfg["decoder"]["datasets_classes"], []))) + 1
     sd = oenc.make_encoder_state_dict(6, 32, 256, 1024, n_union, seed)
+    if sharpen != 1.0:      # emulate a trained encoder: larger q / k projections -> peaked softmax (a few keys dominate)
+        for k in list(sd):
+            if k.endswith("attn.in_proj_weight"):
+                w = sd[k].clone()
+                w[:512] *= sharpen
+                sd[k] = w
     g = torch.Generator().manual_seed(1)
     x = [torch.randn(t, 32, generator=g) for t in T]
     c = [torch.randn(t, 3, generator=g) for t in T]
@@ -53,7 +59,10 @@ def run(mode_qk, mode_pv, T=(1700, 1500), seed=0):
         v = v.view(Tt, num_heads, hd).transpose(0, 1)
         s = prod(q, k.transpose(1, 2), mode_qk) / math.sqrt(hd)
         pm = torch.exp(s - s.max(-1, keepdim=True).values)          # unnormalised, like the online softmax
-        o = prod(pm, v, mode_pv) / pm.sum(-1, keepdim=True)
+        den = pm.sum(-1, keepdim=True)
+        if mode_pv != "f" and "lh" not in mode_pv:      # P enters as a single bf16 term: the row sum uses the same rounded values
+            den = pm.bfloat16().float().sum(-1, keepdim=True)
+        o = prod(pm, v, mode_pv) / den
         o = o.transpose(0, 1).reshape(Tt, d)
         z = o @ sd_[p + ".attn.out_proj.weight"].t() + sd_[p + ".attn.out_proj.bias"] + xx
         return F.layer_norm(z, (d,), sd_[p + ".norm.weight"], sd_[p + ".norm.bias"], 1e-5)
@@ -71,7 +80,8 @@ def run(mode_qk, mode_pv, T=(1700, 1500), seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    sharpen = float(os.environ.get("SHARPEN", "1"))
     for qk, pv in [("hh+lh+hl", "hh+lh+hl"), ("hh+lh+hl", "hh+hl"), ("hh+lh+hl", "hh+lh"), ("hh+lh+hl", "hh"),
                    ("hh+lh", "hh+lh+hl"), ("hh", "hh+lh+hl"), ("hh+lh", "hh"), ("hh", "hh")]:
-        e = run(qk, pv)
-        print(f"QK {qk:9s} PV {pv:9s}: logits rel err {e[0]:.2e}  boxes {e[1]:.2e}", flush=True)
+        e = run(qk, pv, sharpen=sharpen)
+        print(f"sharpen {sharpen}: QK {qk:9s} PV {pv:9s}: logits rel err {e[0]:.2e}  boxes {e[1]:.2e}", flush=True)

@@ -97,7 +97,7 @@ SIGNATURES = {
     "ud3d_attention_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "ud3d_attention_fwd_split": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "ud3d_attention_fwd_opform": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
-    "ud3d_attention_fwd_tc": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "ud3d_attention_fwd_tc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "ud3d_layernorm_split": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "ud3d_bbox_decode": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "ud3d_gather_columns": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),

@@ -109,13 +109,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.w = (v[j * 4 + 3] - mean) * rstd * g.w + b.w;
     if (out) *(float4*)(out + (size_t)row * C + c) = o;
     if (out_split) {
-      // operand form: chunk = c / 32, 4 channels at (c % 32): hi 8 bytes, lo 8 bytes (+16)
+      // operand form: chunk = c / 32, 4 channels at (c % 32): hi 8 bytes, lo 8 bytes (+64)
       uint32_t h0, l0, h1, l1;
       split_bf16x2(o.x, o.y, h0, l0);
       split_bf16x2(o.z, o.w, h1, l1);
-      uint8_t* d = (uint8_t*)(out_split + (size_t)row * C) + (c >> 5) * 128 + opf_hi_off(c & 31);
+      uint8_t* d = (uint8_t*)(out_split + (size_t)row * C) + (c >> 5) * 128 + (c & 31) * 2;
       *(uint2*)d = make_uint2(h0, h1);
-      *(uint2*)(d + kOpfLo) = make_uint2(l0, l1);
+      *(uint2*)(d + 64) = make_uint2(l0, l1);
     }
   }
 }
@@ -318,19 +318,19 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   for (int dn = 0; dn < 4; ++dn) {
     const int col = h * kHeadDim + dn * 8 + 2 * t;
     if constexpr (SPLIT_OUT) {
-      // operand form: head h == 32-channel chunk h
+      // operand form: head h == 32-channel chunk h; hi pair at (dn*8+2t)*2 bytes, lo pair +64
       uint32_t hi, lo;
       if (r0 < T) {
         split_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0, hi, lo);
-        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r0) * d_model) + h * 128 + opf_hi_off(dn * 8 + 2 * t);
+        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r0) * d_model) + h * 128 + (dn * 8 + 2 * t) * 2;
         *(uint32_t*)d = hi;
-        *(uint32_t*)(d + kOpfLo) = lo;
+        *(uint32_t*)(d + 64) = lo;
       }
       if (r1 < T) {
         split_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1, hi, lo);
-        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r1) * d_model) + h * 128 + opf_hi_off(dn * 8 + 2 * t);
+        uint8_t* d = (uint8_t*)(out + (size_t)(t0 + r1) * d_model) + h * 128 + (dn * 8 + 2 * t) * 2;
         *(uint32_t*)d = hi;
-        *(uint32_t*)(d + kOpfLo) = lo;
+        *(uint32_t*)(d + 64) = lo;
       }
     } else {
       if (r0 < T) *(float2*)(out + (size_t)(t0 + r0) * d_model + col) = make_float2(o[dn][0] * inv0, o[dn][1] * inv0);
@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
       const int which = id >> 9, rem = id & 511;
       const int key = rem >> 3, j = rem & 7;
       const int kr = kv0 + key;
-      const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + opf_mem_piece(j) * 16;
-      uint8_t* dst = (which ? sV[stage] : sK[stage]) + key * 128 + ((j ^ (key & 7)) << 4);      // lane j = logical piece j
+      const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + j * 16;
+      uint8_t* dst = (which ? sV[stage] : sK[stage]) + key * 128 + ((j ^ (key & 7)) << 4);
       cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
     }
     cp_async_commit();
@@ -401,9 +401,9 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
         const int col = ks * 16 + 2 * t + ((part >> 1) ? 8 : 0);
         uint32_t vh = 0, vl = 0;
         if (row < T) {
-          const uint8_t* qp = qkv + (size_t)(t0 + row) * ldb + (size_t)h * 128 + opf_hi_off(col);
+          const uint8_t* qp = qkv + (size_t)(t0 + row) * ldb + (size_t)h * 128 + col * 2;
           vh = *(const uint32_t*)qp;
-          vl = *(const uint32_t*)(qp + kOpfLo);
+          vl = *(const uint32_t*)(qp + 64);
         }
         qh[ks][part] = vh;
         ql[ks][part] = vl;
@@ -471,21 +471,14 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
       alpha[r] = ex2_approx(m_run[r] - m_new);
       m_run[r] = m_new;
     }
-    // P is used as ONE bf16 term (P_hi) in P V: the row sum is accumulated from the SAME rounded values, so numerator
-    // and denominator of softmax(S) V agree exactly (the result is an exact convex combination of V rows with weights
-    // perturbed by 2^-9 relative -- a second-order effect, measured 5e-5 on the encoder's final logits / boxes; with the
-    // fp32 row sum a single dominant key would carry the full 2^-9 rounding error of its weight).  V keeps hi + lo.
-    uint32_t pb[8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const float p0 = ex2_approx(fmaf(s[nt][0], qscale, -m_run[0]));     // scale folded into the exponent's FMA
-      const float p1 = ex2_approx(fmaf(s[nt][1], qscale, -m_run[0]));
-      const float p2 = ex2_approx(fmaf(s[nt][2], qscale, -m_run[1]));
-      const float p3 = ex2_approx(fmaf(s[nt][3], qscale, -m_run[1]));
-      pb[nt][0] = cvt_bf16x2_rn(p0, p1);
-      pb[nt][1] = cvt_bf16x2_rn(p2, p3);
-      rs[0] += __uint_as_float(pb[nt][0] << 16) + __uint_as_float(pb[nt][0] & 0xffff0000u);
-      rs[1] += __uint_as_float(pb[nt][1] << 16) + __uint_as_float(pb[nt][1] & 0xffff0000u);
+      s[nt][0] = ex2_approx(fmaf(s[nt][0], qscale, -m_run[0]));     // scale folded into the exponent's FMA
+      s[nt][1] = ex2_approx(fmaf(s[nt][1], qscale, -m_run[0]));
+      s[nt][2] = ex2_approx(fmaf(s[nt][2], qscale, -m_run[1]));
+      s[nt][3] = ex2_approx(fmaf(s[nt][3], qscale, -m_run[1]));
+      rs[0] += s[nt][0] + s[nt][1];
+      rs[1] += s[nt][2] + s[nt][3];
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -501,7 +494,11 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
     // ---- O += P V : V fragments by ldmatrix.trans from the row-major (key, dim) tile
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t ph[4] = {pb[2 * j][0], pb[2 * j][1], pb[2 * j + 1][0], pb[2 * j + 1][1]};
+      uint32_t ph[4], pl[4];
+      split_bf16x2(s[2 * j][0], s[2 * j][1], ph[0], pl[0]);
+      split_bf16x2(s[2 * j][2], s[2 * j][3], ph[1], pl[1]);
+      split_bf16x2(s[2 * j + 1][0], s[2 * j + 1][1], ph[2], pl[2]);
+      split_bf16x2(s[2 * j + 1][2], s[2 * j + 1][3], ph[3], pl[3]);
       // lane -> (matrix = lane >> 3, row = lane & 7): matrices {keys 0-7, keys 8-15} x {dim tile dn, dn + 1}
       const int key = 16 * j + (lane & 7) + ((lane >> 3) & 1) * 8;
       const uint32_t vrow = Vs + key * 128;
@@ -512,8 +509,10 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
         ldmatrix_x4_trans(vh, vrow + (((2 * dp + csel) ^ (key & 7)) << 4));
         ldmatrix_x4_trans(vl, vrow + (((4 + 2 * dp + csel) ^ (key & 7)) << 4));
         mma_bf16_16816(o[2 * dp], ph, vh[0], vh[1]);
+        mma_bf16_16816(o[2 * dp], pl, vh[0], vh[1]);
         mma_bf16_16816(o[2 * dp], ph, vl[0], vl[1]);
         mma_bf16_16816(o[2 * dp + 1], ph, vh[2], vh[3]);
+        mma_bf16_16816(o[2 * dp + 1], pl, vh[2], vh[3]);
         mma_bf16_16816(o[2 * dp + 1], ph, vl[2], vl[3]);
       }
     }
@@ -527,252 +526,17 @@ __global__ void __launch_bounds__(256) attention_opform_kernel(const uint8_t* __
     uint32_t hi, lo;
     if (r0 < T) {
       split_bf16x2(o[dn][0] * inv0, o[dn][1] * inv0, hi, lo);
-      uint8_t* d = out + (size_t)(t0 + r0) * ldo + h * 128 + opf_hi_off(dn * 8 + 2 * t);
+      uint8_t* d = out + (size_t)(t0 + r0) * ldo + h * 128 + (dn * 8 + 2 * t) * 2;
       *(uint32_t*)d = hi;
-      *(uint32_t*)(d + kOpfLo) = lo;
+      *(uint32_t*)(d + 64) = lo;
     }
     if (r1 < T) {
       split_bf16x2(o[dn][2] * inv1, o[dn][3] * inv1, hi, lo);
-      uint8_t* d = out + (size_t)(t0 + r1) * ldo + h * 128 + opf_hi_off(dn * 8 + 2 * t);
+      uint8_t* d = out + (size_t)(t0 + r1) * ldo + h * 128 + (dn * 8 + 2 * t) * 2;
       *(uint32_t*)d = hi;
-      *(uint32_t*)(d + kOpfLo) = lo;
+      *(uint32_t*)(d + 64) = lo;
     }
   }
-}
-
-// ---------------------------------------------------------------- attention on tcgen05 (operand-form q|k|v)
-// CTA = 128 queries of one (scene, head); KV tiles of 64 keys.  Both GEMMs run on the tensor cores with TMEM
-// accumulators; the operand-form rows (128 B = bf16 hi|lo of one head) are used as they are:
-//   S[128 x 64]  = Q K^T : A = Q tile, B = K tile, both K-major SW128 (rows of 128 B), 6 MMAs (hi.hi, lo.hi, hi.lo)
-//   softmax      : 8 warps, thread = (query row, 32-key half): tcgen05.ld S, scale, online max / sum (ex2), P -> bf16 hi|lo
-//                  written to shared memory as the next A operand (two 32-key chunks of 128-byte rows)
-//   O'[128 x 64] = P V'  : B = V tile used MN-major (row = key, 128 B = [V_hi(32 dims) | V_lo(32 dims)] = N 64), so
-//                  O = O'[:, :32] + O'[:, 32:] = (P_hi + P_lo)(V_hi + V_lo); 8 MMAs; accumulated in registers with
-//                  the online-softmax rescale (head_dim 32 -> 32 floats per thread)
-//   warp 4 streams K/V tiles with cp.async through a 2-stage ring, warp 5 issues the MMAs; mbarrier hand-offs only.
-constexpr int kTcQ = 128, kTcKV = 64;
-constexpr int kTcSoftmaxWarps = 8;                 // warps w and w+4 share query rows 32*(w&3).. and split the 64 keys
-constexpr int kTcThreads = 32 * (kTcSoftmaxWarps + 2);
-
-// UMMA descriptor for an MN-major operand tile with 128B swizzle: rows (K index) of 128 bytes, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_m128_bmn(uint32_t N) {   // B operand MN-major
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((N >> 3) << 17) | ((128u >> 4) << 24);
-}
-
-__global__ void __launch_bounds__(kTcThreads) attention_tc_kernel(const uint8_t* __restrict__ qkv, const int32_t* __restrict__ cu,
-                                                                  int num_heads, uint8_t* __restrict__ out) {
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int t0 = cu[b];
-  const int T = cu[b + 1] - t0;
-  const int q0 = blockIdx.x * kTcQ;
-  if (q0 >= T) return;
-  const int d_model = num_heads * kHeadDim;
-  const size_t ldb = (size_t)3 * d_model * 4;
-  const size_t ldo = (size_t)d_model * 4;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;                         // 128 x 128 B
-  uint8_t* sK = sQ + 16384;                   // [2] 64 x 128 B
-  uint8_t* sV = sK + 2 * 8192;                // [2] 64 x 128 B
-  uint8_t* sP = sV + 2 * 8192;                // [2 chunks] 128 x 128 B (hi 32 keys | lo 32 keys); reused for the final O exchange
-  float* s_rmax = (float*)(sP + 2 * 16384);   // [2 halves][128 rows] per-tile row maxima of each key half
-  uint64_t* bars = (uint64_t*)(s_rmax + 256);
-  uint64_t* kv_full = bars;                   // [2]
-  uint64_t* kv_empty = bars + 2;              // [2]
-  uint64_t* s_full = bars + 4;
-  uint64_t* p_full = bars + 5;                // count 8 (softmax warps)
-  uint64_t* o_full = bars + 6;
-  uint64_t* o_free = bars + 7;                // count 8
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
-
-  if (tid == 0) {
-    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-    mbar_init(s_full, 1); mbar_init(p_full, kTcSoftmaxWarps); mbar_init(o_full, 1); mbar_init(o_free, kTcSoftmaxWarps);
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 128);
-    tmem_relinquish();
-  }
-  // Q tile: 128 rows x 8 chunks, swizzled like every K-major operand tile
-  for (int id = tid; id < kTcQ * 8; id += kTcThreads) {
-    const int r = id >> 3, j = id & 7;
-    const int row = q0 + r;
-    const uint8_t* src = qkv + (size_t)(t0 + (row < T ? row : 0)) * ldb + (size_t)h * 128 + opf_mem_piece(j) * 16;
-    cp_async_16_zfill(smem_u32(sQ + r * 128 + ((j ^ (r & 7)) << 4)), src, row < T ? 16u : 0u);
-  }
-  cp_async_commit();
-  cp_async_wait<0>();
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 64;
-  const int n_tiles = (T + kTcKV - 1) / kTcKV;
-
-  if (warp < kTcSoftmaxWarps) {
-    // =========================================================== softmax / output warps: thread = (query row, key half)
-    const int quad = warp & 3, half = warp >> 2;
-    const int row = quad * 32 + lane;
-    const float qscale = 1.44269504088896340736f * 0.17677669529663688110f;
-    float o[32];                               // half 0 accumulates P V_hi, half 1 accumulates P V_lo (summed at the end)
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;      // l_run: this half's share of the row sum (same rescaling in both halves)
-    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int kv0 = j * kTcKV + half * 32;
-      mbar_wait(s_full, j & 1);
-      tc_fence_after_sync();
-      uint32_t r0[32];
-      tmem_ld_32x32(tmem_S + lane_off + half * 32, r0);
-      tmem_ld_wait();
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float a = __uint_as_float(r0[i]) * qscale;
-        if (kv0 + i >= T) a = -INFINITY;
-        r0[i] = __float_as_uint(a);
-        mx = fmaxf(mx, a);
-      }
-      s_rmax[half * 128 + row] = mx;
-      asm volatile("bar.sync 2, 256;" ::: "memory");          // the two key halves of every row exchange their maxima
-      const float m_new = fmaxf(m_run, fmaxf(mx, s_rmax[(half ^ 1) * 128 + row]));
-      const float alpha = ex2_approx(m_run - m_new);
-      m_run = m_new;
-      float rs = 0.f;
-      {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2_approx(__uint_as_float(r0[i]) - m_run);
-          const float p1 = ex2_approx(__uint_as_float(r0[i + 1]) - m_run);
-          rs += p0 + p1;
-          split_bf16x2(p0, p1, hi[i >> 1], lo[i >> 1]);
-        }
-        uint8_t* prow = sP + half * 16384 + row * 128;        // chunk `half` = this thread's 32 keys
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          *(uint4*)(prow + ((c4 ^ (row & 7)) << 4)) = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
-          *(uint4*)(prow + (((4 + c4) ^ (row & 7)) << 4)) = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
-        }
-      }
-      l_run = l_run * alpha + rs;
-      fence_proxy_async_smem();           // P visible to the tensor core
-      tc_fence_before_sync();             // S reads are complete before the MMA warp may overwrite S
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      // ---- O' of this tile: this half's 32 columns
-      mbar_wait(o_full, j & 1);
-      tc_fence_after_sync();
-      tmem_ld_32x32(tmem_O + lane_off + half * 32, r0);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = o[i] * alpha + __uint_as_float(r0[i]);
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
-    }
-    // ---- combine the halves (O = P V_hi + P V_lo, l = l0 + l1) through shared memory, half 0 writes the output
-    float* xo = (float*)sP;                    // [128][33] floats (P is dead: the last o_full has been observed)
-    float* xl = xo + 128 * 33;
-    if (half == 1) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) xo[row * 33 + i] = o[i];
-      xl[row] = l_run;
-    }
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    const int grow = q0 + row;
-    if (half == 0 && grow < T) {
-      const float inv = 1.f / (l_run + xl[row]);
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2)
-        split_bf16x2((o[i] + xo[row * 33 + i]) * inv, (o[i + 1] + xo[row * 33 + i + 1]) * inv, hi[i >> 1], lo[i >> 1]);
-      uint4* dst = (uint4*)(out + (size_t)(t0 + grow) * ldo + (size_t)h * 128);
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        dst[opf_mem_piece(c4)] = make_uint4(hi[4 * c4], hi[4 * c4 + 1], hi[4 * c4 + 2], hi[4 * c4 + 3]);
-        dst[opf_mem_piece(4 + c4)] = make_uint4(lo[4 * c4], lo[4 * c4 + 1], lo[4 * c4 + 2], lo[4 * c4 + 3]);
-      }
-    }
-  } else if (warp == kTcSoftmaxWarps) {
-    // =========================================================== K/V loader: 2-stage cp.async ring
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      if (j >= 2) {
-        if (lane == 0) mbar_wait(&kv_empty[st], ((j >> 1) - 1) & 1);
-        __syncwarp();
-      }
-      const int kv0 = j * kTcKV;
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const int id = lane + 32 * i;                 // 0..1023
-        const int which = id >> 9, rem = id & 511;
-        const int key = rem >> 3, jj = rem & 7;
-        const int kr = kv0 + key;
-        const uint8_t* src = qkv + (size_t)(t0 + (kr < T ? kr : 0)) * ldb + (size_t)((which ? 2 : 1) * num_heads + h) * 128 + opf_mem_piece(jj) * 16;
-        uint8_t* dst = (which ? sV : sK) + st * 8192 + key * 128 + ((jj ^ (key & 7)) << 4);
-        cp_async_16_zfill(smem_u32(dst), src, kr < T ? 16u : 0u);
-      }
-      cp_async_commit();
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&kv_full[st]);
-    }
-  } else {
-    // =========================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t IDESC_S = umma_idesc_bf16_m128(64);
-      constexpr uint32_t IDESC_O = umma_idesc_bf16_m128_bmn(64);
-      const uint64_t qd = umma_desc_sw128(smem_u32(sQ));
-      const uint64_t pd0 = umma_desc_sw128(smem_u32(sP)), pd1 = umma_desc_sw128(smem_u32(sP + 16384));
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        tc_fence_after_sync();
-        const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * 8192));
-        umma_bf16(tmem_S, qd + 0, kd + 0, IDESC_S, 0);
-        umma_bf16(tmem_S, qd + 2, kd + 2, IDESC_S, 1);
-        umma_bf16(tmem_S, qd + 4, kd + 0, IDESC_S, 1);
-        umma_bf16(tmem_S, qd + 6, kd + 2, IDESC_S, 1);
-        umma_bf16(tmem_S, qd + 0, kd + 4, IDESC_S, 1);
-        umma_bf16(tmem_S, qd + 2, kd + 6, IDESC_S, 1);
-        umma_commit(s_full);
-      };
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);                       // P(j) written, S(j) consumed
-        if (j > 0) mbar_wait(o_free, (j - 1) & 1);      // O'(j-1) consumed
-        tc_fence_after_sync();
-        const uint64_t vd = umma_desc_sw128_mn(smem_u32(sV + st * 8192));
-        // k-step i covers keys 16i..16i+15: P chunk i/2, hi at +(i%2)*32 B, lo at +64+(i%2)*32 B; V rows advance by 16*128 B
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint64_t pd = (i < 2 ? pd0 : pd1) + (uint64_t)((i & 1) * 2);
-          const uint64_t vdi = vd + (uint64_t)(i * 128);          // 2048 B >> 4
-          umma_bf16(tmem_O, pd, vdi, IDESC_O, i > 0);
-          umma_bf16(tmem_O, pd + 4, vdi, IDESC_O, 1);
-        }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
-        if (j + 1 < n_tiles) issue_s(j + 1);            // overlaps the softmax warps' O' accumulation of tile j
-      }
-    }
-    __syncwarp();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 // ---------------------------------------------------------------- box decode / column gather
@@ -912,25 +676,6 @@ int ud3d_attention_fwd_opform(const float* qkv_split, const int32_t* cu_seqlens,
   if (max_T == 0) return UD3D_OK;
   dim3 grid(cdiv(max_T, kAtt2Q), num_heads, B);
   attention_opform_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads, (uint8_t*)out_split);
-  UD3D_LAUNCH_CHECK();
-  return UD3D_OK;
-}
-
-int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_seqlens, int B, int max_T, int num_heads,
-                          float* out_split, void* stream) {
-  UD3D_CHECK_ARG(qkv_split && cu_seqlens && out_split, "ud3d_attention_fwd_tc: NULL argument");
-  UD3D_CHECK_ARG(B > 0 && num_heads > 0 && max_T >= 0, "ud3d_attention_fwd_tc: bad sizes");
-  UD3D_CHECK_ARG((((uintptr_t)qkv_split | (uintptr_t)out_split) & 15) == 0, "ud3d_attention_fwd_tc: pointers must be 16-byte aligned");
-  if (max_T == 0) return UD3D_OK;
-  const size_t smem = 1024 + 16384 + 4 * 8192 + 2 * 16384 + 1024 + 128;
-  static bool configured = false;
-  if (!configured) {
-    UD3D_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
-  dim3 grid(cdiv(max_T, kTcQ), num_heads, B);
-  attention_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>((const uint8_t*)qkv_split, cu_seqlens, num_heads,
-                                                                         (uint8_t*)out_split);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

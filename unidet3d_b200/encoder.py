@@ -81,6 +81,9 @@ class UniDet3DEncoder(nn.Module):
         self.out_bboxes = PredBBox(d_model, 8)
         self.activation_fn = activation_fn
         self.eval_aux_outputs = False
+        # attention kernel of the product path: the tcgen05 kernel (csrc/attention_tc.cu); False selects the mma.sync
+        # kernel, kept as the cross-check (2x slower at the same accuracy)
+        self.attention_tcgen05 = True
         self._split_ok = False
         self._plan = None
         self.register_load_state_dict_post_hook(lambda m, keys: m.invalidate_plan())
@@ -169,7 +172,7 @@ class UniDet3DEncoder(nn.Module):
             for li, lp in enumerate(p["layers"]):
                 qkv_s = torch.empty((n, 3 * d), dtype=torch.float32, device=X.device)
                 ops.gemm(H_s, lp["qkv"][0], bias=lp["qkv"][1], in_split=True, no_raw=True, acts=[(qkv_s, None, None, False)])
-                A_s = ops.attention(qkv_s, cu, max_T, self.num_heads, split_in=True)
+                A_s = ops.attention(qkv_s, cu, max_T, self.num_heads, split_in=True, tcgen05=self.attention_tcgen05)
                 Z = ops.gemm(A_s, lp["out"][0], bias=lp["out"][1], residual=H, in_split=True)
                 H, H_s = ops.layernorm_split(Z, lp["n1"][0], lp["n1"][1], eps=lp["n1"][2])
                 F_s = torch.empty((n, hidden), dtype=torch.float32, device=X.device)

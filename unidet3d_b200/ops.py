@@ -324,7 +324,12 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_T: int, num_heads
     out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=qkv.device)
     if tcgen05 and not split_in:
         raise _lib.Ud3dError("attention: the tcgen05 kernel takes operand-form q|k|v (split_in=True)")
-    fn = (_L().ud3d_attention_fwd_tc if tcgen05 else _L().ud3d_attention_fwd_opform) if split_in else (
+    if tcgen05:
+        qkv = _req(qkv, torch.float32, "qkv")
+        check(_L().ud3d_attention_fwd_tc(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, int(max_T), int(qkv.shape[0]),
+                                         num_heads, _p(out), _stream()), "ud3d_attention_fwd_tc")
+        return out
+    fn = _L().ud3d_attention_fwd_opform if split_in else (
         _L().ud3d_attention_fwd_split if split_out else _L().ud3d_attention_fwd)
     check(fn(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, int(max_T), num_heads, _p(out), _stream()),
           "ud3d_attention_fwd")
