@@ -71,29 +71,30 @@ def main():
                 e0 = float((v[0] - ref[0]).abs().max() / ref[0].abs().max())
                 e1 = float((v[1].view(torch.int32) != ref[1].view(torch.int32)).float().mean())
                 print(f"   {k}: raw rel err vs canonical/smem {e0:.2e}, operand-form words differing {e1:.2e}")
-    # encoder-shaped dense GEMMs
+    # encoder-shaped dense GEMMs (the gather-GEMM's identity-gather path), checked against fp32 torch
     T = 13447
-    for (ci, co, actf) in ((256, 768, None), (256, 256, None), (256, 1024, "gelu"), (1024, 256, None)):
+    for (ci, co, actf, res) in ((256, 768, None, False), (256, 256, None, True), (256, 1024, "gelu", False), (1024, 256, None, True),
+                                (256, 100, None, False)):
         xin = torch.randn(T, ci, device="cuda")
         xs = ops.act_split(xin, relu=False)
-        w = ops.PackedWeight(torch.randn(co, ci, device="cuda") * 0.05)
+        wt = torch.randn(co, ci, device="cuda") * 0.05
+        w = ops.PackedWeight(wt)
         b = torch.randn(co, device="cuda")
-        outs = {}
-        for path, fl in (("smem", 1), ("tmem", 2)):
-            lib.ud3d_debug_set_flags(fl if fl > 2 else 0)
+        r = torch.randn(T, co, device="cuda") if res else None
+        if co % 32 == 0:
             act = torch.zeros(T, co, device="cuda")
-            xin_ = xs if fl == 1 else ops.operand_form_interleave(xs)
-        run = lambda: ops.gemm(xin_, w, in_split=fl, bias=b, act=actf, no_raw=True, acts=[(act, None, None, False)])
-            try:
-                us = timed(run)
-            except Exception as e:  # noqa: BLE001
-                print(f"dense {ci}->{co} {path}: FAILED {e}")
-                continue
-            outs[path] = act.clone()
-            print(f"dense {ci}->{co} {actf} {path}: {us:8.1f} us/launch", flush=True)
-        lib.ud3d_debug_set_flags(0)
-        if len(outs) == 2:
-            print("   operand-form words differing:", float((outs["smem"].view(torch.int32) != outs["tmem"].view(torch.int32)).float().mean()))
+            run = lambda: ops.gemm(xs, w, in_split=True, bias=b, act=actf, residual=r, no_raw=False, acts=[(act, None, None, False)])
+        else:
+            run = lambda: ops.gemm(xs, w, in_split=True, bias=b, act=actf)
+        us = timed(run)
+        o = run(); torch.cuda.synchronize()
+        ref = xin.double() @ wt.double().t() + b.double()
+        if actf == "gelu":
+            ref = torch.nn.functional.gelu(ref)
+        if res:
+            ref = ref + r.double()
+        e = float((o.double() - ref).abs().max() / ref.abs().max())
+        print(f"dense {ci}->{co} {actf} res={res}: {us:8.1f} us/launch   rel err vs fp64 {e:.2e}", flush=True)
 
 
 if __name__ == "__main__":

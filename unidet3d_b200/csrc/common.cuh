@@ -309,6 +309,10 @@ __device__ __forceinline__ float4 ld_shared_cluster_f4(uint32_t addr) {
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// same, 64B swizzle: rows of 64 bytes, 8-row atoms 512 B apart (layout_type 4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
 // UMMA instruction descriptor: kind::f16, A=B=BF16, D=F32, both K-major, M=128, N
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_m128(uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24);

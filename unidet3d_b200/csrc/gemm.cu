@@ -59,8 +59,13 @@ static inline int pick_ntile(int c_out) {
 }
 
 // ---------------------------------------------------------------- weight packing
-// image: [n_tile][k][chunk][N_TILE rows][8 x 16B], row n holds hi(32 ch) | lo(32 ch), 16-byte
-// chunk j stored at physical position j ^ (n & 7)  (Swizzle<3,4,3>, 128B rows)
+// Two images of the same size (N_TILE x 128 bytes per (n_tile, k, chunk)):
+//  * stacked (N_TILE <= 128, kStackedB): 2 N_TILE rows of 64 bytes -- row n = bf16 hi of weight row n (32 channels),
+//    row N_TILE + n = its bf16 lo -- 16-byte piece j stored at j ^ ((row >> 1) & 3) (Swizzle<2,4,3>, 64B rows).  One
+//    MMA of N = 2 N_TILE then forms A_hi . [W_hi | W_lo] in one pass over the A tile (see the MMA issuer);
+//  * side by side (N_TILE = 160): [N_TILE rows][8 x 16B], row n holds hi(32 ch) | lo(32 ch), 16-byte
+//    piece j stored at physical position j ^ (n & 7)  (Swizzle<3,4,3>, 128B rows)
+__host__ __device__ constexpr bool stacked_b(int n_tile) { return n_tile <= 128; }
 __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int c_in, int c_out, int n_tile_sz, int n_tiles,
                                    int n_chunks, uint4* __restrict__ out) {
   long long total = (long long)n_tiles * K * n_chunks * n_tile_sz * 8;
@@ -89,7 +94,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int c_in,
       v[e] = (j < 4) ? hi : lo;
     }
     size_t tile = ((size_t)nt * K + k) * n_chunks + c;
-    out[tile * n_tile_sz * 8 + (size_t)n * 8 + (j ^ (n & 7))] = make_uint4(v[0], v[1], v[2], v[3]);
+    if (stacked_b(n_tile_sz)) {
+      const int row = (j < 4) ? n : n_tile_sz + n;
+      out[tile * n_tile_sz * 8 + (size_t)row * 4 + ((j & 3) ^ ((row >> 1) & 3))] = make_uint4(v[0], v[1], v[2], v[3]);
+    } else {
+      out[tile * n_tile_sz * 8 + (size_t)n * 8 + (j ^ (n & 7))] = make_uint4(v[0], v[1], v[2], v[3]);
+    }
   }
 }
 
@@ -143,8 +153,13 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
   constexpr int STAGES = TcCfg<N_TILE>::kStages;
   constexpr int A_BYTES = kTileM * 128;
   constexpr int B_BYTES = N_TILE * 128;
-  constexpr uint32_t TMEM_COLS = N_TILE <= 32 ? 32 : N_TILE <= 64 ? 64 : N_TILE <= 128 ? 128 : 256;
+  // stacked weight tile: the accumulator has 2 N_TILE columns -- [0, N) = hi.hi + lo.hi, [N, 2N) = hi.lo -- summed in
+  // the epilogue
+  constexpr bool STACKED = stacked_b(N_TILE);
+  constexpr int ACC_COLS = STACKED ? 2 * N_TILE : N_TILE;
+  constexpr uint32_t TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : 256;
   constexpr uint32_t IDESC = umma_idesc_bf16_m128(N_TILE);
+  constexpr uint32_t IDESC2 = umma_idesc_bf16_m128(2 * N_TILE <= 256 ? 2 * N_TILE : 256);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
       // one elected lane issues each tcgen05 instruction (elect.sync): operands stay in uniform registers.  Under a
       // `lane == 0` branch the compiler wraps every UTCHMMA in an R2UR / vote loop (~80 cycles of issue per MMA).
       const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
-      const uint64_t bdesc0 = umma_desc_sw128(smem_u32(sB));
+      const uint64_t bdesc0 = STACKED ? umma_desc_sw64(smem_u32(sB)) : umma_desc_sw128(smem_u32(sB));
       long long* tr = (traced && lane == 0) ? p.trace : nullptr;
       int s = rs;
       uint32_t use = ruse;
@@ -453,12 +468,23 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
           // the start-address field is in 16-byte units: stage s, then +2 = 32 B (second K=16 slice), +4 = lo half,
           // +6 = lo second slice
           const uint64_t ad = adesc0 + (uint64_t)(s * (A_BYTES >> 4)), bd = bdesc0 + (uint64_t)(s * (B_BYTES >> 4));
-          umma_bf16_elect(tmem_base, ad + 0, bd + 0, IDESC, t > 0);
-          umma_bf16_elect(tmem_base, ad + 2, bd + 2, IDESC, 1);
-          umma_bf16_elect(tmem_base, ad + 4, bd + 0, IDESC, 1);
-          umma_bf16_elect(tmem_base, ad + 6, bd + 2, IDESC, 1);
-          umma_bf16_elect(tmem_base, ad + 0, bd + 4, IDESC, 1);
-          umma_bf16_elect(tmem_base, ad + 2, bd + 6, IDESC, 1);
+          if constexpr (STACKED) {
+            // 4 MMAs: A_hi x [W_hi | W_lo] (N = 2 N_TILE: columns [0, N) += hi.hi, [N, 2N) += hi.lo) and A_lo x W_hi
+            // (N = N_TILE, the first N rows of the same weight tile) per K = 16 slice.  The A_hi tile is read from shared
+            // memory once instead of twice: the main loop is bound by the shared-memory port (operand reads of the
+            // tensor core + the gather's writes), not by the tensor pipe
+            umma_bf16_elect(tmem_base, ad + 0, bd + 0, IDESC2, t > 0);
+            umma_bf16_elect(tmem_base, ad + 2, bd + 2, IDESC2, 1);
+            umma_bf16_elect(tmem_base, ad + 4, bd + 0, IDESC, 1);
+            umma_bf16_elect(tmem_base, ad + 6, bd + 2, IDESC, 1);
+          } else {
+            umma_bf16_elect(tmem_base, ad + 0, bd + 0, IDESC, t > 0);
+            umma_bf16_elect(tmem_base, ad + 2, bd + 2, IDESC, 1);
+            umma_bf16_elect(tmem_base, ad + 4, bd + 0, IDESC, 1);
+            umma_bf16_elect(tmem_base, ad + 6, bd + 2, IDESC, 1);
+            umma_bf16_elect(tmem_base, ad + 0, bd + 4, IDESC, 1);
+            umma_bf16_elect(tmem_base, ad + 2, bd + 6, IDESC, 1);
+          }
           umma_commit_elect(&empty[s]);      // stage s reusable once these MMAs have read it
         }
         if (tr && t < 64) tr[t * 8 + 6] = clock64();
@@ -505,7 +531,15 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
           uint32_t r[32];
           if (nsteps > 0) {
             tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait();
+            if constexpr (STACKED) {
+              uint32_t r2[32];
+              tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(N_TILE + c0), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+              tmem_ld_wait();
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
@@ -533,7 +567,15 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
           uint32_t r[32];
           if (nsteps > 0) {
             tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-            tmem_ld_wait();
+            if constexpr (STACKED) {
+              uint32_t r2[32];
+              tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(N_TILE + c0), r2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+              tmem_ld_wait();
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
@@ -857,6 +899,7 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
     }
   }
   // operand-form inputs of launches that fill the GPU: the A operand goes global -> registers -> TMEM (gemm_ts.cu)
+  // dense GEMMs on operand-form rows with 128-column weight tiles (the encoder's Linear layers): the persistent TMA kernel
   // The experimental TMEM-operand kernel (gemm_ts.cu) takes its input in the INTERLEAVED operand form (in_split == 2,
   // ops.operand_form_interleave); the product path does not use it: measured on B200 it wins with warm caches
   // (graph-replayed level-1 SubM3 32->32: 127 vs 182 us, 64->64: 61 vs 92 us) but not inside the real step, where every
