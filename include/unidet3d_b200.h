@@ -192,6 +192,47 @@ int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scal
  * (diagnostic cross-check of the tensor-core path; not used by the product path) */
 int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream);
 
+/* ------------------------------------------------------------------ stage plan: the whole U-Net in one call
+ * reference: SpConvUNet.forward, unidet3d/spconv_unet.py:117-240 (eval mode; channel counts multiples of 32).
+ * A plan holds, per level, the packed weights (ud3d_gemm_pack_weight) and the folded eval-mode BatchNorms
+ * (scale = gamma / sqrt(var + eps), shift = beta - mean * scale) of the parameter tree
+ *   blocks.block{i}.conv_branch.{0,2,3,5}, conv.{0,2}, deconv.{0,2}, blocks_tail.block{i}.{i_branch.0, conv_branch.*}
+ * and ud3d_unet_forward issues every convolution of the recursion through ud3d_gemm_fwd with the fusion described there
+ * (operand-form maps under the consumer's BatchNorm, residuals in the epilogue, concat never materialised).  It exists to
+ * take the host off the critical path: ~50 launches marshalled in C instead of through the caller's language runtime.
+ *   x_raw [n_0, c_0] fp32 input features, x_act the same under level[0].blocks[0].bn0 in operand form (ud3d_act_split or a
+ *   producer epilogue); out_raw [n_0, c_0]; level_out: NULL or n_levels pointers ([l] NULL or [n_l, c_l]: the fp32 output
+ *   of level l, the `previous_outputs` of return_blocks=True; [0] ignored).  ws: ud3d_unet_workspace_bytes, 256-byte aligned. */
+#define UD3D_UNET_MAX_LEVELS 8
+#define UD3D_UNET_MAX_REPS 4
+typedef struct {
+  const void* w0; const void* w1;      /* SubM3 c -> c (tail block 0: w0 is 2c -> c) */
+  const void* wi;                      /* SubM1 i_branch (tail block 0 only), else NULL */
+  const float* bn0_scale; const float* bn0_shift;   /* conv_branch.0 (tail block 0: 2c channels) */
+  const float* bn1_scale; const float* bn1_shift;   /* conv_branch.3 */
+} ud3d_unet_block;
+typedef struct {
+  int32_t c;
+  ud3d_unet_block blocks[UD3D_UNET_MAX_REPS];
+  ud3d_unet_block tail[UD3D_UNET_MAX_REPS];         /* unused at the deepest level */
+  const void* down_w; const void* up_w;             /* conv.2 (k2 s2, c -> c_next), deconv.2 (inverse, c_next -> c) */
+  const float* down_scale; const float* down_shift; /* conv.0   [c] */
+  const float* up_scale; const float* up_shift;     /* deconv.0 [c_next] */
+} ud3d_unet_level;
+typedef struct {
+  int32_t n_levels; int32_t block_reps;
+  ud3d_unet_level level[UD3D_UNET_MAX_LEVELS];
+} ud3d_unet_plan;
+typedef struct {                                    /* rulebooks of one level (ud3d_rulebook_subm3 / _down2 / tile order) */
+  int32_t n;
+  const int32_t* subm; const uint32_t* subm_mask; const int32_t* row_perm;   /* row_perm NULL = canonical order */
+  const int32_t* child; const uint32_t* child_mask;                           /* [8, n_next]; NULL at the deepest level */
+  const int32_t* up; const uint32_t* up_mask;                                 /* [8, n] */
+} ud3d_unet_tables;
+size_t ud3d_unet_workspace_bytes(const ud3d_unet_plan* plan, const ud3d_unet_tables* levels);
+int ud3d_unet_forward(const ud3d_unet_plan* plan, const ud3d_unet_tables* levels, const float* x_raw, const float* x_act,
+                      float* out_raw, float* const* level_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ training side of the backbone
  * Train-mode (Sync)BatchNorm of the reference (spconv_unet.py:119-124, unidet3d.py:104-107; torch.nn.SyncBatchNorm,
  * eps 1e-4, momentum 0.1): statistics over ALL active voxels of the (global) batch.
@@ -219,7 +260,10 @@ int ud3d_conv_wgrad(const float* x, int ld_x, int c_in, const float* dy, int ld_
  * BatchNorm+ReLU of unidet3d.py:104-111,129 and the x.features[inverse_mapping] gather fused)
  * and unidet3d.py:446-447 (superpoint centres).
  *   out[s,:] = mean_{p: seg[p]==s} pre(src[gather ? gather[p] : p, :]),  empty s -> 0.
- * seg int64 [n] (reference loader dtype), out [n_seg,C]; ws >= n_seg*4 bytes. */
+ * seg int64 [n] (reference loader dtype), out [n_seg,C]; ws >= ud3d_segmented_mean_workspace_bytes (8-byte aligned).
+ * Deterministic (bit-identical from run to run): partial sums are accumulated as 64-bit fixed point (2^-24), whose
+ * addition is associative; valid for |sum of a segment| < 5e11. */
+size_t ud3d_segmented_mean_workspace_bytes(int n_seg, int C);
 int ud3d_segmented_mean(const float* src, int ld_src, int C, const int32_t* gather, const int64_t* seg,
                         int n, int n_seg, const float* scale, const float* shift, int relu,
                         float* out, void* ws, size_t ws_bytes, void* stream);

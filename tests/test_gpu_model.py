@@ -35,6 +35,34 @@ def test_unet_module_vs_reference_fixture(golden_dir):
     assert relerr(y.features, g["out"]) < 1e-3, relerr(y.features, g["out"])
 
 
+@pytest.mark.parametrize("planes,reps", [([32, 64, 96, 128, 160], 2), ([32, 64], 1), ([64], 2), ([32, 32, 64], 2)])
+def test_unet_stage_plan_matches_per_conv_executor(planes, reps):
+    """ud3d_unet_forward (one C call for the whole recursion) == the Python recursion, bit for bit, incl. the per-level
+    outputs of return_blocks=True."""
+    import unidet3d_b200 as u
+    torch.manual_seed(3)
+    m = u.MODELS.build(dict(type="SpConvUNet", num_planes=planes, block_reps=reps, return_blocks=True)).eval()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm1d):
+            mod.running_mean.normal_(0, 0.2); mod.running_var.uniform_(0.5, 1.5)
+            mod.weight.data.uniform_(0.5, 1.5); mod.bias.data.normal_(0, 0.2)
+    m.to(DEV)
+    g = torch.Generator().manual_seed(0)
+    coords = torch.unique(torch.cat([torch.zeros(4000, 1, dtype=torch.int32),
+                                     torch.randint(0, 40, (4000, 3), generator=g, dtype=torch.int32)], 1), dim=0)
+    feats = torch.randn(coords.shape[0], planes[0], generator=g)
+    outs = {}
+    for plan in (False, True):
+        m.use_stage_plan = plan
+        x = u.SparseConvTensor(feats.to(DEV), coords.to(DEV), [40, 40, 40], 1)
+        y, blocks = m(x)
+        outs[plan] = (y.features.clone(), [b.features.clone() for b in blocks])
+    assert torch.equal(outs[True][0], outs[False][0])
+    assert len(outs[True][1]) == len(outs[False][1]) == len(planes)
+    for a, b in zip(outs[True][1], outs[False][1]):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
 def test_encoder_module_vs_reference_fixture(golden_dir):
     import unidet3d_b200 as u
     g = np.load(os.path.join(golden_dir, "encoder_ref.npz"))

@@ -192,6 +192,11 @@ def test_segmented_mean():
                              shift=shift.to(DEV), relu=True)
     assert relerr(out, ref) < 1e-5
     assert float(out[-3:].abs().max()) == 0.0
+    # deterministic: the fixed-point atomics make repeated calls bit-identical (random ids: ~every point is its own run)
+    for _ in range(5):
+        again = ops.segmented_mean(feats.to(DEV), seg.to(DEV), n_seg, gather=inv.int().to(DEV), scale=scale.to(DEV),
+                                   shift=shift.to(DEV), relu=True)
+        assert torch.equal(again, out)
     # superpoint centres: C=3 of a [n,6] matrix, runs of equal ids
     pts = torch.randn(n_pts, 6, generator=g)
     seg2 = torch.sort(seg)[0]

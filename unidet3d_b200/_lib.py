@@ -36,6 +36,30 @@ class GemmArgs(C.Structure):
     ]
 
 
+class UnetBlock(C.Structure):
+    """Mirror of ``ud3d_unet_block``."""
+    _fields_ = [("w0", C.c_void_p), ("w1", C.c_void_p), ("wi", C.c_void_p),
+                ("bn0_scale", C.c_void_p), ("bn0_shift", C.c_void_p), ("bn1_scale", C.c_void_p), ("bn1_shift", C.c_void_p)]
+
+
+class UnetLevel(C.Structure):
+    """Mirror of ``ud3d_unet_level``."""
+    _fields_ = [("c", C.c_int32), ("blocks", UnetBlock * 4), ("tail", UnetBlock * 4),
+                ("down_w", C.c_void_p), ("up_w", C.c_void_p),
+                ("down_scale", C.c_void_p), ("down_shift", C.c_void_p), ("up_scale", C.c_void_p), ("up_shift", C.c_void_p)]
+
+
+class UnetPlan(C.Structure):
+    """Mirror of ``ud3d_unet_plan``."""
+    _fields_ = [("n_levels", C.c_int32), ("block_reps", C.c_int32), ("level", UnetLevel * 8)]
+
+
+class UnetTables(C.Structure):
+    """Mirror of ``ud3d_unet_tables``."""
+    _fields_ = [("n", C.c_int32), ("subm", C.c_void_p), ("subm_mask", C.c_void_p), ("row_perm", C.c_void_p),
+                ("child", C.c_void_p), ("child_mask", C.c_void_p), ("up", C.c_void_p), ("up_mask", C.c_void_p)]
+
+
 class PostArgs(C.Structure):
     """Mirror of ``ud3d_post_args``."""
     _fields_ = [
@@ -88,6 +112,9 @@ SIGNATURES = {
     "ud3d_bn_batch_sums": (_i, [_vp, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_bn_train_fold": (_i, [_vp, C.c_double, _i, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ud3d_conv_wgrad_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
+    "ud3d_segmented_mean_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "ud3d_unet_workspace_bytes": (C.c_size_t, [_vp, _vp]),
+    "ud3d_unet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, C.c_size_t, _vp]),
     "ud3d_gemm_fwd": (_i, [C.POINTER(GemmArgs), _vp]),
     "ud3d_act_split": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),

@@ -30,16 +30,8 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
-#include <stdlib.h>
 
 namespace ud3d {
-
-// (experiment switch UD3D_ATTN_DBG bit 256: spin on mbarrier.test_wait instead of the suspending try_wait)
-#define ATT_WAIT(bar, parity)                      \
-  do {                                             \
-    if (dbg & 256) mbar_wait_spin((bar), (parity)); \
-    else mbar_wait((bar), (parity));               \
-  } while (0)
 
 constexpr int kAQ = 128, kAK = 64, kAStages = 4;
 constexpr int kASoftmaxWarps = 4;
@@ -114,7 +106,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 
 __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                    const int32_t* __restrict__ cu, int num_heads,
-                                                                   uint8_t* __restrict__ out, int dbg) {
+                                                                   uint8_t* __restrict__ out) {
   const int b = blockIdx.z, h = blockIdx.y;
   const int t0 = cu[b];
   const int T = cu[b + 1] - t0;
@@ -168,13 +160,8 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         float p0, p1;
-        if (dbg & 4) {
-          p0 = fmaf(__uint_as_float(r[i]), qscale, -m_ref);
-          p1 = fmaf(__uint_as_float(r[i + 1]), qscale, -m_ref);
-        } else {
-          p0 = ex2_approx_a(fmaf(__uint_as_float(r[i]), qscale, -m_ref));
-          p1 = ex2_approx_a(fmaf(__uint_as_float(r[i + 1]), qscale, -m_ref));
-        }
+        p0 = ex2_approx_a(fmaf(__uint_as_float(r[i]), qscale, -m_ref));
+        p1 = ex2_approx_a(fmaf(__uint_as_float(r[i + 1]), qscale, -m_ref));
         if (nvc < 32) {
           if (i >= nvc) p0 = 0.f;
           if (i + 1 >= nvc) p1 = 0.f;
@@ -195,7 +182,7 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
       return m;
     };
     uint32_t ra[32], rb[32], pk[32];
-    ATT_WAIT(&s_full[0], 0u);
+    mbar_wait(&s_full[0], 0u);
     tc_fence_after_sync();
     tmem_ld_32x32(t_lane + kAColS, ra);                 // chunk a of tile 0
     for (int j = 0; j < n_tiles; ++j) {
@@ -205,7 +192,7 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
       // S is read from TMEM exactly ONCE (TMEM reads run at ~64 B per cycle and SM: a tile's 32 KB cost as much as its
       // 8192 exponentials), and every load is in flight while the other chunk is exponentiated.
       tmem_ld_wait();                                   // chunk a (requested during the previous tile)
-      if (!(dbg & 8)) tmem_ld_32x32(tSb + 32u, rb);                     // chunk b
+      tmem_ld_32x32(tSb + 32u, rb);                     // chunk b
       const float cmax_a = chunk_max(ra, nv);
       if (j > 0) exp_split(ra, nv, pk);                 // optimistic: with the current reference maximum
       tmem_ld_wait();
@@ -224,7 +211,7 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
         }
         if (j > 0) {
           // O' and L are complete up to tile j-1 once its MMAs have completed (those of tile j wait for p_full below)
-          ATT_WAIT(&o_done[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1u);
+          mbar_wait(&o_done[(j - 1) & 1], (uint32_t)((j - 1) >> 1) & 1u);
           tc_fence_after_sync();
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
@@ -242,27 +229,23 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
         exp_split(ra, nv, pk);                          // chunk a again, with the new reference (ra still holds raw S)
       }
       // P of chunk a over the S columns it came from: hi at +0..15, lo at +16..31
-      if (!(dbg & 64)) {
-        tmem_st_32x32_x16(tSb, pk);
-        tmem_st_32x32_x16(tSb + 16u, pk + 16);
-      }
+      tmem_st_32x32_x16(tSb, pk);
+      tmem_st_32x32_x16(tSb + 16u, pk + 16);
       if (j + 1 < n_tiles) {
-        ATT_WAIT(&s_full[buf ^ 1], (uint32_t)((j + 1) >> 1) & 1u);
+        mbar_wait(&s_full[buf ^ 1], (uint32_t)((j + 1) >> 1) & 1u);
         tc_fence_after_sync();
-        if (!(dbg & 8)) tmem_ld_32x32(t_lane + kAColS + (uint32_t)((buf ^ 1) * 64), ra);      // chunk a of the next tile
+        tmem_ld_32x32(t_lane + kAColS + (uint32_t)((buf ^ 1) * 64), ra);      // chunk a of the next tile
       }
       exp_split(rb, nv - 32, pk);
-      if (!(dbg & 64)) {
-        tmem_st_32x32_x16(tSb + 32u, pk);
-        tmem_st_32x32_x16(tSb + 48u, pk + 16);
-      }
+      tmem_st_32x32_x16(tSb + 32u, pk);
+      tmem_st_32x32_x16(tSb + 48u, pk + 16);
       tmem_st_wait_a();
       tc_fence_before_sync();           // P (and a rescaled O' / L) are written, S has been read
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[buf]);
     }
     // ---- output: O = (O'[:, :32] + O'[:, 32:]) / L, operand form (head h == 32-channel chunk h)
-    ATT_WAIT(&o_done[(n_tiles - 1) & 1], (uint32_t)((n_tiles - 1) >> 1) & 1u);
+    mbar_wait(&o_done[(n_tiles - 1) & 1], (uint32_t)((n_tiles - 1) >> 1) & 1u);
     tc_fence_after_sync();
     uint32_t a[32], c2[32];
     tmem_ld_32x32(t_lane + kAColO, a);
@@ -294,14 +277,10 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
       tma_load_2d(sQ + 8192, &tmap, h * 128, t0 + q0 + 64, q_full);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % kAStages;
-        if (j >= kAStages) ATT_WAIT(&kv_empty[st], (uint32_t)(j / kAStages - 1) & 1u);
+        if (j >= kAStages) mbar_wait(&kv_empty[st], (uint32_t)(j / kAStages - 1) & 1u);
         mbar_arrive_expect_tx(&kv_full[st], 16384);
-        if (!(dbg & 32)) {
-          tma_load_2d(sK + st * 8192, &tmap, (num_heads + h) * 128, t0 + j * kAK, &kv_full[st]);
-          tma_load_2d(sV + st * 8192, &tmap, (2 * num_heads + h) * 128, t0 + j * kAK, &kv_full[st]);
-        } else {
-          asm volatile("mbarrier.complete_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&kv_full[st])), "r"(16384) : "memory");
-        }
+        tma_load_2d(sK + st * 8192, &tmap, (num_heads + h) * 128, t0 + j * kAK, &kv_full[st]);
+        tma_load_2d(sV + st * 8192, &tmap, (2 * num_heads + h) * 128, t0 + j * kAK, &kv_full[st]);
       }
     }
     __syncwarp();
@@ -319,29 +298,27 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
     const uint32_t tS = tmem_base + kAColS, tO = tmem_base + kAColO, tL = tmem_base + kAColL;
     auto issue_s = [&](int j) {
       const int st = j % kAStages;
-      ATT_WAIT(&kv_full[st], (uint32_t)(j / kAStages) & 1u);
+      mbar_wait(&kv_full[st], (uint32_t)(j / kAStages) & 1u);
       tc_fence_after_sync();
       if (elect_one_sync()) {
         const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * 8192));
         const uint32_t tSb = tS + (uint32_t)((j & 1) * 64);
         umma_bf16(tSb, qd + 0, kd + 0, IDESC_S, 0);
-        if (!(dbg & 16)) {
-          umma_bf16(tSb, qd + 2, kd + 2, IDESC_S, 1);
-          umma_bf16(tSb, qd + 4, kd + 0, IDESC_S, 1);
-          umma_bf16(tSb, qd + 6, kd + 2, IDESC_S, 1);
-          umma_bf16(tSb, qd + 0, kd + 4, IDESC_S, 1);
-          umma_bf16(tSb, qd + 2, kd + 6, IDESC_S, 1);
-        }
+        umma_bf16(tSb, qd + 2, kd + 2, IDESC_S, 1);
+        umma_bf16(tSb, qd + 4, kd + 0, IDESC_S, 1);
+        umma_bf16(tSb, qd + 6, kd + 2, IDESC_S, 1);
+        umma_bf16(tSb, qd + 0, kd + 4, IDESC_S, 1);
+        umma_bf16(tSb, qd + 2, kd + 6, IDESC_S, 1);
         umma_commit(&s_full[j & 1]);
       }
       __syncwarp();
     };
-    ATT_WAIT(q_full, 0u);
+    mbar_wait(q_full, 0u);
     issue_s(0);
     if (n_tiles > 1) issue_s(1);
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j % kAStages;
-      ATT_WAIT(&p_full[j & 1], (uint32_t)(j >> 1) & 1u);     // P(j) written, S(j) consumed, O' / L rescaled if needed
+      mbar_wait(&p_full[j & 1], (uint32_t)(j >> 1) & 1u);     // P(j) written, S(j) consumed, O' / L rescaled if needed
       tc_fence_after_sync();
       if (elect_one_sync()) {
         const uint64_t vd = umma_desc_sw128_mn_a(smem_u32(sV + st * 8192));
@@ -353,9 +330,9 @@ __global__ void __launch_bounds__(kAThreads, 2) attention_tc_kernel(const __grid
           const uint32_t ph = tP + (uint32_t)((i >> 1) * 32 + (i & 1) * 8), pl = ph + 16u;
           const uint64_t vdi = vd + (uint64_t)(i * 128);
           umma_bf16_ts(tO, ph, vdi, IDESC_O, (j > 0 || i > 0) ? 1u : 0u);
-          if (!(dbg & 2)) umma_bf16_ts(tO, pl, vdi, IDESC_O, 1u);
-          if (!(dbg & 1)) umma_bf16_ts(tL, ph, od, IDESC_L, (j > 0 || i > 0) ? 1u : 0u);
-          if (!(dbg & 3)) umma_bf16_ts(tL, pl, od, IDESC_L, 1u);
+          umma_bf16_ts(tO, pl, vdi, IDESC_O, 1u);
+          umma_bf16_ts(tL, ph, od, IDESC_L, (j > 0 || i > 0) ? 1u : 0u);
+          umma_bf16_ts(tL, pl, od, IDESC_L, 1u);
         }
         umma_commit(&o_done[j & 1]);
         umma_commit(&kv_empty[st]);
@@ -411,7 +388,6 @@ extern "C" int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_s
     return UD3D_ECUDA;
   }
   const size_t smem = 1024 + 16384 + 2 * kAStages * 8192 + 1024 + 256;
-  const int dbg = getenv("UD3D_ATTN_DBG") ? atoi(getenv("UD3D_ATTN_DBG")) : 0;
   static bool configured[64] = {false};
   int dev = 0;
   UD3D_CUDA(cudaGetDevice(&dev));
@@ -421,7 +397,7 @@ extern "C" int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_s
     configured[dev] = true;
   }
   dim3 grid(cdiv(max_T, kAQ), num_heads, B);
-  attention_tc_kernel<<<grid, kAThreads, smem, (cudaStream_t)stream>>>(tmap, cu_seqlens, num_heads, (uint8_t*)out_split, dbg);
+  attention_tc_kernel<<<grid, kAThreads, smem, (cudaStream_t)stream>>>(tmap, cu_seqlens, num_heads, (uint8_t*)out_split);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

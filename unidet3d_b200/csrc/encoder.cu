@@ -1,5 +1,5 @@
 // Superpoint pooling and the non-GEMM pieces of the superpoint transformer encoder:
-// segmented mean (warp-shuffle run-length reduction + red.add), LayerNorm(+residual),
+// segmented mean (warp-shuffle run-length reduction + 64-bit fixed-point red.add: deterministic), LayerNorm(+residual),
 // varlen multi-head self-attention (flash-style, bf16 hi/lo split on tensor cores), box decode.
 #include "common.cuh"
 
@@ -10,14 +10,19 @@ namespace ud3d {
 // share a segment id are accumulated in registers (shuffle-broadcast ids), one red.global.add per
 // run and channel.  The [n_pts, C] gather of the reference (x.features[inverse_mapping]) is never
 // materialised; the output BatchNorm+ReLU is applied on the fly.
+// DETERMINISTIC: a run's fp32 sum (fixed point order inside a fixed 128-point window) is converted to 64-bit fixed
+// point (2^-24 resolution, |sum| < 5e11) before the atomic: integer addition is associative, so the result does not
+// depend on the order in which the atomics of different warps land.  Counts are integer atomics.
 constexpr int kPoolPtsPerWarp = 128;
+constexpr float kPoolFixScale = 16777216.f;              // 2^24
+constexpr double kPoolFixInv = 1.0 / 16777216.0;
 
 __global__ void __launch_bounds__(256) segmented_sum_kernel(const float* __restrict__ src, int ld, int C,
                                                             const int32_t* __restrict__ gather,
                                                             const int64_t* __restrict__ seg, int n, int n_seg,
                                                             const float* __restrict__ scale,
-                                                            const float* __restrict__ shift, int relu, float* out,
-                                                            float* cnt) {
+                                                            const float* __restrict__ shift, int relu,
+                                                            unsigned long long* acc_fix, int* cnt) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long p0 = (long long)gw * kPoolPtsPerWarp;
@@ -26,7 +31,8 @@ __global__ void __launch_bounds__(256) segmented_sum_kernel(const float* __restr
   const float sc = (scale && lane < C) ? scale[lane] : 1.f;
   const float sh = (shift && lane < C) ? shift[lane] : 0.f;
   long long cur = -1;
-  float acc = 0.f, run = 0.f;
+  float acc = 0.f;
+  int run = 0;
   for (int base = (int)p0; base < pend; base += 32) {
     int p = base + lane;
     long long my_id = p < pend ? seg[p] : -1;
@@ -37,12 +43,12 @@ __global__ void __launch_bounds__(256) segmented_sum_kernel(const float* __restr
       int g = __shfl_sync(0xffffffffu, my_g, j);
       if (id != cur) {
         if (cur >= 0 && cur < n_seg) {
-          if (lane < C) atomicAdd(out + (size_t)cur * C + lane, acc);
+          if (lane < C) atomicAdd(acc_fix + (size_t)cur * C + lane, (unsigned long long)__float2ll_rn(acc * kPoolFixScale));
           if (lane == 0) atomicAdd(cnt + cur, run);
         }
         cur = id;
         acc = 0.f;
-        run = 0.f;
+        run = 0;
       }
       float v = 0.f;
       if (lane < C && g >= 0) {
@@ -51,19 +57,22 @@ __global__ void __launch_bounds__(256) segmented_sum_kernel(const float* __restr
         if (relu) v = fmaxf(v, 0.f);
       }
       acc += v;
-      run += 1.f;
+      run += 1;
     }
   }
   if (cur >= 0 && cur < n_seg) {
-    if (lane < C) atomicAdd(out + (size_t)cur * C + lane, acc);
+    if (lane < C) atomicAdd(acc_fix + (size_t)cur * C + lane, (unsigned long long)__float2ll_rn(acc * kPoolFixScale));
     if (lane == 0) atomicAdd(cnt + cur, run);
   }
 }
 
-__global__ void segmented_norm_kernel(float* out, const float* __restrict__ cnt, int n_seg, int C) {
+__global__ void segmented_norm_kernel(float* out, const unsigned long long* __restrict__ acc_fix, const int* __restrict__ cnt,
+                                      int n_seg, int C) {
   long long total = (long long)n_seg * C;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
-    out[t] = __fdiv_rn(out[t], fmaxf(cnt[t / C], 1.f));
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = cnt[t / C];
+    out[t] = (float)((double)(long long)acc_fix[t] * kPoolFixInv / (double)(c > 1 ? c : 1));
+  }
 }
 
 // ---------------------------------------------------------------- LayerNorm (+ residual), warp per row
@@ -584,29 +593,35 @@ using namespace ud3d;
 
 extern "C" {
 
+size_t ud3d_segmented_mean_workspace_bytes(int n_seg, int C) {
+  return (size_t)(n_seg > 0 ? n_seg : 0) * ((size_t)(C > 0 ? C : 0) * 8 + 4);
+}
+
 int ud3d_segmented_mean(const float* src, int ld_src, int C, const int32_t* gather, const int64_t* seg, int n, int n_seg,
                         const float* scale, const float* shift, int relu, float* out, void* ws, size_t ws_bytes,
                         void* stream) {
   UD3D_CHECK_ARG(src && seg && out && ws, "ud3d_segmented_mean: NULL argument");
   UD3D_CHECK_ARG(C > 0 && C <= 32 && ld_src >= C && n >= 0 && n_seg >= 0, "ud3d_segmented_mean: need 0 < C <= 32, ld >= C");
   UD3D_CHECK_ARG((scale == nullptr) == (shift == nullptr), "ud3d_segmented_mean: scale/shift must both be set");
-  if (ws_bytes < (size_t)n_seg * 4) {
+  UD3D_CHECK_ARG(((uintptr_t)ws & 7) == 0, "ud3d_segmented_mean: workspace must be 8-byte aligned");
+  if (ws_bytes < ud3d_segmented_mean_workspace_bytes(n_seg, C)) {
     set_error("ud3d_segmented_mean: workspace too small");
     return UD3D_EWORKSPACE;
   }
   if (n_seg == 0) return UD3D_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  UD3D_CUDA(cudaMemsetAsync(out, 0, (size_t)n_seg * C * 4, st));
-  UD3D_CUDA(cudaMemsetAsync(ws, 0, (size_t)n_seg * 4, st));
+  unsigned long long* acc_fix = (unsigned long long*)ws;            // [n_seg, C] fixed-point sums
+  int* cnt = (int*)(acc_fix + (size_t)n_seg * C);                   // [n_seg] point counts
+  UD3D_CUDA(cudaMemsetAsync(ws, 0, ud3d_segmented_mean_workspace_bytes(n_seg, C), st));
   if (n > 0) {
     int warps = cdiv(n, kPoolPtsPerWarp);
-    segmented_sum_kernel<<<cdiv(warps, 8), 256, 0, st>>>(src, ld_src, C, gather, seg, n, n_seg, scale, shift, relu, out, (float*)ws);
+    segmented_sum_kernel<<<cdiv(warps, 8), 256, 0, st>>>(src, ld_src, C, gather, seg, n, n_seg, scale, shift, relu, acc_fix, cnt);
     UD3D_LAUNCH_CHECK();
   }
   long long total = (long long)n_seg * C;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  segmented_norm_kernel<<<blocks, 256, 0, st>>>(out, (const float*)ws, n_seg, C);
+  segmented_norm_kernel<<<blocks, 256, 0, st>>>(out, acc_fix, cnt, n_seg, C);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

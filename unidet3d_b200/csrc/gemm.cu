@@ -122,11 +122,11 @@ constexpr bool kPersistent = false;
 // t + S).  Traced on B200: L ~ M ~ 1000 cycles, so D = 1 with S = 4 (T >= M / 2) beats D = 2 (T >= M) and
 // D = 3 (every step pays the full round trip).  S is the largest depth that keeps 2 CTAs/SM (1 for N_TILE >= 160).
 template <int N_TILE> struct TcCfg {
-  static constexpr int kStages = N_TILE <= 64 ? 4 : N_TILE <= 128 ? 3 : N_TILE == 160 ? 5 : 4;
+  static constexpr int kStages = N_TILE <= 32 ? 3 : N_TILE <= 64 ? 4 : N_TILE <= 128 ? 3 : N_TILE == 160 ? 5 : 4;
   // resident CTAs per SM the kernel is compiled for (register cap).  (3 CTAs x 3 stages for N_TILE = 32 and 3 CTAs x 2
   // stages for N_TILE = 64 measured the same as 2 x 4: the main loop is bound by the gather latency x the stages in flight
   // per SM, not by the number of CTAs; a 6-stage, 1 CTA/SM ring for the split-K launches lost more in waves than it won.)
-  static constexpr int kMinCtas = N_TILE <= 128 ? 2 : 1;
+  static constexpr int kMinCtas = N_TILE <= 32 ? 3 : N_TILE <= 128 ? 2 : 1;
 };
 
 // Raw gathered operand of one K-step for this thread: 2 rows x 8 channels
@@ -141,7 +141,7 @@ struct GatherRegs {
 // debug timeline (ud3d_debug_set_trace(buf, -2)): globaltimer of phase `slot` of every CTA (thread 0), 8 slots per CTA
 #define UD3D_TL(slot)                                                                                        \
   do {                                                                                                       \
-    if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0) {                                     \
+    if (UD3D_TRACE_BUF(p) && p.trace_block == -2 && tid == 0 && blockIdx.y == 0) {                                     \
       unsigned long long gt__;                                                                               \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__));                                               \
       p.trace[8 * (blockIdx.x * gridDim.z + blockIdx.z) + (slot)] = (long long)gt__;                         \
@@ -161,8 +161,11 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
   constexpr uint32_t IDESC = umma_idesc_bf16_m128(N_TILE);
   constexpr uint32_t IDESC2 = umma_idesc_bf16_m128(2 * N_TILE <= 256 ? 2 * N_TILE : 256);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // (the dynamic shared memory window starts 1024-byte aligned -- the kernel has no static shared memory -- and the
+  // launch does not pay a kilobyte of slack for it: three CTAs of the N_TILE = 32 instantiation fit one SM)
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* smem = smem_raw;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint8_t* tail = sB + STAGES * B_BYTES;
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
   int32_t* s_tbl = (int32_t*)(s_shift + c_in_pad);   // [K][128] table slice of the current tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (UD3D_TRACE_BUF(p) && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1014] = clock64();
   const int nt = blockIdx.y;
   const int n0 = nt * N_TILE;
   const bool has_table = a.table != nullptr;
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
 
   // ------------------------------------------------------------ once per CTA
   UD3D_TL(0);
-  if (p.trace && p.trace_block == -2 && tid == 0 && blockIdx.y == 0) {
+  if (UD3D_TRACE_BUF(p) && p.trace_block == -2 && tid == 0 && blockIdx.y == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     p.trace[8 * (blockIdx.x * gridDim.z + blockIdx.z) + 2] = smid;
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (UD3D_TRACE_BUF(p) && (int)blockIdx.x == p.trace_block && tid == 0) p.trace[1015] = clock64();
   const uint8_t* wp = (const uint8_t*)a.w_packed + (size_t)nt * a.K * p.n_chunks * B_BYTES;
 
   // ring state: every role walks the same (stage, use) sequence, across tiles
@@ -224,8 +229,9 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
 
   for (int tile = blockIdx.x, it = 0; tile < n_row_tiles; tile += gridDim.x, ++it) {
     const int m0 = tile * kTileM;
-    const bool traced = p.trace && (int)blockIdx.x == p.trace_block && it == p.trace_iter;
+    const bool traced = UD3D_TRACE_BUF(p) && (int)blockIdx.x == p.trace_block && it == p.trace_iter;
     if (traced && tid == 0) p.trace[1019] = clock64();
+    if (traced && tid == 0) p.trace[1016] = p.trace[1015];
     // ---------------------------------------------------------- per tile: rulebook slice -> smem, active offsets
     // (one coalesced pass; removes the dependent table -> row load chain from the mainloop)
     const uint32_t tmask = (has_table && a.tile_mask) ? __ldg(a.tile_mask + tile) : 0u;
@@ -263,18 +269,26 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
       __syncthreads();
       mask = *s_mask;
     }
+    if (traced && tid == 0) p.trace[1017] = clock64();
     if (tid < 32 && ((mask >> tid) & 1u)) s_actk[__popc(mask & ((1u << tid) - 1u))] = (uint8_t)tid;
     __syncthreads();
+    if (traced && tid == 0) p.trace[1018] = clock64();
     UD3D_TL(3);      // prologue done (rulebook slice staged)
     const int nact = __popc(mask);
     const int nsteps_all = nact * p.n_chunks;
     // split-K: this CTA handles steps [t_begin, t_end) of the tile's active (offset, chunk) sequence
-    const int t_begin = (int)((long long)nsteps_all * blockIdx.z / gridDim.z);
-    const int t_end = (int)((long long)nsteps_all * (blockIdx.z + 1) / gridDim.z);
-    const int nsteps = (p.dbg & 512) ? 0 : t_end - t_begin;
+    const int t_begin = gridDim.z == 1 ? 0 : (int)((unsigned)nsteps_all * blockIdx.z / gridDim.z);
+    const int t_end = gridDim.z == 1 ? nsteps_all : (int)((unsigned)nsteps_all * (blockIdx.z + 1) / gridDim.z);
+    const int nsteps = UD3D_DBG(p, 512) ? 0 : t_end - t_begin;
     // (kslot, chunk) of this CTA's first step: the only integer division of the tile
     const int kslot0 = t_begin / p.n_chunks;
     const int chunk0 = t_begin - kslot0 * p.n_chunks;
+    // epilogue row of this thread (warps 0..7: TMEM lane quadrant warp & 3), loaded now so that the epilogue does not
+    // start with a dependent global round trip.  Regrouped rows (ud3d_subm3_tile_order): position m0 + row of the
+    // table stands for output row row_perm[m0 + row]
+    const int epi_row = (warp & 3) * 32 + lane;
+    const bool epi_row_ok = warp < 8 && m0 + epi_row < a.n_out;
+    const int epi_grow = (epi_row_ok && a.row_perm) ? __ldg(a.row_perm + m0 + epi_row) : m0 + epi_row;
 
     if (warp < kProducerWarps) {
       // ========================================================= A producers
@@ -299,7 +313,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         const uint32_t sw0 = (uint32_t)((j ^ g) << 4), sw1 = (uint32_t)(((j ^ g) ^ 4) << 4);   // (4 i + g) & 7 = 4 (i & 1) + g
         const uint8_t* src_base = (const uint8_t*)a.in + opf_mem_piece(j) * 16;
         const uint32_t sA_lane = smem_u32(sA) + (uint32_t)((half * (kTileM / WPG) + g) * 128);
-        long long* tr = (traced && tid == 0) ? p.trace : nullptr;
+        long long* tr = (traced && tid == 0) ? UD3D_TRACE_BUF(p) : nullptr;
         if (tr) { tr[1023] = nsteps; tr[1022] = clock64(); }
         if (grp < STAGES) {
           for (int t = (grp - rs + STAGES) % STAGES; t < nsteps; t += STAGES) {     // the steps that land in stage grp
@@ -324,10 +338,17 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
             const uint8_t* sb = src_base + c * 128;
             const uint32_t as_addr = sA_lane + s * A_BYTES;
             // branch-free: a missing neighbour is a zero-fill copy (src-size 0: no global read)
-            if (!(p.dbg & 4)) {
+            if UD3D_DBG(p, 128) {
 #pragma unroll
               for (int i = 0; i < NI; ++i) {
-                const int ix = (p.dbg & 32) ? -1 : idx[i];
+                const int ix = idx[i];
+                cp_async_16_zfill_ca(as_addr + i * 512 + ((i & 1) ? sw1 : sw0),
+                                     sb + (size_t)((uint32_t)(ix < 0 ? 0 : ix) * (uint64_t)row_bytes), ix < 0 ? 0u : 16u);
+              }
+            } else if (!UD3D_DBG(p, 4)) {
+#pragma unroll
+              for (int i = 0; i < NI; ++i) {
+                const int ix = UD3D_DBG(p, 32) ? -1 : idx[i];
                 cp_async_16_zfill(as_addr + i * 512 + ((i & 1) ? sw1 : sw0),
                                   sb + (size_t)((uint32_t)(ix < 0 ? 0 : ix) * (uint64_t)row_bytes), ix < 0 ? 0u : 16u);
               }
@@ -438,7 +459,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         if (use) mbar_wait(&empty[s], (use & 1u) ^ 1u);
         const int k = s_actk[kslot];
         if (elect_one_sync()) {
-          if (p.dbg & 2) {
+          if UD3D_DBG(p, 2) {
             mbar_arrive(&a_full[s]);
           } else {
             mbar_arrive_expect_tx(&a_full[s], B_BYTES);
@@ -455,14 +476,14 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
       // `lane == 0` branch the compiler wraps every UTCHMMA in an R2UR / vote loop (~80 cycles of issue per MMA).
       const uint64_t adesc0 = umma_desc_sw128(smem_u32(sA));
       const uint64_t bdesc0 = STACKED ? umma_desc_sw64(smem_u32(sB)) : umma_desc_sw128(smem_u32(sB));
-      long long* tr = (traced && lane == 0) ? p.trace : nullptr;
+      long long* tr = (traced && lane == 0) ? UD3D_TRACE_BUF(p) : nullptr;
       int s = rs;
       uint32_t use = ruse;
       for (int t = 0; t < nsteps; ++t) {
         mbar_wait(&a_full[s], use & 1u);   // A rows (producer threads) + weight tile (bulk copy tx bytes)
         if (tr && t < 64) tr[t * 8 + 4] = tr[t * 8 + 5] = clock64();
         tc_fence_after_sync();
-        if (p.dbg & 1) {
+        if UD3D_DBG(p, 1) {
           if (lane == 0) mbar_arrive(&empty[s]);
         } else {
           // the start-address field is in 16-byte units: stage s, then +2 = 32 B (second K=16 slice), +4 = lo half,
@@ -491,7 +512,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         if (++s == STAGES) { s = 0; ++use; }
       }
       if (nsteps > 0) {
-        if (p.dbg & 1) {
+        if UD3D_DBG(p, 1) {
           if (lane == 0) mbar_arrive(acc_full);
         } else {
           umma_commit_elect(acc_full);
@@ -515,6 +536,13 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
       // 128-byte row stores) is latency-bound, so doubling the warps nearly halves the epilogue of the wide GEMMs.
       constexpr int kEpiWarps = N_TILE > 32 ? 8 : 4;
       if (warp < kEpiWarps) {
+        // the producers run ahead of the MMAs by the ring depth: while the last stages drain, pull this thread's residual
+        // row segments towards L2 (a DRAM round trip otherwise paid after the accumulator is complete)
+        if (a.residual && epi_row_ok) {
+#pragma unroll 1
+          for (int c0 = (warp >> 2) * 32; c0 < N_TILE && n0 + c0 < a.c_out; c0 += 32 * (kEpiWarps / 4))
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.residual + (size_t)epi_grow * a.ld_res + n0 + c0));
+        }
         if (nsteps > 0) {
           mbar_wait(acc_full, acc_phase);
           tc_fence_after_sync();
@@ -522,10 +550,8 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
         if (traced && tid == 0) p.trace[1021] = clock64();
         UD3D_TL(4);  // main loop done
         const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const bool row_ok = m0 + row < a.n_out;
-        // regrouped rows (ud3d_subm3_tile_order): position m0 + row of the table stands for output row row_perm[m0 + row]
-        const int grow = (row_ok && a.row_perm) ? __ldg(a.row_perm + m0 + row) : m0 + row;
+        const bool row_ok = epi_row_ok;
+        const int grow = epi_grow;
 #pragma unroll 1
         for (int c0 = (warp >> 2) * 32; c0 < N_TILE; c0 += 32 * (kEpiWarps / 4)) {
           uint32_t r[32];
@@ -544,7 +570,7 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
 #pragma unroll
             for (int j = 0; j < 32; ++j) r[j] = 0u;
           }
-          epilogue_store_chunk(p, r, grow, n0 + c0, row_ok && !(p.dbg & 16), smem_u32(sA) + (uint32_t)warp * 4096u, lane);
+          epilogue_store_chunk(p, r, grow, n0 + c0, row_ok && !UD3D_DBG(p, 16), smem_u32(sA) + (uint32_t)warp * 4096u, lane);
         }
       }
     } else {
@@ -746,24 +772,33 @@ __global__ void gather_gemm_simt_kernel(const ud3d_gemm_args a, const float* __r
 
 template <int N_TILE>
 static size_t tc_smem_bytes(int n_chunks, int K, bool has_table) {
-  return 1024 + (size_t)TcCfg<N_TILE>::kStages * (kTileM * 128 + N_TILE * 128) + 192 + (size_t)n_chunks * kChunk * 4 * 2 +
+  return (size_t)TcCfg<N_TILE>::kStages * (kTileM * 128 + N_TILE * 128) + 192 + (size_t)n_chunks * kChunk * 4 * 2 +
          (has_table ? (size_t)K * kTileM * 4 : 0);
 }
 
 template <int N_TILE>
 static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t st) {
   size_t smem = tc_smem_bytes<N_TILE>(p.n_chunks, p.a.K, p.a.table != nullptr || p.a.in_split);
+#ifdef UD3D_DEBUG_HOOKS
+  smem += (size_t)((p.dbg >> 24) & 255) * 1024;       // extra shared memory (lowers the CTAs per SM)
+#endif
+  static int carve_dev[kMaxDevices] = {0};
   static size_t configured_dev[kMaxDevices] = {0};   // per device: largest size this instantiation was configured for
   int dev = 0;
   const int g_num_sms = device_sms(&dev);
   if (g_num_sms <= 0) { set_error("ud3d_gemm_fwd: cannot query the current device"); return UD3D_ECUDA; }
   size_t& configured = configured_dev[dev];
   int ctas_per_sm = N_TILE <= 128 ? 2 : 1;
-  if (smem > configured) {
-    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   (int)cudaSharedmemCarveoutMaxShared));
-    configured = smem;
+#ifdef UD3D_DEBUG_HOOKS
+  const int carve = ((p.dbg >> 16) & 255) ? ((p.dbg >> 16) & 255) : (int)cudaSharedmemCarveoutMaxShared;   // percent
+#else
+  const int carve = (int)cudaSharedmemCarveoutMaxShared;
+#endif
+  if (smem > configured || carve != carve_dev[dev]) {
+    if (smem > configured) UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    if (smem > configured) configured = smem;
+    carve_dev[dev] = carve;
   }
   // persistent over the row tiles: as many CTAs as are resident at once (the CTAs of the other grid dimensions
   // share the same SMs)
@@ -776,7 +811,7 @@ static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t 
     if (gx > row_tiles) gx = row_tiles;
   }
   dim3 grid(gx, n_tiles, splits);
-  if (p.dbg & 2048) {
+  if UD3D_DBG(p, 2048) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, gather_gemm_tc_kernel<N_TILE>);
     int occ = -1;
@@ -880,6 +915,8 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
   p.vec_ok = (args->ld_in % 4 == 0) && (((uintptr_t)args->in & 15) == 0) && (args->c_in % 8 == 0);
   p.out_vec_ok = (args->ld_out % 4 == 0) && (((uintptr_t)args->out & 15) == 0) &&
                  (!args->bias || ((uintptr_t)args->bias & 15) == 0) &&
+                 (!args->act_scale[0] || (((uintptr_t)args->act_scale[0] | (uintptr_t)args->act_shift[0]) & 15) == 0) &&
+                 (!args->act_scale[1] || (((uintptr_t)args->act_scale[1] | (uintptr_t)args->act_shift[1]) & 15) == 0) &&
                  (!args->residual || ((args->ld_res % 4 == 0) && (((uintptr_t)args->residual & 15) == 0)));
   int nts = pick_ntile(args->c_out);
   int n_tiles = cdiv(args->c_out, nts);
@@ -936,15 +973,21 @@ int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scal
   return launch_act_split(raw, ld_raw, n, c, scale, shift, relu, out_split, ld_out, (cudaStream_t)stream);
 }
 
-/* debug only (not declared in the public header): record clock64 timestamps of one CTA of subsequent
- * ud3d_gemm_fwd launches into `buf` (device, >= 1024 int64), or stop with buf = NULL */
+/* debug only (not declared in the public header; effective only in -DUD3D_DEBUG_HOOKS builds): record clock64
+ * timestamps of one CTA of subsequent ud3d_gemm_fwd launches into `buf` (device, >= 1024 int64), or stop with buf = NULL */
 int ud3d_debug_set_trace(long long* buf, int block) {
+#ifndef UD3D_DEBUG_HOOKS
+  UD3D_CHECK_ARG(buf == nullptr, "ud3d_debug_set_trace: this library was built without -DUD3D_DEBUG_HOOKS");
+#endif
   g_trace = buf;
   g_trace_block = block;
   return UD3D_OK;
 }
 
 int ud3d_debug_set_flags(int flags) {
+#ifndef UD3D_DEBUG_HOOKS
+  UD3D_CHECK_ARG(flags == 0, "ud3d_debug_set_flags: this library was built without -DUD3D_DEBUG_HOOKS");
+#endif
   g_dbg = flags;
   return UD3D_OK;
 }

@@ -19,7 +19,17 @@ struct GemmParams {
   int dbg;            // debug: feature-disable bits for timing breakdowns (ud3d_debug_set_flags), normally 0
 };
 
-// ---------------------------------------------------------------- the tensor-core kernel
+// Timing-breakdown hooks (ud3d_debug_set_flags / ud3d_debug_set_trace, used by tools/*_trace.py and tools/*_probe.py)
+// exist only in builds with -DUD3D_DEBUG_HOOKS (UD3D_NVCC_EXTRA=-DUD3D_DEBUG_HOOKS python -m unidet3d_b200.build --force);
+// in the release library the conditions below are compile-time false and the branches disappear from the kernels.
+#ifdef UD3D_DEBUG_HOOKS
+#define UD3D_DBG(p, bits) (((p).dbg & (bits)) != 0)
+#define UD3D_TRACE_BUF(p) ((p).trace)
+#else
+#define UD3D_DBG(p, bits) (false)
+#define UD3D_TRACE_BUF(p) ((long long*)nullptr)
+#endif
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
   // (an Abramowitz-Stegun 7.1.26 erf -- rcp + ex2 + 5 FMA -- measured slower than libdevice's erff here)
@@ -122,7 +132,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
       for (int j = 0; j < 8; ++j)
         t[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                           __float_as_uint(v[4 * j + 3]));
-      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out + (size_t)grow * a.ld_out + col0) : nullptr, lane, (p.dbg & 64) != 0);
+      warp_store_rows(stage, t, valid ? (uint8_t*)(a.out + (size_t)grow * a.ld_out + col0) : nullptr, lane, UD3D_DBG(p, 64));
     }
 #pragma unroll
     for (int oi = 0; oi < 2; ++oi) {
@@ -132,17 +142,19 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
       const bool do_relu = !((a.act_norelu >> oi) & 1);
       uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float x0 = v[j], x1 = v[j + 1];
-        if (sc) {
-          x0 = fmaf(x0, __ldg(sc + j), __ldg(sh + j));
-          x1 = fmaf(x1, __ldg(sc + j + 1), __ldg(sh + j + 1));
+      for (int j = 0; j < 32; j += 4) {
+        float x[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+        if (sc) {      // (16-byte aligned: part of out_vec_ok)
+          const float4 s4 = __ldg((const float4*)(sc + j)), h4 = __ldg((const float4*)(sh + j));
+          x[0] = fmaf(x[0], s4.x, h4.x); x[1] = fmaf(x[1], s4.y, h4.y);
+          x[2] = fmaf(x[2], s4.z, h4.z); x[3] = fmaf(x[3], s4.w, h4.w);
         }
         if (do_relu) {
-          x0 = fmaxf(x0, 0.f);
-          x1 = fmaxf(x1, 0.f);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
         }
-        split_bf16x2(x0, x1, hi[j >> 1], lo[j >> 1]);
+        split_bf16x2(x[0], x[1], hi[j >> 1], lo[j >> 1]);
+        split_bf16x2(x[2], x[3], hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
       }
       uint4 t[8];
 #pragma unroll
@@ -151,7 +163,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
         t[opf_mem_piece(4 + j)] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
       }
       warp_store_rows(stage, t, valid ? (uint8_t*)(a.out_act[oi] + (size_t)grow * a.ld_act[oi]) + (size_t)col0 * 4 : nullptr, lane,
-                      (p.dbg & 64) != 0);
+                      UD3D_DBG(p, 64));
     }
     return;
   }

@@ -191,7 +191,7 @@ __device__ __forceinline__ void umma_ts_step(uint32_t d_tmem, uint32_t a_tmem, u
     mbar_wait(&full[S], use & 1u);                                                                            \
     tc_fence_after_sync();                                                                                    \
     if (traced && gbase + t < 256) UD3D_TS_TR(8 * (gbase + t) + 0);                                           \
-    if (!(p.dbg & 1)) {                                                                                       \
+    if (!UD3D_DBG(p, 1)) {                                                                                       \
       umma_ts_step(d_tmem, tmem_base + COL_A + (uint32_t)((S) * 32), bdesc0 + (uint64_t)((S) * (B_BYTES >> 4)), IDESC, \
                    t > 0, empty_u32 + 8u * (S));                                                              \
     } else if (lane == 0) {                                                                                   \
@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
   const int n_row_tiles = (a.n_out + kTileM - 1) / kTileM;
   const int n_ntiles = (a.c_out + N_TILE - 1) / N_TILE;
   const int n_items = n_row_tiles * n_ntiles;
-  const bool traced = p.trace != nullptr && (int)blockIdx.x == p.trace_block;
+  const bool traced = UD3D_TRACE_BUF(p) && (int)blockIdx.x == p.trace_block;
   // trace_block == -3: globaltimer at start / end + SM id of every CTA: p.trace[4 * blockIdx.x + {0, 1, 2}]
-  if (p.trace != nullptr && p.trace_block == -3 && tid == 0) {
+  if (UD3D_TRACE_BUF(p) && p.trace_block == -3 && tid == 0) {
     unsigned long long gt;
     unsigned smid;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        epilogue_store_chunk(p, r, grow, n0 + c0, row_ok && !(p.dbg & 16), stage, lane);
+        epilogue_store_chunk(p, r, grow, n0 + c0, row_ok && !UD3D_DBG(p, 16), stage, lane);
       }
       if (warp == 0 && it < 64) UD3D_TS_TR(2048 + 4 * it + 1);
     }
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
       const uint8_t* src = in_q + meta;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
-        ldg256((idx[r] >= 0 && !(p.dbg & 32)) ? src + (size_t)((uint32_t)idx[r]) * row_bytes : zero_q, rows[r]);
+        ldg256((idx[r] >= 0 && !UD3D_DBG(p, 32)) ? src + (size_t)((uint32_t)idx[r]) * row_bytes : zero_q, rows[r]);
       if (traced && quad == 0 && g < 256) UD3D_TS_TR(8 * g + 7);
       ++it;
       gen(meta_n, it & 1u);        // indices of this warp's next step: in flight while the rows arrive and are stored
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
         s = 0;
       }
       gbase += (uint32_t)nsteps;
-      if (!(p.dbg & 1)) {
+      if (!UD3D_DBG(p, 1)) {
         umma_commit_elect(&acc_full[buf]);
       } else if (lane == 0) {
         mbar_arrive(&acc_full[buf]);
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) gather_gemm_ts_kernel(const Gem
   __syncthreads();
   tc_fence_after_sync();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
-  if (p.trace != nullptr && p.trace_block == -3 && tid == 0) {
+  if (UD3D_TRACE_BUF(p) && p.trace_block == -3 && tid == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.trace[4 * blockIdx.x + 1] = (long long)gt;

@@ -288,7 +288,7 @@ def segmented_mean(src: torch.Tensor, seg: torch.Tensor, n_seg: int, *, gather: 
     Cc = src.shape[1] if channels is None else channels
     n = seg.shape[0]
     out = torch.empty((n_seg, Cc), dtype=torch.float32, device=src.device)
-    ws = torch.empty(max(n_seg, 1) * 4, dtype=torch.uint8, device=src.device)
+    ws = torch.empty(max(int(_L().ud3d_segmented_mean_workspace_bytes(n_seg, Cc)), 8), dtype=torch.uint8, device=src.device)
     check(_L().ud3d_segmented_mean(_p(src), src.stride(0), Cc, _p(gather), _p(seg), n, n_seg, _p(scale), _p(shift),
                                    1 if relu else 0, _p(out), _p(ws), ws.numel(), _stream()), "ud3d_segmented_mean")
     return out

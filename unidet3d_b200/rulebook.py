@@ -59,6 +59,26 @@ def _side_stream(dev) -> torch.cuda.Stream:
 class Pyramid:
     def __init__(self, levels: List[Level]):
         self.levels = levels
+        self._c_tables = None
+
+    def c_tables(self, n_levels: int):
+        """``ud3d_unet_tables[n_levels]`` (ctypes) for ud3d_unet_forward; orders the current stream after the side-stream
+        regrouping of each level (``Level.subm_conv``)."""
+        from . import _lib
+        tabs = [lv.subm_conv for lv in self.levels[:n_levels]]      # (waits for order_ready on the current stream)
+        if self._c_tables is None or len(self._c_tables) != n_levels:
+            T = (_lib.UnetTables * n_levels)()
+            for l, lv in enumerate(self.levels[:n_levels]):
+                tb, tm, pm = tabs[l]
+                t = T[l]
+                t.n = lv.n
+                t.subm, t.subm_mask = tb.data_ptr(), tm.data_ptr()
+                t.row_perm = pm.data_ptr() if pm is not None else None
+                if l + 1 < n_levels:
+                    t.child, t.child_mask = lv.child.data_ptr(), lv.child_mask.data_ptr()
+                    t.up, t.up_mask = lv.up.data_ptr(), lv.up_mask.data_ptr()
+            self._c_tables = T
+        return self._c_tables
 
     def __len__(self):
         return len(self.levels)
