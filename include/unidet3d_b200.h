@@ -192,6 +192,31 @@ int ud3d_act_split(const float* raw, int ld_raw, int n, int c, const float* scal
  * (diagnostic cross-check of the tensor-core path; not used by the product path) */
 int ud3d_gemm_fwd_simt(const ud3d_gemm_args* args, const float* w, void* stream);
 
+/* ------------------------------------------------------------------ training-pipeline transforms in front of the path
+ * ElasticTransfrom (unidet3d/transforms_3d.py:12-83): `elastic_coords = elastic(elastic(points/voxel_size, gran0, mag0),
+ * gran1, mag1)`, elastic(x) = x + trilinear(blurred noise grids)(x) * mag.  The caller draws the three float32 noise
+ * grids [3, X, Y, Z] (dims = |x|.max(0).astype(int32) // gran + 3, reference order of np.random calls) and keeps the
+ * coordinates in double like the reference (scipy returns float64):
+ *   ud3d_points_to_voxel_units : out[i, k] = double(float32(points[i, k]) / float32(voxel_size))
+ *   ud3d_elastic_blur          : the six 3-tap box blurs (scipy.ndimage.convolve, mode='constant'), in place
+ *   ud3d_elastic_apply         : out = x + interp(x) * mag  (RegularGridInterpolator: linear, fill_value 0 outside) */
+size_t ud3d_elastic_workspace_bytes(const int32_t dims_host[3]);
+int ud3d_elastic_blur(float* noise, const int32_t dims_host[3], void* ws, size_t ws_bytes, void* stream);
+int ud3d_points_to_voxel_units(const float* points, int ld, int n, float voxel_size, double* out, void* stream);
+int ud3d_elastic_apply(const double* x, int n, const float* noise, const int32_t dims_host[3], double gran, double mag,
+                       double* out, void* stream);
+/* Voxel coordinates of elastic coordinates (unidet3d.py:162-166): coords[p] = (b, floor(el[p] - min over scene b of el)),
+ * computed in double like the reference; max_coord int32 [3] = per-axis maximum over the batch (spatial extents). */
+size_t ud3d_elastic_voxel_coords_workspace_bytes(int B);
+int ud3d_elastic_voxel_coords(const double* elastic, int n, const int32_t* scene_offsets, int B, int32_t* coords,
+                              int32_t* max_coord, void* ws, size_t ws_bytes, void* stream);
+/* PointSample_ (unidet3d/transforms_3d.py:233-295) after the row gather: ids -> dense ranks of the values present
+ * (np.unique(ids, return_inverse=True)[1]); negative ids (the -1 "no instance" label) stay -1, which is what the
+ * reference's `mapping` does for pts_instance_mask.  ids in [-inf, max_id]; n_unique = number of distinct ids >= 0. */
+size_t ud3d_compact_ids_workspace_bytes(int64_t max_id);
+int ud3d_compact_ids(const int64_t* ids, int n, int64_t max_id, int64_t* out, int32_t* n_unique, void* ws, size_t ws_bytes,
+                     void* stream);
+
 /* ------------------------------------------------------------------ stage plan: the whole U-Net in one call
  * reference: SpConvUNet.forward, unidet3d/spconv_unet.py:117-240 (eval mode; channel counts multiples of 32).
  * A plan holds, per level, the packed weights (ud3d_gemm_pack_weight) and the folded eval-mode BatchNorms

@@ -20,7 +20,8 @@ import numpy as np
 
 def point_coords(points_list, voxel_size, elastic_list=None):
     """Per-point int32 (b,x,y,z) and fp32 6-ch features (before dedup).  ``elastic_list`` (unidet3d.py:162-166): per
-    scene fp32 [n,3] coordinates already in voxel units; coords = floor(el - el.min(0)), features unchanged."""
+    scene [n,3] coordinates already in voxel units, float64 when the augmentation was applied and float32 when its
+    coin flip skipped it (transforms_3d.py:39-43); coords = floor(el - el.min(0)) IN THAT DTYPE, features unchanged."""
     coords, feats = [], []
     vs = np.float32(voxel_size)
     for b, p in enumerate(points_list):
@@ -28,7 +29,8 @@ def point_coords(points_list, voxel_size, elastic_list=None):
         xyz = p[:, :3]
         mn = xyz.min(0)
         if elastic_list is not None:
-            el = np.asarray(elastic_list[b], dtype=np.float32)
+            el = np.asarray(elastic_list[b])
+            assert el.dtype in (np.float32, np.float64)
             c = np.floor(el - el.min(0)).astype(np.int32)
         else:
             c = np.floor((xyz - mn) / vs).astype(np.int32)

@@ -509,6 +509,27 @@ def gen_gt_prep():
     print("gt_prep_ref.npz", out["gt_sp_masks"].shape, out2["gt_sp_masks"].shape, len(np.unique(out3["sp_pts_mask"])))
 
 
+def gen_augment():
+    """The reference's ElasticTransfrom (unidet3d/transforms_3d.py:12-83) on synthetic points, numpy RNG seeded."""
+    import scipy.ndimage
+    if not hasattr(scipy.ndimage, "filters"):
+        scipy.ndimage.filters = scipy.ndimage
+    from unidet3d.transforms_3d import ElasticTransfrom
+    rng = np.random.default_rng(77)
+    n = 3000
+    pts = (rng.random((n, 6)) * np.array([7.5, 5.0, 2.8, 1, 1, 1]) - np.array([3.0, 2.0, 0.1, 0, 0, 0])).astype(np.float32)
+    save = dict(points=pts)
+    for tag, gran, mag, vs, p, seed in [("a", [6, 20], [40, 160], 0.02, 1.0, 11), ("b", [6, 20], [40, 160], 0.02, 0.1, 12),
+                                        ("c", [4, 12], [20, 60], 0.05, 1.0, 13)]:
+        np.random.seed(seed)
+        t = ElasticTransfrom(gran=gran, mag=mag, voxel_size=vs, p=p)
+        out = t.transform(dict(points=types.SimpleNamespace(tensor=torch.as_tensor(pts))))["elastic_coords"]
+        save[f"{tag}_cfg"] = np.array([gran[0], gran[1], mag[0], mag[1], vs, p, seed], dtype=np.float64)
+        save[f"{tag}_out"] = np.asarray(out)
+        print("augment", tag, np.asarray(out).dtype, float(np.abs(np.asarray(out) - pts[:, :3] / vs).max()))
+    np.savez_compressed(os.path.join(HERE, "augment_ref.npz"), **save)
+
+
 def gen_post():
     from unidet3d.unidet3d import UniDet3D, get_face_distances
     from unidet3d.encoder import _bbox_pred_to_bbox
@@ -556,6 +577,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "gt_prep"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "gt_prep", "augment"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "gt_prep": gen_gt_prep}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "gt_prep": gen_gt_prep, "augment": gen_augment}[name]()

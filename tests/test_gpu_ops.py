@@ -588,15 +588,21 @@ def test_collate_with_elastic_coords():
     pts = [make_scene(40 + i, n + 50 * i, a, c)[0] for i in range(3)]
     # smooth distortion of the voxel-unit coordinates, like transforms_3d.py:39-43
     els = [(p[:, :3] / v + 3.0 * np.sin(p[:, :3] * 2.0 + rng.uniform(0, 6, 3))).astype(np.float32) for p in pts]
-    coords, feats, inverse, shape = ovox.voxelize(pts, v, 128, elastic_list=els)
     P = torch.as_tensor(np.concatenate(pts)).to(DEV)
-    E = torch.as_tensor(np.concatenate(els)).to(DEV)
     offs = torch.tensor(np.cumsum([0] + [len(p) for p in pts]), dtype=torch.int32, device=DEV)
-    x, inv = model.collate(P, offs, 3, E)
-    assert np.array_equal(x.indices.cpu().numpy(), coords)
-    assert np.array_equal(inv.cpu().numpy().astype(np.int64), inverse)
-    assert x.spatial_shape == list(shape)
-    assert relerr(x.features, feats) < 1e-5
+    # float32 (augmentation skipped) and float64 (applied; values snapped next to integers so that the precision of the
+    # subtraction decides the voxel)
+    els64 = [e.astype(np.float64) + 1e-9 * rng.standard_normal(e.shape) for e in els]
+    for k in range(3):
+        els64[k][::7] = np.round(els64[k][::7]) - 1e-11 + els64[k].min(0)
+    for variant in (els, els64):
+        coords, feats, inverse, shape = ovox.voxelize(pts, v, 128, elastic_list=variant)
+        E = torch.as_tensor(np.concatenate(variant)).to(DEV)
+        x, inv = model.collate(P, offs, 3, E)
+        assert np.array_equal(x.indices.cpu().numpy(), coords)
+        assert np.array_equal(inv.cpu().numpy().astype(np.int64), inverse)
+        assert x.spatial_shape == list(shape)
+        assert relerr(x.features, feats) < 1e-5
     # and it differs from the plain voxelisation
     x0, _ = model.collate(P, offs, 3)
     assert x0.indices.shape != x.indices.shape or not torch.equal(x0.indices, x.indices)

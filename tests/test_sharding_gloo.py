@@ -16,7 +16,15 @@ def _worker(rank, world, port, q):
     cfg, scenes, names, preset = bench.make_workload("small_1", rank)
     fingerprint = float(scenes[0][0][:100].sum())
     t_dev, t_e2e = sharding.aggregate_times([1.0 + rank, 5.0 - rank])
-    q.put((rank, mine, fingerprint, t_dev, t_e2e))
+    # SyncBatchNorm exchange of the train-mode backbone: each rank holds different rows; after ONE all-reduce of
+    # [sum, sum of squares, count] every rank folds the statistics of the union (ops.sync_bn_sums)
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(300 + 200 * rank, 8, generator=g, dtype=torch.float64) * (1 + rank) + rank
+    sums, count = ops.sync_bn_sums(torch.stack((x.sum(0), (x * x).sum(0))), float(x.shape[0]))
+    mean = sums[0] / count
+    var = sums[1] / count - mean * mean
+    q.put((rank, mine, fingerprint, t_dev, t_e2e, count, mean.tolist(), var.tolist()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -30,7 +38,13 @@ def test_two_rank_sharding_and_timing():
     out = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    (r0, s0, f0, a0, b0), (r1, s1, f1, a1, b1) = out
+    (r0, s0, f0, a0, b0, c0, m0, v0), (r1, s1, f1, a1, b1, c1, m1, v1) = out
+    xs = [torch.randn(300 + 200 * r, 8, generator=torch.Generator().manual_seed(100 + r), dtype=torch.float64) * (1 + r) + r
+          for r in range(2)]
+    allx = torch.cat(xs)
+    assert c0 == c1 == 800.0
+    assert torch.allclose(torch.tensor(m0, dtype=torch.float64), allx.mean(0), atol=1e-12) and m0 == m1
+    assert torch.allclose(torch.tensor(v0, dtype=torch.float64), allx.var(0, unbiased=False), atol=1e-10) and v0 == v1
     assert sorted(s0 + s1) == list(range(10)) and not set(s0) & set(s1)       # disjoint cover
     assert f0 != f1                                                           # ranks work on different scenes
     assert a0 == a1 == 2.0 and b0 == b1 == 5.0                                # MAX over ranks, same on every rank

@@ -113,6 +113,14 @@ SIGNATURES = {
     "ud3d_bn_train_fold": (_i, [_vp, C.c_double, _i, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ud3d_conv_wgrad_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "ud3d_segmented_mean_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "ud3d_elastic_workspace_bytes": (C.c_size_t, [_vp]),
+    "ud3d_elastic_blur": (_i, [_vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_points_to_voxel_units": (_i, [_vp, _i, _i, _f, _vp, _vp]),
+    "ud3d_elastic_apply": (_i, [_vp, _i, _vp, _vp, C.c_double, C.c_double, _vp, _vp]),
+    "ud3d_elastic_voxel_coords_workspace_bytes": (C.c_size_t, [_i]),
+    "ud3d_elastic_voxel_coords": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_compact_ids_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "ud3d_compact_ids": (_i, [_vp, _i, C.c_int64, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_unet_workspace_bytes": (C.c_size_t, [_vp, _vp]),
     "ud3d_unet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, C.c_size_t, _vp]),

@@ -101,11 +101,15 @@ class UniDet3D(nn.Module):
         """unidet3d.py:136-176 on a packed [n,6] point tensor.
         -> SparseConvTensor (canonical voxel order, rulebook-ready), inverse_mapping int32 [n].
 
-        ``elastic_points`` (packed fp32 [n,3], the ``elastic_coords`` of the ElasticTransfrom augmentation, already in
-        voxel units): voxel coordinates are ``floor(el - el.min(0))`` per scene (unidet3d.py:162-166) while the features
-        still are (colour, xyz - mean) of the un-distorted points."""
+        ``elastic_points`` (packed [n,3], the ``elastic_coords`` of the ElasticTransfrom augmentation, already in voxel
+        units): voxel coordinates are ``floor(el - el.min(0))`` per scene (unidet3d.py:162-166), evaluated in the dtype
+        of the coordinates like the reference -- float64 when the augmentation was applied, float32 when its coin flip
+        skipped it -- while the features still are (colour, xyz - mean) of the un-distorted points."""
         coords_pt, feats_pt, _, maxc = ops.point_coords(points, scene_offsets, self.voxel_size)
-        if elastic_points is not None:
+        if elastic_points is not None and elastic_points.dtype == torch.float64:
+            from .augment import elastic_voxel_coords
+            coords_pt, maxc = elastic_voxel_coords(elastic_points.contiguous(), scene_offsets, batch_size)
+        elif elastic_points is not None:
             el = torch.cat((elastic_points.to(points.dtype), points[:, 3:]), dim=1).contiguous()
             coords_pt, _, _, maxc = ops.point_coords(el, scene_offsets, 1.0)       # x / 1.0 is exact: floor(el - min)
         ext = (maxc.cpu().numpy() + 1).tolist()                       # host sync #1 (spatial extents)

@@ -524,18 +524,23 @@ def bn_train_fold(sums: torch.Tensor, count: float, bn, update_running: bool = T
     return scale, shift, mean, invstd
 
 
-def bn_train(x: torch.Tensor, bn, group=None, update_running: bool = True):
-    """Batch statistics of ``x`` [N, C] (all active voxels of the batch) -> (scale, shift, mean, invstd).  With an
-    initialised torch.distributed process group of more than one rank the sums and the row count are all-reduced first
-    (SyncBatchNorm, spconv_unet.py:119-121): ONE collective of 2C + 1 doubles per BatchNorm."""
-    sums = bn_batch_sums(x)
-    count = float(x.shape[0])
+def sync_bn_sums(sums: torch.Tensor, count: float, group=None):
+    """The SyncBatchNorm exchange (spconv_unet.py:119-121): ONE all-reduce of the 2C channel sums + the row count.  Pure
+    torch.distributed plumbing (device-agnostic: the gloo test in tests/test_sharding_gloo.py drives it on CPU tensors)."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         buf = torch.cat((sums.flatten(), sums.new_tensor([count])))
         dist.all_reduce(buf, group=group)
         sums = buf[:-1].view(2, -1).contiguous()
         count = float(buf[-1].item())
+    return sums, count
+
+
+def bn_train(x: torch.Tensor, bn, group=None, update_running: bool = True):
+    """Batch statistics of ``x`` [N, C] (all active voxels of the batch) -> (scale, shift, mean, invstd).  With an
+    initialised torch.distributed process group of more than one rank the sums and the row count are all-reduced first
+    (SyncBatchNorm, spconv_unet.py:119-121): ONE collective of 2C + 1 doubles per BatchNorm."""
+    sums, count = sync_bn_sums(bn_batch_sums(x), float(x.shape[0]), group)
     return bn_train_fold(sums, count, bn, update_running)
 
 
