@@ -236,6 +236,19 @@ __global__ void __launch_bounds__(kThreadsTc, TcCfg<N_TILE>::kMinCtas) gather_ge
     // (one coalesced pass; removes the dependent table -> row load chain from the mainloop)
     const uint32_t tmask = (has_table && a.tile_mask) ? __ldg(a.tile_mask + tile) : 0u;
     uint32_t mybits = 0;
+    if (has_table && !kPersistent && blockIdx.y == 0 && blockIdx.z == 0) {
+      // pull the rulebook slice (and output-row list) of the tile that will run on this SM about one CTA life from now
+      // towards L2: the slice is the first thing a CTA waits for, and it comes from DRAM on every launch (the table is
+      // larger than what stays cached between convs)
+      const int ahead = tile + 3 * 148;
+      if (ahead < n_row_tiles) {
+        const int lines = a.K * 4;                                     // 128 rows x 4 B = 4 lines of 128 B per offset
+        if (tid < lines)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.table + (size_t)(tid >> 2) * a.n_out + (size_t)ahead * kTileM + (tid & 3) * 32));
+        else if (a.row_perm && tid < lines + 4)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.row_perm + (size_t)ahead * kTileM + (tid - lines) * 32));
+      }
+    }
     if (has_table) {
       // all loads of a thread are issued back to back (one L2 round trip for the whole slice)
       constexpr int kPer = (32 * kTileM + kThreadsTc - 1) / kThreadsTc;   // 13
