@@ -217,6 +217,22 @@ size_t ud3d_compact_ids_workspace_bytes(int64_t max_id);
 int ud3d_compact_ids(const int64_t* ids, int n, int64_t max_id, int64_t* out, int32_t* n_unique, void* ws, size_t ws_bytes,
                      void* stream);
 
+/* ------------------------------------------------------------------ evaluator (the step after the path)
+ * reference: unidet3d/indoor_eval.py:56-202 (eval_det_cls + average_precision 'area' + eval_map_recall) with the 3-D IoU of
+ * mmdet3d's BaseInstance3DBoxes.overlaps.  All classes and IoU thresholds of a result set in one call:
+ *   detections: det_boxes [D,7] (cx,cy,cz,dx,dy,dz,yaw; gravity centre), det_labels / det_img int32 [D];
+ *     order int32 [D] = detection indices sorted by (label ascending, score descending); class_offsets int32 [n_cls+1]
+ *     = segment of each class inside `order`;
+ *   ground truth: gt_boxes [G,7], gt_labels int32 [G], grouped by image: gt_img_offsets int32 [n_img+1];
+ *   thr_host: n_thr <= 16 IoU thresholds (host array).
+ * Outputs (device): ap float32 [n_cls, n_thr] (nan for a class with detections but no ground truth, like the reference),
+ * rec double [n_cls, n_thr] = final recall tp / npos, npos int32 [n_cls].  A class without detections yields 0 / 0. */
+size_t ud3d_eval_workspace_bytes(int D, int G, int n_thr);
+int ud3d_eval_detections(const float* det_boxes, const int32_t* det_labels, const int32_t* det_img, int D,
+                         const int32_t* order, const int32_t* class_offsets, int n_cls, const float* gt_boxes,
+                         const int32_t* gt_labels, const int32_t* gt_img_offsets, int G, int n_img, const float* thr_host,
+                         int n_thr, float* ap, double* rec, int32_t* npos, void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------ stage plan: the whole U-Net in one call
  * reference: SpConvUNet.forward, unidet3d/spconv_unet.py:117-240 (eval mode; channel counts multiples of 32).
  * A plan holds, per level, the packed weights (ud3d_gemm_pack_weight) and the folded eval-mode BatchNorms

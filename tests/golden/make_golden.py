@@ -530,6 +530,82 @@ def gen_augment():
     np.savez_compressed(os.path.join(HERE, "augment_ref.npz"), **save)
 
 
+def gen_evaluate():
+    """The reference's own indoor_eval (unidet3d/indoor_eval.py) on synthetic detections / ground truth.  Boxes are stub
+    objects whose ``overlaps`` is the oracle's restatement of mmdet3d's (third-party, absent): the fixture pins the
+    evaluation LOGIC (class bookkeeping, TP / FP marking, AP, nan conventions), not the IoU."""
+    import importlib.util
+    for name, attrs in (("mmengine.logging", dict(print_log=lambda *a, **k: None)),
+                        ("terminaltables", dict(AsciiTable=type("AsciiTable", (), {"__init__": lambda self, d: setattr(self, "table", ""),
+                                                                                   "inner_footing_row_border": False})))):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location("ref_indoor_eval", os.path.join(REF, "unidet3d", "indoor_eval.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import evaluate as oev
+
+    class Boxes:
+        def __init__(self, t):
+            self.tensor = torch.as_tensor(t, dtype=torch.float32).reshape(-1, 7)
+        def __len__(self):
+            return self.tensor.shape[0]
+        def __getitem__(self, i):
+            return Boxes(self.tensor[i].reshape(-1, 7))
+        def new_box(self, t):
+            return Boxes(t)
+        def convert_to(self, mode):
+            return self
+        @classmethod
+        def overlaps(cls, a, b):
+            return torch.as_tensor(oev.overlaps_3d(a.tensor.numpy(), b.tensor.numpy()))
+
+    rng = np.random.default_rng(21)
+    n_img, n_cls = 6, 7                       # class 5 has detections but no ground truth, class 6 ground truth but no detections
+    gt_b, gt_l, gt_i, dt_b, dt_s, dt_l, dt_i = [], [], [], [], [], [], []
+    gt_annos, dt_annos = [], []
+    for img in range(n_img):
+        m = int(rng.integers(3, 9))
+        gb = np.concatenate([rng.uniform(0, 6, (m, 3)), rng.uniform(0.3, 1.5, (m, 3)), np.zeros((m, 1))], 1).astype(np.float32)
+        if img % 2:
+            gb[:, 6] = rng.uniform(-1.5, 1.5, m)
+        gl = rng.integers(0, 5, m)
+        if img == 2:
+            gl[0] = 6
+        # detections: jittered copies of the ground truth (several per box, some duplicates of the same box) + clutter
+        k = int(rng.integers(10, 30))
+        src = rng.integers(0, m, k)
+        db = gb[src] + rng.normal(0, 0.08, (k, 7)).astype(np.float32) * np.array([1, 1, 1, 1, 1, 1, 0], np.float32)
+        dl = gl[src].copy()
+        flip = rng.random(k) < 0.2
+        dl[flip] = rng.integers(0, 6, int(flip.sum()))
+        dl[dl == 6] = 0
+        ds = rng.random(k).astype(np.float32)
+        ds[:3] = ds[0]                                   # tied scores
+        if img == 4:
+            db, dl, ds = db[:0], dl[:0], ds[:0]          # an image without detections
+        gt_b.append(gb); gt_l.append(gl); gt_i.append(np.full(m, img)); dt_b.append(db); dt_s.append(ds); dt_l.append(dl)
+        dt_i.append(np.full(len(dl), img))
+        gt_annos.append(dict(gt_bboxes_3d=Boxes(gb), gt_labels_3d=[int(x) for x in gl]))
+        dt_annos.append(dict(labels_3d=torch.as_tensor(dl), bboxes_3d=Boxes(db), scores_3d=torch.as_tensor(ds)))
+    label2cat = {i: f"c{i}" for i in range(n_cls)}
+    # the reference sorts with np.argsort(-confidence) (unstable for ties): make the order reproducible for the fixture
+    _argsort = np.argsort
+    np.argsort = lambda a, *args, **kw: _argsort(a, kind="stable")
+    try:
+        ret = mod.indoor_eval(gt_annos, dt_annos, [0.25, 0.5], label2cat)
+    finally:
+        np.argsort = _argsort
+    save = dict(gt_boxes=np.concatenate(gt_b), gt_labels=np.concatenate(gt_l), gt_img=np.concatenate(gt_i),
+                det_boxes=np.concatenate(dt_b), det_scores=np.concatenate(dt_s), det_labels=np.concatenate(dt_l),
+                det_img=np.concatenate(dt_i), metric=np.array([0.25, 0.5]),
+                keys=np.array(list(ret.keys())), values=np.array([ret[k] for k in ret], dtype=np.float64))
+    np.savez_compressed(os.path.join(HERE, "evaluate_ref.npz"), **save)
+    print("evaluate_ref.npz", {k: round(v, 4) for k, v in ret.items() if k.startswith("m")}, len(ret))
+
+
 def gen_post():
     from unidet3d.unidet3d import UniDet3D, get_face_distances
     from unidet3d.encoder import _bbox_pred_to_bbox
@@ -577,6 +653,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "gt_prep", "augment"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "gt_prep", "augment", "evaluate"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "gt_prep": gen_gt_prep, "augment": gen_augment}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()

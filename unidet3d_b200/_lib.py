@@ -121,6 +121,8 @@ SIGNATURES = {
     "ud3d_elastic_voxel_coords": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_compact_ids_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ud3d_compact_ids": (_i, [_vp, _i, C.c_int64, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_eval_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "ud3d_eval_detections": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_unet_workspace_bytes": (C.c_size_t, [_vp, _vp]),
     "ud3d_unet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, C.c_size_t, _vp]),
