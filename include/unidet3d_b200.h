@@ -39,6 +39,14 @@ int ud3d_version(void);
 const char* ud3d_last_error(void);
 /* number of this library's kernels launched by the calling thread since the last reset */
 int64_t ud3d_launch_count(int reset);
+/* Per-device context: the only state the library keeps -- per device, the SM count and which function
+ * attributes (dynamic shared-memory size, carve-out) its kernels were configured with.  Created lazily for the calling
+ * thread's CURRENT device by the first entry point that needs it, mutex-guarded (entry points may be called from
+ * several host threads; buffers, workspaces and streams are the caller's).  The handle is only for inspection. */
+typedef struct ud3d_ctx ud3d_ctx;
+const ud3d_ctx* ud3d_ctx_current(void);          /* NULL (+ ud3d_last_error) when no CUDA device is current */
+int ud3d_ctx_device(const ud3d_ctx* ctx);
+int ud3d_ctx_sm_count(const ud3d_ctx* ctx);
 
 /* ------------------------------------------------------------------ voxelisation
  * reference: unidet3d/unidet3d.py:136-176 (UniDet3D.collate -> ME.utils.batch_sparse_collate,
@@ -273,6 +281,30 @@ typedef struct {                                    /* rulebooks of one level (u
 size_t ud3d_unet_workspace_bytes(const ud3d_unet_plan* plan, const ud3d_unet_tables* levels);
 int ud3d_unet_forward(const ud3d_unet_plan* plan, const ud3d_unet_tables* levels, const float* x_raw, const float* x_act,
                       float* out_raw, float* const* level_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ stage plan: the encoder in one call
+ * reference: UniDet3DEncoder.forward, unidet3d/encoder.py:203-239 with the last head (:165-201), eval mode, no auxiliary
+ * heads.  x fp32 [n, in_channels] packed over the B scenes (cu_seqlens int32 [B+1], max_T = longest scene).
+ * Outputs: logits [n, n_union] (union of the datasets' classes + no_obj; the per-dataset column gather stays with the
+ * caller), raw_boxes [n, 8] (PredBBox linear output, before ud3d_bbox_decode), h_out NULL or [n, d_model] (the queries
+ * after the last layer).  Weights packed by ud3d_gemm_pack_weight (K = 1).  activation: 1 relu, 2 gelu. */
+#define UD3D_ENCODER_MAX_LAYERS 12
+typedef struct { const void* w; const float* bias; } ud3d_linear;
+typedef struct {
+  ud3d_linear qkv, out, f1, f2;                    /* attn.in_proj, attn.out_proj, ffn.net.0, ffn.net.3 */
+  const float* n1_gamma; const float* n1_beta; float n1_eps;
+  const float* n2_gamma; const float* n2_beta; float n2_eps;
+} ud3d_encoder_layer;
+typedef struct {
+  int32_t num_layers, in_channels, d_model, num_heads, hidden, n_union, activation;
+  ud3d_linear ip0, ip2;                            /* input_proj.0, input_proj.2 */
+  ud3d_encoder_layer layer[UD3D_ENCODER_MAX_LAYERS];
+  const float* on_gamma; const float* on_beta; float on_eps;   /* out_norm */
+  ud3d_linear c0, c2, bb;                          /* outs_cls.0, outs_cls.2, out_bboxes.linear */
+} ud3d_encoder_plan;
+size_t ud3d_encoder_workspace_bytes(const ud3d_encoder_plan* plan, int n);
+int ud3d_encoder_forward(const ud3d_encoder_plan* plan, const float* x, int n, const int32_t* cu_seqlens, int B, int max_T,
+                         float* logits, float* raw_boxes, float* h_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ training side of the backbone
  * Train-mode (Sync)BatchNorm of the reference (spconv_unet.py:119-124, unidet3d.py:104-107; torch.nn.SyncBatchNorm,

@@ -63,6 +63,30 @@ def test_unet_stage_plan_matches_per_conv_executor(planes, reps):
         assert a.shape == b.shape and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("d,heads,hidden,layers,act", [(256, 8, 1024, 3, "gelu"), (128, 4, 256, 1, "relu")])
+def test_encoder_stage_plan_matches_per_op_executor(d, heads, hidden, layers, act):
+    """ud3d_encoder_forward (one C call) == the per-op Python executor, bit for bit."""
+    import unidet3d_b200 as u
+    torch.manual_seed(11)
+    classes = [["chair", "table", "sofa"], ["table", "board"], ["bed", "chair", "oven", "sink"]]
+    m = u.MODELS.build(dict(type="UniDet3DEncoder", num_layers=layers, datasets_classes=classes, in_channels=32, d_model=d,
+                            num_heads=heads, hidden_dim=hidden, dropout=0.0, activation_fn=act,
+                            datasets=["scannet", "s3dis", "arkitscenes"], angles=[False, False, True])).eval().to(DEV)
+    lens = [700, 1, 333, 1290]
+    names = ["scannet", "arkitscenes", "s3dis", "arkitscenes"]
+    x = [torch.randn(t, 32, device=DEV) for t in lens]
+    c = [torch.randn(t, 3, device=DEV) for t in lens]
+    outs = {}
+    for plan in (False, True):
+        m.use_stage_plan = plan
+        o = m(x, c, names)
+        outs[plan] = o
+        assert o["aux_outputs"] == []
+    for k in ("cls_preds", "bboxes"):
+        for a, b in zip(outs[True][k], outs[False][k]):
+            assert a.shape == b.shape and torch.equal(a, b)
+
+
 def test_encoder_module_vs_reference_fixture(golden_dir):
     import unidet3d_b200 as u
     g = np.load(os.path.join(golden_dir, "encoder_ref.npz"))

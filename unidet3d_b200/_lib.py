@@ -60,6 +60,27 @@ class UnetTables(C.Structure):
                 ("child", C.c_void_p), ("child_mask", C.c_void_p), ("up", C.c_void_p), ("up_mask", C.c_void_p)]
 
 
+class Linear(C.Structure):
+    """Mirror of ``ud3d_linear``."""
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class EncoderLayer(C.Structure):
+    """Mirror of ``ud3d_encoder_layer``."""
+    _fields_ = [("qkv", Linear), ("out", Linear), ("f1", Linear), ("f2", Linear),
+                ("n1_gamma", C.c_void_p), ("n1_beta", C.c_void_p), ("n1_eps", C.c_float),
+                ("n2_gamma", C.c_void_p), ("n2_beta", C.c_void_p), ("n2_eps", C.c_float)]
+
+
+class EncoderPlan(C.Structure):
+    """Mirror of ``ud3d_encoder_plan``."""
+    _fields_ = [("num_layers", C.c_int32), ("in_channels", C.c_int32), ("d_model", C.c_int32), ("num_heads", C.c_int32),
+                ("hidden", C.c_int32), ("n_union", C.c_int32), ("activation", C.c_int32),
+                ("ip0", Linear), ("ip2", Linear), ("layer", EncoderLayer * 12),
+                ("on_gamma", C.c_void_p), ("on_beta", C.c_void_p), ("on_eps", C.c_float),
+                ("c0", Linear), ("c2", Linear), ("bb", Linear)]
+
+
 class PostArgs(C.Structure):
     """Mirror of ``ud3d_post_args``."""
     _fields_ = [
@@ -121,8 +142,13 @@ SIGNATURES = {
     "ud3d_elastic_voxel_coords": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_compact_ids_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ud3d_compact_ids": (_i, [_vp, _i, C.c_int64, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_ctx_current": (_vp, []),
+    "ud3d_ctx_device": (_i, [_vp]),
+    "ud3d_ctx_sm_count": (_i, [_vp]),
     "ud3d_eval_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "ud3d_eval_detections": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_encoder_workspace_bytes": (C.c_size_t, [_vp, _i]),
+    "ud3d_encoder_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_unet_workspace_bytes": (C.c_size_t, [_vp, _vp]),
     "ud3d_unet_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _vp, C.c_size_t, _vp]),

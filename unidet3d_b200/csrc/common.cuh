@@ -41,6 +41,18 @@ void count_launch(int n = 1);
     }                                                                                     \
   } while (0)
 
+// ---------------------------------------------------------------- per-device context ("no global state
+// except an opaque ud3d_ctx* per device").  Everything the library caches belongs to one device: the SM count and, per
+// kernel, the largest dynamic shared-memory size / carve-out its function attributes were set to.  Contexts are created
+// lazily for the calling thread's current device and guarded by a mutex (thread-safe; launches themselves are not
+// serialised).  Defined in grid.cu.
+struct DeviceCtx;
+DeviceCtx* device_ctx(int* device_out = nullptr);          // current device; nullptr + set_error on failure
+int ctx_sm_count(const DeviceCtx* c);
+// Returns true when kernel `key` has to be (re)configured on this device for `smem` bytes / `carve` percent, i.e. when
+// the call asks for more than what was configured so far; the caller then issues cudaFuncSetAttribute.
+bool ctx_needs_config(DeviceCtx* c, const void* key, size_t smem, int carve = -1);
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -33,21 +33,6 @@ static int g_dbg = 0;
 int launch_gemm_ts(const GemmParams& p, int nts, int num_sms, cudaStream_t st);
 int launch_pack_weight_ts(const float* w, int K, int c_in, int c_out, int nts, void* packed, cudaStream_t st);
 
-// per-device facts, cached (cudaFuncSetAttribute / the SM count belong to a device, not to the process)
-constexpr int kMaxDevices = 64;
-static int device_sms(int* dev_out) {
-  static int sms[kMaxDevices] = {0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
-  if (sms[dev] == 0) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    sms[dev] = n;
-  }
-  if (dev_out) *dev_out = dev;
-  return sms[dev];
-}
-
 static inline int pick_ntile(int c_out) {
   if (c_out <= 32) return 32;
   if (c_out <= 64) return 64;
@@ -795,23 +780,19 @@ static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t 
 #ifdef UD3D_DEBUG_HOOKS
   smem += (size_t)((p.dbg >> 24) & 255) * 1024;       // extra shared memory (lowers the CTAs per SM)
 #endif
-  static int carve_dev[kMaxDevices] = {0};
-  static size_t configured_dev[kMaxDevices] = {0};   // per device: largest size this instantiation was configured for
-  int dev = 0;
-  const int g_num_sms = device_sms(&dev);
-  if (g_num_sms <= 0) { set_error("ud3d_gemm_fwd: cannot query the current device"); return UD3D_ECUDA; }
-  size_t& configured = configured_dev[dev];
+  DeviceCtx* ctx = device_ctx();
+  if (!ctx) return UD3D_ECUDA;
+  const int g_num_sms = ctx_sm_count(ctx);
   int ctas_per_sm = N_TILE <= 128 ? 2 : 1;
 #ifdef UD3D_DEBUG_HOOKS
   const int carve = ((p.dbg >> 16) & 255) ? ((p.dbg >> 16) & 255) : (int)cudaSharedmemCarveoutMaxShared;   // percent
 #else
   const int carve = (int)cudaSharedmemCarveoutMaxShared;
 #endif
-  if (smem > configured || carve != carve_dev[dev]) {
-    if (smem > configured) UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // function attributes are per device: the context remembers the largest size / the carve-out set for this kernel
+  if (ctx_needs_config(ctx, (const void*)gather_gemm_tc_kernel<N_TILE>, smem, carve)) {
+    UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    if (smem > configured) configured = smem;
-    carve_dev[dev] = carve;
   }
   // persistent over the row tiles: as many CTAs as are resident at once (the CTAs of the other grid dimensions
   // share the same SMs)
@@ -960,9 +941,9 @@ int ud3d_gemm_fwd(const ud3d_gemm_args* args, void* stream) {
                    "w_packed_ts, a tile mask with a table, c_out <= 160 per tile and a launch that fills the GPU");
     UD3D_CHECK_ARG(((uintptr_t)args->w_packed_ts & 127) == 0, "ud3d_gemm_fwd: w_packed_ts misaligned");
     UD3D_CHECK_ARG(((uintptr_t)args->in & 31) == 0 && args->ld_in % 8 == 0, "ud3d_gemm_fwd: operand-form input must be 32-byte aligned");
-    const int sms = device_sms(nullptr);
-    if (sms <= 0) { set_error("ud3d_gemm_fwd: cannot query the current device"); return UD3D_ECUDA; }
-    return launch_gemm_ts(p, nts, sms, st);
+    DeviceCtx* ctx = device_ctx();
+    if (!ctx) return UD3D_ECUDA;
+    return launch_gemm_ts(p, nts, ctx_sm_count(ctx), st);
   }
   int rc2;
   switch (nts) {

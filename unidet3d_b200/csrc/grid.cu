@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <map>
 #include <mutex>
 
 namespace ud3d {
@@ -18,6 +19,48 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+
+// ---------------------------------------------------------------- per-device context
+struct DeviceCtx {
+  int device = -1;
+  int sms = 0;
+  std::mutex mu;
+  struct Cfg { size_t smem = 0; int carve = -2; };
+  std::map<const void*, Cfg> configured;      // kernel -> what its function attributes were last set to on this device
+};
+static std::mutex g_ctx_mu;
+static DeviceCtx* g_ctx[256] = {nullptr};
+
+DeviceCtx* device_ctx(int* device_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 256) {
+    set_error("ud3d: cannot query the current CUDA device");
+    return nullptr;
+  }
+  if (device_out) *device_out = dev;
+  std::lock_guard<std::mutex> lock(g_ctx_mu);
+  if (!g_ctx[dev]) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      set_error("ud3d: cannot query the SM count of device %d", dev);
+      return nullptr;
+    }
+    DeviceCtx* c = new DeviceCtx();
+    c->device = dev;
+    c->sms = sms;
+    g_ctx[dev] = c;
+  }
+  return g_ctx[dev];
+}
+int ctx_sm_count(const DeviceCtx* c) { return c ? c->sms : 0; }
+bool ctx_needs_config(DeviceCtx* c, const void* key, size_t smem, int carve) {
+  std::lock_guard<std::mutex> lock(c->mu);
+  DeviceCtx::Cfg& f = c->configured[key];
+  const bool need = smem > f.smem || carve != f.carve;
+  if (smem > f.smem) f.smem = smem;
+  f.carve = carve;
+  return need;
+}
 
 // ---------------------------------------------------------------- point statistics + coords
 // stats layout per scene: [min x,y,z (as ordered float), sum x,y,z (double)] in workspace
@@ -534,6 +577,9 @@ using namespace ud3d;
 extern "C" {
 
 int ud3d_version(void) { return 100; }
+const ud3d_ctx* ud3d_ctx_current(void) { return (const ud3d_ctx*)device_ctx(); }
+int ud3d_ctx_device(const ud3d_ctx* ctx) { return ctx ? ((const DeviceCtx*)ctx)->device : -1; }
+int ud3d_ctx_sm_count(const ud3d_ctx* ctx) { return ctx_sm_count((const DeviceCtx*)ctx); }
 const char* ud3d_last_error(void) { return g_err; }
 int64_t ud3d_launch_count(int reset) {
   int64_t v = g_launches;

@@ -624,13 +624,10 @@ int ud3d_nms_multiclass(const float* boxes, int box_dim, const float* scores, co
   nms_mask_kernel<<<dim3(nb, nb), 64, 0, st>>>(w, n, mode, iou_thr);
   UD3D_LAUNCH_CHECK();
   size_t smem = (size_t)n * 16 * 8;
-  static bool configured[64] = {false};      // per device: function attributes belong to a device's context
-  int dev = 0;
-  UD3D_CUDA(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64 || !configured[dev]) {
+  DeviceCtx* ctx = device_ctx();
+  if (!ctx) return UD3D_ECUDA;
+  if (ctx_needs_config(ctx, (const void*)nms_sweep_kernel, 1024 * 16 * 8))
     UD3D_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16 * 8));
-    if (dev >= 0 && dev < 64) configured[dev] = true;
-  }
   nms_sweep_kernel<<<1, 1024, smem, st>>>(w, keep_out, n_keep);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;

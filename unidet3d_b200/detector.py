@@ -209,7 +209,22 @@ class UniDet3D(nn.Module):
                 cur.wait_stream(st)
         return per_scene
 
+    # NVTX ranges around the stages of a step (ud3d.collate / backbone / encoder / postprocess) when UD3D_NVTX=1: they
+    # label the ncu / nsys timelines of tools/profile_step.py; off by default (two Python calls per stage)
+    _NVTX_NEXT = {"start": "ud3d.collate", "collate": "ud3d.backbone", "backbone": "ud3d.encoder", "encoder": "ud3d.postprocess"}
+
     def _mark_stage(self, name):
+        if getattr(self, "_nvtx", None) is None:
+            import os
+            self._nvtx = os.environ.get("UD3D_NVTX", "0") == "1"
+            self._nvtx_open = False
+        if self._nvtx:
+            if self._nvtx_open:
+                torch.cuda.nvtx.range_pop()
+            nxt = self._NVTX_NEXT.get(name)
+            self._nvtx_open = nxt is not None
+            if nxt is not None:
+                torch.cuda.nvtx.range_push(nxt)
         ev = getattr(self, "stage_events", None)
         if ev is not None:
             import time
