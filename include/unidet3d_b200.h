@@ -37,7 +37,7 @@ extern "C" {
 
 int ud3d_version(void);
 const char* ud3d_last_error(void);
-/* number of this library's kernels launched by the calling thread since the last reset */
+/* number of this library's kernels launched by the process (all host threads) since the last reset */
 int64_t ud3d_launch_count(int reset);
 /* Per-device context: the only state the library keeps -- per device, the SM count and which function
  * attributes (dynamic shared-memory size, carve-out) its kernels were configured with.  Created lazily for the calling

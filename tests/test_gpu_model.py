@@ -291,9 +291,13 @@ def test_pipelined_batches_match_one_at_a_time():
         scenes = [make_scene(100 + 3 * j + i, n + 100 * i, a, c) for i in range(2 + j % 2)]
         names = [("scannet", "arkitscenes")[(i + j) % 2] for i in range(len(scenes))]
         batches.append(([torch.as_tensor(s[0]).pin_memory() for s in scenes], [torch.as_tensor(s[1]).pin_memory() for s in scenes], names))
+    # the threaded pipeline runs FIRST, on the cold model: with one host thread per batch the first launch of every kernel
+    # (function attributes in the per-device context) happens concurrently from two threads
+    cold = list(model.forward_pipelined(iter(batches), depth=2, threaded=True))
     ref = [model.forward_scenes(*b) for b in batches]
-    for depth in (1, 2, 3):
-        got = list(model.forward_pipelined(iter(batches), depth=depth))
+    runs = [cold] + [list(model.forward_pipelined(iter(batches), depth=depth, threaded=threaded))
+                     for depth in (1, 2, 3) for threaded in (False, True)]
+    for got in runs:
         assert len(got) == len(ref)
         for rb, gb in zip(ref, got):
             assert len(rb) == len(gb)

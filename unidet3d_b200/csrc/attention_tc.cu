@@ -390,9 +390,12 @@ extern "C" int ud3d_attention_fwd_tc(const float* qkv_split, const int32_t* cu_s
   const size_t smem = 1024 + 16384 + 2 * kAStages * 8192 + 1024 + 256;
   DeviceCtx* ctx = device_ctx();
   if (!ctx) return UD3D_ECUDA;
-  if (ctx_needs_config(ctx, (const void*)attention_tc_kernel, smem)) {
+  {
+    CtxGuard guard(ctx);
+    if (ctx_needs_config(ctx, (const void*)attention_tc_kernel, smem)) {
     UD3D_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UD3D_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    }
   }
   dim3 grid(cdiv(max_T, kAQ), num_heads, B);
   attention_tc_kernel<<<grid, kAThreads, smem, (cudaStream_t)stream>>>(tmap, cu_seqlens, num_heads, (uint8_t*)out_split);

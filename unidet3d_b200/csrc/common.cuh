@@ -50,8 +50,20 @@ struct DeviceCtx;
 DeviceCtx* device_ctx(int* device_out = nullptr);          // current device; nullptr + set_error on failure
 int ctx_sm_count(const DeviceCtx* c);
 // Returns true when kernel `key` has to be (re)configured on this device for `smem` bytes / `carve` percent, i.e. when
-// the call asks for more than what was configured so far; the caller then issues cudaFuncSetAttribute.
+// the call asks for more than what was configured so far; the caller then issues cudaFuncSetAttribute.  The caller must
+// hold the context's lock (CtxGuard) from this call until the attributes ARE set: another host thread that finds the
+// kernel "configured" launches at once (a launch asking for more dynamic shared memory than the attribute allows fails
+// with "invalid argument").
 bool ctx_needs_config(DeviceCtx* c, const void* key, size_t smem, int carve = -1);
+void ctx_lock(DeviceCtx* c);
+void ctx_unlock(DeviceCtx* c);
+struct CtxGuard {
+  DeviceCtx* c;
+  explicit CtxGuard(DeviceCtx* ctx) : c(ctx) { ctx_lock(c); }
+  ~CtxGuard() { ctx_unlock(c); }
+  CtxGuard(const CtxGuard&) = delete;
+  CtxGuard& operator=(const CtxGuard&) = delete;
+};
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -790,9 +790,12 @@ static int launch_tc(const GemmParams& p, int n_tiles, int splits, cudaStream_t 
   const int carve = (int)cudaSharedmemCarveoutMaxShared;
 #endif
   // function attributes are per device: the context remembers the largest size / the carve-out set for this kernel
-  if (ctx_needs_config(ctx, (const void*)gather_gemm_tc_kernel<N_TILE>, smem, carve)) {
+  {
+    CtxGuard guard(ctx);
+    if (ctx_needs_config(ctx, (const void*)gather_gemm_tc_kernel<N_TILE>, smem, carve)) {
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_tc_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
   }
   // persistent over the row tiles: as many CTAs as are resident at once (the CTAs of the other grid dimensions
   // share the same SMs)

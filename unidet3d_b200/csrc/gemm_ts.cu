@@ -512,12 +512,15 @@ static int launch_ts(const GemmParams& p, int num_sms, cudaStream_t st) {
   // per-device configuration (cudaFuncSetAttribute applies to the current device)
   DeviceCtx* ctx = device_ctx();
   if (!ctx) return UD3D_ECUDA;
-  if (ctx_needs_config(ctx, (const void*)gather_gemm_ts_kernel<N_TILE>, smem)) {
+  {
+    CtxGuard guard(ctx);
+    if (ctx_needs_config(ctx, (const void*)gather_gemm_ts_kernel<N_TILE>, smem)) {
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_ts_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // leave the rest of the 256 KB to L1: gathered rows are re-used across the kernel offsets of a tile
     int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;
     if (pct > 100) pct = 100;
     UD3D_CUDA(cudaFuncSetAttribute(gather_gemm_ts_kernel<N_TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
   }
   const int n_items = cdiv(p.a.n_out, kTileM) * cdiv(p.a.c_out, N_TILE);
   const int grid = n_items < num_sms ? n_items : num_sms;

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 
@@ -11,14 +12,14 @@ namespace ud3d {
 
 // ---------------------------------------------------------------- error / counters (library-wide)
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};          // process-wide: batches may be issued from several host threads
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-void count_launch(int n) { g_launches += n; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---------------------------------------------------------------- per-device context
 struct DeviceCtx {
@@ -53,8 +54,9 @@ DeviceCtx* device_ctx(int* device_out) {
   return g_ctx[dev];
 }
 int ctx_sm_count(const DeviceCtx* c) { return c ? c->sms : 0; }
-bool ctx_needs_config(DeviceCtx* c, const void* key, size_t smem, int carve) {
-  std::lock_guard<std::mutex> lock(c->mu);
+void ctx_lock(DeviceCtx* c) { c->mu.lock(); }
+void ctx_unlock(DeviceCtx* c) { c->mu.unlock(); }
+bool ctx_needs_config(DeviceCtx* c, const void* key, size_t smem, int carve) {      // caller holds the lock
   DeviceCtx::Cfg& f = c->configured[key];
   const bool need = smem > f.smem || carve != f.carve;
   if (smem > f.smem) f.smem = smem;
@@ -582,9 +584,7 @@ int ud3d_ctx_device(const ud3d_ctx* ctx) { return ctx ? ((const DeviceCtx*)ctx)-
 int ud3d_ctx_sm_count(const ud3d_ctx* ctx) { return ctx_sm_count((const DeviceCtx*)ctx); }
 const char* ud3d_last_error(void) { return g_err; }
 int64_t ud3d_launch_count(int reset) {
-  int64_t v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
 }
 
 size_t ud3d_point_coords_workspace_bytes(int B) { return align_up(sizeof(SceneAcc) * (size_t)(B > 0 ? B : 1), 256); }

@@ -626,8 +626,11 @@ int ud3d_nms_multiclass(const float* boxes, int box_dim, const float* scores, co
   size_t smem = (size_t)n * 16 * 8;
   DeviceCtx* ctx = device_ctx();
   if (!ctx) return UD3D_ECUDA;
-  if (ctx_needs_config(ctx, (const void*)nms_sweep_kernel, 1024 * 16 * 8))
-    UD3D_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16 * 8));
+  {
+    CtxGuard guard(ctx);
+    if (ctx_needs_config(ctx, (const void*)nms_sweep_kernel, 1024 * 16 * 8))
+      UD3D_CUDA(cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 16 * 8));
+  }
   nms_sweep_kernel<<<1, 1024, smem, st>>>(w, keep_out, n_keep);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;

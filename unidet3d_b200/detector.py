@@ -211,6 +211,11 @@ class UniDet3D(nn.Module):
 
     # NVTX ranges around the stages of a step (ud3d.collate / backbone / encoder / postprocess) when UD3D_NVTX=1: they
     # label the ncu / nsys timelines of tools/profile_step.py; off by default (two Python calls per stage)
+    # forward_pipelined: issue the front of every step (staging, voxelisation, rulebooks) on a high-priority stream
+    pipeline_front_stream = False
+    # forward_pipelined: one host thread per in-flight batch (see its docstring)
+    pipeline_threads = True
+
     _NVTX_NEXT = {"start": "ud3d.collate", "collate": "ud3d.backbone", "backbone": "ud3d.encoder", "encoder": "ud3d.postprocess"}
 
     def _mark_stage(self, name):
@@ -248,10 +253,13 @@ class UniDet3D(nn.Module):
 
     @torch.no_grad()
     def submit_scenes(self, points: List, superpoints: List, datasets_names: List[str],
-                      n_superpoints: Optional[Sequence[int]] = None, slot: int = 0):
+                      n_superpoints: Optional[Sequence[int]] = None, slot: int = 0, front_stream=None):
         """Issue the whole forward of one batch on the current stream, including the asynchronous D2H of the packed
         per-scene results, WITHOUT waiting for it.  Returns a handle for ``collect``.  ``slot`` selects the set of
-        pinned result buffers (batches in flight at the same time need different slots, see ``forward_pipelined``)."""
+        pinned result buffers (batches in flight at the same time need different slots, see ``forward_pipelined``).
+        ``front_stream``: optional (high-priority) stream for the front of the step -- staging copies, voxelisation,
+        grids and rulebooks: ~50 small dependent kernels and two host read-backs.  With several batches in flight those
+        small kernels otherwise queue behind the other batch's convolutions and the host stalls at each read-back."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("unidet3d_b200.UniDet3D runs on CUDA only (no CPU fallback)")
@@ -271,24 +279,37 @@ class UniDet3D(nn.Module):
         sp_off = np.concatenate([[0], np.cumsum(n_sps)]).astype(np.int64)
         pt_off = np.concatenate([[0], np.cumsum(n_pts)]).astype(np.int64)
         n_total = int(pt_off[-1])
-        # stage the batch as one packed [n,6] / [n] pair on the device: one async copy per scene straight from the
-        # caller's (ideally pinned) buffers -- no host-side concatenation
-        pts = torch.empty((n_total, 6), dtype=torch.float32, device=dev)
-        sp_b = torch.empty(n_total, dtype=torch.int64, device=dev)
-        for i, (p, s) in enumerate(zip(P, S)):
-            a, b = int(pt_off[i]), int(pt_off[i + 1])
-            pts[a:b].copy_(p, non_blocking=True)
-            sp_b[a:b].copy_(s, non_blocking=True)
-            if sp_off[i]:
-                sp_b[a:b] += int(sp_off[i])
-        offs = torch.tensor(pt_off, dtype=torch.int32).to(dev, non_blocking=True)
+        mark = self._mark_stage                     # optional CUDA-event timeline (tools/stage_timeline.py)
+
+        def front():
+            # stage the batch as one packed [n,6] / [n] pair on the device: one async copy per scene straight from the
+            # caller's (ideally pinned) buffers -- no host-side concatenation
+            pts = torch.empty((n_total, 6), dtype=torch.float32, device=dev)
+            sp_b = torch.empty(n_total, dtype=torch.int64, device=dev)
+            for i, (p, s) in enumerate(zip(P, S)):
+                a, b = int(pt_off[i]), int(pt_off[i + 1])
+                pts[a:b].copy_(p, non_blocking=True)
+                sp_b[a:b].copy_(s, non_blocking=True)
+                if sp_off[i]:
+                    sp_b[a:b] += int(sp_off[i])
+            offs = torch.tensor(pt_off, dtype=torch.int32).to(dev, non_blocking=True)
+            mark("start")
+            sp_centers = ops.segmented_mean(pts, sp_b, int(sp_off[-1]), channels=3)            # unidet3d.py:446-447
+            x, inverse = self.collate(pts, offs, B)
+            return pts, sp_b, offs, sp_centers, x, inverse
+
+        if front_stream is not None:
+            # everything allocated on the front stream stays referenced by the handle until collect() has synchronised,
+            # so the caching allocator cannot recycle it while the batch's own stream still reads it
+            main_stream = torch.cuda.current_stream()
+            front_stream.wait_stream(main_stream)
+            with torch.cuda.stream(front_stream):
+                pts, sp_b, offs, sp_centers, x, inverse = front()
+            main_stream.wait_stream(front_stream)
+        else:
+            pts, sp_b, offs, sp_centers, x, inverse = front()
         self.last_h2d_bytes = int(sum(p.numel() * 4 for p in P if not p.is_cuda) + sum(s.numel() * 8 for s in S if not s.is_cuda)
                                   + offs.numel() * 4)
-
-        mark = self._mark_stage                     # optional CUDA-event timeline (tools/stage_timeline.py)
-        mark("start")
-        sp_centers = ops.segmented_mean(pts, sp_b, int(sp_off[-1]), channels=3)            # unidet3d.py:446-447
-        x, inverse = self.collate(pts, offs, B)
         mark("collate")
         pooled = self.extract_feat(x, sp_b, inverse, sp_off)
         mark("backbone")
@@ -316,7 +337,7 @@ class UniDet3D(nn.Module):
         done.record()
         self.last_d2h_bytes = int(sum(hb.numel() * 4 for hb in host)) + 4 * 4 + 4 * (len(per_scene) + 4)   # + extents / counts read-backs
         # (the handle keeps the device tensors of the step alive until its results have been read)
-        return dict(per_scene=per_scene, host=host, done=done, keep=(pts, sp_b, out))
+        return dict(per_scene=per_scene, host=host, done=done, keep=(pts, sp_b, out, x, inverse, sp_centers, offs, pooled))
 
     def collect(self, handle):
         """Wait for a submitted batch and build the per-scene (boxes, labels, scores) CPU tensors."""
@@ -341,18 +362,29 @@ class UniDet3D(nn.Module):
             results.append((boxes, labels, scores))
         return results
 
-    def forward_pipelined(self, batches, depth: int = 2, pre_submit=None):
+    def forward_pipelined(self, batches, depth: int = 2, pre_submit=None, threaded: Optional[bool] = None):
         """Throughput mode: yields the results of every batch of ``batches`` (an iterable of
         (points, superpoints, datasets_names[, n_superpoints]) tuples) in order, with up to ``depth`` batches in
-        flight on their own CUDA streams.  The host-bound stages of batch i+1 (staging copies, voxelisation with its
-        two small read-backs, ~300 kernel launches) run while the GPU still works on batch i, and the H2D copies of
-        pinned inputs overlap its kernels.  ``pre_submit`` (optional callable) runs on the batch's stream right
-        before its work is issued (bench.py flushes the L2 there)."""
+        flight on their own CUDA streams.  ``pre_submit`` (optional callable) runs on the batch's stream right
+        before its work is issued (bench.py flushes the L2 there).
+
+        ``threaded`` (default ``self.pipeline_threads``): one host thread per stream.  A step has two unavoidable host
+        read-backs (spatial extents, voxel counts); with several batches in flight each of them waits behind the other
+        batch's kernels (measured: 2.7 ms of a 5.2 ms submit), and a single issuing thread makes the whole pipeline
+        host-bound.  With a thread per batch the waits (which release the GIL) overlap the other thread's launches.
+        ``threaded=False``: one thread issues all batches round-robin and collects the oldest when ``depth`` are in
+        flight."""
         dev = next(self.parameters()).device
         if getattr(self, "_pipe_streams", None) is None or len(self._pipe_streams) < depth:
             self._pipe_streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+            self._front_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(depth)]
         cur = torch.cuda.current_stream()
         self.prepare()          # plans are built on `cur`; every pipe stream waits on `cur` before its first batch
+        if threaded is None:
+            threaded = self.pipeline_threads
+        if threaded and depth > 1:
+            yield from self._forward_pipelined_threads(batches, depth, pre_submit, dev, cur)
+            return
         pending = []
         for j, b in enumerate(batches):
             st = self._pipe_streams[j % depth]
@@ -362,9 +394,69 @@ class UniDet3D(nn.Module):
             with torch.cuda.stream(st):
                 if pre_submit is not None:
                     pre_submit()
-                pending.append(self.submit_scenes(*b, slot=j % depth))
+                pending.append(self.submit_scenes(*b, slot=j % depth,
+                                                  front_stream=self._front_streams[j % depth] if self.pipeline_front_stream else None))
         while pending:
             yield self.collect(pending.pop(0))
+
+    def _forward_pipelined_threads(self, batches, depth, pre_submit, dev, cur):
+        import queue
+        import threading
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        in_qs = [queue.Queue() for _ in range(depth)]
+        out_qs = [queue.Queue() for _ in range(depth)]
+
+        def worker(w):
+            try:
+                torch.cuda.set_device(dev)
+                st = self._pipe_streams[w]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    while True:
+                        item = in_qs[w].get()
+                        if item is None:
+                            return
+                        try:
+                            if pre_submit is not None:
+                                pre_submit()
+                            h = self.submit_scenes(*item, slot=w,
+                                                   front_stream=self._front_streams[w] if self.pipeline_front_stream else None)
+                            out_qs[w].put((True, self.collect(h)))
+                        except BaseException as e:  # noqa: BLE001  (re-raised in the consumer)
+                            out_qs[w].put((False, e))
+            except BaseException as e:  # noqa: BLE001
+                out_qs[w].put((False, e))
+
+        threads = [threading.Thread(target=worker, args=(w,), daemon=True) for w in range(depth)]
+        for t in threads:
+            t.start()
+
+        def result(k):
+            ok, val = out_qs[k % depth].get()
+            if not ok:
+                raise val
+            return val
+
+        try:
+            n_out = 0
+            n_in = 0
+            for b in batches:
+                if n_in - n_out >= depth:          # every worker has a batch: hand out the oldest result first
+                    yield result(n_out)
+                    n_out += 1
+                in_qs[n_in % depth].put(b)
+                n_in += 1
+            while n_out < n_in:
+                yield result(n_out)
+                n_out += 1
+        finally:
+            for q in in_qs:
+                q.put(None)
+            for t in threads:
+                t.join(timeout=60)
+            for st in self._pipe_streams[:depth]:
+                cur.wait_stream(st)
 
     def predict(self, batch_inputs_dict, batch_data_samples, **kwargs):
         """unidet3d.py:411-473: fills ``pred_instances_3d`` (bboxes_3d, scores_3d, labels_3d) of every sample."""
