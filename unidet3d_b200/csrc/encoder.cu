@@ -68,6 +68,30 @@ __global__ void __launch_bounds__(256) segmented_sum_kernel(const float* __restr
   }
 }
 
+// C <= 4 (superpoint centres: xyz of a [n, 6] point matrix): one THREAD per point.  The lane-per-channel kernel above
+// keeps 3 of 32 lanes busy and walks the points of a warp one after the other (98 us for 800k points); here every lane
+// has its own point and issues its C fixed-point atomics directly (same sums: integer addition is order-independent).
+__global__ void __launch_bounds__(256) segmented_sum_small_kernel(const float* __restrict__ src, int ld, int C,
+                                                                  const int32_t* __restrict__ gather,
+                                                                  const int64_t* __restrict__ seg, int n, int n_seg,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, int relu,
+                                                                  unsigned long long* acc_fix, int* cnt) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const long long id = seg[p];
+    if (id < 0 || id >= n_seg) continue;
+    const int g = gather ? gather[p] : p;
+    atomicAdd(cnt + id, 1);
+    if (g < 0) continue;
+    for (int c = 0; c < C; ++c) {
+      float v = __ldg(src + (size_t)g * ld + c);
+      if (scale) v = fmaf(v, scale[c], shift[c]);
+      if (relu) v = fmaxf(v, 0.f);
+      atomicAdd(acc_fix + (size_t)id * C + c, (unsigned long long)__float2ll_rn(v * kPoolFixScale));
+    }
+  }
+}
+
 __global__ void segmented_norm_kernel(float* out, const unsigned long long* __restrict__ acc_fix, const int* __restrict__ cnt,
                                       int n_seg, int C) {
   long long total = (long long)n_seg * C;
@@ -615,7 +639,12 @@ int ud3d_segmented_mean(const float* src, int ld_src, int C, const int32_t* gath
   unsigned long long* acc_fix = (unsigned long long*)ws;            // [n_seg, C] fixed-point sums
   int* cnt = (int*)(acc_fix + (size_t)n_seg * C);                   // [n_seg] point counts
   UD3D_CUDA(cudaMemsetAsync(ws, 0, ud3d_segmented_mean_workspace_bytes(n_seg, C), st));
-  if (n > 0) {
+  if (n > 0 && C <= 4) {
+    int blocks = cdiv(n, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    segmented_sum_small_kernel<<<blocks, 256, 0, st>>>(src, ld_src, C, gather, seg, n, n_seg, scale, shift, relu, acc_fix, cnt);
+    UD3D_LAUNCH_CHECK();
+  } else if (n > 0) {
     int warps = cdiv(n, kPoolPtsPerWarp);
     segmented_sum_kernel<<<cdiv(warps, 8), 256, 0, st>>>(src, ld_src, C, gather, seg, n, n_seg, scale, shift, relu, acc_fix, cnt);
     UD3D_LAUNCH_CHECK();
