@@ -319,6 +319,25 @@ int ud3d_bn_batch_sums(const float* x, int ld, int n, int C, double* sums, void*
 int ud3d_bn_train_fold(const double* sums, double count, int C, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift,
                        float* save_mean, float* save_invstd, void* stream);
+/* Backward of the fused train-mode BatchNorm + ReLU in front of a conv (a = relu(x * scale + shift)), given dA = the conv's
+ * input gradient:  g = dA * [a > 0];  sums[0..C) = sum_r g (= dbeta), sums[C..2C) = sum_r g * xhat (= dgamma), fp64, fixed
+ * order (all-reduced across ranks for SyncBatchNorm);  dx (+)= scale * (g - dbeta / count - xhat * dgamma / count).
+ * mean / invstd: the save_mean / save_invstd of ud3d_bn_train_fold.  ws: ud3d_bn_batch_sums_workspace_bytes(n, C). */
+int ud3d_bn_backward_sums(const float* x, int ld_x, const float* da, int ld_da, int n, int C, const float* scale,
+                          const float* shift, const float* mean, const float* invstd, int relu, double* sums, void* ws,
+                          size_t ws_bytes, void* stream);
+int ud3d_bn_backward_apply(const float* x, int ld_x, const float* da, int ld_da, int n, int C, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, int relu, const double* sums,
+                           double count, float* dx, int ld_dx, int accumulate, void* stream);
+/* out = relu?(x * scale + shift) as an fp32 map: the X operand of ud3d_conv_wgrad (recomputed, not stored, in forward) */
+int ud3d_bn_relu_apply(const float* x, int ld_x, int n, int C, const float* scale, const float* shift, int relu, float* out,
+                       int ld_out, void* stream);
+/* Backward of ud3d_segmented_mean without its affine (apply ud3d_bn_backward_* on the result for the fused output
+ * BatchNorm): d_src[gather ? gather[p] : p, :] += d_pooled[seg[p], :] / count[seg[p]];  d_src [n_rows, C] is overwritten.
+ * Deterministic (64-bit fixed-point atomics, 2^-32).  ws 8-byte aligned. */
+size_t ud3d_segmented_mean_backward_workspace_bytes(int n_rows, int n_seg, int C);
+int ud3d_segmented_mean_backward(const float* d_pooled, int C, const int32_t* gather, const int64_t* seg, int n, int n_seg,
+                                 int n_rows, float* d_src, void* ws, size_t ws_bytes, void* stream);
 /* Weight gradient of a sparse convolution / linear layer (autograd of spconv's conv forward, spconv_unet.py:37-72):
  *   dw[co][k][ci] (+)= sum_o dy[o][co] * x[table[k][o]][ci]      (layout of the reference parameter [C_out, K, C_in])
  * x = the conv's input as it entered the contraction (after its BatchNorm + ReLU), fp32; deterministic.  The input

@@ -24,7 +24,14 @@ def _worker(rank, world, port, q):
     sums, count = ops.sync_bn_sums(torch.stack((x.sum(0), (x * x).sum(0))), float(x.shape[0]))
     mean = sums[0] / count
     var = sums[1] / count - mean * mean
-    q.put((rank, mine, fingerprint, t_dev, t_e2e, count, mean.tolist(), var.tolist()))
+    # data-parallel gradient exchange of the training side (unidet3d_b200/train.py): bucketed all-reduce + average
+    from unidet3d_b200 import train
+    ps = [torch.nn.Parameter(torch.zeros(s)) for s in ((3, 5), (7,), (2, 2, 2), (1000,))]
+    for i, p_ in enumerate(ps):
+        p_.grad = torch.full(p_.shape, float((rank + 1) * (i + 1)))
+    n_coll = train.allreduce_gradients(ps, bucket_bytes=4 * 40)        # small buckets: several collectives
+    avg = [float(p_.grad.mean()) for p_ in ps]
+    q.put((rank, mine, fingerprint, t_dev, t_e2e, count, mean.tolist(), var.tolist(), n_coll, avg))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -38,7 +45,8 @@ def test_two_rank_sharding_and_timing():
     out = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    (r0, s0, f0, a0, b0, c0, m0, v0), (r1, s1, f1, a1, b1, c1, m1, v1) = out
+    (r0, s0, f0, a0, b0, c0, m0, v0, nc0, g0), (r1, s1, f1, a1, b1, c1, m1, v1, nc1, g1) = out
+    assert nc0 == nc1 == 2 and g0 == g1 == [1.5 * (i + 1) for i in range(4)]       # mean of ranks' (rank + 1) * (i + 1)
     xs = [torch.randn(300 + 200 * r, 8, generator=torch.Generator().manual_seed(100 + r), dtype=torch.float64) * (1 + r) + r
           for r in range(2)]
     allx = torch.cat(xs)

@@ -134,6 +134,11 @@ SIGNATURES = {
     "ud3d_bn_train_fold": (_i, [_vp, C.c_double, _i, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ud3d_conv_wgrad_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "ud3d_segmented_mean_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "ud3d_bn_backward_sums": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_bn_backward_apply": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, C.c_double, _vp, _i, _i, _vp]),
+    "ud3d_bn_relu_apply": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "ud3d_segmented_mean_backward_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
+    "ud3d_segmented_mean_backward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_elastic_workspace_bytes": (C.c_size_t, [_vp]),
     "ud3d_elastic_blur": (_i, [_vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_points_to_voxel_units": (_i, [_vp, _i, _i, _f, _vp, _vp]),

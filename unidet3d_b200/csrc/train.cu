@@ -58,6 +58,90 @@ __global__ void bn_train_fold_kernel(const double* __restrict__ sums, double cou
   }
 }
 
+// ---------------------------------------------------------------- backward of the fused BatchNorm(train) + ReLU
+// Forward (folded into the consumer conv's operand load): a = relu(x * scale + shift), scale = gamma * invstd,
+// shift = beta - mean * scale.  Given dA (the conv's input gradient):
+//   g      = dA * [x * scale + shift > 0]                       (relu == 0: g = dA)
+//   dbeta  = sum_r g,   dgamma = sum_r g * xhat,   xhat = (x - mean) * invstd
+//   dx     = scale * (g - dbeta / count - xhat * dgamma / count)       (batch statistics depend on every row)
+// Two passes like the forward statistics: deterministic fp64 partial sums (all-reduced across ranks for SyncBatchNorm,
+// the "bwd all_reduce of [2C]" of SURVEY.md 8e), then the element-wise pass.
+__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ da,
+                                                             int ld_da, int n, int C, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, int relu, double* __restrict__ part) {
+  const int r0 = blockIdx.x * kBnRowsPerBlock;
+  const int r1 = min(n, r0 + kBnRowsPerBlock);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+    double s = 0.0, q = 0.0;
+    for (int r = r0; r < r1; ++r) {
+      const float xv = x[(size_t)r * ld_x + c];
+      float g = da[(size_t)r * ld_da + c];
+      if (relu && !(fmaf(xv, sc, sh) > 0.f)) g = 0.f;
+      s += (double)g;
+      q += (double)g * (double)((xv - mu) * is);
+    }
+    part[((size_t)blockIdx.x * 2 + 0) * C + c] = s;
+    part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
+  }
+}
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ da, int ld_da, int n, int C,
+                                    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, int relu, const double* __restrict__ sums, double count,
+                                    float* __restrict__ dx, int ld_dx, int accumulate) {
+  const long long total = (long long)n * C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / C), c = (int)(t - (long long)r * C);
+    const float xv = x[(size_t)r * ld_x + c];
+    float g = da[(size_t)r * ld_da + c];
+    if (relu && !(fmaf(xv, scale[c], shift[c]) > 0.f)) g = 0.f;
+    const float xhat = (xv - mean[c]) * invstd[c];
+    const float v = scale[c] * (g - (float)(sums[c] / count) - xhat * (float)(sums[C + c] / count));
+    float* o = dx + (size_t)r * ld_dx + c;
+    *o = accumulate ? *o + v : v;
+  }
+}
+// a = relu?(x * scale + shift) as a plain fp32 map (the X operand of ud3d_conv_wgrad)
+__global__ void bn_relu_apply_kernel(const float* __restrict__ x, int ld_x, int n, int C, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, int relu, float* __restrict__ out, int ld_out) {
+  const long long total = (long long)n * C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / C), c = (int)(t - (long long)r * C);
+    float v = fmaf(x[(size_t)r * ld_x + c], scale[c], shift[c]);
+    if (relu) v = fmaxf(v, 0.f);
+    out[(size_t)r * ld_out + c] = v;
+  }
+}
+// Backward of the superpoint mean-pool (unidet3d.py:130): d_vox[inverse[p], :] += d_pooled[seg[p], :] / count[seg[p]].
+// One warp per point row segment; 64-bit fixed-point atomics (2^-32 resolution of a gradient) keep the scatter
+// deterministic; a second pass converts.
+__global__ void pool_bwd_scatter_kernel(const float* __restrict__ d_pooled, int C, const int32_t* __restrict__ gather,
+                                        const int64_t* __restrict__ seg, const int32_t* __restrict__ cnt, int n, int n_seg,
+                                        unsigned long long* __restrict__ acc) {
+  const long long total = (long long)n * C;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t / C), c = (int)(t - (long long)p * C);
+    const long long s = seg[p];
+    if (s < 0 || s >= n_seg) continue;
+    const int v = gather ? gather[p] : p;
+    if (v < 0) continue;
+    const int k = cnt[s] > 1 ? cnt[s] : 1;
+    const double g = (double)d_pooled[(size_t)s * C + c] / (double)k;
+    atomicAdd(acc + (size_t)v * C + c, (unsigned long long)__double2ll_rn(g * 4294967296.0));
+  }
+}
+__global__ void seg_count_kernel(const int64_t* __restrict__ seg, int n, int n_seg, int32_t* __restrict__ cnt) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const long long s = seg[p];
+    if (s >= 0 && s < n_seg) atomicAdd(cnt + s, 1);
+  }
+}
+__global__ void fix32_to_float_kernel(const unsigned long long* __restrict__ acc, long long total, float* __restrict__ out) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+    out[t] = (float)((double)(long long)acc[t] * (1.0 / 4294967296.0));
+}
+
 // ---------------------------------------------------------------- sparse-conv weight gradient
 // dW[co][k][ci] = sum_o dY[o][co] * X[table[k][o]][ci]   (X = the conv's input AFTER its BatchNorm+ReLU).
 // One CTA = (kernel offset k, 32 x 32 tile of (co, ci), slice of the output rows); rows are staged through shared memory
@@ -157,6 +241,92 @@ int ud3d_bn_train_fold(const double* sums, double count, int C, const float* gam
   bn_train_fold_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, C, gamma, beta, eps, momentum, running_mean,
                                                                      running_var, scale, shift, save_mean, save_invstd);
   UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_bn_backward_sums(const float* x, int ld_x, const float* da, int ld_da, int n, int C, const float* scale, const float* shift,
+                          const float* mean, const float* invstd, int relu, double* sums, void* ws, size_t ws_bytes, void* stream) {
+  UD3D_CHECK_ARG(x && da && scale && shift && mean && invstd && sums && ws && C > 0 && n >= 0 && ld_x >= C && ld_da >= C,
+                 "ud3d_bn_backward_sums: bad argument");
+  if (ws_bytes < ud3d_bn_batch_sums_workspace_bytes(n, C)) {
+    set_error("ud3d_bn_backward_sums: workspace too small");
+    return UD3D_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblocks = cdiv(n > 0 ? n : 1, kBnRowsPerBlock);
+  if (n == 0) {
+    UD3D_CUDA(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
+    return UD3D_OK;
+  }
+  bn_bwd_partial_kernel<<<nblocks, 256, 0, st>>>(x, ld_x, da, ld_da, n, C, scale, shift, mean, invstd, relu, (double*)ws);
+  UD3D_LAUNCH_CHECK();
+  bn_final_sums_kernel<<<cdiv(2 * C, 128), 128, 0, st>>>((const double*)ws, nblocks, C, sums);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_bn_backward_apply(const float* x, int ld_x, const float* da, int ld_da, int n, int C, const float* scale, const float* shift,
+                           const float* mean, const float* invstd, int relu, const double* sums, double count, float* dx, int ld_dx,
+                           int accumulate, void* stream) {
+  UD3D_CHECK_ARG(x && da && scale && shift && mean && invstd && sums && dx && C > 0 && n >= 0 && ld_x >= C && ld_da >= C && ld_dx >= C &&
+                     count > 0.0,
+                 "ud3d_bn_backward_apply: bad argument");
+  if (n == 0) return UD3D_OK;
+  long long total = (long long)n * C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld_x, da, ld_da, n, C, scale, shift, mean, invstd, relu, sums, count, dx,
+                                                                ld_dx, accumulate);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_bn_relu_apply(const float* x, int ld_x, int n, int C, const float* scale, const float* shift, int relu, float* out, int ld_out,
+                       void* stream) {
+  UD3D_CHECK_ARG(x && scale && shift && out && C > 0 && n >= 0 && ld_x >= C && ld_out >= C, "ud3d_bn_relu_apply: bad argument");
+  if (n == 0) return UD3D_OK;
+  long long total = (long long)n * C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bn_relu_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld_x, n, C, scale, shift, relu, out, ld_out);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+size_t ud3d_segmented_mean_backward_workspace_bytes(int n_rows, int n_seg, int C) {
+  return (size_t)(n_rows > 0 ? n_rows : 1) * (size_t)(C > 0 ? C : 1) * 8 + (size_t)(n_seg > 0 ? n_seg : 1) * 4;
+}
+
+int ud3d_segmented_mean_backward(const float* d_pooled, int C, const int32_t* gather, const int64_t* seg, int n, int n_seg, int n_rows,
+                                 float* d_src, void* ws, size_t ws_bytes, void* stream) {
+  UD3D_CHECK_ARG(d_pooled && seg && d_src && ws && C > 0 && n >= 0 && n_seg >= 0 && n_rows >= 0, "ud3d_segmented_mean_backward: bad argument");
+  UD3D_CHECK_ARG(((uintptr_t)ws & 7) == 0, "ud3d_segmented_mean_backward: workspace must be 8-byte aligned");
+  if (ws_bytes < ud3d_segmented_mean_backward_workspace_bytes(n_rows, n_seg, C)) {
+    set_error("ud3d_segmented_mean_backward: workspace too small");
+    return UD3D_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* acc = (unsigned long long*)ws;
+  int32_t* cnt = (int32_t*)(acc + (size_t)(n_rows > 0 ? n_rows : 1) * C);
+  UD3D_CUDA(cudaMemsetAsync(ws, 0, ud3d_segmented_mean_backward_workspace_bytes(n_rows, n_seg, C), st));
+  if (n > 0 && n_seg > 0) {
+    int b1 = cdiv(n, 256);
+    if (b1 > 148 * 16) b1 = 148 * 16;
+    seg_count_kernel<<<b1, 256, 0, st>>>(seg, n, n_seg, cnt);
+    UD3D_LAUNCH_CHECK();
+    long long total = (long long)n * C;
+    int b2 = (int)((total + 255) / 256);
+    if (b2 > 148 * 32) b2 = 148 * 32;
+    pool_bwd_scatter_kernel<<<b2, 256, 0, st>>>(d_pooled, C, gather, seg, cnt, n, n_seg, acc);
+    UD3D_LAUNCH_CHECK();
+  }
+  if (n_rows > 0) {
+    long long total = (long long)n_rows * C;
+    int b3 = (int)((total + 255) / 256);
+    if (b3 > 148 * 16) b3 = 148 * 16;
+    fix32_to_float_kernel<<<b3, 256, 0, st>>>(acc, total, d_src);
+    UD3D_LAUNCH_CHECK();
+  }
   return UD3D_OK;
 }
 

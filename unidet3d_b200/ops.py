@@ -544,6 +544,53 @@ def bn_train(x: torch.Tensor, bn, group=None, update_running: bool = True):
     return bn_train_fold(sums, count, bn, update_running)
 
 
+def bn_relu_apply(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, relu: bool = True) -> torch.Tensor:
+    """relu?(x * scale + shift) as an fp32 map (recomputed in the backward pass as the X operand of ``conv_wgrad``)."""
+    if not x.is_cuda or x.dtype != torch.float32 or x.stride(1) != 1:
+        raise _lib.Ud3dError("bn_relu_apply: x must be a CUDA fp32 matrix with unit column stride")
+    n, c = x.shape
+    out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    check(_L().ud3d_bn_relu_apply(_p(x), x.stride(0), n, c, _p(scale), _p(shift), 1 if relu else 0, _p(out), c, _stream()),
+          "ud3d_bn_relu_apply")
+    return out
+
+
+def bn_relu_backward(x: torch.Tensor, d_act: torch.Tensor, scale, shift, mean, invstd, relu: bool = True, group=None,
+                     dx: Optional[torch.Tensor] = None, accumulate: bool = False):
+    """Backward of a = relu?(batchnorm_train(x)) given d_act = dL/da -> (dx, dgamma, dbeta).  With a torch.distributed
+    group of more than one rank the two per-channel sums are all-reduced (SyncBatchNorm backward: ONE collective of
+    2C + 1 doubles)."""
+    for t, nme in ((x, "x"), (d_act, "d_act")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.stride(1) != 1:
+            raise _lib.Ud3dError(f"bn_relu_backward: {nme} must be a CUDA fp32 matrix with unit column stride")
+    n, c = x.shape
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    wsb = int(_L().ud3d_bn_batch_sums_workspace_bytes(n, c))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
+    check(_L().ud3d_bn_backward_sums(_p(x), x.stride(0), _p(d_act), d_act.stride(0), n, c, _p(scale), _p(shift), _p(mean),
+                                     _p(invstd), 1 if relu else 0, _p(sums), _p(ws), ws.numel(), _stream()), "ud3d_bn_backward_sums")
+    sums, count = sync_bn_sums(sums, float(n), group)
+    if dx is None:
+        dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        accumulate = False
+    check(_L().ud3d_bn_backward_apply(_p(x), x.stride(0), _p(d_act), d_act.stride(0), n, c, _p(scale), _p(shift), _p(mean),
+                                      _p(invstd), 1 if relu else 0, _p(sums), float(max(count, 1.0)), _p(dx), dx.stride(0),
+                                      1 if accumulate else 0, _stream()), "ud3d_bn_backward_apply")
+    return dx, sums[1].float(), sums[0].float()
+
+
+def segmented_mean_backward(d_pooled: torch.Tensor, seg: torch.Tensor, n_rows: int, gather: Optional[torch.Tensor] = None):
+    """d_src [n_rows, C]: the gradient of ``segmented_mean`` (without its affine) w.r.t. its source rows."""
+    _req(d_pooled, torch.float32, "d_pooled"), _req(seg, torch.int64, "seg")
+    n_seg, c = d_pooled.shape
+    out = torch.empty((n_rows, c), dtype=torch.float32, device=d_pooled.device)
+    wsb = int(_L().ud3d_segmented_mean_backward_workspace_bytes(n_rows, n_seg, c))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=d_pooled.device)
+    check(_L().ud3d_segmented_mean_backward(_p(d_pooled), c, _p(gather), _p(seg), seg.numel(), n_seg, n_rows, _p(out), _p(ws), wsb,
+                                            _stream()), "ud3d_segmented_mean_backward")
+    return out
+
+
 def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, K: int, table: Optional[torch.Tensor] = None,
                out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """dW [C_out, K, C_in] (+)= sum_o dy[o]^T x[table[k][o]]   (``x`` = the conv's input after its BatchNorm + ReLU)."""
