@@ -332,6 +332,19 @@ int ud3d_bn_backward_apply(const float* x, int ld_x, const float* da, int ld_da,
 /* out = relu?(x * scale + shift) as an fp32 map: the X operand of ud3d_conv_wgrad (recomputed, not stored, in forward) */
 int ud3d_bn_relu_apply(const float* x, int ld_x, int n, int C, const float* scale, const float* shift, int relu, float* out,
                        int ld_out, void* stream);
+/* Backward of the attention core (encoder.py:36-37; head_dim 32, no mask): qkv fp32 [T_total, 3 d] (q | k | v), out / d_out
+ * [T_total, d] = the forward result and its gradient -> dqkv [T_total, 3 d].  fp32 on the CUDA cores, deterministic.
+ * ws: ud3d_attention_bwd_workspace_bytes (row log-sum-exp and D = rowsum(dO o O)). */
+size_t ud3d_attention_bwd_workspace_bytes(int total_T, int num_heads);
+int ud3d_attention_bwd(const float* qkv, const int32_t* cu_seqlens, int B, int total_T, int num_heads, const float* out,
+                       const float* d_out, float* dqkv, void* ws, size_t ws_bytes, void* stream);
+/* LayerNorm backward (encoder.py:38-39,77-78,189): dx [rows, C]; dgamma_dbeta fp64 [2, C] = (sum_r dy * xhat, sum_r dy).
+ * Statistics are recomputed from x (= the LayerNorm's input, residual already added). */
+size_t ud3d_layernorm_backward_workspace_bytes(int rows, int C);
+int ud3d_layernorm_backward(const float* x, const float* dy, const float* gamma, int rows, int C, float eps, float* dx,
+                            double* dgamma_dbeta, void* ws, size_t ws_bytes, void* stream);
+/* dx = dy * act'(pre) element-wise; act 1 = relu, 2 = gelu(erf) (the activation codes of ud3d_gemm_args.act) */
+int ud3d_activation_backward(const float* pre, const float* dy, long long total, int act, float* dx, void* stream);
 /* Backward of ud3d_segmented_mean without its affine (apply ud3d_bn_backward_* on the result for the fused output
  * BatchNorm): d_src[gather ? gather[p] : p, :] += d_pooled[seg[p], :] / count[seg[p]];  d_src [n_rows, C] is overwritten.
  * Deterministic (64-bit fixed-point atomics, 2^-32).  ws 8-byte aligned. */

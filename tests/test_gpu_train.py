@@ -255,3 +255,42 @@ def test_backbone_backward_vs_autograd(smooth):
     assert not bad, (len(bad), bad[:12], sorted((e, k) for k, e in errs.items())[:3])
     if smooth:
         assert float((xo.detach() > 0).float().mean()) == 1.0          # the premise: no inactive ReLU at the output layer
+
+
+def test_encoder_backward_pieces_vs_autograd():
+    """LayerNorm, GELU / ReLU and attention-core backward kernels against torch.autograd."""
+    from unidet3d_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    rows, c = 1333, 256
+    x = torch.randn(rows, c, generator=g, requires_grad=True)
+    gamma = (torch.rand(c, generator=g) + 0.5).requires_grad_(True)
+    beta = torch.randn(c, generator=g).requires_grad_(True)
+    y = torch.nn.functional.layer_norm(x, (c,), gamma, beta, 1e-5)
+    dy = torch.randn(rows, c, generator=g)
+    y.backward(dy)
+    dx, dgamma, dbeta = ops.layernorm_backward(x.detach().to(DEV), dy.to(DEV), gamma.detach().to(DEV), 1e-5)
+    assert relerr(dx, x.grad) < 1e-4 and relerr(dgamma, gamma.grad) < 1e-4 and relerr(dbeta, beta.grad) < 1e-4
+    again = ops.layernorm_backward(x.detach().to(DEV), dy.to(DEV), gamma.detach().to(DEV), 1e-5)
+    assert torch.equal(again[1], dgamma) and torch.equal(again[0], dx)          # deterministic
+    for act, fn in (("gelu", torch.nn.functional.gelu), ("relu", torch.relu)):
+        z = (torch.randn(rows, c, generator=g) * 2).requires_grad_(True)
+        fn(z).backward(dy)
+        assert relerr(ops.activation_backward(z.detach().to(DEV), dy.to(DEV), act), z.grad) < 1e-5
+    # attention core: 3 scenes of different lengths (one shorter than a warp), 8 heads x 32
+    lens = [700, 17, 333]
+    H, d = 8, 256
+    T = sum(lens)
+    qkv = (torch.randn(T, 3 * d, generator=g) * 0.7).requires_grad_(True)
+    outs, a0 = [], 0
+    for n_ in lens:
+        q, k, v = [qkv[a0:a0 + n_, i * d:(i + 1) * d].reshape(n_, H, 32).transpose(0, 1) for i in range(3)]
+        o = torch.softmax(q @ k.transpose(1, 2) / 32 ** 0.5, -1) @ v
+        outs.append(o.transpose(0, 1).reshape(n_, d))
+        a0 += n_
+    out = torch.cat(outs)
+    d_out = torch.randn(T, d, generator=g)
+    out.backward(d_out)
+    cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=DEV)
+    dqkv = ops.attention_backward(qkv.detach().to(DEV), cu, H, out.detach().to(DEV), d_out.to(DEV))
+    assert relerr(dqkv[:, :d], qkv.grad[:, :d]) < 1e-4, relerr(dqkv[:, :d], qkv.grad[:, :d])
+    assert relerr(dqkv[:, d:2 * d], qkv.grad[:, d:2 * d]) < 1e-4 and relerr(dqkv[:, 2 * d:], qkv.grad[:, 2 * d:]) < 1e-4

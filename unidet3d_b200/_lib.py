@@ -137,6 +137,11 @@ SIGNATURES = {
     "ud3d_bn_backward_sums": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_bn_backward_apply": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, C.c_double, _vp, _i, _i, _vp]),
     "ud3d_bn_relu_apply": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
+    "ud3d_attention_bwd_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "ud3d_attention_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_layernorm_backward_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "ud3d_layernorm_backward": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_activation_backward": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _vp]),
     "ud3d_segmented_mean_backward_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "ud3d_segmented_mean_backward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_elastic_workspace_bytes": (C.c_size_t, [_vp]),

@@ -142,6 +142,66 @@ __global__ void fix32_to_float_kernel(const unsigned long long* __restrict__ acc
     out[t] = (float)((double)(long long)acc[t] * (1.0 / 4294967296.0));
 }
 
+// ---------------------------------------------------------------- encoder-side backward pieces
+// LayerNorm over the last dimension (encoder.py:38-39,77-78,189), y = (x - mu) * rstd * gamma + beta:
+//   dx = rstd * (gy - mean_c(gy) - xhat * mean_c(gy * xhat)),  gy = dy * gamma;   dgamma = sum_r dy * xhat,  dbeta = sum_r dy.
+// One warp per row (statistics recomputed from x); the per-channel sums are written as per-block partials and reduced by
+// bn_final_sums_kernel (fixed order: deterministic).
+constexpr int kLnRowsPerBlock = 64;      // 8 warps x 8 rows
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                            const float* __restrict__ gamma, int rows, int C, float eps,
+                                                            float* __restrict__ dx, double* __restrict__ part) {
+  extern __shared__ float s_acc[];                 // [8 warps][2][C]: every warp sums its own rows (no atomics: deterministic)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < 16 * C; c += blockDim.x) s_acc[c] = 0.f;
+  __syncthreads();
+  float* mine = s_acc + (size_t)warp * 2 * C;
+  const int r0 = blockIdx.x * kLnRowsPerBlock;
+  for (int rr = warp; rr < kLnRowsPerBlock; rr += 8) {
+    const int r = r0 + rr;
+    if (r >= rows) break;
+    const float* xr = x + (size_t)r * C;
+    const float* gr = dy + (size_t)r * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mu = warp_sum(s) / (float)C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mu; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float a = 0.f, b = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float gy = gr[c] * gamma[c], xh = (xr[c] - mu) * rstd;
+      a += gy;
+      b = fmaf(gy, xh, b);
+    }
+    a = warp_sum(a) / (float)C;
+    b = warp_sum(b) / (float)C;
+    for (int c = lane; c < C; c += 32) {
+      const float xh = (xr[c] - mu) * rstd;
+      dx[(size_t)r * C + c] = rstd * (gr[c] * gamma[c] - a - xh * b);
+      mine[c] += gr[c] * xh;
+      mine[C + c] += gr[c];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += (double)s_acc[(size_t)w * 2 * C + c];
+    part[(size_t)blockIdx.x * 2 * C + c] = t;
+  }
+}
+// dX = dY * act'(pre):  act 1 = relu (pre > 0), 2 = gelu(erf): 0.5 (1 + erf(z / sqrt2)) + z exp(-z^2 / 2) / sqrt(2 pi)
+__global__ void act_bwd_kernel(const float* __restrict__ pre, const float* __restrict__ dy, long long total, int act,
+                               float* __restrict__ dx) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const float z = pre[t];
+    float d;
+    if (act == 1) d = z > 0.f ? 1.f : 0.f;
+    else d = 0.5f * (1.f + erff(z * 0.70710678118654752440f)) + z * expf(-0.5f * z * z) * 0.39894228040143267794f;
+    dx[t] = dy[t] * d;
+  }
+}
+
 // ---------------------------------------------------------------- sparse-conv weight gradient
 // dW[co][k][ci] = sum_o dY[o][co] * X[table[k][o]][ci]   (X = the conv's input AFTER its BatchNorm+ReLU).
 // One CTA = (kernel offset k, 32 x 32 tile of (co, ci), slice of the output rows); rows are staged through shared memory
@@ -289,6 +349,40 @@ int ud3d_bn_relu_apply(const float* x, int ld_x, int n, int C, const float* scal
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   bn_relu_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld_x, n, C, scale, shift, relu, out, ld_out);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+size_t ud3d_layernorm_backward_workspace_bytes(int rows, int C) {
+  return (size_t)cdiv(rows > 0 ? rows : 1, kLnRowsPerBlock) * 2 * (size_t)(C > 0 ? C : 1) * sizeof(double);
+}
+
+int ud3d_layernorm_backward(const float* x, const float* dy, const float* gamma, int rows, int C, float eps, float* dx, double* dgamma_dbeta,
+                            void* ws, size_t ws_bytes, void* stream) {
+  UD3D_CHECK_ARG(x && dy && gamma && dx && dgamma_dbeta && ws && rows >= 0 && C > 0 && C <= 768, "ud3d_layernorm_backward: bad argument (C <= 768)");
+  if (ws_bytes < ud3d_layernorm_backward_workspace_bytes(rows, C)) {
+    set_error("ud3d_layernorm_backward: workspace too small");
+    return UD3D_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows == 0) {
+    UD3D_CUDA(cudaMemsetAsync(dgamma_dbeta, 0, (size_t)2 * C * sizeof(double), st));
+    return UD3D_OK;
+  }
+  const int nblocks = cdiv(rows, kLnRowsPerBlock);
+  layernorm_bwd_kernel<<<nblocks, 256, (size_t)16 * C * sizeof(float), st>>>(x, dy, gamma, rows, C, eps, dx, (double*)ws);
+  UD3D_LAUNCH_CHECK();
+  bn_final_sums_kernel<<<cdiv(2 * C, 128), 128, 0, st>>>((const double*)ws, nblocks, C, dgamma_dbeta);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_activation_backward(const float* pre, const float* dy, long long total, int act, float* dx, void* stream) {
+  UD3D_CHECK_ARG(pre && dy && dx && total >= 0 && (act == 1 || act == 2), "ud3d_activation_backward: bad argument (act 1 relu, 2 gelu)");
+  if (total == 0) return UD3D_OK;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  act_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pre, dy, total, act, dx);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

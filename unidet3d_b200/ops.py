@@ -591,6 +591,42 @@ def segmented_mean_backward(d_pooled: torch.Tensor, seg: torch.Tensor, n_rows: i
     return out
 
 
+def attention_backward(qkv: torch.Tensor, cu_seqlens: torch.Tensor, num_heads: int, out: torch.Tensor, d_out: torch.Tensor):
+    """fp32 qkv [T, 3d], forward result ``out`` [T, d] and its gradient -> dqkv [T, 3d]."""
+    for t, nme in ((qkv, "qkv"), (out, "out"), (d_out, "d_out")):
+        _req(t, torch.float32, nme)
+    _req(cu_seqlens, torch.int32, "cu_seqlens")
+    T = qkv.shape[0]
+    dqkv = torch.empty_like(qkv)
+    wsb = int(_L().ud3d_attention_bwd_workspace_bytes(T, num_heads))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=qkv.device)
+    check(_L().ud3d_attention_bwd(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, T, num_heads, _p(out), _p(d_out), _p(dqkv), _p(ws),
+                                  ws.numel(), _stream()), "ud3d_attention_bwd")
+    return dqkv
+
+
+def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, eps: float = 1e-5):
+    """x = the LayerNorm's input (residual already added) -> (dx, dgamma, dbeta)."""
+    _req(x, torch.float32, "x"), _req(dy, torch.float32, "dy")
+    rows, c = x.shape
+    dx = torch.empty_like(x)
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    wsb = int(_L().ud3d_layernorm_backward_workspace_bytes(rows, c))
+    ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
+    check(_L().ud3d_layernorm_backward(_p(x), _p(dy), _p(gamma), rows, c, float(eps), _p(dx), _p(sums), _p(ws), ws.numel(), _stream()),
+          "ud3d_layernorm_backward")
+    return dx, sums[0].float(), sums[1].float()
+
+
+def activation_backward(pre: torch.Tensor, dy: torch.Tensor, act: str) -> torch.Tensor:
+    """dy * act'(pre) for act in {"relu", "gelu"} (pre = the pre-activation values)."""
+    _req(pre, torch.float32, "pre"), _req(dy, torch.float32, "dy")
+    dx = torch.empty_like(pre)
+    check(_L().ud3d_activation_backward(_p(pre), _p(dy), pre.numel(), {"relu": 1, "gelu": 2}[act], _p(dx), _stream()),
+          "ud3d_activation_backward")
+    return dx
+
+
 def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, K: int, table: Optional[torch.Tensor] = None,
                out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """dW [C_out, K, C_in] (+)= sum_o dy[o]^T x[table[k][o]]   (``x`` = the conv's input after its BatchNorm + ReLU)."""
