@@ -345,6 +345,9 @@ int ud3d_layernorm_backward(const float* x, const float* dy, const float* gamma,
                             double* dgamma_dbeta, void* ws, size_t ws_bytes, void* stream);
 /* dx = dy * act'(pre) element-wise; act 1 = relu, 2 = gelu(erf) (the activation codes of ud3d_gemm_args.act) */
 int ud3d_activation_backward(const float* pre, const float* dy, long long total, int act, float* dx, void* stream);
+/* out = act(pre) as its own pass: the training forward keeps the pre-activation values for the backward pass (the
+ * inference path applies the activation in the GEMM epilogue) */
+int ud3d_activation_forward(const float* pre, long long total, int act, float* out, void* stream);
 /* Backward of ud3d_segmented_mean without its affine (apply ud3d_bn_backward_* on the result for the fused output
  * BatchNorm): d_src[gather ? gather[p] : p, :] += d_pooled[seg[p], :] / count[seg[p]];  d_src [n_rows, C] is overwritten.
  * Deterministic (64-bit fixed-point atomics, 2^-32).  ws 8-byte aligned. */

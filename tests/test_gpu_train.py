@@ -294,3 +294,61 @@ def test_encoder_backward_pieces_vs_autograd():
     dqkv = ops.attention_backward(qkv.detach().to(DEV), cu, H, out.detach().to(DEV), d_out.to(DEV))
     assert relerr(dqkv[:, :d], qkv.grad[:, :d]) < 1e-4, relerr(dqkv[:, :d], qkv.grad[:, :d])
     assert relerr(dqkv[:, d:2 * d], qkv.grad[:, d:2 * d]) < 1e-4 and relerr(dqkv[:, 2 * d:], qkv.grad[:, 2 * d:]) < 1e-4
+
+
+def test_encoder_backward_vs_autograd():
+    """Gradients of every encoder parameter and of the pooled input features, from random gradients on the class logits
+    and boxes of all seven heads (train mode evaluates them all, encoder.py:219-229): the tape of unidet3d_b200/train.py
+    against torch.autograd through the oracle encoder (pinned to the reference's own encoder.py)."""
+    import unidet3d_b200 as u
+    from unidet3d_b200 import configs, train
+    from oracle import encoder as oenc
+    cfg = configs.model_cfg(("scannet", "s3dis", "arkitscenes"), topk_insts=100)
+    d = cfg["decoder"]
+    n_union = len(set(sum(d["datasets_classes"], []))) + 1
+    enc_sd = oenc.make_encoder_state_dict(d["num_layers"], d["in_channels"], d["d_model"], d["hidden_dim"], n_union, 3)
+    enc = u.MODELS.build(d)
+    assert not enc.load_state_dict(enc_sd, strict=False).missing_keys
+    enc.to(DEV).train()
+    g = torch.Generator().manual_seed(21)
+    lens = [410, 37, 655]
+    names = ["scannet", "arkitscenes", "s3dis"]
+    xs = [torch.randn(t, d["in_channels"], generator=g) for t in lens]
+    cs = [torch.randn(t, 3, generator=g) for t in lens]
+    bounds = [0] + list(np.cumsum(lens))
+    X = torch.cat(xs).to(DEV)
+    Cn = torch.cat(cs).to(DEV)
+    with torch.no_grad():
+        out, tape = train.encoder_forward(enc, X, Cn, [int(b) for b in bounds], names)
+    # oracle
+    sd = {k: t.clone().float().requires_grad_(True) for k, t in enc_sd.items()}
+    xo = [x.clone().requires_grad_(True) for x in xs]
+    ref = oenc.encoder_forward(sd, configs.oracle_cfg(cfg)["encoder"], xo, cs, names, all_heads=True)
+    heads_ref = ref["aux_outputs"] + [dict(cls_preds=ref["cls_preds"], bboxes=ref["bboxes"])]
+    heads_out = out["aux_outputs"] + [dict(cls_preds=out["cls_preds"], bboxes=out["bboxes"])]
+    assert len(heads_ref) == len(heads_out) == d["num_layers"] + 1
+    loss = 0.0
+    d_cls, d_box = [], []
+    for hr, ho in zip(heads_ref, heads_out):
+        dc, db = [], []
+        for i in range(len(lens)):
+            assert relerr(ho["cls_preds"][i], hr["cls_preds"][i]) < 1e-3 and relerr(ho["bboxes"][i], hr["bboxes"][i]) < 1e-3
+            gc = torch.randn(hr["cls_preds"][i].shape, generator=g)
+            gb = torch.randn(hr["bboxes"][i].shape, generator=g) * 0.1
+            loss = loss + (hr["cls_preds"][i] * gc).sum() + (hr["bboxes"][i] * gb).sum()
+            dc.append(gc.to(DEV)), db.append(gb.to(DEV))
+        d_cls.append(dc), d_box.append(db)
+    loss.backward()
+    train.encoder_backward(tape, out, d_cls, d_box)
+    errs = {"dX": relerr(tape.grad(X), torch.cat([x.grad for x in xo]))}
+    for k, p in enc.named_parameters():
+        assert p.grad is not None, k
+        errs[k] = relerr(p.grad, sd[k].grad)
+    # measured: 3e-6 .. 2.3e-3 on 82 of the 85 tensors.  The tensors right behind a ReLU (input_proj.0 -> dX, the class
+    # MLP's outs_cls.0, evaluated by seven heads) see a few masks flip on last-bit forward differences, like the backbone's
+    # (test_backbone_backward_vs_autograd): percent-level on those sums, bounded here by 2e-2; 5e-3 everywhere else
+    def tol(k):
+        return 2e-2 if (k == "dX" or k.startswith(("input_proj.0", "outs_cls.0"))) else 5e-3
+    bad = sorted(((e, k) for k, e in errs.items() if not e < tol(k)), reverse=True)
+    assert not bad, (len(bad), bad[:10], sorted((e, k) for k, e in errs.items())[:3])
+    assert len(errs) == 1 + len(enc_sd)

@@ -142,6 +142,7 @@ SIGNATURES = {
     "ud3d_layernorm_backward_workspace_bytes": (C.c_size_t, [_i, _i]),
     "ud3d_layernorm_backward": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_activation_backward": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _vp]),
+    "ud3d_activation_forward": (_i, [_vp, C.c_longlong, _i, _vp, _vp]),
     "ud3d_segmented_mean_backward_workspace_bytes": (C.c_size_t, [_i, _i, _i]),
     "ud3d_segmented_mean_backward": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_elastic_workspace_bytes": (C.c_size_t, [_vp]),

@@ -202,6 +202,13 @@ __global__ void act_bwd_kernel(const float* __restrict__ pre, const float* __res
   }
 }
 
+__global__ void act_fwd_kernel(const float* __restrict__ pre, long long total, int act, float* __restrict__ out) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const float z = pre[t];
+    out[t] = act == 1 ? fmaxf(z, 0.f) : 0.5f * z * (1.f + erff(z * 0.70710678118654752440f));
+  }
+}
+
 // ---------------------------------------------------------------- sparse-conv weight gradient
 // dW[co][k][ci] = sum_o dY[o][co] * X[table[k][o]][ci]   (X = the conv's input AFTER its BatchNorm+ReLU).
 // One CTA = (kernel offset k, 32 x 32 tile of (co, ci), slice of the output rows); rows are staged through shared memory
@@ -383,6 +390,16 @@ int ud3d_activation_backward(const float* pre, const float* dy, long long total,
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   act_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pre, dy, total, act, dx);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
+
+int ud3d_activation_forward(const float* pre, long long total, int act, float* out, void* stream) {
+  UD3D_CHECK_ARG(pre && out && total >= 0 && (act == 1 || act == 2), "ud3d_activation_forward: bad argument (act 1 relu, 2 gelu)");
+  if (total == 0) return UD3D_OK;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  act_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pre, total, act, out);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

@@ -618,6 +618,13 @@ def layernorm_backward(x: torch.Tensor, dy: torch.Tensor, gamma: torch.Tensor, e
     return dx, sums[0].float(), sums[1].float()
 
 
+def activation_forward(pre: torch.Tensor, act: str) -> torch.Tensor:
+    _req(pre, torch.float32, "pre")
+    out = torch.empty_like(pre)
+    check(_L().ud3d_activation_forward(_p(pre), pre.numel(), {"relu": 1, "gelu": 2}[act], _p(out), _stream()), "ud3d_activation_forward")
+    return out
+
+
 def activation_backward(pre: torch.Tensor, dy: torch.Tensor, act: str) -> torch.Tensor:
     """dy * act'(pre) for act in {"relu", "gelu"} (pre = the pre-activation values)."""
     _req(pre, torch.float32, "pre"), _req(dy, torch.float32, "dy")

@@ -173,3 +173,153 @@ def allreduce_gradients(params, group=None, bucket_bytes: int = 32 << 20):
         n_coll += 1
         i = j
     return n_coll
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Encoder (reference unidet3d/encoder.py:113-239 in train mode: all num_layers + 1 heads are evaluated, :219-229)
+def _linear(tape: Tape, x: torch.Tensor, lin: torch.nn.Linear, act: Optional[str] = None, residual: Optional[torch.Tensor] = None,
+            weight=None, bias=None) -> torch.Tensor:
+    """y = act(x W^T + b) (+ residual); the pre-activation map is kept for the backward pass."""
+    W = lin.weight if weight is None else weight
+    b = lin.bias if bias is None else bias
+    pre = ops.gemm(x, ops.PackedWeight(W), bias=b.detach().float().contiguous(), residual=residual if act is None else None)
+    y = pre if act is None else ops.activation_forward(pre, act)
+    if act is not None and residual is not None:
+        raise NotImplementedError("activation + residual does not occur in the encoder")
+
+    def bwd():
+        dy = tape.grad(y)
+        if dy is None:
+            return
+        dy = dy.contiguous()
+        if residual is not None:
+            tape.add(residual, dy)
+        dpre = dy if act is None else ops.activation_backward(pre, dy, act)
+        Wd = W.detach()
+        _acc_param(W, ops.conv_wgrad(x, dpre, 1))
+        _acc_param(b, ops.bn_batch_sums(dpre)[0].float())
+        tape.add(x, ops.conv_dgrad(dpre, Wd.reshape(Wd.shape[0], 1, Wd.shape[1]), None, x.shape[0], reverse_offsets=False))
+
+    tape.steps.append(bwd)
+    return y
+
+
+def _layernorm(tape: Tape, x: torch.Tensor, ln: torch.nn.LayerNorm) -> torch.Tensor:
+    g = ln.weight.detach().float().contiguous()
+    y = ops.layernorm(x, g, ln.bias.detach().float().contiguous(), eps=ln.eps)
+
+    def bwd():
+        dy = tape.grad(y)
+        if dy is None:
+            return
+        dx, dgamma, dbeta = ops.layernorm_backward(x, dy.contiguous(), g, ln.eps)
+        _acc_param(ln.weight, dgamma)
+        _acc_param(ln.bias, dbeta)
+        tape.add(x, dx)
+
+    tape.steps.append(bwd)
+    return y
+
+
+def _bbox_decode_torch(raw: torch.Tensor, centers: torch.Tensor, with_angle: bool) -> torch.Tensor:
+    """PredBBox's exp + ``_bbox_pred_to_bbox`` (encoder.py:109-111,241-283) in torch ops: used only to differentiate this
+    8-value-per-query element-wise map with autograd (the forward value comes from ud3d_bbox_decode)."""
+    p = torch.cat((torch.exp(raw[:, :6]), raw[:, 6:]), 1)
+    cx = centers[:, 0] + (p[:, 1] - p[:, 0]) / 2
+    cy = centers[:, 1] + (p[:, 3] - p[:, 2]) / 2
+    cz = centers[:, 2] + (p[:, 5] - p[:, 4]) / 2
+    if not with_angle:
+        return torch.stack([cx, cy, cz, p[:, 0] + p[:, 1], p[:, 2] + p[:, 3], p[:, 4] + p[:, 5]], -1)
+    scale = p[:, 0] + p[:, 1] + p[:, 2] + p[:, 3]
+    q = torch.exp(torch.sqrt(torch.pow(p[:, 6], 2) + torch.pow(p[:, 7], 2)))
+    alpha = 0.5 * torch.atan2(p[:, 6], p[:, 7])
+    return torch.stack((cx, cy, cz, scale / (1 + q), scale / (1 + q) * q, p[:, 5] + p[:, 4], alpha), dim=-1)
+
+
+def _head(tape: Tape, enc, Hq: torch.Tensor, centers: torch.Tensor, bounds, ds_idx):
+    """encoder.py:165-201: out_norm -> class MLP (union of classes, per-dataset column gather) and box Linear + decode."""
+    plan = enc._get_plan()
+    nq = _layernorm(tape, Hq, enc.out_norm)
+    h = _linear(tape, nq, enc.outs_cls[0], act="relu")
+    logits = _linear(tape, h, enc.outs_cls[2])
+    raw = _linear(tape, nq, enc.out_bboxes.linear)
+    cls_preds, bboxes = [], []
+    for i, j in enumerate(ds_idx):
+        a, b = bounds[i], bounds[i + 1]
+        cls_preds.append(ops.gather_columns(logits[a:b], plan["cols"][j]))
+        bboxes.append(ops.bbox_decode(raw[a:b], centers[a:b], bool(enc.angles[j])))
+
+    def bwd():
+        d_logits = torch.zeros_like(logits)
+        d_raw = torch.zeros_like(raw)
+        any_grad = False
+        for i, j in enumerate(ds_idx):
+            a, b = bounds[i], bounds[i + 1]
+            dc, db = tape.grad(cls_preds[i]), tape.grad(bboxes[i])
+            if dc is not None:
+                d_logits[a:b].index_add_(1, plan["cols"][j].long(), dc)
+                any_grad = True
+            if db is not None:
+                with torch.enable_grad():
+                    r = raw[a:b].detach().clone().requires_grad_(True)
+                    box = _bbox_decode_torch(r, centers[a:b], bool(enc.angles[j]))
+                    (gr,) = torch.autograd.grad(box, r, db)
+                d_raw[a:b] = gr
+                any_grad = True
+        if any_grad:
+            tape.add(logits, d_logits)
+            tape.add(raw, d_raw)
+
+    tape.steps.append(bwd)
+    return cls_preds, bboxes
+
+
+def encoder_forward(enc, X: torch.Tensor, centers: torch.Tensor, bounds, datasets_names, tape: Optional[Tape] = None):
+    """``UniDet3DEncoder.forward`` on packed rows with a tape: -> (dict(cls_preds, bboxes, aux_outputs) exactly as the
+    module returns it with all heads, tape).  fp32 dataflow (pre-activation maps are kept for the backward pass)."""
+    tape = Tape() if tape is None else tape
+    ds_idx = [enc.datasets.index(n) for n in datasets_names]
+    cu = torch.tensor(bounds, dtype=torch.int32).to(X.device)
+    max_T = max(b - a for a, b in zip(bounds[:-1], bounds[1:]))
+    cls_all, box_all = [], []
+    Hq = _linear(tape, X, enc.input_proj[0], act="relu")
+    Hq = _linear(tape, Hq, enc.input_proj[2])
+    c, b = _head(tape, enc, Hq, centers, bounds, ds_idx)
+    cls_all.append(c), box_all.append(b)
+    d = enc.d_model
+    for sa, ff in zip(enc.self_attn_layers, enc.ffn_layers):
+        qkv = _linear(tape, Hq, None, weight=sa.attn.in_proj_weight, bias=sa.attn.in_proj_bias)
+        A = ops.attention(qkv, cu, max_T, enc.num_heads)
+
+        def attn_bwd(qkv=qkv, A=A):
+            dA = tape.grad(A)
+            if dA is not None:
+                tape.add(qkv, ops.attention_backward(qkv, cu, enc.num_heads, A, dA.contiguous()))
+
+        tape.steps.append(attn_bwd)
+        Z = _linear(tape, A, sa.attn.out_proj, residual=Hq)
+        Hq = _layernorm(tape, Z, sa.norm)
+        F1 = _linear(tape, Hq, ff.net[0], act=enc.activation_fn)
+        Z = _linear(tape, F1, ff.net[3], residual=Hq)
+        Hq = _layernorm(tape, Z, ff.norm)
+        c, b = _head(tape, enc, Hq, centers, bounds, ds_idx)
+        cls_all.append(c), box_all.append(b)
+    aux = [dict(cls_preds=c, bboxes=b) for c, b in zip(cls_all[:-1], box_all[:-1])]
+    return dict(cls_preds=cls_all[-1], bboxes=box_all[-1], aux_outputs=aux), tape
+
+
+def encoder_backward(tape: Tape, outputs, d_cls, d_boxes):
+    """d_cls / d_boxes: per head (aux heads first, final head last, like ``aux_outputs + [final]``) lists over scenes of
+    gradients w.r.t. cls_preds / bboxes (None = no gradient).  Fills ``.grad`` of the encoder's parameters; returns the
+    tape so that ``tape.grad(X)`` gives the gradient w.r.t. the pooled input features."""
+    heads = outputs["aux_outputs"] + [dict(cls_preds=outputs["cls_preds"], bboxes=outputs["bboxes"])]
+    for hd, dc, db in zip(heads, d_cls, d_boxes):
+        for t, g in zip(hd["cls_preds"], dc):
+            if g is not None:
+                tape.add(t, g)
+        for t, g in zip(hd["bboxes"], db):
+            if g is not None:
+                tape.add(t, g)
+    with torch.no_grad():
+        tape.backward()
+    return tape
