@@ -481,18 +481,9 @@ class UniDet3D(nn.Module):
             queries.append(xi), centers.append(ci), qmasks.append(mi)
         return queries, centers, qmasks
 
-    @torch.no_grad()
-    def loss(self, batch_inputs_dict, batch_data_samples, **kwargs):
-        """unidet3d.py:277-364 -- the VALUE of the training loss, ``{'det_loss': tensor}``.
-
-        GT boxes from instance masks (``get_bboxes_by_masks``) or shifted GT boxes, superpoint centres, distance
-        targets (``get_targets``), backbone + pooling, query selection, the encoder with all seven heads, and the
-        criterion, every stage on our kernels.  Not implemented yet (SURVEY.md section 8f rank 2): gradients, and the
-        batch statistics of train-mode (Sync)BatchNorm -- the backbone runs with the running statistics, so this is
-        the validation-style loss of the current weights.  ``elastic_coords`` (the ElasticTransfrom augmentation's
-        side input, unidet3d.py:349) replaces the voxel coordinates like in the reference."""
-        if self.criterion is None:
-            raise RuntimeError("UniDet3D was built without a criterion config")
+    def _loss_inputs(self, batch_inputs_dict, batch_data_samples):
+        """GT side of ``loss`` (unidet3d.py:277-349): per-scene GT boxes (by instance masks or shifted annotations),
+        superpoint centres, query masks (distance targets or superpoint masks) and the packed point batch."""
         dev = next(self.parameters()).device
         B = len(batch_data_samples)
         names = [self.get_dataset(s.lidar_path) for s in batch_data_samples]
@@ -530,6 +521,24 @@ class UniDet3D(nn.Module):
         el = batch_inputs_dict.get("elastic_coords")
         if el is not None:
             el = torch.cat([torch.as_tensor(e).to(dev, torch.float32) for e in el]).contiguous()
+        return dict(B=B, names=names, pts=pts, sp_b=sp_b, offs=offs, el=el, sp_off=sp_off, gt_insts=gt_insts,
+                    sp_centers=sp_centers, sp_masks=sp_masks)
+
+    @torch.no_grad()
+    def loss(self, batch_inputs_dict, batch_data_samples, **kwargs):
+        """unidet3d.py:277-364 -- the VALUE of the training loss, ``{'det_loss': tensor}``.
+
+        GT boxes from instance masks (``get_bboxes_by_masks``) or shifted GT boxes, superpoint centres, distance
+        targets (``get_targets``), backbone + pooling, query selection, the encoder with all seven heads, and the
+        criterion, every stage on our kernels.  Not implemented yet (SURVEY.md section 8f rank 2): gradients, and the
+        batch statistics of train-mode (Sync)BatchNorm -- the backbone runs with the running statistics, so this is
+        the validation-style loss of the current weights.  ``elastic_coords`` (the ElasticTransfrom augmentation's
+        side input, unidet3d.py:349) replaces the voxel coordinates like in the reference."""
+        if self.criterion is None:
+            raise RuntimeError("UniDet3D was built without a criterion config")
+        li = self._loss_inputs(batch_inputs_dict, batch_data_samples)
+        B, names, pts, sp_b, offs, el, sp_off = li["B"], li["names"], li["pts"], li["sp_b"], li["offs"], li["el"], li["sp_off"]
+        gt_insts, sp_centers, sp_masks = li["gt_insts"], li["sp_centers"], li["sp_masks"]
         x, inverse = self.collate(pts, offs, B, el)
         pooled = self.extract_feat(x, sp_b, inverse, sp_off)
         xs = [pooled[int(sp_off[i]):int(sp_off[i + 1])] for i in range(B)]

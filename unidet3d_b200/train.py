@@ -323,3 +323,145 @@ def encoder_backward(tape: Tape, outputs, d_cls, d_boxes):
     with torch.no_grad():
         tape.backward()
     return tape
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Criterion gradients.  The MATCHING (UniMatcher cost / threshold / match, criterion.py:200-320) is the GPU kernel
+# ud3d_criterion_layer; given its match matrix the loss of one (head, scene) is a short differentiable expression on
+# [T, C] logits and the few hundred matched boxes -- weighted cross-entropy (criterion.py:100-111) and the axis-aligned
+# DIoU of the matched pairs (criterion.py:113-134, axis_aligned_iou_loss.py:14-53) -- evaluated with torch ops and
+# differentiated with torch.autograd.  (The rotated DIoU of ARKitScenes-style boxes is not differentiated here.)
+def _corners(b: torch.Tensor) -> torch.Tensor:
+    """criterion.py:180-198 ``_bbox_to_loss``: (cx, cy, cz, dx, dy, dz) -> (x1, y1, z1, x2, y2, z2)."""
+    return torch.stack((b[..., 0] - b[..., 3] / 2, b[..., 1] - b[..., 4] / 2, b[..., 2] - b[..., 5] / 2,
+                        b[..., 0] + b[..., 3] / 2, b[..., 1] + b[..., 4] / 2, b[..., 2] + b[..., 5] / 2), -1)
+
+
+def _aligned_diou_pairs(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """axis_aligned_iou_loss.py:14-53 on corner boxes [N, 6] (IoU = mmdet3d AxisAlignedBboxOverlaps3D, eps 1e-6)."""
+    a1 = (pred[:, 3] - pred[:, 0]) * (pred[:, 4] - pred[:, 1]) * (pred[:, 5] - pred[:, 2])
+    a2 = (target[:, 3] - target[:, 0]) * (target[:, 4] - target[:, 1]) * (target[:, 5] - target[:, 2])
+    wh = (torch.minimum(pred[:, 3:], target[:, 3:]) - torch.maximum(pred[:, :3], target[:, :3])).clamp(min=0)
+    ov = wh[:, 0] * wh[:, 1] * wh[:, 2]
+    iou = ov / torch.clamp(a1 + a2 - ov, min=1e-6)
+    r2 = (((pred[:, :3] + pred[:, 3:]) / 2 - (target[:, :3] + target[:, 3:]) / 2) ** 2).sum(-1)
+    c2 = ((torch.minimum(pred[:, :3], target[:, :3]) - torch.maximum(pred[:, 3:], target[:, 3:])) ** 2).sum(-1)
+    return 1 - iou + r2 / c2
+
+
+def layer_loss_from_matches(crit, cls_preds, bboxes, gts, datasets_names, matches):
+    """One decoder layer's loss (criterion.py:44-142) as a differentiable torch expression, given the match matrices
+    ``matches[i]`` bool [T_i, G_i].  gts[i] = (labels int64 [G], boxes [G, 6], query_masks)."""
+    cls_losses, box_losses = [], []
+    for name, cp, pb, (labels, gboxes, _), m in zip(datasets_names, cls_preds, bboxes, gts, matches):
+        w = crit.datasets_weights[crit.datasets.index(name)]
+        C = cp.shape[1] - 1
+        tgt = torch.full((cp.shape[0],), C, dtype=torch.long, device=cp.device)
+        iq = ig = None
+        if labels.numel() and m is not None:
+            iq, ig = m.nonzero(as_tuple=True)              # query-major, like the reference's argwhere: the last pair wins
+            tgt[iq] = labels[ig]
+        cw = torch.ones(C + 1, device=cp.device)
+        cw[C] = crit.non_object_weight
+        cls_losses.append(w * torch.nn.functional.cross_entropy(cp, tgt, cw))
+        if iq is None or iq.numel() == 0:
+            continue
+        if gboxes.shape[1] != 6:
+            raise NotImplementedError("gradient of the rotated DIoU loss (arkitscenes boxes) is not implemented")
+        box_losses.append(w * _aligned_diou_pairs(_corners(pb[iq]), _corners(gboxes[ig])).mean())
+    cls_loss = torch.stack(cls_losses).mean()
+    box_loss = torch.stack(box_losses).mean() if box_losses else cls_loss.new_zeros(())
+    return crit.loss_weight[0] * cls_loss + crit.loss_weight[1] * box_loss
+
+
+def criterion_backward(crit, outputs, insts, datasets_names, match_fn=None):
+    """-> (det_loss value, d_cls, d_boxes) with d_* per head (aux heads first, final head last) lists over scenes, in
+    the layout ``encoder_backward`` takes.  ``match_fn(cls_pred, bbox, boxes, labels, query_masks, topk) -> match``
+    defaults to the GPU matcher (ud3d_criterion_layer)."""
+    heads = outputs["aux_outputs"] + [dict(cls_preds=outputs["cls_preds"], bboxes=outputs["bboxes"])]
+    gts = [crit._gt(inst) for inst in insts]
+    if match_fn is None:
+        def match_fn(cp, pb, boxes, labels, qm, topk):
+            return ops.criterion_layer(cp, pb.contiguous(), boxes, labels, qm, topk, crit.w_cls, crit.w_box, crit.non_object_weight)[0]
+    total = 0.0
+    leaves_c, leaves_b = [], []
+    with torch.enable_grad():
+        for hd in heads:
+            cps = [t.detach().clone().requires_grad_(True) for t in hd["cls_preds"]]
+            pbs = [t.detach().clone().requires_grad_(True) for t in hd["bboxes"]]
+            matches = []
+            for cp, pb, (labels, boxes, qm), name in zip(cps, pbs, gts, datasets_names):
+                topk = crit.topk[crit.datasets.index(name)]
+                matches.append(match_fn(cp.detach(), pb.detach(), boxes, labels, qm, topk) if labels.numel() else None)
+            total = total + layer_loss_from_matches(crit, cps, pbs, gts, datasets_names, matches)
+            leaves_c.append(cps), leaves_b.append(pbs)
+        flat = [t for lst in leaves_c + leaves_b for t in lst]
+        grads = torch.autograd.grad(total, flat, allow_unused=True)
+    it = iter(grads)
+    d_cls = [[next(it) for _ in lst] for lst in leaves_c]
+    d_box = [[next(it) for _ in lst] for lst in leaves_b]
+    return total.detach(), d_cls, d_box
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The training step (reference: UniDet3D.loss, unidet3d/unidet3d.py:277-364, under torch.autograd + DDP + AdamW,
+# tools/train.py:49-52, configs/unidet3d_1xb8_scannet.py optim_wrapper)
+def loss_backward(model, batch_inputs_dict, batch_data_samples, group=None):
+    """Forward of ``UniDet3D.loss`` in train mode with a tape, then the backward pass: fills ``.grad`` of every parameter
+    of the detector (accumulating like torch) and returns ``{'det_loss': value}``.  ``model.training`` must be True
+    (batch-statistics BatchNorm; under a torch.distributed ``group`` of several ranks its sums are all-reduced in both
+    directions).  Query selection uses ``torch.randperm`` on the host like the reference when a scene has more than
+    ``query_thr`` superpoints."""
+    if not model.training:
+        raise RuntimeError("loss_backward: call model.train() first (the backward pass is the train-mode executor's)")
+    with torch.no_grad():
+        li = model._loss_inputs(batch_inputs_dict, batch_data_samples)
+        B, names, sp_off = li["B"], li["names"], li["sp_off"]
+        x, inverse = model.collate(li["pts"], li["offs"], B, li["el"])
+        pooled, tape = backbone_forward(model, x, li["sp_b"], inverse, int(sp_off[-1]), group=group)
+        # query selection (unidet3d.py:182-218): rows of `pooled` are scene-contiguous already
+        sel, bounds, centers, qmasks = [], [0], [], []
+        for i in range(B):
+            a, b = int(sp_off[i]), int(sp_off[i + 1])
+            ids = torch.arange(a, b, device=pooled.device)
+            c, m = li["sp_centers"][i], li["sp_masks"][i]
+            if b - a > model.query_thr:
+                keep = torch.randperm(b - a)[:model.query_thr].to(pooled.device)
+                ids, c, m = ids[keep], c[keep], m[:, keep]
+            sel.append(ids), centers.append(c), qmasks.append(m)
+            bounds.append(bounds[-1] + int(ids.numel()))
+        for g, m in zip(li["gt_insts"], qmasks):
+            g.query_masks = m
+        if bounds[-1] == pooled.shape[0]:
+            X = pooled                                   # nothing dropped: the encoder reads the pooled rows directly
+        else:
+            idx = torch.cat(sel)
+            X = pooled.index_select(0, idx)
+
+            def sel_bwd():
+                dX = tape.grad(X)
+                if dX is not None:
+                    tape.add(pooled, torch.zeros_like(pooled).index_add_(0, idx, dX))
+
+            tape.steps.append(sel_bwd)
+        out, _ = encoder_forward(model.decoder, X, torch.cat(centers).contiguous(), bounds, names, tape=tape)
+        loss, d_cls, d_box = criterion_backward(model.criterion, out, li["gt_insts"], names)
+        encoder_backward(tape, out, d_cls, d_box)        # replays the whole tape: encoder steps, then the backbone's
+    return {"det_loss": loss}
+
+
+def train_step(model, optimizer, batch_inputs_dict, batch_data_samples, group=None, clip_grad_norm: Optional[float] = 10.0):
+    """zero_grad -> loss_backward -> gradient all-reduce (data parallel) -> clip (configs: max_norm 10) -> optimizer.step().
+    Packed weight images / folded BatchNorms are invalidated because the parameters change."""
+    optimizer.zero_grad(set_to_none=True)
+    out = loss_backward(model, batch_inputs_dict, batch_data_samples, group=group)
+    params = [p for p in model.parameters() if p.grad is not None]
+    allreduce_gradients(params, group=group)
+    if clip_grad_norm is not None:
+        torch.nn.utils.clip_grad_norm_(params, clip_grad_norm)
+    optimizer.step()
+    model.unet.invalidate_plan()
+    model.decoder.invalidate_plan()
+    if hasattr(model, "_plan"):
+        model._plan = None
+    return out
