@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["make_scene", "make_batch", "SCENE_PRESETS", "make_unet_state_dict",
+__all__ = ["make_scene", "make_batch", "make_scannet_gt", "SCENE_PRESETS", "make_unet_state_dict",
            "make_detector_backbone_state_dict", "make_encoder_state_dict", "make_model_state_dict"]
 
 # name -> (n_points, voxel_size, surface area m^2, superpoint cell m)
@@ -106,6 +106,19 @@ def make_batch(preset: str = "scannet100k", batch_size: int = 8, seed0: int = 0)
     n_points, voxel, area, sp_cell = SCENE_PRESETS[preset]
     scenes = [make_scene(seed0 + i, n_points, area, sp_cell) for i in range(batch_size)]
     return scenes, voxel
+
+
+def make_scannet_gt(superpoints: np.ndarray, n_inst: int, seed: int, n_classes: int = 18):
+    """ScanNet-style training annotations for a synthetic scene: every instance is a union of superpoints (that is how the
+    reference's loader delivers them: ``sp_masks`` [G, n_sp], ``pts_instance_mask`` [N] with -1 = no instance).
+    -> (labels int64 [G], sp_masks bool [G, n_sp], pts_instance_mask int64 [N])."""
+    rng = np.random.default_rng(seed)
+    n_sp = int(superpoints.max()) + 1
+    sp_inst = rng.integers(-1, n_inst, n_sp)
+    sp_inst[:n_inst] = np.arange(n_inst)              # every instance owns at least one superpoint
+    labels = rng.integers(0, n_classes, n_inst).astype(np.int64)
+    sp_masks = sp_inst[None, :] == np.arange(n_inst)[:, None]
+    return labels, sp_masks, sp_inst[superpoints].astype(np.int64)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -10,8 +10,8 @@ gradient of the pooled superpoint features, on the library's kernels:
 
 The forward is the train-mode executor of ``SpConvUNet`` re-run op by op while a tape records one closure per op; the
 backward replays the tape in reverse, accumulating gradients per tensor (a residual input or the skip concat has two
-consumers).  Activations after BatchNorm + ReLU are recomputed, not stored.  Scope: the backbone only -- the encoder /
-criterion backward kernels do not exist yet, so this is not a training step.
+consumers).  Activations after BatchNorm + ReLU are recomputed, not stored.  Further down: the encoder's tape, the
+criterion's gradients and the training step (``loss_backward`` / ``train_step``).
 """
 from __future__ import annotations
 
@@ -374,7 +374,7 @@ def layer_loss_from_matches(crit, cls_preds, bboxes, gts, datasets_names, matche
     return crit.loss_weight[0] * cls_loss + crit.loss_weight[1] * box_loss
 
 
-def criterion_backward(crit, outputs, insts, datasets_names, match_fn=None):
+def criterion_backward(crit, outputs, insts, datasets_names, match_fn=None, debug: Optional[dict] = None):
     """-> (det_loss value, d_cls, d_boxes) with d_* per head (aux heads first, final head last) lists over scenes, in
     the layout ``encoder_backward`` takes.  ``match_fn(cls_pred, bbox, boxes, labels, query_masks, topk) -> match``
     defaults to the GPU matcher (ud3d_criterion_layer)."""
@@ -394,6 +394,8 @@ def criterion_backward(crit, outputs, insts, datasets_names, match_fn=None):
                 topk = crit.topk[crit.datasets.index(name)]
                 matches.append(match_fn(cp.detach(), pb.detach(), boxes, labels, qm, topk) if labels.numel() else None)
             total = total + layer_loss_from_matches(crit, cps, pbs, gts, datasets_names, matches)
+            if debug is not None:
+                debug.setdefault("matches", []).append(matches)
             leaves_c.append(cps), leaves_b.append(pbs)
         flat = [t for lst in leaves_c + leaves_b for t in lst]
         grads = torch.autograd.grad(total, flat, allow_unused=True)
@@ -406,7 +408,36 @@ def criterion_backward(crit, outputs, insts, datasets_names, match_fn=None):
 # ---------------------------------------------------------------------------------------------------------------------
 # The training step (reference: UniDet3D.loss, unidet3d/unidet3d.py:277-364, under torch.autograd + DDP + AdamW,
 # tools/train.py:49-52, configs/unidet3d_1xb8_scannet.py optim_wrapper)
-def loss_backward(model, batch_inputs_dict, batch_data_samples, group=None):
+class _Marks:
+    """CUDA-event marks around the stages of one step (``profile_step``)."""
+
+    def __init__(self):
+        self.ev = []
+
+    def __call__(self, name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.ev.append((name, e))
+
+    def result(self):
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.ev[:-1], self.ev[1:]):
+            out[name + "_ms"] = out.get(name + "_ms", 0.0) + a.elapsed_time(b)
+        return out
+
+
+def profile_step(model, batch_inputs_dict, batch_data_samples, group=None):
+    """One ``loss_backward`` with CUDA events between its stages -> {stage_ms}: targets + collate, backbone forward,
+    encoder forward, matcher + criterion gradients, encoder backward, backbone backward."""
+    marks = _Marks()
+    for p in model.parameters():
+        p.grad = None
+    loss_backward(model, batch_inputs_dict, batch_data_samples, group=group, marks=marks)
+    return marks.result()
+
+
+def loss_backward(model, batch_inputs_dict, batch_data_samples, group=None, debug: Optional[dict] = None, marks=None):
     """Forward of ``UniDet3D.loss`` in train mode with a tape, then the backward pass: fills ``.grad`` of every parameter
     of the detector (accumulating like torch) and returns ``{'det_loss': value}``.  ``model.training`` must be True
     (batch-statistics BatchNorm; under a torch.distributed ``group`` of several ranks its sums are all-reduced in both
@@ -414,11 +445,16 @@ def loss_backward(model, batch_inputs_dict, batch_data_samples, group=None):
     ``query_thr`` superpoints."""
     if not model.training:
         raise RuntimeError("loss_backward: call model.train() first (the backward pass is the train-mode executor's)")
+    mark = marks if marks is not None else (lambda name: None)
     with torch.no_grad():
+        mark("start")
         li = model._loss_inputs(batch_inputs_dict, batch_data_samples)
         B, names, sp_off = li["B"], li["names"], li["sp_off"]
         x, inverse = model.collate(li["pts"], li["offs"], B, li["el"])
+        mark("targets_collate")
         pooled, tape = backbone_forward(model, x, li["sp_b"], inverse, int(sp_off[-1]), group=group)
+        mark("backbone_fwd")
+        tape.steps.append(lambda: mark("encoder_bwd"))       # replayed in reverse: the encoder's steps end here
         # query selection (unidet3d.py:182-218): rows of `pooled` are scene-contiguous already
         sel, bounds, centers, qmasks = [], [0], [], []
         for i in range(B):
@@ -445,8 +481,13 @@ def loss_backward(model, batch_inputs_dict, batch_data_samples, group=None):
 
             tape.steps.append(sel_bwd)
         out, _ = encoder_forward(model.decoder, X, torch.cat(centers).contiguous(), bounds, names, tape=tape)
-        loss, d_cls, d_box = criterion_backward(model.criterion, out, li["gt_insts"], names)
+        mark("encoder_fwd")
+        loss, d_cls, d_box = criterion_backward(model.criterion, out, li["gt_insts"], names, debug=debug)
+        mark("criterion")
+        if debug is not None:
+            debug.update(outputs=out, pooled=pooled, gt_insts=li["gt_insts"])
         encoder_backward(tape, out, d_cls, d_box)        # replays the whole tape: encoder steps, then the backbone's
+        mark("backbone_bwd")
     return {"det_loss": loss}
 
 
