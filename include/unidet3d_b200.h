@@ -452,7 +452,7 @@ size_t ud3d_postprocess_workspace_bytes(const ud3d_post_args* args);
 int ud3d_postprocess_scene(const ud3d_post_args* args, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ training-side targets, matcher, loss values
- * (forward values only -- no gradients yet)
+ * (forward values here, gradients in ud3d_criterion_layer_grad below)
  *
  * get_bboxes_by_masks (unidet3d.py:220-275): inst int64 [n] (-1 = no instance), points [n, >=3] ->
  * out [n_inst, 6] = (centre, size) of the tight AABB of every instance's points.  ws >= n_inst*6*4 bytes. */
@@ -485,6 +485,28 @@ typedef struct {
 } ud3d_criterion_args;
 size_t ud3d_criterion_workspace_bytes(int T, int G);
 int ud3d_criterion_layer(const ud3d_criterion_args* args, void* ws, size_t ws_bytes, void* stream);
+/* Gradients of the same (decoder layer, scene) -- what torch.autograd computes through criterion.py:86-142 in the
+ * reference (F.cross_entropy with class weights; bbox_loss_simple / bbox_loss_rotated of the matched pairs,
+ * axis_aligned_iou_loss.py:14-53, rotated_iou_loss.py:14-82 over mmcv's differentiable rotated intersection):
+ *   d_logits[q,c] = scales[0] * w[target[q]] / sums[1] * (softmax(logits[q])[c] - [c == target[q]])
+ *   d_boxes[q,:]  = scales[1] / sums[3] * sum over matched g of d DIoU_loss(boxes[q], gt_boxes[g]) / d boxes[q]   (0 if no pair)
+ * match / sums: the outputs of ud3d_criterion_layer for these inputs.  scales: DEVICE float[2] = d det_loss / d (this
+ * scene's weighted CE) and d det_loss / d (this scene's mean box loss) -- loss weights, dataset weight and the means over
+ * scenes (criterion.py:111,136-142), kept on the device because the second depends on how many scenes matched at all.
+ * The DIoU derivatives are forward-mode (dual numbers through the same polygon clipping that evaluates the loss,
+ * csrc/box_loss.cuh).  Deterministic. */
+typedef struct {
+  const float* logits; int32_t ld_logits; int32_t T; int32_t C1;     /* [T, C+1] */
+  const float* boxes; int32_t box_dim;                               /* [T, box_dim] */
+  const float* gt_boxes; const int64_t* gt_labels; int32_t G;        /* [G, box_dim], [G] */
+  const uint8_t* match;                                              /* [T, G] */
+  const float* sums;                                                 /* [4] */
+  const float* scales;                                               /* [2] */
+  float non_object_weight;
+  float* d_logits; int32_t ld_dlogits;                               /* out [T, C+1] */
+  float* d_boxes;                                                    /* out [T, box_dim] */
+} ud3d_criterion_grad_args;
+int ud3d_criterion_layer_grad(const ud3d_criterion_grad_args* args, void* stream);
 
 #ifdef __cplusplus
 }

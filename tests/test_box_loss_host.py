@@ -1,0 +1,83 @@
+"""CPU: the dual-number DIoU templates of unidet3d_b200/csrc/box_loss.cuh (what the GPU criterion-gradient kernel
+instantiates), built for the host with g++ by this test: values against the oracle's DIoU losses (pinned to the
+reference's criterion fixtures), gradients against torch.autograd (axis-aligned) and against central finite differences of
+the same templates in double (rotated: the reference differentiates mmcv's oriented_box_intersection_2d with autograd,
+which is not installable here -- the polygon-area gradient is the same function's derivative)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import criterion as oc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("bl") / "libbl_host.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "harness", "box_loss_host.cpp")],
+                   check=True)
+    return C.CDLL(so)
+
+
+def _call(lib, name, pred, tgt, dtype, with_grad=True):
+    pred, tgt = np.ascontiguousarray(pred, dtype), np.ascontiguousarray(tgt, dtype)
+    n, dim = pred.shape
+    loss, grad = np.zeros(n, dtype), np.zeros((n, dim), dtype)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    if with_grad:
+        getattr(lib, name)(ptr(pred), ptr(tgt), C.c_int(n), C.c_int(dim), ptr(loss), ptr(grad))
+        return loss, grad
+    getattr(lib, name)(ptr(pred), ptr(tgt), C.c_int(n), C.c_int(dim), ptr(loss))
+    return loss
+
+
+def _boxes(rng, n, dim):
+    """pairs with every overlap regime: heavy, partial, touching-free disjoint"""
+    t = np.concatenate([rng.uniform(0, 4, (n, 3)), rng.uniform(0.3, 1.5, (n, 3))], 1)
+    shift = rng.normal(0, 1, (n, 3)) * rng.choice([0.05, 0.3, 1.5], (n, 1))
+    p = np.concatenate([t[:, :3] + shift, t[:, 3:] * rng.uniform(0.6, 1.6, (n, 3))], 1)
+    if dim == 7:
+        t = np.concatenate([t, rng.uniform(-3.1, 3.1, (n, 1))], 1)
+        p = np.concatenate([p, t[:, 6:] + rng.normal(0, 0.4, (n, 1))], 1)
+    return p, t
+
+
+def test_aligned_diou_gradient_vs_torch_autograd(lib):
+    rng = np.random.default_rng(0)
+    p, t = _boxes(rng, 400, 6)
+    loss, grad = _call(lib, "bl_pair_loss_grad_f32", p, t, np.float32)
+    pt = torch.tensor(p, dtype=torch.float32, requires_grad=True)
+    ref = oc.aligned_diou_loss(oc.bbox_to_loss(pt), oc.bbox_to_loss(torch.tensor(t, dtype=torch.float32)))
+    ref.sum().backward()
+    assert np.allclose(loss, ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    assert np.allclose(grad, pt.grad.numpy(), rtol=1e-4, atol=1e-5)
+    assert (ref.detach().numpy() > 1.0).any() and (ref.detach().numpy() < 0.5).any()        # disjoint and overlapping pairs
+
+
+def test_rotated_diou_value_vs_oracle_and_gradient_vs_finite_differences(lib):
+    rng = np.random.default_rng(1)
+    p, t = _boxes(rng, 300, 7)
+    loss32, grad32 = _call(lib, "bl_pair_loss_grad_f32", p, t, np.float32)
+    ref = oc.rotated_diou_loss(torch.tensor(p, dtype=torch.float32), torch.tensor(t, dtype=torch.float32)).numpy()
+    assert np.allclose(loss32, ref, rtol=2e-4, atol=2e-5), np.abs(loss32 - ref).max()
+    loss64, grad64 = _call(lib, "bl_pair_loss_grad_f64", p, t, np.float64)
+    assert np.allclose(loss64, _call(lib, "bl_pair_loss_f64", p, t, np.float64, with_grad=False), rtol=1e-12, atol=1e-12)
+    h = 1e-6
+    fd = np.zeros_like(grad64)
+    for k in range(7):
+        e = np.zeros(7)
+        e[k] = h
+        fd[:, k] = (_call(lib, "bl_pair_loss_f64", p + e, t, np.float64, with_grad=False) -
+                    _call(lib, "bl_pair_loss_f64", p - e, t, np.float64, with_grad=False)) / (2 * h)
+    err = np.abs(grad64 - fd).max(1) / np.maximum(np.abs(fd).max(1), 1e-3)
+    # a finite difference that straddles a kink of the loss (a vertex entering / leaving the polygon, a min / max switching)
+    # is not a derivative: allow a handful of such pairs, everything else must agree to 1e-5
+    assert np.quantile(err, 0.97) < 1e-5, np.sort(err)[-12:]
+    assert (err < 1e-5).sum() >= 0.97 * len(err)
+    assert np.allclose(grad32, grad64, rtol=5e-3, atol=5e-4), np.abs(grad32 - grad64).max()
+    assert (np.abs(grad64[:, 6]) > 1e-3).mean() > 0.5            # the yaw gradient is exercised

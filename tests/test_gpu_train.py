@@ -487,3 +487,126 @@ def test_train_step_updates_parameters_and_reduces_the_loss():
     res = model.forward_scenes([torch.as_tensor(s[0]).to(DEV) for s in scenes], [torch.as_tensor(s[1]).to(DEV) for s in scenes],
                                ["scannet"] * 2)
     assert len(res) == 2 and all(torch.isfinite(r[2]).all() for r in res)
+
+
+def _criterion_case(datasets, names, Ts, Gs, dims, seed, masked_scene=None):
+    """Random heads + GT for the criterion tests -> (crit, outputs on CPU, insts on DEV, oracle gts, oracle cfg)."""
+    import types
+    from unidet3d_b200.criterion import UniDet3DCriterion
+    g = torch.Generator().manual_seed(seed)
+    topk = [3, 2, 2][:len(datasets)]
+    wts = [1.0, 0.7, 1.3][:len(datasets)]
+    crit = UniDet3DCriterion(matcher=dict(costs=[dict(type="QueryClassificationCost", weight=0.5), dict(type="BboxCostJointTraining", weight=2.0)]),
+                             loss_weight=[0.5, 1.0], non_object_weight=0.1, iter_matcher=True, bbox_loss_simple=dict(mode="diou"),
+                             bbox_loss_rotated=dict(mode="diou"), datasets=datasets, datasets_weights=wts, topk=topk)
+    Cs = [6 if n == "scannet" else 4 for n in names]
+    gts, insts = [], []
+    for i, (T, G, C, dim) in enumerate(zip(Ts, Gs, Cs, dims)):
+        labels = torch.randint(0, C, (G,), generator=g)
+        boxes = torch.cat((torch.rand(G, 3, generator=g) * 4, torch.rand(G, 3, generator=g) + 0.3), 1)
+        if dim == 7:
+            boxes = torch.cat((boxes, torch.rand(G, 1, generator=g) * 6 - 3), 1)
+        qm = torch.rand(G, T, generator=g) < 0.7
+        if masked_scene == i:
+            qm[:] = False
+        gts.append(dict(labels=labels, boxes=boxes, query_masks=qm))
+        insts.append(types.SimpleNamespace(labels_3d=labels.to(DEV), query_masks=qm.to(DEV),
+                                           bboxes_3d=types.SimpleNamespace(gravity_center=boxes[:, :3].to(DEV), tensor=boxes.to(DEV), with_yaw=dim == 7)))
+
+    def head():
+        cps = [torch.randn(T, C + 1, generator=g) for T, C in zip(Ts, Cs)]
+        bbs = []
+        for T, dim in zip(Ts, dims):
+            b = torch.cat((torch.rand(T, 3, generator=g) * 4, torch.rand(T, 3, generator=g) + 0.2), 1)
+            bbs.append(torch.cat((b, torch.rand(T, 1, generator=g) * 6 - 3), 1) if dim == 7 else b)
+        return dict(cls_preds=cps, bboxes=bbs)
+
+    final, aux = head(), [head(), head()]
+    out = dict(cls_preds=final["cls_preds"], bboxes=final["bboxes"], aux_outputs=aux)
+    cfg = dict(datasets=datasets, datasets_weights=wts, topk=topk, loss_weight=[0.5, 1.0], non_object_weight=0.1, w_cls=0.5, w_box=2.0,
+               iter_matcher=True)
+    return crit, out, insts, gts, cfg
+
+
+def _to_dev(out):
+    mv = lambda hd: dict(cls_preds=[t.to(DEV) for t in hd["cls_preds"]], bboxes=[t.to(DEV) for t in hd["bboxes"]])
+    d = mv(out)
+    d["aux_outputs"] = [mv(a) for a in out["aux_outputs"]]
+    return d
+
+
+@pytest.mark.parametrize("masked_scene", [None, 0])
+def test_criterion_gradients_vs_oracle_autograd(masked_scene):
+    """ud3d_criterion_layer_grad through train.criterion_backward (three heads; scenes with 5, 0 and 3 ground truths, two
+    datasets with different weights; optionally a scene whose GT is fully masked = no matched pair): loss value and the
+    gradients w.r.t. every head's logits and boxes against torch.autograd through the oracle criterion (pinned to the
+    reference's criterion.py fixtures), on the matches of the GPU matcher (itself checked in test_gpu_ops.py)."""
+    from unidet3d_b200 import train
+    from oracle import criterion as oc
+    names = ["scannet", "s3dis", "scannet"]
+    crit, out, insts, gts, cfg = _criterion_case(["scannet", "s3dis"], names, [60, 45, 30], [5, 0, 3], [6, 6, 6], 5, masked_scene)
+    dbg = {}
+    loss, d_cls, d_box = train.criterion_backward(crit, _to_dev(out), insts, names, debug=dbg)
+    heads = out["aux_outputs"] + [dict(cls_preds=out["cls_preds"], bboxes=out["bboxes"])]
+    ref, leaves = 0.0, []
+    for hd, ms in zip(heads, dbg["matches"]):
+        r = dict(cls_preds=[t.clone().requires_grad_(True) for t in hd["cls_preds"]], bboxes=[t.clone().requires_grad_(True) for t in hd["bboxes"]])
+        leaves.append(r)
+        idx = [tuple(t.cpu() for t in m.nonzero(as_tuple=True)) if m.numel() else (torch.zeros(0, dtype=torch.long),) * 2 for m in ms]
+        l, _ = oc.layer_loss(r["cls_preds"], r["bboxes"], gts, names, cfg, indices=idx)
+        ref = ref + l
+    ref.backward()
+    assert abs(float(loss) - float(ref.detach())) < 1e-5 * max(1.0, abs(float(ref.detach())))
+    n_box = 0
+    for hd, dc, db in zip(leaves, d_cls, d_box):
+        for t, g_ in zip(hd["cls_preds"], dc):
+            assert torch.allclose(g_.cpu(), t.grad, atol=1e-6, rtol=1e-4)
+        for t, g_ in zip(hd["bboxes"], db):
+            want = t.grad if t.grad is not None else torch.zeros_like(t)
+            assert torch.allclose(g_.cpu(), want, atol=1e-6, rtol=2e-4), float((g_.cpu() - want).abs().max())
+            n_box += int((want != 0).any(1).sum())
+    assert n_box > 20
+
+
+def test_criterion_gradients_rotated_boxes(tmp_path):
+    """7-parameter (yaw) boxes: the loss value against the oracle criterion, the logit gradients against torch.autograd
+    through it, and the box gradients against the host build of the same dual-number templates (tests/harness; they are
+    checked against finite differences in tests/test_box_loss_host.py -- mmcv's differentiable rotated IoU is not
+    installable here)."""
+    import ctypes as C
+    import os
+    import subprocess
+    from unidet3d_b200 import train
+    from oracle import criterion as oc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "libbl_host.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, os.path.join(root, "tests", "harness", "box_loss_host.cpp")], check=True)
+    lib = C.CDLL(so)
+    names = ["arkitscenes", "scannet"]
+    crit, out, insts, gts, cfg = _criterion_case(["scannet", "arkitscenes"], names, [50, 40], [4, 3], [7, 6], 8)
+    dbg = {}
+    loss, d_cls, d_box = train.criterion_backward(crit, _to_dev(out), insts, names, debug=dbg)
+    heads = out["aux_outputs"] + [dict(cls_preds=out["cls_preds"], bboxes=out["bboxes"])]
+    ref = 0.0
+    for hd, ms, dc, db in zip(heads, dbg["matches"], d_cls, d_box):
+        cps = [t.clone().requires_grad_(True) for t in hd["cls_preds"]]
+        idx = [tuple(t.cpu() for t in m.nonzero(as_tuple=True)) for m in ms]
+        l, _ = oc.layer_loss(cps, hd["bboxes"], gts, names, cfg, indices=idx)
+        ref = ref + l.detach()
+        l.backward()
+        for t, g_ in zip(cps, dc):
+            assert torch.allclose(g_.cpu(), t.grad, atol=1e-6, rtol=1e-4)
+        # rotated scene (0): expected box gradient = lw_box * w_ds / n_scenes_with_pairs / n_pairs * sum of pair gradients
+        iq, ig = idx[0]
+        assert len(iq) > 0
+        p = np.ascontiguousarray(hd["bboxes"][0][iq].numpy(), np.float32)
+        t = np.ascontiguousarray(gts[0]["boxes"][ig].numpy(), np.float32)
+        lo, gr = np.zeros(len(iq), np.float32), np.zeros((len(iq), 7), np.float32)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        lib.bl_pair_loss_grad_f32(ptr(p), ptr(t), C.c_int(len(iq)), C.c_int(7), ptr(lo), ptr(gr))
+        want = torch.zeros_like(hd["bboxes"][0]).index_add_(0, iq, torch.as_tensor(gr))
+        n_has = sum(1 for a, _ in idx if len(a))
+        want *= 1.0 * cfg["datasets_weights"][1] / n_has / len(iq)
+        assert torch.allclose(db[0].cpu(), want, atol=2e-6, rtol=2e-3), float((db[0].cpu() - want).abs().max())
+        assert float(want[:, 6].abs().max()) > 0
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))

@@ -106,6 +106,19 @@ class CriterionArgs(C.Structure):
     ]
 
 
+class CriterionGradArgs(C.Structure):
+    """Mirror of ``ud3d_criterion_grad_args``."""
+    _fields_ = [
+        ("logits", C.c_void_p), ("ld_logits", C.c_int32), ("T", C.c_int32), ("C1", C.c_int32),
+        ("boxes", C.c_void_p), ("box_dim", C.c_int32),
+        ("gt_boxes", C.c_void_p), ("gt_labels", C.c_void_p), ("G", C.c_int32),
+        ("match", C.c_void_p), ("sums", C.c_void_p), ("scales", C.c_void_p),
+        ("non_object_weight", C.c_float),
+        ("d_logits", C.c_void_p), ("ld_dlogits", C.c_int32),
+        ("d_boxes", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list EVERY symbol declared in include/unidet3d_b200.h
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -185,6 +198,7 @@ SIGNATURES = {
     "ud3d_targets_by_distance": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "ud3d_criterion_workspace_bytes": (_sz, [_i, _i]),
     "ud3d_criterion_layer": (_i, [C.POINTER(CriterionArgs), _vp, _sz, _vp]),
+    "ud3d_criterion_layer_grad": (_i, [C.POINTER(CriterionGradArgs), _vp]),
     "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _f, _f, _vp, _vp, _sz, _vp]),
 }
 

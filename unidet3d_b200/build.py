@@ -11,8 +11,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libunidet3d_b200.so")
-SOURCES = ["grid.cu", "gemm.cu", "gemm_ts.cu", "encoder.cu", "attention_tc.cu", "post.cu", "criterion.cu", "train.cu", "unet_plan.cu", "augment.cu", "eval.cu", "encoder_plan.cu", "attention_bwd.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "gemm_common.cuh"), os.path.join(CSRC, "boxes.cuh"), os.path.join(HERE, "..", "include", "unidet3d_b200.h")]
+SOURCES = ["grid.cu", "gemm.cu", "gemm_ts.cu", "encoder.cu", "attention_tc.cu", "post.cu", "criterion.cu", "train.cu", "unet_plan.cu", "augment.cu", "eval.cu", "encoder_plan.cu", "attention_bwd.cu", "criterion_grad.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "gemm_common.cuh"), os.path.join(CSRC, "boxes.cuh"), os.path.join(CSRC, "box_loss.cuh"), os.path.join(HERE, "..", "include", "unidet3d_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

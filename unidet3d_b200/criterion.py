@@ -1,4 +1,4 @@
-"""UniDet3DCriterion: matcher + loss VALUES on the GPU (reference: unidet3d/criterion.py:7-178, 200-320).
+"""UniDet3DCriterion: matcher + loss values on the GPU (reference: unidet3d/criterion.py:7-178, 200-320).
 
 Same registry name and constructor arguments as the reference class; ``__call__(pred, insts, datasets_names)``
 returns ``{'det_loss': tensor}`` like criterion.py:144-178.  One C-ABI call per (decoder layer, scene)
@@ -6,8 +6,9 @@ returns ``{'det_loss': tensor}`` like criterion.py:144-178.  One C-ABI call per 
 terms); the handful of scalar combinations (per-scene weights, means over scenes, loss weights, sum over layers) are
 done on the 4-float results with torch.
 
-Forward values only: gradients (and the backward kernels of the backbone / encoder) are SURVEY.md section 8f rank 2 and
-not implemented yet -- the returned tensor does not carry a graph.
+The returned tensor does not carry an autograd graph: the gradients w.r.t. the logits and boxes come from
+``ud3d_criterion_layer_grad`` (``unidet3d_b200.train.criterion_backward``), which the training step feeds into the
+encoder's and the backbone's backward passes.
 """
 from __future__ import annotations
 
@@ -67,7 +68,13 @@ class UniDet3DCriterion:
             raise NotImplementedError("iter_matcher=False")
         terms = self.layer_terms(aux_outputs, insts, datasets_names)
         sums = torch.stack([s for _, s in terms])                              # [B, 4]
-        w = sums.new_tensor([self.datasets_weights[self.datasets.index(n)] for n in datasets_names])
+        return self.combine(sums, self.scene_weights(sums, datasets_names))
+
+    def scene_weights(self, sums, datasets_names):
+        return sums.new_tensor([self.datasets_weights[self.datasets.index(n)] for n in datasets_names])
+
+    def combine(self, sums, w):
+        """criterion.py:111,136-142: per-scene sums [B, 4] + dataset weights [B] -> the layer's loss (device scalar)."""
         cls_loss = (w * sums[:, 0] / sums[:, 1]).mean()
         has = sums[:, 3] > 0
         n_has = has.sum()

@@ -492,6 +492,36 @@ def criterion_layer(logits: torch.Tensor, boxes: torch.Tensor, gt_boxes: torch.T
     return match.bool(), sums
 
 
+def criterion_layer_grad(logits: torch.Tensor, boxes: torch.Tensor, gt_boxes: torch.Tensor, gt_labels: torch.Tensor,
+                         match: torch.Tensor, sums: torch.Tensor, scales: torch.Tensor, non_object_weight: float):
+    """Gradients of one (layer, scene) of the criterion (ud3d_criterion_layer_grad) given ``match`` / ``sums`` of
+    ``criterion_layer`` and the DEVICE scalars ``scales`` = (d loss / d CE term, d loss / d box term) of this scene.
+    -> (d_logits [T, C+1], d_boxes [T, box_dim])."""
+    if not logits.is_cuda or logits.dtype != torch.float32 or logits.stride(1) != 1:
+        raise _lib.Ud3dError("criterion_layer_grad: logits must be a CUDA fp32 matrix with unit column stride")
+    _req(boxes, torch.float32, "boxes"), _req(sums, torch.float32, "sums"), _req(scales, torch.float32, "scales")
+    if sums.numel() != 4 or scales.numel() != 2:
+        raise _lib.Ud3dError("criterion_layer_grad: sums must hold 4 and scales 2 floats")
+    T, G = logits.shape[0], gt_labels.shape[0]
+    d_logits = torch.empty((T, logits.shape[1]), dtype=torch.float32, device=logits.device)
+    d_boxes = torch.empty_like(boxes)
+    a = _lib.CriterionGradArgs()
+    a.logits = logits.data_ptr(); a.ld_logits = logits.stride(0); a.T = T; a.C1 = logits.shape[1]
+    a.boxes = boxes.data_ptr(); a.box_dim = boxes.shape[1]
+    if G:
+        _req(gt_boxes, torch.float32, "gt_boxes"), _req(gt_labels, torch.int64, "gt_labels")
+        m = match.view(torch.uint8) if match.dtype == torch.bool else match
+        m = _req(m, torch.uint8, "match")
+        if tuple(m.shape) != (T, G) or gt_boxes.shape[1] != boxes.shape[1]:
+            raise _lib.Ud3dError("criterion_layer_grad: match must be [T, G] and gt_boxes match the predicted box_dim")
+        a.gt_boxes = gt_boxes.data_ptr(); a.gt_labels = gt_labels.data_ptr(); a.match = m.data_ptr()
+    a.G = G
+    a.sums = sums.data_ptr(); a.scales = scales.data_ptr(); a.non_object_weight = float(non_object_weight)
+    a.d_logits = d_logits.data_ptr(); a.ld_dlogits = d_logits.stride(0); a.d_boxes = d_boxes.data_ptr()
+    check(_L().ud3d_criterion_layer_grad(C.byref(a), _stream()), "ud3d_criterion_layer_grad")
+    return d_logits, d_boxes
+
+
 # ------------------------------------------------------------------ training side of the backbone
 def bn_batch_sums(x: torch.Tensor) -> torch.Tensor:
     """-> fp64 [2, C]: per-channel sum and sum of squares over the rows of ``x`` (deterministic)."""

@@ -326,83 +326,37 @@ def encoder_backward(tape: Tape, outputs, d_cls, d_boxes):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Criterion gradients.  The MATCHING (UniMatcher cost / threshold / match, criterion.py:200-320) is the GPU kernel
-# ud3d_criterion_layer; given its match matrix the loss of one (head, scene) is a short differentiable expression on
-# [T, C] logits and the few hundred matched boxes -- weighted cross-entropy (criterion.py:100-111) and the axis-aligned
-# DIoU of the matched pairs (criterion.py:113-134, axis_aligned_iou_loss.py:14-53) -- evaluated with torch ops and
-# differentiated with torch.autograd.  (The rotated DIoU of ARKitScenes-style boxes is not differentiated here.)
-def _corners(b: torch.Tensor) -> torch.Tensor:
-    """criterion.py:180-198 ``_bbox_to_loss``: (cx, cy, cz, dx, dy, dz) -> (x1, y1, z1, x2, y2, z2)."""
-    return torch.stack((b[..., 0] - b[..., 3] / 2, b[..., 1] - b[..., 4] / 2, b[..., 2] - b[..., 5] / 2,
-                        b[..., 0] + b[..., 3] / 2, b[..., 1] + b[..., 4] / 2, b[..., 2] + b[..., 5] / 2), -1)
-
-
-def _aligned_diou_pairs(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-    """axis_aligned_iou_loss.py:14-53 on corner boxes [N, 6] (IoU = mmdet3d AxisAlignedBboxOverlaps3D, eps 1e-6)."""
-    a1 = (pred[:, 3] - pred[:, 0]) * (pred[:, 4] - pred[:, 1]) * (pred[:, 5] - pred[:, 2])
-    a2 = (target[:, 3] - target[:, 0]) * (target[:, 4] - target[:, 1]) * (target[:, 5] - target[:, 2])
-    wh = (torch.minimum(pred[:, 3:], target[:, 3:]) - torch.maximum(pred[:, :3], target[:, :3])).clamp(min=0)
-    ov = wh[:, 0] * wh[:, 1] * wh[:, 2]
-    iou = ov / torch.clamp(a1 + a2 - ov, min=1e-6)
-    r2 = (((pred[:, :3] + pred[:, 3:]) / 2 - (target[:, :3] + target[:, 3:]) / 2) ** 2).sum(-1)
-    c2 = ((torch.minimum(pred[:, :3], target[:, :3]) - torch.maximum(pred[:, 3:], target[:, 3:])) ** 2).sum(-1)
-    return 1 - iou + r2 / c2
-
-
-def layer_loss_from_matches(crit, cls_preds, bboxes, gts, datasets_names, matches):
-    """One decoder layer's loss (criterion.py:44-142) as a differentiable torch expression, given the match matrices
-    ``matches[i]`` bool [T_i, G_i].  gts[i] = (labels int64 [G], boxes [G, 6], query_masks)."""
-    cls_losses, box_losses = [], []
-    for name, cp, pb, (labels, gboxes, _), m in zip(datasets_names, cls_preds, bboxes, gts, matches):
-        w = crit.datasets_weights[crit.datasets.index(name)]
-        C = cp.shape[1] - 1
-        tgt = torch.full((cp.shape[0],), C, dtype=torch.long, device=cp.device)
-        iq = ig = None
-        if labels.numel() and m is not None:
-            iq, ig = m.nonzero(as_tuple=True)              # query-major, like the reference's argwhere: the last pair wins
-            tgt[iq] = labels[ig]
-        cw = torch.ones(C + 1, device=cp.device)
-        cw[C] = crit.non_object_weight
-        cls_losses.append(w * torch.nn.functional.cross_entropy(cp, tgt, cw))
-        if iq is None or iq.numel() == 0:
-            continue
-        if gboxes.shape[1] != 6:
-            raise NotImplementedError("gradient of the rotated DIoU loss (arkitscenes boxes) is not implemented")
-        box_losses.append(w * _aligned_diou_pairs(_corners(pb[iq]), _corners(gboxes[ig])).mean())
-    cls_loss = torch.stack(cls_losses).mean()
-    box_loss = torch.stack(box_losses).mean() if box_losses else cls_loss.new_zeros(())
-    return crit.loss_weight[0] * cls_loss + crit.loss_weight[1] * box_loss
-
-
-def criterion_backward(crit, outputs, insts, datasets_names, match_fn=None, debug: Optional[dict] = None):
+# Criterion gradients (reference: torch.autograd through criterion.py:44-178).  Per (head, scene): ud3d_criterion_layer
+# (UniMatcher + loss sums) and ud3d_criterion_layer_grad (softmax - one-hot with the class weights; forward-mode DIoU
+# derivatives of the matched pairs, axis-aligned and rotated).  The scalar bookkeeping between the two -- dataset
+# weights, means over scenes, loss weights -- is a handful of ops on the [B, 4] sums and stays on the device (no host
+# synchronisation: whether a scene contributes a box term depends on its number of matched pairs).
+def criterion_backward(crit, outputs, insts, datasets_names, debug: Optional[dict] = None):
     """-> (det_loss value, d_cls, d_boxes) with d_* per head (aux heads first, final head last) lists over scenes, in
-    the layout ``encoder_backward`` takes.  ``match_fn(cls_pred, bbox, boxes, labels, query_masks, topk) -> match``
-    defaults to the GPU matcher (ud3d_criterion_layer)."""
+    the layout ``encoder_backward`` takes."""
+    if not crit.iter_matcher:
+        raise NotImplementedError("iter_matcher=False")
     heads = outputs["aux_outputs"] + [dict(cls_preds=outputs["cls_preds"], bboxes=outputs["bboxes"])]
     gts = [crit._gt(inst) for inst in insts]
-    if match_fn is None:
-        def match_fn(cp, pb, boxes, labels, qm, topk):
-            return ops.criterion_layer(cp, pb.contiguous(), boxes, labels, qm, topk, crit.w_cls, crit.w_box, crit.non_object_weight)[0]
-    total = 0.0
-    leaves_c, leaves_b = [], []
-    with torch.enable_grad():
-        for hd in heads:
-            cps = [t.detach().clone().requires_grad_(True) for t in hd["cls_preds"]]
-            pbs = [t.detach().clone().requires_grad_(True) for t in hd["bboxes"]]
-            matches = []
-            for cp, pb, (labels, boxes, qm), name in zip(cps, pbs, gts, datasets_names):
-                topk = crit.topk[crit.datasets.index(name)]
-                matches.append(match_fn(cp.detach(), pb.detach(), boxes, labels, qm, topk) if labels.numel() else None)
-            total = total + layer_loss_from_matches(crit, cps, pbs, gts, datasets_names, matches)
-            if debug is not None:
-                debug.setdefault("matches", []).append(matches)
-            leaves_c.append(cps), leaves_b.append(pbs)
-        flat = [t for lst in leaves_c + leaves_b for t in lst]
-        grads = torch.autograd.grad(total, flat, allow_unused=True)
-    it = iter(grads)
-    d_cls = [[next(it) for _ in lst] for lst in leaves_c]
-    d_box = [[next(it) for _ in lst] for lst in leaves_b]
-    return total.detach(), d_cls, d_box
+    B = len(datasets_names)
+    total = None
+    d_cls, d_box = [], []
+    for hd in heads:
+        terms = crit.layer_terms(hd, insts, datasets_names)
+        sums = torch.stack([s for _, s in terms])                               # [B, 4]
+        w = crit.scene_weights(sums, datasets_names)
+        loss = crit.combine(sums, w)
+        total = loss if total is None else total + loss
+        n_has = (sums[:, 3] > 0).sum().clamp(min=1)
+        scales = torch.stack((crit.loss_weight[0] * w / B, crit.loss_weight[1] * w / n_has), dim=1).contiguous()   # [B, 2]
+        dc, db = [], []
+        for i, (cp, pb, (labels, boxes, _), (match, s)) in enumerate(zip(hd["cls_preds"], hd["bboxes"], gts, terms)):
+            g_c, g_b = ops.criterion_layer_grad(cp, pb.contiguous(), boxes, labels, match, s, scales[i], crit.non_object_weight)
+            dc.append(g_c), db.append(g_b)
+        d_cls.append(dc), d_box.append(db)
+        if debug is not None:
+            debug.setdefault("matches", []).append([m for m, _ in terms])
+    return total, d_cls, d_box
 
 
 # ---------------------------------------------------------------------------------------------------------------------
