@@ -338,6 +338,10 @@ int ud3d_bn_relu_apply(const float* x, int ld_x, int n, int C, const float* scal
 size_t ud3d_attention_bwd_workspace_bytes(int total_T, int num_heads);
 int ud3d_attention_bwd(const float* qkv, const int32_t* cu_seqlens, int B, int total_T, int num_heads, const float* out,
                        const float* d_out, float* dqkv, void* ws, size_t ws_bytes, void* stream);
+/* Same contract and results (up to fp32 summation order); one thread per query / key with register-resident rows and
+ * accumulators, the other side staged through shared memory: the variant the training step uses. */
+int ud3d_attention_bwd_reg(const float* qkv, const int32_t* cu_seqlens, int B, int total_T, int num_heads, const float* out,
+                       const float* d_out, float* dqkv, void* ws, size_t ws_bytes, void* stream);
 /* LayerNorm backward (encoder.py:38-39,77-78,189): dx [rows, C]; dgamma_dbeta fp64 [2, C] = (sum_r dy * xhat, sum_r dy).
  * Statistics are recomputed from x (= the LayerNorm's input, residual already added). */
 size_t ud3d_layernorm_backward_workspace_bytes(int rows, int C);

@@ -291,9 +291,12 @@ def test_encoder_backward_pieces_vs_autograd():
     d_out = torch.randn(T, d, generator=g)
     out.backward(d_out)
     cu = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=DEV)
-    dqkv = ops.attention_backward(qkv.detach().to(DEV), cu, H, out.detach().to(DEV), d_out.to(DEV))
-    assert relerr(dqkv[:, :d], qkv.grad[:, :d]) < 1e-4, relerr(dqkv[:, :d], qkv.grad[:, :d])
-    assert relerr(dqkv[:, d:2 * d], qkv.grad[:, d:2 * d]) < 1e-4 and relerr(dqkv[:, 2 * d:], qkv.grad[:, 2 * d:]) < 1e-4
+    for variant in ("reg", "warp"):             # thread-per-token with register-resident rows (product) / warp-per-token
+        dqkv = ops.attention_backward(qkv.detach().to(DEV), cu, H, out.detach().to(DEV), d_out.to(DEV), variant=variant)
+        assert relerr(dqkv[:, :d], qkv.grad[:, :d]) < 1e-4, (variant, relerr(dqkv[:, :d], qkv.grad[:, :d]))
+        assert relerr(dqkv[:, d:2 * d], qkv.grad[:, d:2 * d]) < 1e-4 and relerr(dqkv[:, 2 * d:], qkv.grad[:, 2 * d:]) < 1e-4, variant
+        again = ops.attention_backward(qkv.detach().to(DEV), cu, H, out.detach().to(DEV), d_out.to(DEV), variant=variant)
+        assert torch.equal(again, dqkv)                                                   # deterministic
 
 
 def test_encoder_backward_vs_autograd():

@@ -152,6 +152,7 @@ SIGNATURES = {
     "ud3d_bn_relu_apply": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "ud3d_attention_bwd_workspace_bytes": (C.c_size_t, [_i, _i]),
     "ud3d_attention_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    "ud3d_attention_bwd_reg": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_layernorm_backward_workspace_bytes": (C.c_size_t, [_i, _i]),
     "ud3d_layernorm_backward": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, C.c_size_t, _vp]),
     "ud3d_activation_backward": (_i, [_vp, _vp, C.c_longlong, _i, _vp, _vp]),

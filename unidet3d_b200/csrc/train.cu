@@ -6,6 +6,8 @@
 //   * weight gradient of a sparse convolution: dW[co, k, ci] = sum_o dY[o, co] * X[table[k][o], ci].
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ud3d {
 
 constexpr int kBnRowsPerBlock = 512;
@@ -258,6 +260,131 @@ __global__ void __launch_bounds__(256) conv_wgrad_partial_kernel(const float* __
     if (co < c_out && ci < c_in) part[(((size_t)slice * c_out + co) * K + k) * c_in + ci] = acc[j];
   }
 }
+// Register-tiled version (the product path): a CTA owns a TM x TN tile of (co, ci) for one kernel offset and row slice;
+// every thread accumulates a 4 x 4 block of it, reading its 4 dY values and 4 X values of a staged row as two 16-byte
+// shared-memory loads (2 LDS.128 per 16 FMAs instead of 5 LDS.32 per 4 FMAs above: the FMA pipe is the limit, not the
+// shared-memory port).  Tiles smaller than 64 x 64 leave threads over: the 256 threads then form G = 2 or 4 groups that
+// take alternate rows of the 32 staged ones and combine their blocks through shared memory in a fixed order at the end.
+constexpr int kWg2Rows = 32;
+template <int TM, int TN>
+__global__ void __launch_bounds__(256) conv_wgrad_tiled_kernel(const float* __restrict__ x, int ld_x, int c_in,
+                                                               const float* __restrict__ dy, int ld_dy, int c_out,
+                                                               const int32_t* __restrict__ table, int n_out, int K,
+                                                               int rows_per_slice, int vec_x, int vec_y, float* __restrict__ part) {
+  constexpr int TPG = (TM / 4) * (TN / 4);       // threads per group
+  constexpr int G = 256 / TPG;                   // row-interleaved groups
+  static_assert(TPG * G == 256 && (TM % 4) == 0 && (TN % 4) == 0, "tile shape");
+  constexpr int kRedFloats = (G > 1) ? (G - 1) * TM * TN : 1;
+  constexpr int kStageFloats = kWg2Rows * (TM + TN);
+  __shared__ __align__(16) float smem[kStageFloats > kRedFloats ? kStageFloats : kRedFloats];
+  float4(*sx)[TN / 4] = reinterpret_cast<float4(*)[TN / 4]>(smem);
+  float4(*sy)[TM / 4] = reinterpret_cast<float4(*)[TM / 4]>(smem + kWg2Rows * TN);
+  const int k = blockIdx.y;
+  const int tiles_ci = (c_in + TN - 1) / TN;
+  const int tco = blockIdx.x / tiles_ci, tci = blockIdx.x - tco * tiles_ci;
+  const int slice = blockIdx.z;
+  const int r_begin = slice * rows_per_slice, r_end = min(n_out, r_begin + rows_per_slice);
+  const int grp = threadIdx.x / TPG, tig = threadIdx.x - grp * TPG;
+  const int tx = tig % (TN / 4), ty = tig / (TN / 4);        // ci block tx, co block ty
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const int ci0 = tci * TN, co0 = tco * TM;
+  for (int r0 = r_begin; r0 < r_end; r0 += kWg2Rows) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kWg2Rows * (TN / 4); idx += 256) {
+      const int rr = idx / (TN / 4), c4 = idx - rr * (TN / 4);
+      const int o = r0 + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (o < r_end) {
+        const int src = table ? __ldg(table + (size_t)k * n_out + o) : o;
+        const int c = ci0 + c4 * 4;
+        if (src >= 0 && c < c_in) {
+          const float* px = x + (size_t)src * ld_x + c;
+          if (vec_x && c + 3 < c_in) {
+            v = __ldg((const float4*)px);
+          } else {
+            v.x = px[0];
+            if (c + 1 < c_in) v.y = px[1];
+            if (c + 2 < c_in) v.z = px[2];
+            if (c + 3 < c_in) v.w = px[3];
+          }
+        }
+      }
+      sx[rr][c4] = v;
+    }
+    for (int idx = threadIdx.x; idx < kWg2Rows * (TM / 4); idx += 256) {
+      const int rr = idx / (TM / 4), c4 = idx - rr * (TM / 4);
+      const int o = r0 + rr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int c = co0 + c4 * 4;
+      if (o < r_end && c < c_out) {
+        const float* py = dy + (size_t)o * ld_dy + c;
+        if (vec_y && c + 3 < c_out) {
+          v = __ldg((const float4*)py);
+        } else {
+          v.x = py[0];
+          if (c + 1 < c_out) v.y = py[1];
+          if (c + 2 < c_out) v.z = py[2];
+          if (c + 3 < c_out) v.w = py[3];
+        }
+      }
+      sy[rr][c4] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = grp; rr < kWg2Rows; rr += G) {
+      const float4 xv = sx[rr][tx];
+      const float4 yv = sy[rr][ty];
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(ys[a], xs[b], acc[a][b]);
+    }
+  }
+  if (G > 1) {       // groups 1 .. G-1 park their blocks in shared memory, group 0 adds them in order
+    __syncthreads();
+    if (grp > 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) smem[((size_t)(grp - 1) * 16 + a * 4 + b) * TPG + tig] = acc[a][b];
+    }
+    __syncthreads();
+    if (grp == 0) {
+      for (int g2 = 1; g2 < G; ++g2)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] += smem[((size_t)(g2 - 1) * 16 + a * 4 + b) * TPG + tig];
+    }
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int co = co0 + ty * 4 + a;
+      if (co >= c_out) continue;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int ci = ci0 + tx * 4 + b;
+        if (ci < c_in) part[(((size_t)slice * c_out + co) * K + k) * c_in + ci] = acc[a][b];      // part[slice][co][k][ci]
+      }
+    }
+  }
+}
+
+template <int TM, int TN>
+static void launch_wgrad_tiled(const float* x, int ld_x, int c_in, const float* dy, int ld_dy, int c_out, const int32_t* table, int n_out,
+                               int K, int rps, int slices, float* part, cudaStream_t st) {
+  const int vec_x = (ld_x % 4 == 0) && (((uintptr_t)x & 15) == 0);
+  const int vec_y = (ld_dy % 4 == 0) && (((uintptr_t)dy & 15) == 0);
+  dim3 grid(cdiv(c_out, TM) * cdiv(c_in, TN), K, slices);
+  conv_wgrad_tiled_kernel<TM, TN><<<grid, 256, 0, st>>>(x, ld_x, c_in, dy, ld_dy, c_out, table, n_out, K, rps, vec_x, vec_y, part);
+}
+
 __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ part, int n_slices, size_t n_w, float* __restrict__ dw,
                                          int accumulate) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -458,8 +585,19 @@ int ud3d_conv_wgrad(const float* x, int ld_x, int c_in, const float* dy, int ld_
   cudaStream_t st = (cudaStream_t)stream;
   const int slices = wgrad_slices(n_out);
   const int rps = cdiv(n_out > 0 ? n_out : 1, slices);
-  dim3 grid(cdiv(c_out, 32) * cdiv(c_in, 32), K, slices);
-  conv_wgrad_partial_kernel<<<grid, 256, 0, st>>>(x, ld_x, c_in, dy, ld_dy, c_out, table, n_out, K, rps, (float*)ws);
+  static const bool use_v1 = [] { const char* e = getenv("UD3D_WGRAD"); return e && e[0] == 'v' && e[1] == '1'; }();   // measurement switch
+  if (use_v1) {
+    dim3 grid(cdiv(c_out, 32) * cdiv(c_in, 32), K, slices);
+    conv_wgrad_partial_kernel<<<grid, 256, 0, st>>>(x, ld_x, c_in, dy, ld_dy, c_out, table, n_out, K, rps, (float*)ws);
+  } else if (c_out > 32 && c_in > 32) {
+    launch_wgrad_tiled<64, 64>(x, ld_x, c_in, dy, ld_dy, c_out, table, n_out, K, rps, slices, (float*)ws, st);
+  } else if (c_out > 32) {
+    launch_wgrad_tiled<64, 32>(x, ld_x, c_in, dy, ld_dy, c_out, table, n_out, K, rps, slices, (float*)ws, st);
+  } else if (c_in > 32) {
+    launch_wgrad_tiled<32, 64>(x, ld_x, c_in, dy, ld_dy, c_out, table, n_out, K, rps, slices, (float*)ws, st);
+  } else {
+    launch_wgrad_tiled<32, 32>(x, ld_x, c_in, dy, ld_dy, c_out, table, n_out, K, rps, slices, (float*)ws, st);
+  }
   UD3D_LAUNCH_CHECK();
   const size_t n_w = (size_t)c_out * K * c_in;
   conv_wgrad_reduce_kernel<<<cdiv((long long)n_w, 256), 256, 0, st>>>((const float*)ws, slices, n_w, dw, accumulate);

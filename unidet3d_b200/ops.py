@@ -3,6 +3,7 @@ kernel is ours).  All functions require CUDA tensors and raise otherwise -- ther
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -621,8 +622,13 @@ def segmented_mean_backward(d_pooled: torch.Tensor, seg: torch.Tensor, n_rows: i
     return out
 
 
-def attention_backward(qkv: torch.Tensor, cu_seqlens: torch.Tensor, num_heads: int, out: torch.Tensor, d_out: torch.Tensor):
-    """fp32 qkv [T, 3d], forward result ``out`` [T, d] and its gradient -> dqkv [T, 3d]."""
+ATTN_BWD_VARIANT = os.environ.get("UD3D_ATTN_BWD", "reg")      # measurement switch: "warp" = the first implementation
+
+
+def attention_backward(qkv: torch.Tensor, cu_seqlens: torch.Tensor, num_heads: int, out: torch.Tensor, d_out: torch.Tensor,
+                       variant: Optional[str] = None):
+    """fp32 qkv [T, 3d], forward result ``out`` [T, d] and its gradient -> dqkv [T, 3d].  ``variant``: "reg" (thread per
+    query / key, register-resident rows; the default) or "warp" (warp per token, the first implementation)."""
     for t, nme in ((qkv, "qkv"), (out, "out"), (d_out, "d_out")):
         _req(t, torch.float32, nme)
     _req(cu_seqlens, torch.int32, "cu_seqlens")
@@ -630,8 +636,9 @@ def attention_backward(qkv: torch.Tensor, cu_seqlens: torch.Tensor, num_heads: i
     dqkv = torch.empty_like(qkv)
     wsb = int(_L().ud3d_attention_bwd_workspace_bytes(T, num_heads))
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=qkv.device)
-    check(_L().ud3d_attention_bwd(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, T, num_heads, _p(out), _p(d_out), _p(dqkv), _p(ws),
-                                  ws.numel(), _stream()), "ud3d_attention_bwd")
+    fn = {"reg": _L().ud3d_attention_bwd_reg, "warp": _L().ud3d_attention_bwd}[variant or ATTN_BWD_VARIANT]
+    check(fn(_p(qkv), _p(cu_seqlens), cu_seqlens.numel() - 1, T, num_heads, _p(out), _p(d_out), _p(dqkv), _p(ws), ws.numel(), _stream()),
+          "ud3d_attention_bwd")
     return dqkv
 
 
