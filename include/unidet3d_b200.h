@@ -313,12 +313,14 @@ int ud3d_encoder_forward(const ud3d_encoder_plan* plan, const float* x, int n, c
  *     For SyncBatchNorm the caller all-reduces `sums` (and the row count) across ranks before the fold.
  *   ud3d_bn_train_fold : mean / biased variance -> scale = gamma / sqrt(var + eps), shift = beta - mean * scale (the
  *     form ud3d_gemm_args.in_scale / in_shift and ud3d_act_split consume), running_mean / running_var updated in place
- *     (unbiased variance, like torch); save_mean / save_invstd optional (for the backward pass). */
+ *     (unbiased variance, like torch); save_mean / save_invstd optional (for the backward pass).
+ *   count_dev (both fold and backward_apply; may be NULL): the row count as a DEVICE double -- under SyncBatchNorm it comes out
+ *     of the same all-reduce as the sums, and reading it on the host would cost one synchronisation per BatchNorm. */
 size_t ud3d_bn_batch_sums_workspace_bytes(int n, int C);
 int ud3d_bn_batch_sums(const float* x, int ld, int n, int C, double* sums, void* ws, size_t ws_bytes, void* stream);
 int ud3d_bn_train_fold(const double* sums, double count, int C, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                       float* save_mean, float* save_invstd, void* stream);
+                       float* save_mean, float* save_invstd, const double* count_dev, void* stream);
 /* Backward of the fused train-mode BatchNorm + ReLU in front of a conv (a = relu(x * scale + shift)), given dA = the conv's
  * input gradient:  g = dA * [a > 0];  sums[0..C) = sum_r g (= dbeta), sums[C..2C) = sum_r g * xhat (= dgamma), fp64, fixed
  * order (all-reduced across ranks for SyncBatchNorm);  dx (+)= scale * (g - dbeta / count - xhat * dgamma / count).
@@ -328,7 +330,7 @@ int ud3d_bn_backward_sums(const float* x, int ld_x, const float* da, int ld_da, 
                           size_t ws_bytes, void* stream);
 int ud3d_bn_backward_apply(const float* x, int ld_x, const float* da, int ld_da, int n, int C, const float* scale,
                            const float* shift, const float* mean, const float* invstd, int relu, const double* sums,
-                           double count, float* dx, int ld_dx, int accumulate, void* stream);
+                           double count, float* dx, int ld_dx, int accumulate, const double* count_dev, void* stream);
 /* out = relu?(x * scale + shift) as an fp32 map: the X operand of ud3d_conv_wgrad (recomputed, not stored, in forward) */
 int ud3d_bn_relu_apply(const float* x, int ld_x, int n, int C, const float* scale, const float* shift, int relu, float* out,
                        int ld_out, void* stream);
@@ -511,6 +513,12 @@ typedef struct {
   float* d_boxes;                                                    /* out [T, box_dim] */
 } ud3d_criterion_grad_args;
 int ud3d_criterion_layer_grad(const ud3d_criterion_grad_args* args, void* stream);
+/* Backward of one scene's head outputs (what torch.autograd does through encoder.py:165-201,241-283): the per-dataset
+ * class column gather and PredBBox's exp + _bbox_pred_to_bbox.  raw [T, ld_raw >= 8] (the box Linear's output),
+ * d_box [T, with_angle ? 7 : 6] or NULL, d_cls [T, n_cols] or NULL with cols int32 [n_cols] (distinct columns) ->
+ * d_raw [T, 8] = J^T d_box,  d_logits [T, n_union] = scatter of d_cls (every element is written: zeros elsewhere). */
+int ud3d_head_backward(const float* raw, int ld_raw, const float* d_box, int with_angle, const float* d_cls, const int32_t* cols,
+                       int n_cols, int T, float* d_raw, int ld_draw, float* d_logits, int ld_dlogits, int n_union, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,4 +22,14 @@ void bl_pair_loss_f64(const double* pred, const double* tgt, int n, int dim, dou
     loss[i] = dim == 7 ? diou_rotated<double>(p, t) : diou_aligned<double>(p, t);
   }
 }
+
+void bl_bbox_decode_backward_f32(const float* raw, int n, int with_angle, const float* d_box, float* d_raw) {
+  const int dim = with_angle ? 7 : 6;
+  for (int i = 0; i < n; ++i) bbox_decode_backward<float>(raw + (long)i * 8, with_angle != 0, d_box + (long)i * dim, d_raw + (long)i * 8);
+}
+
+void bl_bbox_decode_f32(const float* raw, const float* centers, int n, int with_angle, float* box) {
+  const int dim = with_angle ? 7 : 6;
+  for (int i = 0; i < n; ++i) bbox_decode<float, float>(raw + (long)i * 8, centers + (long)i * 3, with_angle != 0, box + (long)i * dim);
+}
 }

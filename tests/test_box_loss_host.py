@@ -81,3 +81,27 @@ def test_rotated_diou_value_vs_oracle_and_gradient_vs_finite_differences(lib):
     assert (err < 1e-5).sum() >= 0.97 * len(err)
     assert np.allclose(grad32, grad64, rtol=5e-3, atol=5e-4), np.abs(grad32 - grad64).max()
     assert (np.abs(grad64[:, 6]) > 1e-3).mean() > 0.5            # the yaw gradient is exercised
+
+
+@pytest.mark.parametrize("with_angle", [False, True])
+def test_bbox_decode_backward_vs_torch_autograd(lib, with_angle):
+    """PredBBox exp + _bbox_pred_to_bbox (encoder.py:109-111,241-283): value and J^T d_box of the dual-number template
+    against torch.autograd through the oracle's restatement."""
+    from oracle.encoder import bbox_pred_to_bbox
+    g = torch.Generator().manual_seed(3)
+    n, dim = 300, 7 if with_angle else 6
+    raw = (torch.randn(n, 8, generator=g) * 0.8).requires_grad_(True)
+    centers = torch.randn(n, 3, generator=g)
+    d_box = torch.randn(n, dim, generator=g)
+    pred = torch.cat((torch.exp(raw[:, :6]), raw[:, 6:]), 1) if with_angle else torch.exp(raw[:, :6])
+    box = bbox_pred_to_bbox(centers, pred)
+    box.backward(d_box)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    r = np.ascontiguousarray(raw.detach().numpy(), np.float32)
+    got_box, got = np.zeros((n, dim), np.float32), np.zeros((n, 8), np.float32)
+    lib.bl_bbox_decode_f32(ptr(r), ptr(np.ascontiguousarray(centers.numpy())), C.c_int(n), C.c_int(int(with_angle)), ptr(got_box))
+    lib.bl_bbox_decode_backward_f32(ptr(r), C.c_int(n), C.c_int(int(with_angle)), ptr(np.ascontiguousarray(d_box.numpy())), ptr(got))
+    assert np.allclose(got_box, box.detach().numpy(), rtol=1e-5, atol=1e-6)
+    assert np.allclose(got, raw.grad.numpy(), rtol=1e-4, atol=1e-5), np.abs(got - raw.grad.numpy()).max()
+    if not with_angle:
+        assert not got[:, 6:].any()

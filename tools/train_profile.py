@@ -13,7 +13,7 @@ import bench  # noqa: E402
 
 
 def main():
-    workload = sys.argv[1] if len(sys.argv) > 1 else "train_b8"
+    workload = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "train_b8"
     import unidet3d_b200 as u
     from unidet3d_b200 import train
     from unidet3d_b200.structures import Det3DDataSample, InstanceData, PointData
@@ -40,6 +40,24 @@ def main():
     torch.cuda.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
     print(json.dumps({"loss": float(out["det_loss"]), "stages_ms": train.profile_step(model, inputs, samples)}))
+    if "--cprofile" in sys.argv:
+        import cProfile
+        import io
+        import pstats
+        import time
+        pr = cProfile.Profile()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pr.enable()
+        train.train_step(model, opt, inputs, samples)
+        pr.disable()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        buf = io.StringIO()
+        pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(45)
+        print(f"host issue time of one step {1e3 * (t1 - t0):.1f} ms (under cProfile), GPU drained {1e3 * (t2 - t1):.1f} ms later")
+        print(buf.getvalue())
 
 
 if __name__ == "__main__":

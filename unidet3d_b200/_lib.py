@@ -144,11 +144,11 @@ SIGNATURES = {
     "ud3d_gemm_pack_weight_ts": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "ud3d_bn_batch_sums_workspace_bytes": (C.c_size_t, [_i, _i]),
     "ud3d_bn_batch_sums": (_i, [_vp, _i, _i, _i, _vp, _vp, C.c_size_t, _vp]),
-    "ud3d_bn_train_fold": (_i, [_vp, C.c_double, _i, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ud3d_bn_train_fold": (_i, [_vp, C.c_double, _i, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ud3d_conv_wgrad_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i]),
     "ud3d_segmented_mean_workspace_bytes": (C.c_size_t, [_i, _i]),
     "ud3d_bn_backward_sums": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, C.c_size_t, _vp]),
-    "ud3d_bn_backward_apply": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, C.c_double, _vp, _i, _i, _vp]),
+    "ud3d_bn_backward_apply": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, C.c_double, _vp, _i, _i, _vp, _vp]),
     "ud3d_bn_relu_apply": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp]),
     "ud3d_attention_bwd_workspace_bytes": (C.c_size_t, [_i, _i]),
     "ud3d_attention_bwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
@@ -200,6 +200,7 @@ SIGNATURES = {
     "ud3d_criterion_workspace_bytes": (_sz, [_i, _i]),
     "ud3d_criterion_layer": (_i, [C.POINTER(CriterionArgs), _vp, _sz, _vp]),
     "ud3d_criterion_layer_grad": (_i, [C.POINTER(CriterionGradArgs), _vp]),
+    "ud3d_head_backward": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _i, _i, _vp]),
     "ud3d_trim_boxes": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _f, _f, _vp, _vp, _sz, _vp]),
 }
 

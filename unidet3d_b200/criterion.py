@@ -71,7 +71,14 @@ class UniDet3DCriterion:
         return self.combine(sums, self.scene_weights(sums, datasets_names))
 
     def scene_weights(self, sums, datasets_names):
-        return sums.new_tensor([self.datasets_weights[self.datasets.index(n)] for n in datasets_names])
+        """dataset weight of every scene of the batch as a device vector (cached per batch composition)."""
+        key = (tuple(datasets_names), sums.device)
+        cache = self.__dict__.setdefault("_w_cache", {})
+        if key not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = sums.new_tensor([self.datasets_weights[self.datasets.index(n)] for n in datasets_names])
+        return cache[key]
 
     def combine(self, sums, w):
         """criterion.py:111,136-142: per-scene sums [B, 4] + dataset weights [B] -> the layer's loss (device scalar)."""

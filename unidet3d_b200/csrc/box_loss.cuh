@@ -94,6 +94,31 @@ template <class F, int N> UD3D_BL_HD Dual<F, N> s_cos(const Dual<F, N>& a) {
   for (int i = 0; i < N; ++i) r.d[i] = s * a.d[i];
   return r;
 }
+UD3D_BL_HD float s_exp(float x) { return expf(x); }
+UD3D_BL_HD double s_exp(double x) { return exp(x); }
+template <class F, int N> UD3D_BL_HD Dual<F, N> s_exp(const Dual<F, N>& a) {
+  Dual<F, N> r; r.v = s_exp(a.v);
+  for (int i = 0; i < N; ++i) r.d[i] = r.v * a.d[i];
+  return r;
+}
+// sqrt(x^2 + y^2) and atan2(y, x) of two scalars; at the origin the derivative is taken as 0 (torch.autograd gives NaN there)
+UD3D_BL_HD float s_hypot(float x, float y) { return sqrtf(x * x + y * y); }
+UD3D_BL_HD double s_hypot(double x, double y) { return sqrt(x * x + y * y); }
+template <class F, int N> UD3D_BL_HD Dual<F, N> s_hypot(const Dual<F, N>& x, const Dual<F, N>& y) {
+  Dual<F, N> r; r.v = s_hypot(x.v, y.v);
+  const F inv = r.v > F(0) ? F(1) / r.v : F(0);
+  for (int i = 0; i < N; ++i) r.d[i] = (x.v * x.d[i] + y.v * y.d[i]) * inv;
+  return r;
+}
+UD3D_BL_HD float s_atan2(float y, float x) { return atan2f(y, x); }
+UD3D_BL_HD double s_atan2(double y, double x) { return atan2(y, x); }
+template <class F, int N> UD3D_BL_HD Dual<F, N> s_atan2(const Dual<F, N>& y, const Dual<F, N>& x) {
+  Dual<F, N> r; r.v = s_atan2(y.v, x.v);
+  const F n2 = x.v * x.v + y.v * y.v;
+  const F inv = n2 > F(0) ? F(1) / n2 : F(0);
+  for (int i = 0; i < N; ++i) r.d[i] = (x.v * y.d[i] - y.v * x.d[i]) * inv;
+  return r;
+}
 // selections on the values (torch.min / torch.max / clamp / abs propagate the gradient of the selected operand)
 template <class S> UD3D_BL_HD S s_min(const S& a, const S& b) { return val(b) < val(a) ? b : a; }
 template <class S> UD3D_BL_HD S s_max(const S& a, const S& b) { return val(b) > val(a) ? b : a; }
@@ -285,6 +310,50 @@ UD3D_BL_HDN F pair_loss_grad(const F* pred, const F* target, int dim, F* grad) {
   const D l = dim == 7 ? diou_rotated(p, t) : diou_aligned(p, t);
   for (int i = 0; i < dim; ++i) grad[i] = l.d[i];
   return l.v;
+}
+
+// PredBBox's exp + _bbox_pred_to_bbox (unidet3d/encoder.py:109-111,241-283): raw[8] (6 log-distances to the faces + the two
+// angle logits), query centre -> box[6] (centre, size) or box[7] (x, y, z, w, l, h, alpha).  Same expressions as
+// bbox_decode_kernel (encoder.cu), which produces the forward value.
+template <class S, class F>
+UD3D_BL_HDN void bbox_decode(const S* raw, const F* center, bool with_angle, S* box) {
+  S e[6];
+  for (int j = 0; j < 6; ++j) e[j] = s_exp(raw[j]);
+  box[0] = center[0] + (e[1] - e[0]) * F(0.5);
+  box[1] = center[1] + (e[3] - e[2]) * F(0.5);
+  box[2] = center[2] + (e[5] - e[4]) * F(0.5);
+  if (!with_angle) {
+    box[3] = e[0] + e[1];
+    box[4] = e[2] + e[3];
+    box[5] = e[4] + e[5];
+    return;
+  }
+  const S scale = e[0] + e[1] + e[2] + e[3];
+  const S q = s_exp(s_hypot(raw[6], raw[7]));
+  const S w = scale / (q + F(1));
+  box[3] = w;
+  box[4] = w * q;
+  box[5] = e[5] + e[4];
+  box[6] = s_atan2(raw[6], raw[7]) * F(0.5);
+}
+
+// d_raw[8] = J^T d_box for the decode above (forward-mode over the 8 raw values)
+template <class F>
+UD3D_BL_HDN void bbox_decode_backward(const F* raw, bool with_angle, const F* d_box, F* d_raw) {
+  typedef Dual<F, 8> D;
+  D r[8], box[7];
+  for (int i = 0; i < 8; ++i) {
+    r[i] = D(raw[i]);
+    r[i].d[i] = F(1);
+  }
+  const F zero[3] = {F(0), F(0), F(0)};
+  bbox_decode(r, zero, with_angle, box);
+  const int dim = with_angle ? 7 : 6;
+  for (int i = 0; i < 8; ++i) {
+    F s = F(0);
+    for (int j = 0; j < dim; ++j) s += d_box[j] * box[j].d[i];
+    d_raw[i] = s;
+  }
 }
 
 }  // namespace bl

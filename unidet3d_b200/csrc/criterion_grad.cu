@@ -62,9 +62,49 @@ __global__ void __launch_bounds__(128) crit_grad_kernel(ud3d_criterion_grad_args
   for (int c = lane; c < a.C1; c += 32) out[c] = cscale * (expf(row[c] - m) / s - (c == target ? 1.f : 0.f));
 }
 
+// Backward of one scene's head outputs (encoder.py:165-201): the per-dataset class column gather and the box decode.
+//   d_logits[t, :] = 0;  d_logits[t, cols[j]] = d_cls[t, j]         (cols are distinct: a gather, encoder.py:191-194)
+//   d_raw[t, :]    = J_decode(raw[t])^T d_box[t]                    (PredBBox exp + _bbox_pred_to_bbox, encoder.py:109-111,241-283)
+// One thread per query row; a NULL d_cls / d_box means "no gradient" (zeros are written).
+__global__ void __launch_bounds__(128) head_bwd_kernel(const float* __restrict__ raw, int ld_raw, const float* __restrict__ d_box,
+                                                       int with_angle, const float* __restrict__ d_cls, const int32_t* __restrict__ cols,
+                                                       int n_cols, int T, float* __restrict__ d_raw, int ld_draw,
+                                                       float* __restrict__ d_logits, int ld_dlogits, int n_union) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float* dl = d_logits + (size_t)t * ld_dlogits;
+  for (int c = 0; c < n_union; ++c) dl[c] = 0.f;
+  if (d_cls)
+    for (int j = 0; j < n_cols; ++j) dl[cols[j]] = d_cls[(size_t)t * n_cols + j];
+  float out[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (d_box) {
+    const int dim = with_angle ? 7 : 6;
+    float r[8], g[7];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = raw[(size_t)t * ld_raw + i];
+    for (int j = 0; j < dim; ++j) g[j] = d_box[(size_t)t * dim + j];
+    bl::bbox_decode_backward<float>(r, with_angle != 0, g, out);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d_raw[(size_t)t * ld_draw + i] = out[i];
+}
+
 }  // namespace ud3d
 
 using namespace ud3d;
+
+extern "C" int ud3d_head_backward(const float* raw, int ld_raw, const float* d_box, int with_angle, const float* d_cls, const int32_t* cols,
+                                  int n_cols, int T, float* d_raw, int ld_draw, float* d_logits, int ld_dlogits, int n_union,
+                                  void* stream) {
+  UD3D_CHECK_ARG(raw && d_raw && d_logits && ld_raw >= 8 && ld_draw >= 8 && T >= 0 && n_union > 0 && ld_dlogits >= n_union,
+                 "ud3d_head_backward: bad argument");
+  UD3D_CHECK_ARG(!d_cls || (cols && n_cols > 0 && n_cols <= n_union), "ud3d_head_backward: d_cls needs the column list");
+  if (T == 0) return UD3D_OK;
+  head_bwd_kernel<<<cdiv(T, 128), 128, 0, (cudaStream_t)stream>>>(raw, ld_raw, d_box, with_angle, d_cls, cols, n_cols, T, d_raw, ld_draw,
+                                                                d_logits, ld_dlogits, n_union);
+  UD3D_LAUNCH_CHECK();
+  return UD3D_OK;
+}
 
 extern "C" int ud3d_criterion_layer_grad(const ud3d_criterion_grad_args* a, void* stream) {
   UD3D_CHECK_ARG(a && a->logits && a->boxes && a->sums && a->scales && a->d_logits && a->d_boxes, "ud3d_criterion_layer_grad: NULL argument");

@@ -12,21 +12,57 @@ namespace ud3d {
 
 constexpr int kBnRowsPerBlock = 512;
 
-// block b: rows [b * 512, ...); thread t: channels t, t + 256, ... (coalesced along a row)
+// block b: rows [b * 512, ...).  C >= 256: thread t takes channels t, t + 256, ...  C < 256: the 256 threads form
+// RG = 256 / C row groups (thread t: channel t % C, rows r0 + t / C, + RG, ...), so that narrow maps (32 channels at the
+// finest level, the largest by rows) still use every thread and every row is read as full 128-byte lines; the groups'
+// sums are combined through shared memory in group order (fixed order: deterministic).
+__device__ __forceinline__ void bn_block_combine(double s, double q, int C, int RG, int c, int rg, int block, double* __restrict__ part) {
+  __shared__ double sh[2][256];
+  if (RG > 1) {
+    sh[0][threadIdx.x] = s;
+    sh[1][threadIdx.x] = q;
+    __syncthreads();
+    if (rg == 0 && c < C) {
+      for (int g = 1; g < RG; ++g) {
+        s += sh[0][g * C + c];
+        q += sh[1][g * C + c];
+      }
+    }
+  }
+  if (rg == 0 && c < C) {
+    part[((size_t)block * 2 + 0) * C + c] = s;
+    part[((size_t)block * 2 + 1) * C + c] = q;
+  }
+}
 __global__ void __launch_bounds__(256) bn_partial_sums_kernel(const float* __restrict__ x, int ld, int n, int C,
                                                               double* __restrict__ part) {
   const int r0 = blockIdx.x * kBnRowsPerBlock;
   const int r1 = min(n, r0 + kBnRowsPerBlock);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int r = r0; r < r1; ++r) {
+  if (C >= 256) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      double s = 0.0, q = 0.0;
+      for (int r = r0; r < r1; ++r) {
+        const double v = (double)x[(size_t)r * ld + c];
+        s += v;
+        q += v * v;
+      }
+      part[((size_t)blockIdx.x * 2 + 0) * C + c] = s;
+      part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
+    }
+    return;
+  }
+  const int RG = 256 / C;
+  const int rg = threadIdx.x / C, c = threadIdx.x - rg * C;
+  double s = 0.0, q = 0.0;
+  if (rg < RG) {
+#pragma unroll 4
+    for (int r = r0 + rg; r < r1; r += RG) {
       const double v = (double)x[(size_t)r * ld + c];
       s += v;
       q += v * v;
     }
-    part[((size_t)blockIdx.x * 2 + 0) * C + c] = s;
-    part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
   }
+  bn_block_combine(s, q, C, RG, c, rg, blockIdx.x, part);
 }
 // fixed-order sum of the partials: sums[0][c] = sum x, sums[1][c] = sum x^2
 __global__ void bn_final_sums_kernel(const double* __restrict__ part, int nblocks, int C, double* __restrict__ sums) {
@@ -38,12 +74,13 @@ __global__ void bn_final_sums_kernel(const double* __restrict__ part, int nblock
   sums[i] = s;
 }
 // torch.nn.(Sync)BatchNorm in training mode: biased variance normalises, unbiased variance updates running_var
-__global__ void bn_train_fold_kernel(const double* __restrict__ sums, double count, int C, const float* __restrict__ gamma,
+__global__ void bn_train_fold_kernel(const double* __restrict__ sums, double count_host, const double* __restrict__ count_dev, int C, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float eps, float momentum, float* running_mean,
                                      float* running_var, float* __restrict__ scale, float* __restrict__ shift,
                                      float* __restrict__ save_mean, float* __restrict__ save_invstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  const double count = count_dev ? *count_dev : count_host;
   const double mean = sums[c] / count;
   double var = sums[C + c] / count - mean * mean;
   var = var > 0.0 ? var : 0.0;
@@ -74,24 +111,44 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(const float* __rest
                                                              const float* __restrict__ invstd, int relu, double* __restrict__ part) {
   const int r0 = blockIdx.x * kBnRowsPerBlock;
   const int r1 = min(n, r0 + kBnRowsPerBlock);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  if (C >= 256) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+      double s = 0.0, q = 0.0;
+      for (int r = r0; r < r1; ++r) {
+        const float xv = x[(size_t)r * ld_x + c];
+        float g = da[(size_t)r * ld_da + c];
+        if (relu && !(fmaf(xv, sc, sh) > 0.f)) g = 0.f;
+        s += (double)g;
+        q += (double)g * (double)((xv - mu) * is);
+      }
+      part[((size_t)blockIdx.x * 2 + 0) * C + c] = s;
+      part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
+    }
+    return;
+  }
+  const int RG = 256 / C;                         // row groups, see bn_partial_sums_kernel
+  const int rg = threadIdx.x / C, c = threadIdx.x - rg * C;
+  double s = 0.0, q = 0.0;
+  if (rg < RG) {
     const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
-    double s = 0.0, q = 0.0;
-    for (int r = r0; r < r1; ++r) {
+#pragma unroll 4
+    for (int r = r0 + rg; r < r1; r += RG) {
       const float xv = x[(size_t)r * ld_x + c];
       float g = da[(size_t)r * ld_da + c];
       if (relu && !(fmaf(xv, sc, sh) > 0.f)) g = 0.f;
       s += (double)g;
       q += (double)g * (double)((xv - mu) * is);
     }
-    part[((size_t)blockIdx.x * 2 + 0) * C + c] = s;
-    part[((size_t)blockIdx.x * 2 + 1) * C + c] = q;
   }
+  bn_block_combine(s, q, C, RG, c, rg, blockIdx.x, part);
 }
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ x, int ld_x, const float* __restrict__ da, int ld_da, int n, int C,
                                     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-                                    const float* __restrict__ invstd, int relu, const double* __restrict__ sums, double count,
+                                    const float* __restrict__ invstd, int relu, const double* __restrict__ sums, double count_host,
+                                    const double* __restrict__ count_dev,
                                     float* __restrict__ dx, int ld_dx, int accumulate) {
+  const double count = count_dev ? fmax(*count_dev, 1.0) : count_host;
   const long long total = (long long)n * C;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(t / C), c = (int)(t - (long long)r * C);
@@ -430,9 +487,9 @@ int ud3d_bn_batch_sums(const float* x, int ld, int n, int C, double* sums, void*
 
 int ud3d_bn_train_fold(const double* sums, double count, int C, const float* gamma, const float* beta, float eps,
                        float momentum, float* running_mean, float* running_var, float* scale, float* shift,
-                       float* save_mean, float* save_invstd, void* stream) {
-  UD3D_CHECK_ARG(sums && scale && shift && C > 0 && count > 0.0, "ud3d_bn_train_fold: bad argument");
-  bn_train_fold_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, C, gamma, beta, eps, momentum, running_mean,
+                       float* save_mean, float* save_invstd, const double* count_dev, void* stream) {
+  UD3D_CHECK_ARG(sums && scale && shift && C > 0 && (count_dev || count > 0.0), "ud3d_bn_train_fold: bad argument");
+  bn_train_fold_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, count, count_dev, C, gamma, beta, eps, momentum, running_mean,
                                                                      running_var, scale, shift, save_mean, save_invstd);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
@@ -461,16 +518,16 @@ int ud3d_bn_backward_sums(const float* x, int ld_x, const float* da, int ld_da, 
 
 int ud3d_bn_backward_apply(const float* x, int ld_x, const float* da, int ld_da, int n, int C, const float* scale, const float* shift,
                            const float* mean, const float* invstd, int relu, const double* sums, double count, float* dx, int ld_dx,
-                           int accumulate, void* stream) {
+                           int accumulate, const double* count_dev, void* stream) {
   UD3D_CHECK_ARG(x && da && scale && shift && mean && invstd && sums && dx && C > 0 && n >= 0 && ld_x >= C && ld_da >= C && ld_dx >= C &&
-                     count > 0.0,
+                     (count_dev || count > 0.0),
                  "ud3d_bn_backward_apply: bad argument");
   if (n == 0) return UD3D_OK;
   long long total = (long long)n * C;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld_x, da, ld_da, n, C, scale, shift, mean, invstd, relu, sums, count, dx,
-                                                                ld_dx, accumulate);
+  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld_x, da, ld_da, n, C, scale, shift, mean, invstd, relu, sums, count, count_dev,
+                                                                dx, ld_dx, accumulate);
   UD3D_LAUNCH_CHECK();
   return UD3D_OK;
 }

@@ -173,7 +173,7 @@ class PackedWeight:
     """Weight in the kernel's shared-memory image.  ``w``: [C_out, K, C_in] fp32 (reference layout
     flattened: spconv [C_out,k,k,k,C_in]; nn.Linear [C_out,C_in] with K=1)."""
 
-    def __init__(self, w: torch.Tensor):
+    def __init__(self, w: torch.Tensor, ts: bool = True):
         if w.dim() == 2:
             w = w.unsqueeze(1)
         if w.dim() == 5:
@@ -183,7 +183,11 @@ class PackedWeight:
         nbytes = int(_L().ud3d_gemm_packed_weight_bytes(self.K, self.c_in, self.c_out))
         self.data = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         check(_L().ud3d_gemm_pack_weight(_p(w), self.K, self.c_in, self.c_out, _p(self.data), _stream()), "ud3d_gemm_pack_weight")
-        # second image in the K order of the kernel variant whose A operand goes through registers into TMEM
+        # second image in the K order of the kernel variant whose A operand goes through registers into TMEM (``ts``: the
+        # training step re-packs every weight every step and never uses that variant)
+        self.data_ts = None
+        if not ts:
+            return
         self.data_ts = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
         check(_L().ud3d_gemm_pack_weight_ts(_p(w), self.K, self.c_in, self.c_out, _p(self.data_ts), _stream()),
               "ud3d_gemm_pack_weight_ts")
@@ -242,7 +246,7 @@ def gemm(x: torch.Tensor, w: PackedWeight, *, table: Optional[torch.Tensor] = No
     c_in = w.c_in if not in_split else (w.c_in + 31) // 32 * 32     # operand form pads the last chunk with zeros
     assert out.stride(1) == 1 and out.shape[1] == w.c_out and x.shape[1] == c_in
     a = _gemm_args(x, w.K, c_in, w.c_out, n_out, table, tile_mask, out, in_scale, in_shift, in_relu, bias, act,
-                   residual, w.data.data_ptr(), in_split, no_raw, acts, row_perm, w.data_ts.data_ptr())
+                   residual, w.data.data_ptr(), in_split, no_raw, acts, row_perm, w.data_ts.data_ptr() if w.data_ts is not None else None)
     check(_L().ud3d_gemm_fwd(C.byref(a), _stream()), "ud3d_gemm_fwd")
     return out
 
@@ -523,6 +527,30 @@ def criterion_layer_grad(logits: torch.Tensor, boxes: torch.Tensor, gt_boxes: to
     return d_logits, d_boxes
 
 
+def head_backward(raw: torch.Tensor, d_box: Optional[torch.Tensor], with_angle: bool, d_cls: Optional[torch.Tensor],
+                  cols: torch.Tensor, d_raw: torch.Tensor, d_logits: torch.Tensor):
+    """Backward of one scene's head outputs (ud3d_head_backward): writes ``d_raw`` [T, 8] and ``d_logits`` [T, n_union]
+    (row slices of the packed buffers) from the gradients of the decoded boxes and of the gathered class columns."""
+    for t, nme in ((raw, "raw"), (d_raw, "d_raw"), (d_logits, "d_logits")):
+        if not t.is_cuda or t.dtype != torch.float32 or t.stride(1) != 1:
+            raise _lib.Ud3dError(f"head_backward: {nme} must be a CUDA fp32 matrix with unit column stride")
+    T = raw.shape[0]
+    if d_box is not None:
+        _req(d_box, torch.float32, "d_box")
+        if tuple(d_box.shape) != (T, 7 if with_angle else 6):
+            raise _lib.Ud3dError("head_backward: d_box must be [T, 7] with an angle and [T, 6] without")
+    _req(cols, torch.int32, "cols")
+    if d_cls is not None:
+        _req(d_cls, torch.float32, "d_cls")
+        if tuple(d_cls.shape) != (T, cols.numel()):
+            raise _lib.Ud3dError("head_backward: d_cls must be [T, len(cols)]")
+    if d_raw.shape[0] != T or d_logits.shape[0] != T or d_raw.shape[1] != 8:
+        raise _lib.Ud3dError("head_backward: d_raw must be [T, 8] and d_logits [T, n_union]")
+    check(_L().ud3d_head_backward(_p(raw), raw.stride(0), _p(d_box), 1 if with_angle else 0, _p(d_cls), _p(cols), cols.numel(), T,
+                                  _p(d_raw), d_raw.stride(0), _p(d_logits), d_logits.stride(0), d_logits.shape[1], _stream()),
+          "ud3d_head_backward")
+
+
 # ------------------------------------------------------------------ training side of the backbone
 def bn_batch_sums(x: torch.Tensor) -> torch.Tensor:
     """-> fp64 [2, C]: per-channel sum and sum of squares over the rows of ``x`` (deterministic)."""
@@ -536,7 +564,7 @@ def bn_batch_sums(x: torch.Tensor) -> torch.Tensor:
     return sums
 
 
-def bn_train_fold(sums: torch.Tensor, count: float, bn, update_running: bool = True):
+def bn_train_fold(sums: torch.Tensor, count: float, bn, update_running: bool = True, count_dev: Optional[torch.Tensor] = None):
     """Train-mode BatchNorm as (scale, shift) [+ (mean, invstd) for the backward pass]: ``bn`` is the nn.BatchNorm1d /
     SyncBatchNorm holding gamma, beta, eps, momentum and the running statistics (updated in place like torch)."""
     c = sums.shape[1]
@@ -549,30 +577,36 @@ def bn_train_fold(sums: torch.Tensor, count: float, bn, update_running: bool = T
     rv = bn.running_var if update_running else None
     mom = 0.1 if bn.momentum is None else float(bn.momentum)
     check(_L().ud3d_bn_train_fold(_p(sums), float(count), c, _p(bn.weight.detach()), _p(bn.bias.detach()), float(bn.eps), mom,
-                                  _p(rm), _p(rv), _p(scale), _p(shift), _p(mean), _p(invstd), _stream()), "ud3d_bn_train_fold")
+                                  _p(rm), _p(rv), _p(scale), _p(shift), _p(mean), _p(invstd), _p(count_dev), _stream()), "ud3d_bn_train_fold")
     if update_running and getattr(bn, "num_batches_tracked", None) is not None:
         bn.num_batches_tracked += 1
     return scale, shift, mean, invstd
 
 
-def sync_bn_sums(sums: torch.Tensor, count: float, group=None):
+def sync_bn_sums(sums: torch.Tensor, count: float, group=None, device_count: bool = False):
     """The SyncBatchNorm exchange (spconv_unet.py:119-121): ONE all-reduce of the 2C channel sums + the row count.  Pure
-    torch.distributed plumbing (device-agnostic: the gloo test in tests/test_sharding_gloo.py drives it on CPU tensors)."""
+    torch.distributed plumbing (device-agnostic: the gloo test in tests/test_sharding_gloo.py drives it on CPU tensors).
+    -> (sums, count), or with ``device_count`` (sums, local count, global count as a 1-element tensor or None when there is
+    nothing to exchange): the kernels then read the count on the device and the host never waits for the collective."""
     import torch.distributed as dist
+    count_dev = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         buf = torch.cat((sums.flatten(), sums.new_tensor([count])))
         dist.all_reduce(buf, group=group)
         sums = buf[:-1].view(2, -1).contiguous()
-        count = float(buf[-1].item())
-    return sums, count
+        if device_count:
+            count_dev = buf[-1:]
+        else:
+            count = float(buf[-1].item())
+    return (sums, count, count_dev) if device_count else (sums, count)
 
 
 def bn_train(x: torch.Tensor, bn, group=None, update_running: bool = True):
     """Batch statistics of ``x`` [N, C] (all active voxels of the batch) -> (scale, shift, mean, invstd).  With an
     initialised torch.distributed process group of more than one rank the sums and the row count are all-reduced first
-    (SyncBatchNorm, spconv_unet.py:119-121): ONE collective of 2C + 1 doubles per BatchNorm."""
-    sums, count = sync_bn_sums(bn_batch_sums(x), float(x.shape[0]), group)
-    return bn_train_fold(sums, count, bn, update_running)
+    (SyncBatchNorm, spconv_unet.py:119-121): ONE collective of 2C + 1 doubles per BatchNorm, no host synchronisation."""
+    sums, count, count_dev = sync_bn_sums(bn_batch_sums(x), float(x.shape[0]), group, device_count=x.is_cuda)
+    return bn_train_fold(sums, max(count, 1.0), bn, update_running, count_dev=count_dev)
 
 
 def bn_relu_apply(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, relu: bool = True) -> torch.Tensor:
@@ -600,13 +634,13 @@ def bn_relu_backward(x: torch.Tensor, d_act: torch.Tensor, scale, shift, mean, i
     ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=x.device)
     check(_L().ud3d_bn_backward_sums(_p(x), x.stride(0), _p(d_act), d_act.stride(0), n, c, _p(scale), _p(shift), _p(mean),
                                      _p(invstd), 1 if relu else 0, _p(sums), _p(ws), ws.numel(), _stream()), "ud3d_bn_backward_sums")
-    sums, count = sync_bn_sums(sums, float(n), group)
+    sums, count, count_dev = sync_bn_sums(sums, float(n), group, device_count=True)
     if dx is None:
         dx = torch.empty((n, c), dtype=torch.float32, device=x.device)
         accumulate = False
     check(_L().ud3d_bn_backward_apply(_p(x), x.stride(0), _p(d_act), d_act.stride(0), n, c, _p(scale), _p(shift), _p(mean),
                                       _p(invstd), 1 if relu else 0, _p(sums), float(max(count, 1.0)), _p(dx), dx.stride(0),
-                                      1 if accumulate else 0, _stream()), "ud3d_bn_backward_apply")
+                                      1 if accumulate else 0, _p(count_dev), _stream()), "ud3d_bn_backward_apply")
     return dx, sums[1].float(), sums[0].float()
 
 
@@ -701,4 +735,4 @@ def conv_dgrad(dy: torch.Tensor, weight: torch.Tensor, table_t: Optional[torch.T
     wt = w.permute(2, 1, 0)                                   # [C_in, K, C_out]
     if reverse_offsets:
         wt = wt.flip(1)
-    return gemm(dy, PackedWeight(wt.contiguous()), table=table_t, tile_mask=tile_mask_t, n_out=n_in)
+    return gemm(dy, PackedWeight(wt.contiguous(), ts=False), table=table_t, tile_mask=tile_mask_t, n_out=n_in)

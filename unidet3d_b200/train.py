@@ -53,7 +53,7 @@ def conv(tape: Tape, x: torch.Tensor, conv_mod: SparseConvWeight, K: int, table,
     s = h = mean = invstd = None
     if bn is not None:
         s, h, mean, invstd = ops.bn_train(x, bn, group=tape.group)
-    y = ops.gemm(x, ops.PackedWeight(conv_mod.weight), table=table, tile_mask=mask, n_out=n_out, in_scale=s, in_shift=h,
+    y = ops.gemm(x, ops.PackedWeight(conv_mod.weight, ts=False), table=table, tile_mask=mask, n_out=n_out, in_scale=s, in_shift=h,
                  in_relu=bn is not None, residual=residual, out=out)
     n_in = x.shape[0]
 
@@ -182,7 +182,7 @@ def _linear(tape: Tape, x: torch.Tensor, lin: torch.nn.Linear, act: Optional[str
     """y = act(x W^T + b) (+ residual); the pre-activation map is kept for the backward pass."""
     W = lin.weight if weight is None else weight
     b = lin.bias if bias is None else bias
-    pre = ops.gemm(x, ops.PackedWeight(W), bias=b.detach().float().contiguous(), residual=residual if act is None else None)
+    pre = ops.gemm(x, ops.PackedWeight(W, ts=False), bias=b.detach().float().contiguous(), residual=residual if act is None else None)
     y = pre if act is None else ops.activation_forward(pre, act)
     if act is not None and residual is not None:
         raise NotImplementedError("activation + residual does not occur in the encoder")
@@ -221,21 +221,6 @@ def _layernorm(tape: Tape, x: torch.Tensor, ln: torch.nn.LayerNorm) -> torch.Ten
     return y
 
 
-def _bbox_decode_torch(raw: torch.Tensor, centers: torch.Tensor, with_angle: bool) -> torch.Tensor:
-    """PredBBox's exp + ``_bbox_pred_to_bbox`` (encoder.py:109-111,241-283) in torch ops: used only to differentiate this
-    8-value-per-query element-wise map with autograd (the forward value comes from ud3d_bbox_decode)."""
-    p = torch.cat((torch.exp(raw[:, :6]), raw[:, 6:]), 1)
-    cx = centers[:, 0] + (p[:, 1] - p[:, 0]) / 2
-    cy = centers[:, 1] + (p[:, 3] - p[:, 2]) / 2
-    cz = centers[:, 2] + (p[:, 5] - p[:, 4]) / 2
-    if not with_angle:
-        return torch.stack([cx, cy, cz, p[:, 0] + p[:, 1], p[:, 2] + p[:, 3], p[:, 4] + p[:, 5]], -1)
-    scale = p[:, 0] + p[:, 1] + p[:, 2] + p[:, 3]
-    q = torch.exp(torch.sqrt(torch.pow(p[:, 6], 2) + torch.pow(p[:, 7], 2)))
-    alpha = 0.5 * torch.atan2(p[:, 6], p[:, 7])
-    return torch.stack((cx, cy, cz, scale / (1 + q), scale / (1 + q) * q, p[:, 5] + p[:, 4], alpha), dim=-1)
-
-
 def _head(tape: Tape, enc, Hq: torch.Tensor, centers: torch.Tensor, bounds, ds_idx):
     """encoder.py:165-201: out_norm -> class MLP (union of classes, per-dataset column gather) and box Linear + decode."""
     plan = enc._get_plan()
@@ -250,25 +235,18 @@ def _head(tape: Tape, enc, Hq: torch.Tensor, centers: torch.Tensor, bounds, ds_i
         bboxes.append(ops.bbox_decode(raw[a:b], centers[a:b], bool(enc.angles[j])))
 
     def bwd():
-        d_logits = torch.zeros_like(logits)
-        d_raw = torch.zeros_like(raw)
-        any_grad = False
+        grads = [(tape.grad(c), tape.grad(b)) for c, b in zip(cls_preds, bboxes)]
+        if all(dc is None and db is None for dc, db in grads):
+            return
+        d_logits = torch.empty_like(logits)
+        d_raw = torch.empty_like(raw)
         for i, j in enumerate(ds_idx):
             a, b = bounds[i], bounds[i + 1]
-            dc, db = tape.grad(cls_preds[i]), tape.grad(bboxes[i])
-            if dc is not None:
-                d_logits[a:b].index_add_(1, plan["cols"][j].long(), dc)
-                any_grad = True
-            if db is not None:
-                with torch.enable_grad():
-                    r = raw[a:b].detach().clone().requires_grad_(True)
-                    box = _bbox_decode_torch(r, centers[a:b], bool(enc.angles[j]))
-                    (gr,) = torch.autograd.grad(box, r, db)
-                d_raw[a:b] = gr
-                any_grad = True
-        if any_grad:
-            tape.add(logits, d_logits)
-            tape.add(raw, d_raw)
+            dc, db = grads[i]
+            ops.head_backward(raw[a:b], None if db is None else db.contiguous(), bool(enc.angles[j]),
+                              None if dc is None else dc.contiguous(), plan["cols"][j], d_raw[a:b], d_logits[a:b])
+        tape.add(logits, d_logits)
+        tape.add(raw, d_raw)
 
     tape.steps.append(bwd)
     return cls_preds, bboxes
@@ -442,6 +420,9 @@ def loss_backward(model, batch_inputs_dict, batch_data_samples, group=None, debu
             debug.update(outputs=out, pooled=pooled, gt_insts=li["gt_insts"])
         encoder_backward(tape, out, d_cls, d_box)        # replays the whole tape: encoder steps, then the backbone's
         mark("backbone_bwd")
+        # the closures hold the tape and the tape holds the closures: break the cycle now, or the activations of this step
+        # stay allocated until Python's cycle collector happens to run
+        tape.steps.clear(), tape.grads.clear(), tape.keep.clear(), tape.named.clear()
     return {"det_loss": loss}
 
 
