@@ -24,6 +24,9 @@ def _worker(rank, world, port, q):
     sums, count = ops.sync_bn_sums(torch.stack((x.sum(0), (x * x).sum(0))), float(x.shape[0]))
     mean = sums[0] / count
     var = sums[1] / count - mean * mean
+    # the variant the GPU path uses: the global row count stays a tensor (read by the kernels on the device, no host wait)
+    sums_d, local_count, count_t = ops.sync_bn_sums(torch.stack((x.sum(0), (x * x).sum(0))), float(x.shape[0]), device_count=True)
+    assert local_count == float(x.shape[0]) and count_t.shape == (1,) and float(count_t) == count and torch.equal(sums_d, sums)
     # data-parallel gradient exchange of the training side (unidet3d_b200/train.py): bucketed all-reduce + average
     from unidet3d_b200 import train
     ps = [torch.nn.Parameter(torch.zeros(s)) for s in ((3, 5), (7,), (2, 2, 2), (1000,))]
