@@ -58,3 +58,46 @@ def test_criterion_entry_point_argument_errors():
     assert lib.ud3d_criterion_workspace_bytes(3000, 40) >= 2 * 3000 * 4 + 40 * 4
     assert lib.ud3d_subm3_tile_order_workspace_bytes(1000) >= 65536 * 4 + 2000
     assert lib.ud3d_subm3_tile_order(None, 5, None, None, None, None, 0, None) == -1
+
+
+def test_training_entry_points_have_no_cpu_path_and_check_their_arguments():
+    """The training step's host logic: loss_backward needs train mode, the criterion gradients need iter_matcher=True
+    (every reference config), and the new ops refuse CPU tensors (no fallback)."""
+    import types
+    import unidet3d_b200 as u
+    from unidet3d_b200 import _lib, configs, ops, train
+    model = u.MODELS.build(configs.model_cfg(("scannet",))).eval()
+    with pytest.raises(RuntimeError, match="train"):
+        train.loss_backward(model, dict(points=[]), [])
+    crit = u.MODELS.build(configs.criterion_cfg(("scannet",)))
+    crit.iter_matcher = False
+    with pytest.raises(NotImplementedError):
+        train.criterion_backward(crit, dict(cls_preds=[], bboxes=[], aux_outputs=[]), [], [])
+    T, G = 8, 2
+    logits, boxes = torch.zeros(T, 19), torch.zeros(T, 6)
+    with pytest.raises(_lib.Ud3dError):
+        ops.criterion_layer_grad(logits, boxes, torch.zeros(G, 6), torch.zeros(G, dtype=torch.long), torch.zeros(T, G, dtype=torch.bool),
+                                 torch.zeros(4), torch.zeros(2), 0.1)
+    with pytest.raises(_lib.Ud3dError):
+        ops.head_backward(torch.zeros(T, 8), None, False, None, torch.zeros(19, dtype=torch.int32), torch.zeros(T, 8), torch.zeros(T, 19))
+    with pytest.raises(_lib.Ud3dError):
+        ops.attention_backward(torch.zeros(T, 768), torch.tensor([0, T], dtype=torch.int32), 8, torch.zeros(T, 256), torch.zeros(T, 256))
+    # the dataset-weight vector of a batch is cached per batch composition
+    w1 = crit.scene_weights(torch.zeros(2, 4), ["scannet", "scannet"])
+    assert w1 is crit.scene_weights(torch.zeros(2, 4), ["scannet", "scannet"]) and w1.tolist() == [1.0, 1.0]
+
+
+def test_synthetic_scannet_annotations_are_consistent():
+    """unidet3d_b200.synthetic.make_scannet_gt (bench.py --workload train_b8): instances are unions of superpoints, every
+    instance owns at least one, the per-point instance ids agree with the superpoint masks."""
+    import numpy as np
+    from unidet3d_b200.synthetic import make_scene, make_scannet_gt, SCENE_PRESETS
+    n, v, a, c = SCENE_PRESETS["tiny"]
+    pts, sp = make_scene(3, n, a, c)
+    labels, sp_masks, inst = make_scannet_gt(sp, 6, 11)
+    assert labels.shape == (6,) and sp_masks.shape == (6, int(sp.max()) + 1) and inst.shape == sp.shape
+    assert sp_masks.any(1).all() and sp_masks.sum(0).max() <= 1 and inst.min() >= -1 and inst.max() == 5
+    for k in range(6):
+        assert np.array_equal(inst == k, sp_masks[k][sp])
+    again = make_scannet_gt(sp, 6, 11)
+    assert all(np.array_equal(x, y) for x, y in zip((labels, sp_masks, inst), again))
