@@ -4,7 +4,7 @@ Run (build container only -- /root/reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,gt_prep_ref}.npz (all, or the ones named on the command line).  The reference modules are
+Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
 imported unmodified from /root/reference; their absent third-party imports
 (mmengine, mmdet3d, spconv, MinkowskiEngine, torch_scatter, mmcv) are replaced by
 minimal stand-ins defined here:
@@ -469,6 +469,82 @@ def gen_criterion():
           [[len(save.get(f"l{l}_iq{i}", [])) for i in range(len(names))] for l in range(3)])
 
 
+def gen_criterion_grad():
+    """GRADIENTS of the reference's own criterion.py (with axis_aligned_iou_loss.py) under torch.autograd: det_loss of a
+    3-scene axis-aligned batch (two datasets with different weights, a scene without GT, a GT with every query masked
+    out), final layer + 2 aux layers, differentiated w.r.t. every layer's class logits and boxes.  (Rotated boxes are
+    left out: the reference differentiates mmcv's CUDA-backed ``oriented_box_intersection_2d``, which is not installable
+    here -- the rotated DIoU derivative is checked against finite differences instead, tests/test_box_loss_host.py.)"""
+    import unidet3d.axis_aligned_iou_loss  # noqa: F401
+    import unidet3d.rotated_iou_loss  # noqa: F401
+    from unidet3d.criterion import UniDet3DCriterion
+    InstanceData = sys.modules["mmengine.structures"].InstanceData
+    Boxes = sys.modules["mmdet3d.structures"].DepthInstance3DBoxes
+    torch.manual_seed(33)
+    rng = np.random.default_rng(33)
+    datasets = ["scannet", "s3dis"]
+    diou = lambda t: dict(type=t, mode="diou", reduction="none")
+    simple, rotated = diou("UniDet3DAxisAlignedIoULoss"), diou("UniDet3DRotatedIoU3DLoss")
+    crit = UniDet3DCriterion(
+        matcher=dict(type="UniMatcher", costs=[dict(type="QueryClassificationCost", weight=0.5),
+                                               dict(type="BboxCostJointTraining", weight=2.0, loss_simple=simple,
+                                                    loss_rotated=rotated)]),
+        loss_weight=[0.5, 1.0], non_object_weight=0.1, iter_matcher=True, bbox_loss_simple=simple,
+        bbox_loss_rotated=rotated, datasets=datasets, datasets_weights=[1.0, 0.7], topk=[4, 3])
+    names = ["scannet", "s3dis", "scannet", "s3dis"]
+    T = [80, 60, 50, 45]
+    G = [6, 5, 0, 3]
+    C = {"scannet": 5, "s3dis": 4}
+    save = {"names": np.array(names), "datasets": np.array(datasets), "datasets_weights": np.array([1.0, 0.7]),
+            "topk": np.array([4, 3])}
+
+    def rand_boxes(n):
+        return torch.as_tensor(np.concatenate([rng.uniform(0.5, 3.5, (n, 3)), rng.uniform(0.3, 1.6, (n, 3))], 1).astype(np.float32))
+    insts = []
+    for i, nm in enumerate(names):
+        gt = rand_boxes(G[i])
+        labels = torch.as_tensor(rng.integers(0, C[nm], G[i]))
+        qm = torch.as_tensor(rng.random((G[i], T[i])) < 0.5)
+        if i == 3:
+            qm[1, :] = False                                   # a GT nobody may match: no pair from it
+        insts.append(InstanceData(labels_3d=labels, bboxes_3d=Boxes(gt, box_dim=6, with_yaw=False, origin=(0.5, 0.5, 0.5)),
+                                  query_masks=qm))
+        save.update({f"gt_boxes{i}": gt.numpy(), f"gt_labels{i}": labels.numpy(), f"qmask{i}": qm.numpy()})
+
+    def layer():
+        cls, box = [], []
+        for i, nm in enumerate(names):
+            cls.append((torch.randn(T[i], C[nm] + 1) * 1.5).requires_grad_(True))
+            b = rand_boxes(T[i])
+            if G[i]:
+                b[:G[i]] = insts[i].bboxes_3d.tensor + 0.05 * torch.randn(G[i], 6)
+                b[G[i]:2 * G[i]] = insts[i].bboxes_3d.tensor + 0.2 * torch.randn(G[i], 6)
+            box.append(b.requires_grad_(True))
+        return dict(cls_preds=cls, bboxes=box)
+    layers = [layer(), layer(), layer()]
+    pred = dict(layers[0], aux_outputs=layers[1:])
+    out = crit(pred, insts, names)
+    out["det_loss"].backward()
+    save["det_loss"] = out["det_loss"].detach().numpy()
+    n_pairs = []
+    for l, lay in enumerate(layers):
+        for i in range(len(names)):
+            save[f"l{l}_cls{i}"], save[f"l{l}_box{i}"] = lay["cls_preds"][i].detach().numpy(), lay["bboxes"][i].detach().numpy()
+            save[f"l{l}_dcls{i}"] = lay["cls_preds"][i].grad.numpy()
+            g = lay["bboxes"][i].grad
+            save[f"l{l}_dbox{i}"] = (g if g is not None else torch.zeros_like(lay["bboxes"][i])).numpy()
+            if G[i]:
+                pi = InstanceData(scores=lay["cls_preds"][i].detach(), bboxes=lay["bboxes"][i].detach())
+                gi = InstanceData(labels=insts[i].labels_3d, query_masks=insts[i].query_masks, bboxes=insts[i].bboxes_3d.tensor)
+                iq, ig = crit.matcher(pi, gi, crit.topk[datasets.index(names[i])])
+                save[f"l{l}_iq{i}"], save[f"l{l}_ig{i}"] = iq.numpy(), ig.numpy()
+                n_pairs.append(len(iq))
+    np.savez_compressed(os.path.join(HERE, "criterion_grad_ref.npz"), **save)
+    print("criterion_grad_ref.npz det_loss", float(out["det_loss"]), "pairs", n_pairs,
+          "max |dcls|", max(float(np.abs(save[k]).max()) for k in save if "_dcls" in k),
+          "max |dbox|", max(float(np.abs(save[k]).max()) for k in save if "_dbox" in k))
+
+
 def gen_gt_prep():
     """The reference's GT-preparation transforms (unidet3d/transforms_3d.py) on synthetic masks."""
     from unidet3d.transforms_3d import PointDetClassMappingScanNet, PointDetClassMappingS3DIS, PointSample_
@@ -653,6 +729,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "gt_prep", "augment", "evaluate"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "gt_prep", "augment", "evaluate"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()

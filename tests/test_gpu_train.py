@@ -613,3 +613,31 @@ def test_criterion_gradients_rotated_boxes(tmp_path):
         assert torch.allclose(db[0].cpu(), want, atol=2e-6, rtol=2e-3), float((db[0].cpu() - want).abs().max())
         assert float(want[:, 6].abs().max()) > 0
     assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+
+
+def test_criterion_gradients_vs_reference_fixture():
+    """The library's criterion gradients (GPU matcher + ud3d_criterion_layer_grad) against the gradients of the
+    REFERENCE's own criterion.py under torch.autograd (tests/golden/criterion_grad_ref.npz, generated in the build
+    container): det_loss and d det_loss / d (logits, boxes) of three layers x four scenes (two datasets, a scene without
+    GT, a GT no query may match, queries matched to several GTs)."""
+    import types
+    import criterion_grad_case as case
+    from unidet3d_b200 import train
+    from unidet3d_b200.criterion import UniDet3DCriterion
+
+    def run(names, layers, gts, cfg):
+        crit = UniDet3DCriterion(matcher=dict(costs=[dict(type="QueryClassificationCost", weight=cfg["w_cls"]),
+                                                     dict(type="BboxCostJointTraining", weight=cfg["w_box"])]),
+                                 loss_weight=cfg["loss_weight"], non_object_weight=cfg["non_object_weight"], iter_matcher=True,
+                                 bbox_loss_simple=dict(mode="diou"), bbox_loss_rotated=dict(mode="diou"), datasets=cfg["datasets"],
+                                 datasets_weights=cfg["datasets_weights"], topk=cfg["topk"])
+        insts = [types.SimpleNamespace(labels_3d=g["labels"].to(DEV), query_masks=g["query_masks"].to(DEV),
+                                       bboxes_3d=types.SimpleNamespace(gravity_center=g["boxes"][:, :3].to(DEV), tensor=g["boxes"].to(DEV),
+                                                                       with_yaw=False)) for g in gts]
+        dbg = {}
+        loss, d_cls, d_box = train.criterion_backward(crit, _to_dev(dict(layers[0], aux_outputs=layers[1:])), insts, names, debug=dbg)
+        # criterion_backward lists the heads aux first, final last; the fixture (and the checker) final first
+        order = [len(layers) - 1] + list(range(len(layers) - 1))
+        return loss, [d_cls[k] for k in order], [d_box[k] for k in order], [dbg["matches"][k] for k in order]
+
+    case.check(run)
