@@ -8,8 +8,9 @@ Same registry name and constructor arguments as the reference; ``input_conv.0.we
 Differences from the reference, all documented in DESIGN.md:
   * ``predict`` post-processes EVERY scene of the batch (the reference reads scene 0 only,
     unidet3d.py:498-502; scene 0 is identical);
-  * ``loss`` returns the VALUE of the training loss (matcher + criterion on the GPU); gradients and train-mode
-    BatchNorm statistics are not implemented yet.
+  * ``loss`` returns the VALUE of the training loss (matcher + criterion on the GPU) without an autograd graph; the
+    training step -- the same forward with a tape, then the library's own backward pass -- is
+    ``unidet3d_b200.train.loss_backward`` / ``train_step``.
 """
 from __future__ import annotations
 
@@ -134,7 +135,7 @@ class UniDet3D(nn.Module):
         lv0 = x.pyramid.levels[0]
         if self.training:
             # train mode: batch-statistics BatchNorm everywhere (SpConvUNet._forward_level_train) incl. the output layer
-            # (unidet3d.py:104-107, 129); forward values only
+            # (unidet3d.py:104-107, 129); the taped version with the backward pass is train.backbone_forward
             f = ops.gemm(x.features, ops.PackedWeight(self.input_conv[0].weight), table=lv0.subm, tile_mask=lv0.subm_mask)
             y, _ = self.unet(x.replace_feature(f)) if self.unet.return_blocks else (self.unet(x.replace_feature(f)), None)
             sc, sh, _, _ = ops.bn_train(y.features, self.output_layer[0])
@@ -530,9 +531,9 @@ class UniDet3D(nn.Module):
 
         GT boxes from instance masks (``get_bboxes_by_masks``) or shifted GT boxes, superpoint centres, distance
         targets (``get_targets``), backbone + pooling, query selection, the encoder with all seven heads, and the
-        criterion, every stage on our kernels.  Not implemented yet: gradients, and the
-        batch statistics of train-mode (Sync)BatchNorm -- the backbone runs with the running statistics, so this is
-        the validation-style loss of the current weights.  ``elastic_coords`` (the ElasticTransfrom augmentation's
+        criterion, every stage on our kernels.  ``self.training`` decides the BatchNorm mode (train: batch statistics +
+        running-stat updates; eval: running statistics = the validation-style loss).  The result carries no autograd
+        graph: gradients come from ``unidet3d_b200.train.loss_backward``.  ``elastic_coords`` (the ElasticTransfrom augmentation's
         side input, unidet3d.py:349) replaces the voxel coordinates like in the reference."""
         if self.criterion is None:
             raise RuntimeError("UniDet3D was built without a criterion config")

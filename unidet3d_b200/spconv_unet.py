@@ -313,8 +313,8 @@ class SpConvUNet(nn.Module):
     #      voxels of the global batch; running statistics updated with momentum 0.1).  A BatchNorm's statistics need the
     #      producer's complete output, so the producer-epilogue fusion of the eval executor does not apply: each conv
     #      writes its fp32 map, ud3d_bn_batch_sums reduces it (+ one all-reduce under torch.distributed), and the
-    #      normalisation + ReLU is folded into the CONSUMER's operand load.  Forward values only -- the backward kernels
-    #      available so far are the weight / input gradients of the convolutions (ops.conv_wgrad / ops.conv_dgrad).
+    #      normalisation + ReLU is folded into the CONSUMER's operand load.  Forward values only here -- the same op sequence
+    #      with a tape and the complete backward pass is unidet3d_b200/train.py (unet_forward / backbone_backward).
     @staticmethod
     def _block_train(blk: ResidualBlock, x, lv):
         cb = blk.conv_branch

@@ -11,8 +11,8 @@ torch.library custom ops"), namespace ``unidet3d_b200``:
 Each op has a fake (meta) implementation, so FakeTensor tracing / ``torch.compile`` graphs and export see the output
 shapes without running a kernel; the real implementations launch on the current stream and are CUDA-graph capturable
 (no host synchronisation, workspaces allocated through the caching allocator).  They are thin wrappers over
-``unidet3d_b200.ops`` -- the module classes call ``ops`` directly.  Autograd formulas are not registered (the backward
-kernels that exist -- ``ops.conv_wgrad`` / ``ops.conv_dgrad`` -- are exposed as functions, not yet as ``backward``).
+``unidet3d_b200.ops`` -- the module classes call ``ops`` directly.  Autograd formulas are not registered: the backward
+pass is the library's own tape (``unidet3d_b200.train``), not torch.autograd.
 """
 from __future__ import annotations
 
