@@ -4,7 +4,7 @@ Run (build container only -- /root/reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
+Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,backward_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
 imported unmodified from /root/reference; their absent third-party imports
 (mmengine, mmdet3d, spconv, MinkowskiEngine, torch_scatter, mmcv) are replaced by
 minimal stand-ins defined here:
@@ -545,6 +545,79 @@ def gen_criterion_grad():
           "max |dbox|", max(float(np.abs(save[k]).max()) for k in save if "_dbox" in k))
 
 
+def gen_backward():
+    """PARAMETER GRADIENTS of the reference's own modules under torch.autograd, in train mode:
+    * UniDet3DEncoder (encoder.py; all num_layers + 1 heads are evaluated in train mode): loss = sum of randomly weighted
+      class logits and boxes of every head -> gradient of every parameter and of the input features;
+    * SpConvUNet (spconv_unet.py over the dense spconv stand-in; BatchNorm with BATCH statistics): loss = sum of randomly
+      weighted output features -> gradient of every conv weight / BatchNorm affine and of the input features.
+    The oracle under autograd must reproduce them (tests/test_oracle_golden.py): the backward passes of the library are
+    compared with autograd through that oracle."""
+    from unidet3d.encoder import UniDet3DEncoder
+    from unidet3d.spconv_unet import SpConvUNet
+    torch.manual_seed(17)
+    classes = [["chair", "table", "sofa"], ["table", "board"], ["bed", "chair", "oven", "sink"]]
+    cfg = dict(num_layers=2, datasets_classes=classes, in_channels=8, d_model=64, num_heads=2, hidden_dim=128,
+               dropout=0.0, activation_fn="gelu", datasets=["scannet", "s3dis", "arkitscenes"], angles=[False, False, True])
+    m = UniDet3DEncoder(**cfg).train()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    T = [33, 19, 41]
+    names = ["scannet", "arkitscenes", "s3dis"]
+    x = [torch.randn(t, 8).requires_grad_(True) for t in T]
+    c = [torch.randn(t, 3) for t in T]
+    out = m(x, c, names)
+    heads = out["aux_outputs"] + [dict(cls_preds=out["cls_preds"], bboxes=out["bboxes"])]
+    assert len(heads) == 3
+    save = {"enc_sd." + k: v for k, v in t2n(m.state_dict()).items()}
+    loss = 0.0
+    for h, hd in enumerate(heads):
+        for i in range(3):
+            gc, gb = torch.randn_like(hd["cls_preds"][i]), 0.1 * torch.randn_like(hd["bboxes"][i])
+            save[f"enc_gc{h}_{i}"], save[f"enc_gb{h}_{i}"] = gc.numpy(), gb.numpy()
+            loss = loss + (hd["cls_preds"][i] * gc).sum() + (hd["bboxes"][i] * gb).sum()
+    loss.backward()
+    for i in range(3):
+        save[f"enc_x{i}"], save[f"enc_c{i}"], save[f"enc_dx{i}"] = x[i].detach().numpy(), c[i].numpy(), x[i].grad.numpy()
+    for k, p in m.named_parameters():
+        save["enc_grad." + k] = p.grad.numpy()
+    save["enc_names"] = np.array(names)
+
+    torch.manual_seed(19)
+    planes = [8, 16, 24]
+    u = SpConvUNet(planes, return_blocks=True).train()
+    with torch.no_grad():
+        for mod in u.modules():
+            if isinstance(mod, nn.BatchNorm1d):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.1)
+    shape = [20, 18, 13]
+    rng = np.random.default_rng(5)
+    coords = []
+    for b in range(2):
+        n = 500
+        xy = rng.integers(0, [shape[0], shape[1]], (n, 2))
+        z = np.clip((0.3 * xy[:, 0] + rng.integers(0, 3, n)).astype(np.int64), 0, shape[2] - 1)
+        cc = np.unique(np.concatenate([np.concatenate([xy, z[:, None]], 1), rng.integers(0, shape, (150, 3))]), axis=0)
+        cc = cc[rng.permutation(len(cc))]
+        coords.append(np.concatenate([np.full((len(cc), 1), b), cc], 1))
+    coords = torch.as_tensor(np.concatenate(coords), dtype=torch.int32)
+    feats = torch.randn(len(coords), planes[0]).requires_grad_(True)
+    sd0 = {k: v.clone() for k, v in u.state_dict().items()}           # before the forward updates the running statistics
+    y, _ = u(SparseConvTensor(feats, coords, shape, 2))
+    R = torch.randn_like(y.features)
+    (y.features * R).sum().backward()
+    save.update({"unet_sd." + k: v.numpy() for k, v in sd0.items()})
+    save.update(unet_coords=coords.numpy(), unet_feats=feats.detach().numpy(), unet_shape=np.array(shape), unet_R=R.numpy(),
+                unet_out=y.features.detach().numpy(), unet_dfeats=feats.grad.numpy())
+    for k, p in u.named_parameters():
+        save["unet_grad." + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "backward_ref.npz"), **save)
+    print("backward_ref.npz: encoder", sum(1 for k in save if k.startswith("enc_grad.")), "parameter gradients; unet",
+          sum(1 for k in save if k.startswith("unet_grad.")), "parameter gradients,", len(coords), "voxels")
+
+
 def gen_gt_prep():
     """The reference's GT-preparation transforms (unidet3d/transforms_3d.py) on synthetic masks."""
     from unidet3d.transforms_3d import PointDetClassMappingScanNet, PointDetClassMappingS3DIS, PointSample_
@@ -729,6 +802,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "gt_prep", "augment", "evaluate"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "backward", "gt_prep", "augment", "evaluate"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "backward": gen_backward, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()

@@ -17,7 +17,7 @@ def _load(golden_dir, name):
 
 
 def _relerr(a, b):
-    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    a, b = torch.as_tensor(a).detach().double(), torch.as_tensor(b).detach().double()
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
 
 
@@ -183,3 +183,58 @@ def test_criterion_edge_cases_match_reference(golden_dir, tag):
     assert np.array_equal(iq.numpy(), g[f"e_{tag}_iq"]) and np.array_equal(ig.numpy(), g[f"e_{tag}_ig"])
     loss, _ = oc.layer_loss([cls], [box], [gt], ["scannet"], cfg)
     assert abs(float(loss) - float(g[f"e_{tag}_loss"])) < 1e-5 * max(1.0, abs(float(g[f"e_{tag}_loss"])))
+
+
+def test_encoder_parameter_gradients_match_reference_module_under_autograd(golden_dir):
+    """backward_ref.npz: the reference's UniDet3DEncoder in train mode (all three heads), loss = randomly weighted logits
+    and boxes, torch.autograd -> the oracle under autograd gives the same gradient for every parameter and input."""
+    g = _load(golden_dir, "backward_ref.npz")
+    sd = {k[len("enc_sd."):]: torch.as_tensor(g[k]).clone().requires_grad_(torch.as_tensor(g[k]).is_floating_point())
+          for k in g.files if k.startswith("enc_sd.")}
+    classes = [["chair", "table", "sofa"], ["table", "board"], ["bed", "chair", "oven", "sink"]]
+    cfg = dict(num_layers=2, num_heads=2, activation_fn="gelu", datasets=["scannet", "s3dis", "arkitscenes"],
+               datasets_classes=classes, angles=[False, False, True])
+    x = [torch.as_tensor(g[f"enc_x{i}"]).clone().requires_grad_(True) for i in range(3)]
+    c = [torch.as_tensor(g[f"enc_c{i}"]) for i in range(3)]
+    out = oenc.encoder_forward(sd, cfg, x, c, [str(n) for n in g["enc_names"]], all_heads=True)
+    heads = out["aux_outputs"] + [dict(cls_preds=out["cls_preds"], bboxes=out["bboxes"])]
+    loss = 0.0
+    for h, hd in enumerate(heads):
+        for i in range(3):
+            loss = loss + (hd["cls_preds"][i] * torch.as_tensor(g[f"enc_gc{h}_{i}"])).sum() + (hd["bboxes"][i] * torch.as_tensor(g[f"enc_gb{h}_{i}"])).sum()
+    loss.backward()
+    names = [k[len("enc_grad."):] for k in g.files if k.startswith("enc_grad.")]
+    assert len(names) == 36
+    for k in names:
+        assert sd[k].grad is not None, k
+        assert _relerr(sd[k].grad, g["enc_grad." + k]) < 2e-4, (k, _relerr(sd[k].grad, g["enc_grad." + k]))
+    for i in range(3):
+        assert _relerr(x[i].grad, g[f"enc_dx{i}"]) < 2e-4
+
+
+def test_unet_parameter_gradients_match_reference_module_under_autograd(golden_dir):
+    """backward_ref.npz: the reference's SpConvUNet in TRAIN mode (BatchNorm batch statistics) over the dense conv3d stand-in,
+    loss = randomly weighted output features -> the oracle (gather / mm / index_add convs, F.batch_norm(training=True))
+    under autograd gives the same output, the same gradient for all 74 parameters and for the input features."""
+    from oracle import spconv as ospconv
+    g = _load(golden_dir, "backward_ref.npz")
+    sd = {}
+    for k in g.files:
+        if k.startswith("unet_sd."):
+            t = torch.as_tensor(g[k]).clone()
+            track = t.is_floating_point() and not k.endswith(("running_mean", "running_var"))
+            sd[k[len("unet_sd."):]] = t.requires_grad_(True) if track else t
+    feats = torch.as_tensor(g["unet_feats"]).clone().requires_grad_(True)
+    levels = ounet.build_pyramid(g["unet_coords"], g["unet_shape"], 3)
+    ospconv.TRAIN_MODE = True
+    try:
+        y = ounet.unet_forward(sd, feats, levels)
+    finally:
+        ospconv.TRAIN_MODE = False
+    assert _relerr(y, g["unet_out"]) < 2e-5
+    (y * torch.as_tensor(g["unet_R"])).sum().backward()
+    names = [k[len("unet_grad."):] for k in g.files if k.startswith("unet_grad.")]
+    assert len(names) == 74
+    worst = max((_relerr(sd[k].grad, g["unet_grad." + k]), k) for k in names)
+    assert worst[0] < 1e-3, worst
+    assert _relerr(feats.grad, g["unet_dfeats"]) < 1e-3
