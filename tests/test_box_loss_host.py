@@ -105,3 +105,43 @@ def test_bbox_decode_backward_vs_torch_autograd(lib, with_angle):
     assert np.allclose(got, raw.grad.numpy(), rtol=1e-4, atol=1e-5), np.abs(got - raw.grad.numpy()).max()
     if not with_angle:
         assert not got[:, 6:].any()
+
+
+def test_rotated_diou_invariances_and_regimes(lib):
+    """Size-independent properties of the rotated DIoU templates: translating both boxes changes nothing; a yaw of
+    alpha + pi is the same rectangle; swapping (w, h) together with alpha + pi/2 keeps the geometry (only the reference's
+    (x, y, w) centre penalty sees the swap, so that is checked with equal w on both sides); disjoint pairs have zero
+    intersection gradient but a non-zero centre-penalty gradient; a box inside the other has IoU = volume ratio."""
+    rng = np.random.default_rng(7)
+    p, t = _boxes(rng, 200, 7)
+    base, gbase = _call(lib, "bl_pair_loss_grad_f64", p, t, np.float64)
+    shift = np.zeros(7)
+    shift[:3] = (3.25, -1.5, 0.75)
+    moved, gmoved = _call(lib, "bl_pair_loss_grad_f64", p + shift, t + shift, np.float64)
+    assert np.allclose(moved, base, atol=1e-9) and np.allclose(gmoved, gbase, atol=1e-7)
+    turn = np.zeros(7)
+    turn[6] = np.pi
+    flipped, gflipped = _call(lib, "bl_pair_loss_grad_f64", p + turn, t, np.float64)
+    assert np.allclose(flipped, base, atol=1e-9) and np.allclose(gflipped, gbase, atol=1e-6)
+    # w <-> h with a quarter turn, on pairs with the same w (r2's third term is (w_p - w_t)^2 in the reference)
+    p2, t2 = p.copy(), t.copy()
+    p2[:, 3] = t2[:, 3] = 0.9
+    p2[:, 4] = t2[:, 4] = 0.9            # squares in BEV: the swap is then exactly a quarter turn
+    a = _call(lib, "bl_pair_loss_f64", p2, t2, np.float64, with_grad=False)
+    q = p2.copy()
+    q[:, 6] += np.pi / 2
+    assert np.allclose(_call(lib, "bl_pair_loss_f64", q, t2, np.float64, with_grad=False), a, atol=1e-9)
+    # disjoint: loss = 1 + r2 / c2 > 1, gradient w.r.t. the yaw comes from the enclosing box only
+    far = p.copy()
+    far[:, :2] = t[:, :2] + 10.0
+    lf, gf = _call(lib, "bl_pair_loss_grad_f64", far, t, np.float64)
+    assert (lf > 1.0).all() and (np.abs(gf[:, :2]).max(1) > 0).all()
+    # containment: same centre and yaw, every size of p half of t -> IoU = 1/8, no centre penalty except (w_p - w_t)^2 / c2
+    inner = t.copy()
+    inner[:, 3:6] *= 0.5
+    li = _call(lib, "bl_pair_loss_f64", inner, t, np.float64, with_grad=False)
+    c2 = t[:, 3] ** 2 + t[:, 4] ** 2 + t[:, 5] ** 2
+    # the enclosing box of two concentric, equally rotated rectangles is the larger one's axis-aligned hull, so c2 is at
+    # least |size|^2: bound the penalty instead of restating it
+    pen = (0.5 * t[:, 3]) ** 2 / c2
+    assert (li >= 1 - 0.125 - 1e-9).all() and (li <= 1 - 0.125 + pen + 1e-9).all()
