@@ -4,7 +4,7 @@ Run (build container only -- /root/reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,backward_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
+Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,backward_ref,train_step_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
 imported unmodified from /root/reference; their absent third-party imports
 (mmengine, mmdet3d, spconv, MinkowskiEngine, torch_scatter, mmcv) are replaced by
 minimal stand-ins defined here:
@@ -618,6 +618,139 @@ def gen_backward():
           sum(1 for k in save if k.startswith("unet_grad.")), "parameter gradients,", len(coords), "voxels")
 
 
+def _install_me_standin():
+    """MinkowskiEngine stand-in for UniDet3D.collate (unidet3d.py:136-176): ``batch_sparse_collate`` floors the coordinates and
+    prepends the batch index, ``TensorField.sparse()`` keeps one row per distinct coordinate with the UNWEIGHTED AVERAGE of its
+    points' features (ME's default quantisation mode), ``inverse_mapping`` maps every point to its voxel row.  Voxel rows come
+    out in ascending (b, x, y, z) order (ME's own order is hash-defined).  numpy ``unique``: shares no code with the oracle."""
+    class _Sparse:
+        def __init__(self, coordinates, features):
+            self.coordinates, self.features, self.coordinate_map_key = coordinates, features, object()
+
+    class TensorField:
+        def __init__(self, features, coordinates):
+            self.features, self.coordinates = features, coordinates
+
+        def sparse(self):
+            uniq, inv = np.unique(self.coordinates.long().numpy(), axis=0, return_inverse=True)
+            inv = torch.as_tensor(inv.reshape(-1)).long()
+            cnt = torch.zeros(len(uniq)).index_add_(0, inv, torch.ones(len(inv)))
+            feats = torch.zeros(len(uniq), self.features.shape[1]).index_add_(0, inv, self.features) / cnt[:, None]
+            self._inv = inv
+            return _Sparse(torch.as_tensor(uniq).int(), feats)
+
+        def inverse_mapping(self, key):
+            return self._inv
+
+    def batch_sparse_collate(data):
+        cs, fs = [], []
+        for b, (c, f) in enumerate(data):
+            cs.append(torch.cat((torch.full((len(c), 1), b, dtype=torch.int32), torch.floor(c).int()), 1))
+            fs.append(f)
+        return torch.cat(cs), torch.cat(fs)
+    me = sys.modules["MinkowskiEngine"]
+    me.TensorField = TensorField
+    me.utils = types.SimpleNamespace(batch_sparse_collate=batch_sparse_collate)
+
+
+def gen_train_step():
+    """The reference's own ``UniDet3D.loss`` (unidet3d.py:277-364) END TO END in train mode under torch.autograd: GT boxes by
+    instance masks (scannet scene) / shifted GT boxes + distance targets (3rscan scene), collate (ME stand-in), SpConvUNet over
+    the dense spconv stand-in with batch-statistics BatchNorm, superpoint pooling, the encoder with all heads, the criterion
+    -> det_loss and the gradient of EVERY parameter of the detector.  The oracle pipeline under autograd must reproduce them
+    (tests/test_oracle_golden.py), which pins the composition the GPU training step is compared with."""
+    import unidet3d.axis_aligned_iou_loss  # noqa: F401
+    import unidet3d.rotated_iou_loss  # noqa: F401
+    import unidet3d.criterion  # noqa: F401
+    import unidet3d.encoder  # noqa: F401
+    import unidet3d.spconv_unet  # noqa: F401
+    from unidet3d.unidet3d import UniDet3D
+    from unidet3d_b200.synthetic import make_scene, SCENE_PRESETS
+    _install_me_standin()
+    InstanceData = sys.modules["mmengine.structures"].InstanceData
+    Boxes = sys.modules["mmdet3d.structures"].DepthInstance3DBoxes
+    MODELS = sys.modules["mmdet3d.registry"].MODELS
+    torch.manual_seed(41)
+    rng = np.random.default_rng(41)
+    datasets = ["scannet", "3rscan"]
+    classes = [["chair", "table", "sofa", "bed", "sink"], ["table", "board", "bed", "oven"]]
+    planes, voxel = [8, 16, 24], 0.05
+    diou = lambda t: dict(type=t, mode="diou", reduction="none")
+    simple, rotated = diou("UniDet3DAxisAlignedIoULoss"), diou("UniDet3DRotatedIoU3DLoss")
+    cfg = dict(
+        backbone=dict(type="SpConvUNet", num_planes=planes, return_blocks=True),
+        decoder=dict(type="UniDet3DEncoder", num_layers=2, datasets_classes=classes, in_channels=planes[0], d_model=64, num_heads=2,
+                     hidden_dim=128, dropout=0.0, activation_fn="gelu", datasets=datasets, angles=[False, False]),
+        criterion=dict(type="UniDet3DCriterion", datasets=datasets, datasets_weights=[1.0, 0.7], bbox_loss_simple=simple,
+                       bbox_loss_rotated=rotated,
+                       matcher=dict(type="UniMatcher", costs=[dict(type="QueryClassificationCost", weight=0.5),
+                                                              dict(type="BboxCostJointTraining", weight=2.0, loss_simple=simple,
+                                                                   loss_rotated=rotated)]),
+                       loss_weight=[0.5, 1.0], non_object_weight=0.1, topk=[3, 2], iter_matcher=True))
+    det = object.__new__(UniDet3D)                       # the constructor's body (unidet3d.py:76-94) without mmengine's BaseModel
+    nn.Module.__init__(det)
+    det.unet, det.decoder, det.criterion = MODELS.build(cfg["backbone"]), MODELS.build(cfg["decoder"]), MODELS.build(cfg["criterion"])
+    det.voxel_size, det.min_spatial_shape, det.query_thr = voxel, 32, 3000
+    det.use_superpoints, det.bbox_by_mask, det.target_by_distance, det.fast_nms = [True, False], [True, False], [False, True], [True, True]
+    det.train_cfg, det.test_cfg, det.use_sync_bn = types.SimpleNamespace(topk=4), None, True
+    det._init_layers(6, planes[0])
+    with torch.no_grad():
+        for mod in det.modules():
+            if isinstance(mod, nn.BatchNorm1d):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.1)
+        for k, p in det.decoder.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    det.train()
+    n, _, area, cell = SCENE_PRESETS["tiny"]
+    scenes = [make_scene(300 + i, n, area, cell) for i in range(2)]
+    names = ["scannet", "3rscan"]
+    save = {"names": np.array(names), "voxel_size": np.array(voxel), "planes": np.array(planes)}
+    samples, pts_in = [], []
+    for i, (pts, sp) in enumerate(scenes):
+        P, S = torch.as_tensor(pts), torch.as_tensor(sp)
+        n_sp = int(sp.max()) + 1
+        save[f"points{i}"], save[f"sp{i}"] = pts, sp
+        if names[i] == "scannet":
+            G = 5
+            sp_inst = rng.integers(-1, G, n_sp)
+            sp_inst[:G] = np.arange(G)
+            inst = sp_inst[sp]
+            labels = rng.integers(0, 5, G)
+            sp_masks = sp_inst[None, :] == np.arange(G)[:, None]
+            gi = InstanceData(labels_3d=torch.as_tensor(labels), sp_masks=torch.as_tensor(sp_masks))
+            seg = types.SimpleNamespace(sp_pts_mask=S.clone(), pts_instance_mask=torch.as_tensor(inst))
+            save.update({f"inst{i}": inst, f"labels{i}": labels, f"sp_masks{i}": sp_masks})
+        else:
+            G = 4
+            lo, hi = pts[:, :3].min(0), pts[:, :3].max(0)
+            gt = np.concatenate([rng.uniform(lo, hi, (G, 3)), rng.uniform(0.3, 1.0, (G, 3))], 1).astype(np.float32)
+            labels = rng.integers(0, 4, G)
+            gi = InstanceData(labels_3d=torch.as_tensor(labels), bboxes_3d=Boxes(torch.as_tensor(gt), box_dim=6, with_yaw=False,
+                                                                                origin=(0.5, 0.5, 0.5)))
+            seg = types.SimpleNamespace(sp_pts_mask=S.clone())
+            save.update({f"gt_boxes{i}": gt, f"labels{i}": labels})
+        samples.append(types.SimpleNamespace(lidar_path=f"data/{names[i]}/points/x.bin", gt_pts_seg=seg, gt_instances_3d=gi))
+        pts_in.append(P)
+    sd0 = {k: v.clone() for k, v in det.state_dict().items()}
+    out = det.loss(dict(points=pts_in), samples)
+    out["det_loss"].backward()
+    save["det_loss"] = out["det_loss"].detach().numpy()
+    save.update({"sd." + k: v.numpy() for k, v in sd0.items()})
+    n_grad = 0
+    for k, p in det.named_parameters():
+        assert p.grad is not None, k
+        save["grad." + k] = p.grad.numpy()
+        n_grad += 1
+    for i, smp in enumerate(samples):                    # what loss() derived on the way (unidet3d.py:306-336)
+        gi = smp.gt_instances_3d
+        save[f"used_boxes{i}"] = gi.bboxes_3d.tensor.numpy()
+        save[f"used_sp_masks{i}"] = gi.sp_masks.numpy()
+    np.savez_compressed(os.path.join(HERE, "train_step_ref.npz"), **save)
+    print("train_step_ref.npz det_loss", float(save["det_loss"]), "parameter gradients", n_grad,
+          "max |grad|", max(float(np.abs(save[k]).max()) for k in save if k.startswith("grad.")))
+
+
 def gen_gt_prep():
     """The reference's GT-preparation transforms (unidet3d/transforms_3d.py) on synthetic masks."""
     from unidet3d.transforms_3d import PointDetClassMappingScanNet, PointDetClassMappingS3DIS, PointSample_
@@ -802,6 +935,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "backward", "gt_prep", "augment", "evaluate"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "backward", "train_step", "gt_prep", "augment", "evaluate"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "backward": gen_backward, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "backward": gen_backward, "train_step": gen_train_step, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()
