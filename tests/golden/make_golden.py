@@ -4,7 +4,7 @@ Run (build container only -- /root/reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,backward_ref,train_step_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
+Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,backward_ref,train_step_ref,predict_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
 imported unmodified from /root/reference; their absent third-party imports
 (mmengine, mmdet3d, spconv, MinkowskiEngine, torch_scatter, mmcv) are replaced by
 minimal stand-ins defined here:
@@ -751,6 +751,62 @@ def gen_train_step():
           "max |grad|", max(float(np.abs(save[k]).max()) for k in save if k.startswith("grad.")))
 
 
+def gen_predict():
+    """The reference's own ``UniDet3D.predict`` (unidet3d.py:411-473) END TO END in eval mode, one call per scene (the
+    reference post-processes scene 0 of a batch only, :498-502): collate (ME stand-in), input conv + SpConvUNet over the
+    dense spconv stand-in, output BN + ReLU, superpoint pooling, the encoder, ``predict_by_feat`` (top-k, multi-class NMS,
+    superpoint trimming).  Three flavours: scannet (fast NMS + superpoint trim), s3dis (3-D aligned NMS + trim), 3rscan
+    (fast NMS, no superpoints: [n, 7] boxes with yaw 0).  Pins the COMPOSITION oracle/detector.py::forward_scenes restates
+    (the NMS kernels themselves are the oracle's restatements on both sides, see the module docstring)."""
+    import unidet3d.encoder  # noqa: F401
+    import unidet3d.spconv_unet  # noqa: F401
+    from unidet3d.unidet3d import UniDet3D
+    from unidet3d_b200.synthetic import make_scene, SCENE_PRESETS
+    _install_me_standin()
+    MODELS = sys.modules["mmdet3d.registry"].MODELS
+    InstanceData = sys.modules["mmengine.structures"].InstanceData
+    sys.modules["unidet3d.structures"].InstanceData_ = InstanceData
+    torch.manual_seed(53)
+    datasets = ["scannet", "s3dis", "3rscan"]
+    classes = [["chair", "table", "sofa", "bed", "sink"], ["table", "board", "bed", "oven"], ["chair", "sofa", "lamp"]]
+    planes, voxel = [8, 16, 24], 0.05
+    det = object.__new__(UniDet3D)
+    nn.Module.__init__(det)
+    det.unet = MODELS.build(dict(type="SpConvUNet", num_planes=planes, return_blocks=True))
+    det.decoder = MODELS.build(dict(type="UniDet3DEncoder", num_layers=2, datasets_classes=classes, in_channels=planes[0], d_model=64,
+                                    num_heads=2, hidden_dim=128, dropout=0.0, activation_fn="gelu", datasets=datasets,
+                                    angles=[False, False, False]))
+    det.voxel_size, det.min_spatial_shape, det.query_thr = voxel, 32, 3000
+    det.use_superpoints, det.fast_nms = [True, True, False], [True, False, True]
+    det.test_cfg = types.SimpleNamespace(topk_insts=120, score_thr=0.0, iou_thr=[0.5, 0.55, 0.55], low_sp_thr=0.18, up_sp_thr=0.81)
+    det.use_sync_bn = True
+    det._init_layers(6, planes[0])
+    with torch.no_grad():
+        for mod in det.modules():
+            if isinstance(mod, nn.BatchNorm1d):
+                mod.weight.uniform_(0.5, 1.5); mod.bias.normal_(0, 0.1)
+                mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
+        for k, p in det.decoder.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+        det.decoder.out_bboxes.linear.bias.add_(-1.0)                       # box sizes of a few decimetres: NMS has work to do
+    det.eval()
+    n, _, area, cell = SCENE_PRESETS["tiny"]
+    save = {"names": np.array(datasets), "voxel_size": np.array(voxel), "planes": np.array(planes)}
+    save.update({"sd." + k: v.numpy() for k, v in det.state_dict().items()})
+    for i, name in enumerate(datasets):
+        pts, sp = make_scene(400 + i, n, area, cell)
+        sample = types.SimpleNamespace(lidar_path=f"data/{name}/points/x.bin",
+                                       gt_pts_seg=types.SimpleNamespace(sp_pts_mask=torch.as_tensor(sp).clone()))
+        with torch.no_grad():
+            res = det.predict(dict(points=[torch.as_tensor(pts)]), [sample])
+        pi = res[0].pred_instances_3d
+        save.update({f"points{i}": pts, f"sp{i}": sp, f"boxes{i}": pi.bboxes_3d.tensor.numpy(), f"labels{i}": pi.labels_3d.numpy(),
+                     f"scores{i}": pi.scores_3d.numpy()})
+        print("predict", name, pi.bboxes_3d.tensor.shape, float(pi.scores_3d.max()))
+    np.savez_compressed(os.path.join(HERE, "predict_ref.npz"), **save)
+
+
 def gen_gt_prep():
     """The reference's GT-preparation transforms (unidet3d/transforms_3d.py) on synthetic masks."""
     from unidet3d.transforms_3d import PointDetClassMappingScanNet, PointDetClassMappingS3DIS, PointSample_
@@ -935,6 +991,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "backward", "train_step", "gt_prep", "augment", "evaluate"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "backward", "train_step", "predict", "gt_prep", "augment", "evaluate"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "backward": gen_backward, "train_step": gen_train_step, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "backward": gen_backward, "train_step": gen_train_step, "predict": gen_predict, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()

@@ -275,3 +275,32 @@ def test_training_loss_and_all_parameter_gradients_match_the_reference_loss_end_
     # measured: loss identical, gradients median 1.2e-6, max 3.7e-6
     assert worst < 1e-4, sorted(((e, k) for k, e in errs.items()), reverse=True)[:5]
     assert sorted(errs.values())[len(errs) // 2] < 1e-5
+
+
+def test_forward_scenes_matches_the_reference_predict_end_to_end(golden_dir):
+    """predict_ref.npz: the reference's own ``UniDet3D.predict`` (collate, backbone, pooling, encoder, predict_by_feat) on
+    one scene per dataset flavour -- scannet (fast NMS + superpoint trim), s3dis (aligned 3-D NMS + trim), 3rscan (fast NMS,
+    no superpoints, [n, 7] boxes) -- against oracle/detector.py::forward_scenes, the function the GPU detector is compared
+    with: same detections (labels exact, scores / boxes to fp32 round-off)."""
+    from oracle import detector as odet
+    g = _load(golden_dir, "predict_ref.npz")
+    names = [str(n) for n in g["names"]]
+    sd = {k[3:]: torch.as_tensor(g[k]) for k in g.files if k.startswith("sd.")}
+    det_sd = {k: t for k, t in sd.items() if not k.startswith("decoder.")}
+    enc_sd = {k[len("decoder."):]: t for k, t in sd.items() if k.startswith("decoder.")}
+    classes = [["chair", "table", "sofa", "bed", "sink"], ["table", "board", "bed", "oven"], ["chair", "sofa", "lamp"]]
+    cfg = dict(voxel_size=float(g["voxel_size"]), min_spatial_shape=32,
+               encoder=dict(num_layers=2, num_heads=2, activation_fn="gelu", datasets=names, datasets_classes=classes,
+                            angles=[False, False, False]),
+               test_cfg=dict(topk_insts=120, score_thr=0.0, iou_thr=[0.5, 0.55, 0.55], low_sp_thr=0.18, up_sp_thr=0.81),
+               fast_nms=[True, False, True], use_superpoints=[True, True, False])
+    for i, name in enumerate(names):
+        (b, l, s), = odet.forward_scenes(det_sd, enc_sd, cfg, [g[f"points{i}"]], [g[f"sp{i}"]], [name])
+        assert b.shape == g[f"boxes{i}"].shape, (name, b.shape, g[f"boxes{i}"].shape)
+        assert np.array_equal(np.asarray(l), g[f"labels{i}"]), name
+        assert np.allclose(np.asarray(s), g[f"scores{i}"], rtol=1e-4, atol=1e-6), name
+        ref = g[f"boxes{i}"]
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(np.asarray(b)), fin)
+        assert np.allclose(np.asarray(b)[fin], ref[fin], rtol=1e-4, atol=1e-5), (name, np.abs(np.asarray(b)[fin] - ref[fin]).max())
+    assert g["boxes2"].shape[1] == 7 and not g["boxes2"][:, 6].any()           # the yaw-0 padding quirk of the fast-NMS path
