@@ -4,7 +4,7 @@ Run (build container only -- /root/reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,backward_ref,train_step_ref,predict_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
+Writes tests/golden/{encoder_ref,unet_ref,post_ref,criterion_ref,criterion_grad_ref,backward_ref,train_step_ref,predict_ref,collate_ref,gt_prep_ref,augment_ref,evaluate_ref}.npz (all, or the ones named on the command line).  The reference modules are
 imported unmodified from /root/reference; their absent third-party imports
 (mmengine, mmdet3d, spconv, MinkowskiEngine, torch_scatter, mmcv) are replaced by
 minimal stand-ins defined here:
@@ -807,6 +807,30 @@ def gen_predict():
     np.savez_compressed(os.path.join(HERE, "predict_ref.npz"), **save)
 
 
+def gen_collate():
+    """The reference's own ``UniDet3D.collate`` (unidet3d.py:136-176) over the numpy MinkowskiEngine stand-in, plain and with
+    ``elastic_points`` (float64 where ElasticTransfrom applied, float32 where its coin flip skipped it): the coordinate
+    recipe (per-scene min shift, division by the voxel size, floor), the feature recipe (colour | xyz - per-scene mean), the
+    spatial shape clip and the inverse mapping."""
+    from unidet3d.unidet3d import UniDet3D
+    _install_me_standin()
+    rng = np.random.default_rng(61)
+    det = object.__new__(UniDet3D)
+    nn.Module.__init__(det)
+    det.voxel_size, det.min_spatial_shape = 0.05, 16
+    pts = [rng.uniform(-1.5, 1.7, (1500, 6)).astype(np.float32), rng.uniform(0.2, 2.4, (900, 6)).astype(np.float32)]
+    pts[0][:40, :3] = pts[0][40:80, :3]                                    # exact duplicates share a voxel
+    el = [(pts[0][:, :3].astype(np.float64) / 0.05 + rng.normal(0, 0.8, (1500, 3))), (pts[1][:, :3] / np.float32(0.05))]
+    assert el[0].dtype == np.float64 and el[1].dtype == np.float32
+    save = {"points0": pts[0], "points1": pts[1], "elastic0": el[0], "elastic1": el[1], "voxel_size": np.array(0.05)}
+    for tag, elastic in (("plain", None), ("elastic", [torch.as_tensor(e) for e in el])):
+        c, f, inv, shape = det.collate([torch.as_tensor(p) for p in pts], elastic)
+        save.update({f"{tag}_coords": c.numpy(), f"{tag}_feats": f.numpy(), f"{tag}_inverse": inv.numpy(),
+                     f"{tag}_shape": shape.numpy()})
+        print("collate", tag, tuple(c.shape), shape.tolist())
+    np.savez_compressed(os.path.join(HERE, "collate_ref.npz"), **save)
+
+
 def gen_gt_prep():
     """The reference's GT-preparation transforms (unidet3d/transforms_3d.py) on synthetic masks."""
     from unidet3d.transforms_3d import PointDetClassMappingScanNet, PointDetClassMappingS3DIS, PointSample_
@@ -991,6 +1015,6 @@ def gen_post():
 if __name__ == "__main__":
     assert os.path.isdir(REF), "reference checkout not present: goldens can only be generated in the build container"
     install_stubs()
-    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "backward", "train_step", "predict", "gt_prep", "augment", "evaluate"]
+    which = sys.argv[1:] or ["encoder", "unet", "post", "criterion", "criterion_grad", "backward", "train_step", "predict", "collate", "gt_prep", "augment", "evaluate"]
     for name in which:
-        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "backward": gen_backward, "train_step": gen_train_step, "predict": gen_predict, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()
+        {"encoder": gen_encoder, "unet": gen_unet, "post": gen_post, "criterion": gen_criterion, "criterion_grad": gen_criterion_grad, "backward": gen_backward, "train_step": gen_train_step, "predict": gen_predict, "collate": gen_collate, "gt_prep": gen_gt_prep, "augment": gen_augment, "evaluate": gen_evaluate}[name]()

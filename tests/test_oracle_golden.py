@@ -304,3 +304,18 @@ def test_forward_scenes_matches_the_reference_predict_end_to_end(golden_dir):
         assert np.array_equal(np.isfinite(np.asarray(b)), fin)
         assert np.allclose(np.asarray(b)[fin], ref[fin], rtol=1e-4, atol=1e-5), (name, np.abs(np.asarray(b)[fin] - ref[fin]).max())
     assert g["boxes2"].shape[1] == 7 and not g["boxes2"][:, 6].any()           # the yaw-0 padding quirk of the fast-NMS path
+
+
+def test_voxelize_matches_the_reference_collate(golden_dir):
+    """collate_ref.npz: the reference's own ``UniDet3D.collate`` (over a numpy MinkowskiEngine stand-in), plain and with
+    elastic coordinates of both dtypes, against oracle.voxelize: coordinates, inverse map and spatial shape bit-exact,
+    voxel features to fp32 round-off of the mean."""
+    g = _load(golden_dir, "collate_ref.npz")
+    pts = [g["points0"], g["points1"]]
+    for tag, el in (("plain", None), ("elastic", [g["elastic0"], g["elastic1"]])):
+        coords, feats, inverse, shape = ovox.voxelize(pts, float(g["voxel_size"]), 16, el)
+        assert np.array_equal(coords, g[f"{tag}_coords"]) and coords.dtype == np.int32
+        assert np.array_equal(inverse, g[f"{tag}_inverse"])
+        assert np.array_equal(shape, g[f"{tag}_shape"])
+        assert np.allclose(feats, g[f"{tag}_feats"], rtol=1e-6, atol=1e-6)
+    assert not np.array_equal(g["plain_coords"], g["elastic_coords"])
